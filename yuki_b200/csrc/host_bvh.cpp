@@ -1,0 +1,258 @@
+// Host BVH builder for the B200 backend: produces, directly in pre-order, the same 32-byte linear
+// nodes and the same leaf ordering as yuki's BoundingVolumeHierarchy::new (yuki/src/bvh.rs:39-115,
+// recursive_build :305-390, split_* :422-523, flatten_tree :396-419), so that device traversal visits
+// exactly the nodes the reference visits (its intersection_test_count, bvh.rs:177, is a parity gate).
+//
+// Not a port of the reference's two-phase build (arena tree + flatten): subtrees are emitted straight
+// into a flat vector, and large subtrees are built concurrently and spliced (their leaf ranges are
+// disjoint slices of the primitive array, so the result does not depend on the schedule).
+#include <algorithm>
+#include <atomic>
+#include <future>
+#include <thread>
+#include <vector>
+
+#include "host_math.h"
+#include "yuki_gpu.h"
+
+namespace ykh {
+
+struct Prim {
+    uint32_t index;
+    box3 box;
+    f3 key;  // the reference's "centroid": p_min + diagonal / 0.5 (bvh.rs:56) — twice the diagonal, reproduced
+};
+
+struct Builder {
+    Prim* prims;
+    uint32_t leaf_max;
+    uint32_t method;
+    std::atomic<bool> failed{false};
+
+    static constexpr int kBuckets = 12;
+    static constexpr size_t kParallelCutoff = 1u << 16;
+
+    // centroid_bounds.offset(c)[axis] (yuki_derive/src/impl_bounds.rs:230-234), then the bucket index of
+    // bvh.rs:476-479: (12*o).max(0) as usize, min 11. `as usize` truncates and saturates, NaN -> 0.
+    static int bucket_index(const box3& kb, const Prim& p, int axis) {
+        float o = p.key.get(axis) - kb.lo.get(axis);
+        const float ext_hi = kb.hi.get(axis), ext_lo = kb.lo.get(axis);
+        if (ext_hi != ext_lo) o /= ext_hi - ext_lo;
+        const float scaled = fmaxf((float)kBuckets * o, 0.0f);
+        if (!(scaled == scaled)) return 0;
+        if (scaled >= (float)kBuckets) return kBuckets - 1;
+        return std::min((int)scaled, kBuckets - 1);
+    }
+
+    // itertools::partition (third-party, itertools 0.10): two-ended scan with swaps; deterministic.
+    template <class Keep>
+    static size_t stable_front_partition(Prim* a, size_t n, Keep keep) {
+        size_t lo = 0, hi = n, kept = 0;
+        while (lo < hi) {
+            Prim& front = a[lo++];
+            if (!keep(front)) {
+                bool swapped = false;
+                while (lo < hi) {
+                    Prim& back = a[--hi];
+                    if (keep(back)) {
+                        std::swap(front, back);
+                        swapped = true;
+                        break;
+                    }
+                }
+                if (!swapped) break;
+            }
+            ++kept;
+        }
+        return kept;
+    }
+
+    size_t median_split(size_t lo, size_t hi, int axis) {  // split_equal_counts, bvh.rs:422-436
+        const size_t mid = (lo + hi) / 2;
+        std::nth_element(prims + lo, prims + mid, prims + hi,
+                         [axis](const Prim& a, const Prim& b) { return a.key.get(axis) < b.key.get(axis); });
+        return mid;
+    }
+
+    // Returns the split position, `lo` when the method declines (caller falls back to the median), or
+    // SIZE_MAX when SAH prefers a leaf (bvh.rs:510-521).
+    size_t choose_split(const box3& box, const box3& kb, size_t lo, size_t hi, int axis) {
+        const size_t n = hi - lo;
+        if (method == YK_SPLIT_EQUAL_COUNTS) return median_split(lo, hi, axis);
+        if (method == YK_SPLIT_MIDDLE) {  // split_middle, bvh.rs:438-450
+            const float pivot = (kb.lo.get(axis) + kb.hi.get(axis)) / 2.0f;
+            return lo + stable_front_partition(prims + lo, n, [=](const Prim& p) { return p.key.get(axis) < pivot; });
+        }
+        if (n <= 2) return lo;  // bvh.rs:461-462
+        size_t count[kBuckets] = {};
+        box3 bbox[kBuckets];
+        for (auto& b : bbox) b = empty_box();
+        for (size_t i = lo; i < hi; ++i) {
+            const int b = bucket_index(kb, prims[i], axis);
+            count[b] += 1;
+            bbox[b] = merge(bbox[b], prims[i].box);
+        }
+        // Suffix boxes/counts once instead of the reference's O(buckets^2) folds; min/max unions are exact
+        // and association-free, so each side's box and count are identical.
+        box3 right_box[kBuckets];
+        size_t right_count[kBuckets];
+        box3 acc = empty_box();
+        size_t cacc = 0;
+        for (int b = kBuckets - 1; b >= 1; --b) {
+            acc = merge(bbox[b], acc);
+            cacc += count[b];
+            right_box[b] = acc;
+            right_count[b] = cacc;
+        }
+        const float denom = fmaxf(half_area_x2(box), 1e-10f);
+        box3 left = empty_box();
+        size_t left_count = 0;
+        int best = 0;
+        float best_cost = 0.0f;
+        for (int s = 0; s < kBuckets - 1; ++s) {
+            left = merge(left, bbox[s]);
+            left_count += count[s];
+            const float cost =
+                1.0f + ((float)left_count * half_area_x2(left) + (float)right_count[s + 1] * half_area_x2(right_box[s + 1])) / denom;
+            if (s == 0 || cost < best_cost) {  // min_by keeps the first minimum (bvh.rs:504-508)
+                best = s;
+                best_cost = cost;
+            }
+        }
+        if (!(best_cost < (float)n)) return SIZE_MAX;
+        return lo + stable_front_partition(prims + lo, n, [&](const Prim& p) { return bucket_index(kb, p, axis) <= best; });
+    }
+
+    static void emit_leaf(std::vector<yk_bvh_node>& out, const box3& box, size_t lo, size_t hi) {
+        yk_bvh_node nd{};
+        store3(box.lo, nd.p_min);
+        store3(box.hi, nd.p_max);
+        nd.offset = (uint32_t)lo;  // == ordered_shapes.len() at emission time in the reference's DFS
+        nd.shape_count = (uint16_t)(hi - lo);
+        nd.is_leaf = 1;
+        out.push_back(nd);
+    }
+
+    // Appends the subtree over prims[lo, hi) to `out` in pre-order; returns its bounds. Node indices
+    // written into `offset` are relative to out[0]; `depth` bounds how far down subtrees run as tasks.
+    box3 emit(std::vector<yk_bvh_node>& out, size_t lo, size_t hi, int task_depth) {
+        box3 box = empty_box();
+        for (size_t i = lo; i < hi; ++i) box = merge(box, prims[i].box);
+        const size_t n = hi - lo;
+        if (n <= leaf_max) {
+            emit_leaf(out, box, lo, hi);
+            return box;
+        }
+        box3 kb = empty_box();
+        for (size_t i = lo; i < hi; ++i) kb = grow(kb, prims[i].key);
+        const int axis = widest_axis(kb);
+        if (kb.hi.get(axis) == kb.lo.get(axis)) {  // bvh.rs:343
+            emit_leaf(out, box, lo, hi);
+            return box;
+        }
+        size_t mid = choose_split(box, kb, lo, hi, axis);
+        if (method != YK_SPLIT_EQUAL_COUNTS && (mid == lo || mid == hi)) mid = median_split(lo, hi, axis);
+        if (mid == lo) {  // assert_ne!(mid, start, "BVH: Split failed") — bvh.rs:368
+            failed = true;
+            emit_leaf(out, box, lo, hi);
+            return box;
+        }
+        if (mid == SIZE_MAX) {
+            emit_leaf(out, box, lo, hi);
+            return box;
+        }
+        const size_t self = out.size();
+        out.push_back(yk_bvh_node{});
+        box3 lbox, rbox;
+        uint32_t second;
+        if (task_depth > 0 && n >= kParallelCutoff) {
+            std::vector<yk_bvh_node> lsub, rsub;
+            auto fut = std::async(std::launch::async, [&] { return emit(rsub, mid, hi, task_depth - 1); });
+            lbox = emit(lsub, lo, mid, task_depth - 1);
+            rbox = fut.get();
+            const uint32_t lbase = (uint32_t)out.size();
+            for (auto nd : lsub) {
+                if (!nd.is_leaf) nd.offset += lbase;
+                out.push_back(nd);
+            }
+            second = (uint32_t)out.size();
+            for (auto nd : rsub) {
+                if (!nd.is_leaf) nd.offset += second;
+                out.push_back(nd);
+            }
+        } else {
+            lbox = emit(out, lo, mid, 0);
+            second = (uint32_t)out.size();
+            rbox = emit(out, mid, hi, 0);
+        }
+        const box3 both = merge(lbox, rbox);  // BVHBuildNode::interior, bvh.rs:605-614
+        yk_bvh_node& nd = out[self];
+        store3(both.lo, nd.p_min);
+        store3(both.hi, nd.p_max);
+        nd.offset = second;
+        nd.shape_count = 0;
+        nd.split_axis = (uint8_t)axis;
+        nd.is_leaf = 0;
+        return both;
+    }
+};
+
+// Deepest root-to-leaf path; the traversal stack holds 64 entries (bvh.rs:172-174).
+static uint32_t tree_height(const yk_bvh_node* nodes, uint32_t n_nodes) {
+    std::vector<std::pair<uint32_t, uint32_t>> stack{{0u, 1u}};
+    uint32_t best = 0;
+    while (!stack.empty()) {
+        auto [i, d] = stack.back();
+        stack.pop_back();
+        if (i >= n_nodes) continue;
+        best = std::max(best, d);
+        if (!nodes[i].is_leaf) {
+            stack.push_back({i + 1, d + 1});
+            stack.push_back({nodes[i].offset, d + 1});
+        }
+    }
+    return best;
+}
+
+int bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
+              std::vector<yk_bvh_node>* nodes, std::vector<uint32_t>* order, const char** why) {
+    if (!tri_vertices || n_tris == 0) {
+        *why = "yk_bvh_build: empty triangle list";
+        return YK_ERR_INVALID;
+    }
+    if (split_method > YK_SPLIT_EQUAL_COUNTS) {
+        *why = "yk_bvh_build: unknown split method";
+        return YK_ERR_INVALID;
+    }
+    std::vector<Prim> prims(n_tris);
+    for (uint32_t i = 0; i < n_tris; ++i) {
+        const float* v = tri_vertices + (size_t)i * 9;
+        // Triangle::world_bound (triangle.rs:229-235): Bounds3::new(p0, p1).union_p(p2)
+        box3 b{min3(load3(v), load3(v + 3)), max3(load3(v), load3(v + 3))};
+        b = grow(b, load3(v + 6));
+        prims[i] = {i, b, add(b.lo, divs(sub(b.hi, b.lo), 0.5f))};
+    }
+    Builder bld;
+    bld.prims = prims.data();
+    bld.leaf_max = max_shapes_in_node;
+    bld.method = split_method;
+    nodes->clear();
+    nodes->reserve((size_t)2 * n_tris);
+    unsigned hw = std::thread::hardware_concurrency();
+    int task_depth = 0;
+    while ((1u << task_depth) < hw && task_depth < 6) ++task_depth;
+    bld.emit(*nodes, 0, n_tris, task_depth);
+    if (bld.failed) {
+        *why = "BVH: Split failed (bvh.rs:368)";
+        return YK_ERR_BVH;
+    }
+    if (tree_height(nodes->data(), (uint32_t)nodes->size()) > 64) {
+        *why = "BVH deeper than the 64-entry traversal stack (bvh.rs:172-174)";
+        return YK_ERR_BVH;
+    }
+    order->resize(n_tris);
+    for (uint32_t i = 0; i < n_tris; ++i) (*order)[i] = prims[i].index;
+    return YK_OK;
+}
+
+}  // namespace ykh

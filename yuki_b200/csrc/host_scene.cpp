@@ -1,0 +1,321 @@
+// Host-side scene assembly for the B200 backend and the Level-2 entry points of include/yuki_gpu.h.
+// Mirrors what yuki's loaders do before the hot path starts: Mesh::new (shapes/mesh.rs:21-43),
+// Triangle::new (shapes/triangle.rs:27-46), the light constructors (lights/*.rs), Camera::new
+// (camera.rs:52-102), film_tiles (film.rs:299-376) — then flattens everything into the leaf-ordered SoA
+// arrays yk_scene_create uploads.
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host_math.h"
+#include "yuki_gpu.h"
+
+namespace ykh {
+int bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
+              std::vector<yk_bvh_node>* nodes, std::vector<uint32_t>* order, const char** why);
+}
+
+// ---- error channel (shared with the device side) ------------------------------------------------
+static thread_local std::string g_last_error;
+extern "C" const char* yk_last_error(void) { return g_last_error.c_str(); }
+int yk_set_error(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+using namespace ykh;
+
+static xform to_xform(const yk_transform& t) {
+    xform x;
+    std::memcpy(x.m.e, t.m, 64);
+    std::memcpy(x.inv.e, t.m_inv, 64);
+    return x;
+}
+static void from_xform(const xform& x, yk_transform* t) {
+    std::memcpy(t->m, x.m.e, 64);
+    std::memcpy(t->m_inv, x.inv.e, 64);
+}
+
+struct yk_host_scene {
+    std::vector<yk_bvh_node> nodes;
+    std::vector<float> tri_vertices, tri_normals, tri_uvs;
+    std::vector<uint32_t> tri_orig_id, tri_material;
+    std::vector<int32_t> tri_area_light;
+    std::vector<uint8_t> tri_flags;
+    std::vector<yk_texture_desc> textures;
+    std::vector<std::vector<float>> texel_storage;
+    std::vector<yk_material_desc> materials;
+    std::vector<yk_light> lights;
+    float background[3];
+};
+
+extern "C" {
+
+int yk_light_make(const yk_light_desc* d, yk_light* out) {
+    if (!d || !out) return yk_set_error(YK_ERR_INVALID, "yk_light_make: null argument");
+    std::memset(out, 0, sizeof(*out));
+    out->kind = d->kind;
+    std::memcpy(out->i, d->intensity, 12);
+    const xform l2w = to_xform(d->light_to_world);
+    switch (d->kind) {
+        case YK_LIGHT_POINT:  // PointLight::new, point_light.rs:18-24
+            store3(apply_point(l2w.m, mk3(0, 0, 0)), out->p);
+            break;
+        case YK_LIGHT_SPOT: {  // SpotLight::new, spot_light.rs:23-36
+            store3(apply_point(l2w.m, mk3(0, 0, 0)), out->p);
+            std::memcpy(out->world_to_light, l2w.inv.e, 64);
+            out->cos_total_width = cosf(deg2rad(d->total_width_deg));
+            out->cos_falloff_start = cosf(deg2rad(d->falloff_start_deg));
+        } break;
+        case YK_LIGHT_RECT: {  // RectangularLight::new, rectangular_light.rs:27-43
+            const xform s2l = xf_compose(xf_scaling(d->size[0], 1.0f, d->size[1]), xf_translate(mk3(-0.5f, 0.0f, -0.5f)));
+            const xform s2w = xf_compose(l2w, s2l);
+            std::memcpy(out->sample_to_world, s2w.m.e, 64);
+            std::memcpy(out->sample_to_world_inv, s2w.inv.e, 64);
+            out->area = d->size[0] * d->size[1];
+        } break;
+        case YK_LIGHT_DISTANT:  // DistantLight::new, distant_light.rs:17-21
+            std::memcpy(out->p, d->direction, 12);
+            break;
+        default:
+            return yk_set_error(YK_ERR_INVALID, "yk_light_make: unknown light kind");
+    }
+    return YK_OK;
+}
+
+int yk_bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
+                 yk_bvh_node* nodes, uint32_t* n_nodes, uint32_t* order) {
+    if (!nodes || !n_nodes || !order) return yk_set_error(YK_ERR_INVALID, "yk_bvh_build: null output");
+    std::vector<yk_bvh_node> nv;
+    std::vector<uint32_t> ov;
+    const char* why = "";
+    int rc = bvh_build(tri_vertices, n_tris, max_shapes_in_node, split_method, &nv, &ov, &why);
+    if (rc != YK_OK) return yk_set_error(rc, why);
+    std::memcpy(nodes, nv.data(), nv.size() * sizeof(yk_bvh_node));
+    std::memcpy(order, ov.data(), ov.size() * sizeof(uint32_t));
+    *n_nodes = (uint32_t)nv.size();
+    return YK_OK;
+}
+
+int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
+    if (!d || !out) return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: null argument");
+    auto hs = std::make_unique<yk_host_scene>();
+
+    // Triangles in declaration order (the reference's `shapes` Vec before the BVH reorders it).
+    std::vector<float> verts, norms, uvs;
+    std::vector<uint32_t> mats;
+    std::vector<int32_t> alights;
+    std::vector<uint8_t> flags;
+    bool any_normals = false, any_uvs = false;
+    for (uint32_t mi = 0; mi < d->n_meshes; ++mi) {
+        any_normals |= d->meshes[mi].normals != nullptr;
+        any_uvs |= d->meshes[mi].uvs != nullptr;
+    }
+    for (uint32_t mi = 0; mi < d->n_meshes; ++mi) {
+        const yk_mesh_desc& m = d->meshes[mi];
+        if (m.material < 0 || (uint32_t)m.material >= d->n_materials)
+            return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: mesh material index out of range");
+        if (m.area_light >= (int32_t)d->n_lights || (m.area_light >= 0 && d->lights[m.area_light].kind != YK_LIGHT_RECT))
+            return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: mesh area_light must index a rectangular light");
+        const xform o2w = to_xform(m.object_to_world);
+        std::vector<f3> wp(m.n_points), wn;
+        for (uint32_t k = 0; k < m.n_points; ++k) wp[k] = apply_point(o2w.m, load3(m.points + 3 * k));  // mesh.rs:27-29
+        if (m.normals) {
+            wn.resize(m.n_points);
+            for (uint32_t k = 0; k < m.n_points; ++k) wn[k] = apply_normal(o2w.inv, load3(m.normals + 3 * k));  // :31-33
+        }
+        const uint8_t fl = (flips_handedness(o2w.m) ? YK_TRI_SWAPS_HANDEDNESS : 0u) | (m.normals ? YK_TRI_HAS_NORMALS : 0u) |
+                           (m.uvs ? YK_TRI_HAS_UVS : 0u);
+        for (uint32_t i0 = 0; i0 + 2 < m.n_indices; i0 += 3) {
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t vi = m.indices[i0 + c];
+                if (vi >= m.n_points) return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: vertex index out of range");
+                float tmp[3];
+                store3(wp[vi], tmp);
+                verts.insert(verts.end(), tmp, tmp + 3);
+                if (any_normals) {
+                    if (m.normals) store3(wn[vi], tmp);
+                    else tmp[0] = tmp[1] = tmp[2] = 0.0f;
+                    norms.insert(norms.end(), tmp, tmp + 3);
+                }
+                if (any_uvs) {
+                    uvs.push_back(m.uvs ? m.uvs[2 * vi] : 0.0f);
+                    uvs.push_back(m.uvs ? m.uvs[2 * vi + 1] : 0.0f);
+                }
+            }
+            mats.push_back((uint32_t)m.material);
+            alights.push_back(m.area_light);
+            flags.push_back(fl);
+        }
+    }
+    const uint32_t n_tris = (uint32_t)mats.size();
+    std::vector<uint32_t> order;
+    const char* why = "";
+    int rc = bvh_build(verts.data(), n_tris, d->max_shapes_in_node ? d->max_shapes_in_node : 1u, d->split_method, &hs->nodes,
+                       &order, &why);
+    if (rc != YK_OK) return yk_set_error(rc, why);
+
+    // Gather into leaf order.
+    hs->tri_vertices.resize((size_t)n_tris * 9);
+    if (any_normals) hs->tri_normals.resize((size_t)n_tris * 9);
+    if (any_uvs) hs->tri_uvs.resize((size_t)n_tris * 6);
+    hs->tri_orig_id = order;
+    hs->tri_material.resize(n_tris);
+    hs->tri_area_light.resize(n_tris);
+    hs->tri_flags.resize(n_tris);
+    for (uint32_t i = 0; i < n_tris; ++i) {
+        const uint32_t s = order[i];
+        std::memcpy(&hs->tri_vertices[(size_t)i * 9], &verts[(size_t)s * 9], 36);
+        if (any_normals) std::memcpy(&hs->tri_normals[(size_t)i * 9], &norms[(size_t)s * 9], 36);
+        if (any_uvs) std::memcpy(&hs->tri_uvs[(size_t)i * 6], &uvs[(size_t)s * 6], 24);
+        hs->tri_material[i] = mats[s];
+        hs->tri_area_light[i] = alights[s];
+        hs->tri_flags[i] = flags[s];
+    }
+
+    hs->texel_storage.resize(d->n_textures);
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        yk_texture_desc t = d->textures[i];
+        if (t.kind == YK_TEX_IMAGE) {
+            if (!t.texels || !t.width || !t.height) return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: empty image texture");
+            hs->texel_storage[i].assign(t.texels, t.texels + (size_t)t.width * t.height * 3);
+            t.texels = hs->texel_storage[i].data();
+        } else {
+            t.texels = nullptr;
+        }
+        hs->textures.push_back(t);
+    }
+    hs->materials.assign(d->materials, d->materials + d->n_materials);
+    for (uint32_t i = 0; i < d->n_lights; ++i) {
+        yk_light l;
+        rc = yk_light_make(&d->lights[i], &l);
+        if (rc != YK_OK) return rc;
+        hs->lights.push_back(l);
+    }
+    std::memcpy(hs->background, d->background, 12);
+    *out = hs.release();
+    return YK_OK;
+}
+
+void yk_host_scene_destroy(yk_host_scene* hs) { delete hs; }
+
+void yk_host_scene_flat(const yk_host_scene* hs, yk_scene_desc* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->n_nodes = (uint32_t)hs->nodes.size();
+    o->nodes = hs->nodes.data();
+    o->n_tris = (uint32_t)hs->tri_material.size();
+    o->tri_vertices = hs->tri_vertices.data();
+    o->tri_normals = hs->tri_normals.empty() ? nullptr : hs->tri_normals.data();
+    o->tri_uvs = hs->tri_uvs.empty() ? nullptr : hs->tri_uvs.data();
+    o->tri_orig_id = hs->tri_orig_id.data();
+    o->tri_material = hs->tri_material.data();
+    o->tri_area_light = hs->tri_area_light.data();
+    o->tri_flags = hs->tri_flags.data();
+    o->n_textures = (uint32_t)hs->textures.size();
+    o->n_materials = (uint32_t)hs->materials.size();
+    o->n_lights = (uint32_t)hs->lights.size();
+    o->textures = hs->textures.data();
+    o->materials = hs->materials.data();
+    o->lights = hs->lights.data();
+    std::memcpy(o->background, hs->background, 12);
+}
+
+// Camera::new, camera.rs:52-102
+int yk_camera_make(const yk_camera_params* p, uint32_t res_x, uint32_t res_y, yk_camera* out) {
+    if (!p || !out || !res_x || !res_y) return yk_set_error(YK_ERR_INVALID, "yk_camera_make: bad argument");
+    xform w2c;
+    if (!xf_look_at(load3(p->position), load3(p->target), load3(p->up), &w2c))
+        return yk_set_error(YK_ERR_SINGULAR, "Can't invert, singular matrix (look_at)");
+    const xform c2w = xf_flip(w2c);
+    const float z_near = 1e-2f, z_far = 1000.0f;
+    const float inv_tan = 1.0f / tanf(deg2rad(p->fov_deg) / 2.0f);
+    mat4 proj{};
+    proj.at(0, 0) = 1.0f;
+    proj.at(1, 1) = 1.0f;
+    proj.at(2, 2) = z_far / (z_far - z_near);
+    proj.at(2, 3) = -(z_far * z_near) / (z_far - z_near);
+    proj.at(3, 2) = 1.0f;
+    xform proj_t;
+    if (!xf_from_matrix(proj, &proj_t)) return yk_set_error(YK_ERR_SINGULAR, "Can't invert, singular matrix (projection)");
+    const xform cam_to_screen = xf_compose(xf_scaling(inv_tan, inv_tan, 1.0f), proj_t);
+    const float fx = (float)res_x, fy = (float)res_y;
+    float lo_x, lo_y, hi_x, hi_y;  // screen window, camera.rs:78-87
+    if (p->fov_axis == YK_FOV_X) {
+        const float ar = fx / fy;
+        lo_x = -1.0f; lo_y = -1.0f / ar; hi_x = 1.0f; hi_y = 1.0f / ar;
+    } else {
+        const float ar = fy / fx;
+        lo_x = -1.0f / ar; lo_y = -1.0f; hi_x = 1.0f / ar; hi_y = 1.0f;
+    }
+    const xform screen_to_raster =
+        xf_compose(xf_scaling(fx, fy, 1.0f),
+                   xf_compose(xf_scaling(1.0f / (hi_x - lo_x), 1.0f / (lo_y - hi_y), 1.0f), xf_translate(mk3(-lo_x, -hi_y, 0.0f))));
+    const xform raster_to_cam = xf_compose(xf_flip(cam_to_screen), xf_flip(screen_to_raster));
+    std::memcpy(out->camera_to_world, c2w.m.e, 64);
+    std::memcpy(out->raster_to_camera, raster_to_cam.m.e, 64);
+    return YK_OK;
+}
+
+// generate_tiles + outward_spiral, film.rs:299-376. Walks the square spiral around the centre tile and
+// emits the in-range tiles; tile rectangles are computed on the fly instead of through a hash map.
+uint32_t yk_film_tiles(uint32_t res_x, uint32_t res_y, uint32_t tile_dim, yk_tile* out, uint32_t cap) {
+    if (!res_x || !res_y || !tile_dim) return 0;
+    const int cols = (int)ceilf((float)res_x / (float)tile_dim);
+    const int rows = (int)ceilf((float)res_y / (float)tile_dim);
+    const int cx = cols / 2 - (1 - cols % 2), cy = rows / 2 - (1 - rows % 2);
+    const int side = cols > rows ? cols : rows;
+    int x = 0, y = 0, dx = 0, dy = -1;
+    uint32_t n = 0;
+    for (int step = 0; step < side * side; ++step) {
+        const int tx = cx + x, ty = cy + y;
+        if (tx >= 0 && tx < cols && ty >= 0 && ty < rows) {
+            if (out && n < cap) {
+                const uint32_t px = (uint32_t)tx * tile_dim, py = (uint32_t)ty * tile_dim;
+                yk_tile t;
+                t.x0 = (uint16_t)px;
+                t.y0 = (uint16_t)py;
+                t.x1 = (uint16_t)(px + tile_dim < res_x ? px + tile_dim : res_x);
+                t.y1 = (uint16_t)(py + tile_dim < res_y ? py + tile_dim : res_y);
+                t.sample = 0;
+                t._pad = 0;
+                t.index = (uint32_t)(ty * cols + tx);  // flat_index, film.rs:308-326
+                out[n] = t;
+            }
+            ++n;
+        }
+        if (x == y || (x < 0 && x == -y) || (x > 0 && x == 1 - y)) {
+            const int t = dx;
+            dx = -dy;
+            dy = t;
+        }
+        x += dx;
+        y += dy;
+    }
+    return n;
+}
+
+void yk_xf_identity(yk_transform* o) { from_xform(xf_id(), o); }
+void yk_xf_translation(const float* d, yk_transform* o) { from_xform(xf_translate(load3(d)), o); }
+void yk_xf_scale(float x, float y, float z, yk_transform* o) { from_xform(xf_scaling(x, y, z), o); }
+void yk_xf_rotation(float theta, const float* axis, yk_transform* o) { from_xform(xf_rotate(theta, load3(axis)), o); }
+int yk_xf_new(const float* m16, yk_transform* o) {
+    mat4 m;
+    std::memcpy(m.e, m16, 64);
+    xform t;
+    if (!xf_from_matrix(m, &t)) return yk_set_error(YK_ERR_SINGULAR, "Can't invert, singular matrix");
+    from_xform(t, o);
+    return YK_OK;
+}
+int yk_xf_look_at(const float* pos, const float* target, const float* up, yk_transform* o) {
+    xform t;
+    if (!xf_look_at(load3(pos), load3(target), load3(up), &t)) return yk_set_error(YK_ERR_SINGULAR, "Can't invert, singular matrix");
+    from_xform(t, o);
+    return YK_OK;
+}
+void yk_xf_mul(const yk_transform* a, const yk_transform* b, yk_transform* o) { from_xform(xf_compose(to_xform(*a), to_xform(*b)), o); }
+void yk_xf_inverted(const yk_transform* a, yk_transform* o) { from_xform(xf_flip(to_xform(*a)), o); }
+void yk_xf_point(const yk_transform* t, const float* p, float* o) { store3(apply_point(to_xform(*t).m, load3(p)), o); }
+void yk_xf_vec(const yk_transform* t, const float* v, float* o) { store3(apply_vec(to_xform(*t).m, load3(v)), o); }
+void yk_xf_normal(const yk_transform* t, const float* n, float* o) { store3(apply_normal(to_xform(*t).inv, load3(n)), o); }
+
+}  // extern "C"

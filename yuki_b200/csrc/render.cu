@@ -1,0 +1,1260 @@
+// B200 (sm_100a) wavefront renderer behind yk_render: replaces Integrator::render + Film::update_tile
+// (yuki/src/integrators/mod.rs:120-185, film.rs:210-282) for a list of film tiles.
+//
+// Pipeline per batch of (pixel, sample) paths, all state in HBM as SoA:
+//   raygen -> [ trace_closest -> classify(compact by material) -> shade_{matte,glass,metal,glossy}
+//               -> trace_any(shadow) -> resolve(+compact survivors) ]* -> film_accumulate
+// Nothing here is a dense contraction, so no tensor cores: the hot kernel (trace_closest) is a
+// dependent-load graph walk bounded by L2/HBM latency and bandwidth.
+//
+// Compiled with --fmad=false: every float op is the reference's un-fused IEEE op.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <memory>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "yk_device.cuh"
+#include "yuki_gpu.h"
+
+int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
+
+using namespace ykd;
+
+namespace {
+
+constexpr int kMaxLights = 16;
+constexpr int kStackDepth = 64;  // bvh.rs:172
+constexpr uint32_t kMiss = 0xffffffffu;
+constexpr int kTraceThreads = 128;
+constexpr int kShadeThreads = 128;
+
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return yk_set_error(YK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+// ---- device-resident scene ------------------------------------------------------------------------
+struct DevTexture {
+    uint32_t kind, width, height, _pad;
+    float value[3];
+    float _pad2;
+    const float* texels;
+};
+struct DevMaterial {
+    uint32_t kind;
+    int32_t tex[3];
+    float eta;
+    uint32_t remap;
+    float const_alpha;  // >= 0: roughness texture is constant, alpha fully evaluated on the host
+    uint32_t _pad;
+};
+struct DevScene {
+    const float4* nodes;   // 2 x float4 per node: (p_min, offset) (p_max, meta)
+    const float4* tris;    // 3 x float4 per triangle: (v0, area_light) (v1, material | flags<<24) (v2, orig_id)
+    const float* normals;  // 9 per triangle or null
+    const float* uvs;      // 6 per triangle or null
+    const DevTexture* textures;
+    const DevMaterial* materials;
+    const yk_light* lights;
+    uint32_t n_lights, n_tris, n_nodes;
+    float background[3];
+};
+constexpr uint32_t kMetaLeaf = 0x80000000u;  // meta: leaf bit | axis << 16 | shape_count
+
+// ---- per-iteration device counters ----------------------------------------------------------------
+struct Counters {
+    uint32_t mat[4];       // material queue lengths
+    uint32_t shadow;       // shadow queue length
+    uint32_t next;         // next active queue length
+    uint32_t work_closest; // dynamic ray fetch cursors
+    uint32_t work_any;
+};
+struct Totals {
+    unsigned long long closest_nodes, closest_tris, any_nodes, any_tris, hit_hash, shadow_rays;
+};
+
+struct Job {  // one pixel's share of the batch
+    uint16_t x, y;
+    uint32_t sample_begin;
+};
+// Path i of a batch is sample (sample_begin + sample_off + i / n_jobs) of pixel jobs[i % n_jobs]: a warp holds
+// 32 neighbouring pixels of one tile row at the same sample index.
+struct Batch {
+    const Job* jobs;
+    uint32_t n_jobs, sample_off, n_samples, n_paths;
+};
+
+// ---- wavefront state (SoA, capacity `cap` paths) --------------------------------------------------
+struct Wave {
+    uint32_t cap, n_lights, stack_entries;
+    float4* ray_o;   // o.xyz, t_max
+    float4* ray_d;   // d.xyz, -
+    uint2* hit;      // t bits, triangle index (kMiss = none)
+    uint2* bvh_counts;  // BVHIntersections: tests, hits
+    unsigned long long* rng_state;
+    unsigned long long* rng_inc;
+    uint32_t* dim;
+    float4* beta;    // throughput (path) / node weight (whitted); w = flags
+    float4* L;       // accumulated radiance
+    float4* pend_beta;   // weight to apply to this bounce's radiance
+    float4* pend_extra;  // emitted term of this bounce
+    float4* contrib;     // cap * n_lights: (f*li*cos/pdf, visible flag)
+    float4* sh_o;        // shadow rays: o.xyz, t_max
+    float4* sh_d;        // d.xyz, area light id (int bits)
+    uint32_t* sh_ref;    // index into contrib
+    float4* stack;       // whitted: stack_entries * cap * 3 float4
+    uint32_t* stack_top; // whitted
+    uint32_t* q_active[2];
+    uint32_t* q_mat;     // 4 * cap
+    Counters* counters;
+    Totals* totals;
+};
+// beta.w flag word
+constexpr uint32_t kFlagSpecular = 0x100u;   // path: specular_bounce / whitted: is_specular
+constexpr uint32_t kFlagAlive = 0x200u;
+constexpr uint32_t kDepthMask = 0xffu;       // path: bounces / whitted: depth
+
+struct RenderCfg {
+    SamplerCfg sampler;
+    uint32_t integrator, max_depth, has_clamp;
+    float clamp;
+    float c2w[16], r2c[16];
+    uint32_t res_x, res_y;
+    uint32_t aux_sample;
+    int32_t* hit_ids;  // device, or null
+};
+
+// ---- helpers --------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 f4v(float4 a) { return {a.x, a.y, a.z}; }
+
+// Warp-aggregated append: one atomic per warp per queue.
+__device__ __forceinline__ void queue_push(bool pred, uint32_t value, uint32_t* queue, uint32_t* counter) {
+    const unsigned active = __activemask();
+    const unsigned votes = __ballot_sync(active, pred);
+    if (votes == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(votes) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(votes));
+    base = __shfl_sync(active, base, leader);
+    if (pred) queue[base + __popc(votes & ((1u << lane) - 1u))] = value;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long mix_hit(uint32_t x, uint32_t y, uint32_t sample, uint32_t id) {
+    unsigned long long h = ((unsigned long long)x << 48) ^ ((unsigned long long)y << 32) ^ ((unsigned long long)sample << 8) ^
+                           (unsigned long long)id * 0x9E3779B97F4A7C15ULL;
+    h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 29;
+    return h;
+}
+
+// ---- raygen: Integrator::render loop head (integrators/mod.rs:145-169) -----------------------------
+__global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bt.n_paths) return;
+    const Job job = bt.jobs[i % bt.n_jobs];
+    const uint32_t sample = job.sample_begin + bt.sample_off + i / bt.n_jobs;
+    SamplerState s;
+    s.start(cfg.sampler, job.x, job.y, sample);
+    const V2 j = s.get_2d(cfg.sampler);
+    // Camera::ray, camera.rs:105-114
+    const V3 p_cam = xf_point(cfg.r2c, mk((float)job.x + j.x, (float)job.y + j.y, 0.0f));
+    const V3 d_cam = unit(p_cam);
+    const V3 o = xf_point(cfg.c2w, mk(0.0f, 0.0f, 0.0f));
+    const V3 d = xf_vec(cfg.c2w, d_cam);
+    w.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
+    w.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    w.rng_state[i] = s.rng.state;
+    w.rng_inc[i] = s.rng.inc;
+    w.dim[i] = s.dim;
+    w.beta[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(kFlagAlive));
+    w.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (w.stack_top) w.stack_top[i] = 0;
+}
+
+// ---- BVH traversal (bvh.rs:160-302, math/bounds.rs:176-215, shapes/triangle.rs:49-139) --------------
+// Persistent warps pull 32 rays at a time from a global cursor. One ray per lane, per-lane 64-entry stack.
+template <bool ANY>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, Wave w, const uint32_t* queue, const uint32_t* n_ptr,
+                                                          uint32_t n_fixed, uint32_t* cursor, int write_counts) {
+    const uint32_t n = n_ptr ? *n_ptr : n_fixed;
+    const int lane = threadIdx.x & 31;
+    unsigned long long sum_nodes = 0, sum_tris = 0;
+    uint32_t stack[kStackDepth];
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t slot = base + lane;
+        if (slot < n) {
+            const uint32_t path = ANY ? slot : (queue ? queue[slot] : slot);
+            const float4 ro = ANY ? w.sh_o[slot] : w.ray_o[path];
+            const float4 rd = ANY ? w.sh_d[slot] : w.ray_d[path];
+            const V3 o = f4v(ro), d = f4v(rd);
+            float t_max = ro.w;
+            const int target_light = ANY ? __float_as_int(rd.w) : -1;
+            const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+            const bool neg[3] = {ix < 0.0f, iy < 0.0f, iz < 0.0f};
+            TriRay tr;
+            tr.setup(d);
+            uint32_t cur = 0, sp = 0, n_tests = 0, n_hits = 0, n_tris = 0, hit_tri = kMiss;
+            float hit_t = 0.0f;
+            bool occluded = false;
+            for (;;) {
+                const float4 n0 = __ldg(&sc.nodes[2 * cur]);
+                const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
+                n_tests += 1;
+                // slab test: (bound - o) * inv_dir, NaN-ignoring min/max exactly like f32::min/max
+                const float t0x = (n0.x - o.x) * ix, t0y = (n0.y - o.y) * iy, t0z = (n0.z - o.z) * iz;
+                const float t1x = (n1.x - o.x) * ix, t1y = (n1.y - o.y) * iy, t1z = (n1.z - o.z) * iz;
+                const float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
+                const float tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), t_max);
+                bool pop = true;
+                if (tmin <= tmax) {
+                    n_hits += 1;
+                    const uint32_t offset = __float_as_uint(n0.w), meta = __float_as_uint(n1.w);
+                    if (!(meta & kMetaLeaf)) {
+                        const uint32_t axis = (meta >> 16) & 3u;
+                        if (neg[axis]) { stack[sp++] = cur + 1; cur = offset; }
+                        else { stack[sp++] = offset; cur = cur + 1; }
+                        pop = false;
+                    } else {
+                        const uint32_t count = meta & 0xffffu;
+                        for (uint32_t s = offset; s < offset + count; ++s) {
+                            const float4 a = __ldg(&sc.tris[3 * s]);
+                            const float4 b = __ldg(&sc.tris[3 * s + 1]);
+                            const float4 c = __ldg(&sc.tris[3 * s + 2]);
+                            n_tris += 1;
+                            TriHit h;
+                            if (tri_test(tr, o, t_max, f4v(a), f4v(b), f4v(c), &h)) {
+                                if (ANY) {
+                                    // bvh.rs:269-280: the target light's own emissive triangles do not occlude
+                                    const int tri_light = __float_as_int(a.w);
+                                    if (!(target_light >= 0 && tri_light >= 0 && tri_light == target_light)) { occluded = true; break; }
+                                } else {
+                                    hit_tri = s; hit_t = h.t; t_max = h.t;  // later equal-t hit replaces (bvh.rs:204-207)
+                                }
+                            }
+                        }
+                        if (ANY && occluded) break;
+                    }
+                }
+                if (pop) {
+                    if (sp == 0) break;
+                    cur = stack[--sp];
+                }
+            }
+            if (ANY) {
+                if (occluded) w.contrib[w.sh_ref[slot]].w = 0.0f;
+            } else {
+                w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
+                if (write_counts) w.bvh_counts[path] = make_uint2(n_tests, n_hits);
+            }
+            sum_nodes += n_tests;
+            sum_tris += n_tris;
+        }
+    }
+    sum_nodes = warp_sum(sum_nodes);
+    sum_tris = warp_sum(sum_tris);
+    if (lane == 0 && (sum_nodes | sum_tris)) {
+        atomicAdd(ANY ? &w.totals->any_nodes : &w.totals->closest_nodes, sum_nodes);
+        atomicAdd(ANY ? &w.totals->any_tris : &w.totals->closest_tris, sum_tris);
+    }
+}
+
+// ---- whitted stack ------------------------------------------------------------------------------------
+struct StackEntry {
+    V3 o, d;
+    RGB weight;
+    uint32_t flags;  // depth | specular
+};
+__device__ __forceinline__ void stack_push(const Wave& w, uint32_t path, const StackEntry& e) {
+    const uint32_t top = w.stack_top[path];
+    float4* base = w.stack + ((size_t)top * w.cap + path) * 3;
+    base[0] = make_float4(e.o.x, e.o.y, e.o.z, e.d.x);
+    base[1] = make_float4(e.d.y, e.d.z, e.weight.r, e.weight.g);
+    base[2] = make_float4(e.weight.b, __uint_as_float(e.flags), 0.0f, 0.0f);
+    w.stack_top[path] = top + 1;
+}
+// Pops the next pending node into the path's ray/weight slots. Returns false when the tree is done.
+__device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path) {
+    const uint32_t top = w.stack_top[path];
+    if (top == 0) return false;
+    const float4* base = w.stack + ((size_t)(top - 1) * w.cap + path) * 3;
+    const float4 a = base[0], b = base[1], c = base[2];
+    w.stack_top[path] = top - 1;
+    w.ray_o[path] = make_float4(a.x, a.y, a.z, __int_as_float(0x7f800000));
+    w.ray_d[path] = make_float4(a.w, b.x, b.y, 0.0f);
+    w.beta[path] = make_float4(b.z, b.w, c.x, __uint_as_float(__float_as_uint(c.y) | kFlagAlive));
+    return true;
+}
+
+// ---- classify: miss handling + compaction by material ("ray-queue sort/compaction pass") ---------------
+__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, const uint32_t* n_ptr, uint32_t n_fixed,
+                           int first_iteration, uint32_t* q_next) {
+    const uint32_t n = n_ptr ? *n_ptr : n_fixed;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t path = 0, kind = 4;
+    bool requeue = false;
+    unsigned long long hh = 0;
+    if (valid) {
+        path = queue ? queue[i] : i;
+        const uint2 h = w.hit[path];
+        uint32_t orig = 0xffffffffu;
+        if (h.y != kMiss) {
+            const uint32_t m = __float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) & 0xffffffu;
+            kind = sc.materials[m].kind;
+            if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
+        } else {
+            // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
+            const float4 b = w.beta[path];
+            float4 L = w.L[path];
+            L.x = L.x + b.x * sc.background[0];
+            L.y = L.y + b.y * sc.background[1];
+            L.z = L.z + b.z * sc.background[2];
+            w.L[path] = L;
+            if (cfg.integrator == YK_INTEGRATOR_WHITTED) requeue = stack_pop(w, path);
+        }
+        if (first_iteration) {
+            const Job job = bt.jobs[path % bt.n_jobs];
+            const uint32_t sample = job.sample_begin + bt.sample_off + path / bt.n_jobs;
+            hh = mix_hit(job.x, job.y, sample, orig);
+            if (cfg.hit_ids && sample == cfg.aux_sample) cfg.hit_ids[(size_t)job.y * cfg.res_x + job.x] = (int32_t)orig;
+        }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) queue_push(valid && kind == k, path, w.q_mat + (size_t)k * w.cap, &w.counters->mat[k]);
+    queue_push(requeue, path, q_next, &w.counters->next);
+    if (first_iteration) {
+        hh = warp_sum(hh);
+        if ((threadIdx.x & 31) == 0 && hh) atomicAdd(&w.totals->hit_hash, hh);
+    }
+}
+
+// ---- surface set-up: Triangle::intersect's SurfaceInteraction part (triangle.rs:141-226) ----------------
+__device__ __forceinline__ void make_surface(const DevScene& sc, uint32_t tri, V3 o, V3 d, Surface* si, uint32_t* material) {
+    const float4 a4 = __ldg(&sc.tris[3 * tri]), b4 = __ldg(&sc.tris[3 * tri + 1]), c4 = __ldg(&sc.tris[3 * tri + 2]);
+    const V3 p0 = f4v(a4), p1 = f4v(b4), p2 = f4v(c4);
+    const uint32_t packed = __float_as_uint(b4.w);
+    const uint32_t flags = packed >> 24;
+    *material = packed & 0xffffffu;
+    // Barycentrics: re-run the (deterministic) triangle test that the traversal accepted.
+    TriRay tr;
+    tr.setup(d);
+    TriHit h{0, 0, 0, 0};
+    tri_test(tr, o, __int_as_float(0x7f800000), p0, p1, p2, &h);
+    V2 uv0{0.0f, 0.0f}, uv1{1.0f, 0.0f}, uv2{1.0f, 1.0f};  // triangle.rs:143-155
+    if (flags & YK_TRI_HAS_UVS) {
+        const float* u = sc.uvs + (size_t)tri * 6;
+        uv0 = {u[0], u[1]}; uv1 = {u[2], u[3]}; uv2 = {u[4], u[5]};
+    }
+    const float du02 = uv0.x - uv2.x, dv02 = uv0.y - uv2.y, du12 = uv1.x - uv2.x, dv12 = uv1.y - uv2.y;
+    const V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    const float uv_det = du02 * dv12 - dv02 * du12;
+    V3 dpdu;
+    if (uv_det == 0.0f) {
+        V3 unused;
+        frame_from(unit(cross64(p2 - p0, p1 - p0)), &dpdu, &unused);
+    } else {
+        const float inv = 1.0f / uv_det;
+        dpdu = (dp02 * dv12 - dp12 * dv02) * inv;
+    }
+    si->p = p0 * h.b0 + p1 * h.b1 + p2 * h.b2;
+    si->uv = {uv0.x * h.b0 + uv1.x * h.b1 + uv2.x * h.b2, uv0.y * h.b0 + uv1.y * h.b1 + uv2.y * h.b2};
+    si->wo = -d;
+    si->area_light = __float_as_int(a4.w);
+    V3 n = unit(cross64(dp02, dp12));
+    if (flags & YK_TRI_SWAPS_HANDEDNESS) n = -n;
+    si->n = n;
+    si->sh_n = n;
+    si->sh_dpdu = dpdu;
+    if (flags & YK_TRI_HAS_NORMALS) {  // triangle.rs:197-224 + set_shading_geometry, interaction.rs:126-132
+        const float* nn = sc.normals + (size_t)tri * 9;
+        const V3 n0 = mk(nn[0], nn[1], nn[2]), n1 = mk(nn[3], nn[4], nn[5]), n2 = mk(nn[6], nn[7], nn[8]);
+        V3 ns = unit(n0 * h.b0 + n1 * h.b1 + n2 * h.b2);
+        if (dot0(ns, ns) > 0.0f) ns = unit(ns);
+        else ns = si->n;
+        V3 ss = unit(dpdu);
+        V3 ts = cross64(ss, ns);
+        if (dot0(ts, ts) > 0.0f) {
+            ts = unit(ts);
+            ss = cross64(ts, ns);
+        } else {
+            frame_from(ns, &ss, &ts);
+        }
+        si->sh_n = unit(cross64(ss, ts));
+        si->n = flip_toward_n(si->n, si->sh_n);
+        si->sh_dpdu = ss;
+    }
+}
+
+// textures/constant.rs:23-30, textures/image_texture.rs:81-111
+__device__ __forceinline__ RGB tex_eval(const DevScene& sc, int32_t index, V2 uv) {
+    const DevTexture& t = sc.textures[index];
+    if (t.kind == YK_TEX_CONSTANT) return rgb(t.value[0], t.value[1], t.value[2]);
+    float sx = uv.x - truncf(uv.x), sy = uv.y - truncf(uv.y);
+    if (sx < 0.0f) sx = 1.0f + sx;
+    if (sy < 0.0f) sy = 1.0f + sy;
+    sy = 1.0f - sy;
+    sx = sx * (float)t.width - 0.5f;
+    sy = sy * (float)t.height - 0.5f;
+    const uint32_t ix = sx > 0.0f ? (uint32_t)sx : 0u, iy = sy > 0.0f ? (uint32_t)sy : 0u;
+    const float* px = t.texels + ((size_t)iy * t.width + ix) * 3;
+    return rgb(__ldg(px), __ldg(px + 1), __ldg(px + 2));
+}
+
+__device__ __forceinline__ float roughness_to_alpha(float r) {  // trowbridge_reitz.rs:22-30
+    const float x = (float)log((double)fmaxf(r, 0.001f));
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+template <uint32_t KIND>
+__device__ __forceinline__ void make_bsdf(const DevScene& sc, const DevMaterial& m, const Surface& si, Bsdf* b) {
+    b->kind = KIND;
+    b->empty = false;
+    b->ng = si.n;
+    b->ns = si.sh_n;
+    b->ss = unit(si.sh_dpdu);
+    b->ts = cross64(b->ns, b->ss);
+    b->c1 = gray(0.0f);
+    b->p0 = 0.0f;
+    b->p1 = -1.0f;
+    if (KIND == YK_MAT_MATTE) {  // matte.rs:22-40, oren_nayar.rs:18-25
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        const float sigma = tex_eval(sc, m.tex[1], si.uv).r;
+        b->empty = black(b->c0);
+        if (sigma != 0.0f) {
+            const float s2 = sigma * sigma;
+            b->p0 = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+            b->p1 = 0.45f * s2 / (s2 + 0.09f);
+            if (b->p1 < 0.0f) b->p1 = 0.0f;  // cannot happen for real sigma; keeps the Lambertian tag (p1 < 0) unambiguous
+        }
+    } else if (KIND == YK_MAT_GLASS) {  // glass.rs:27-45
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        b->c1 = tex_eval(sc, m.tex[1], si.uv);
+        b->p0 = m.eta;
+    } else if (KIND == YK_MAT_METAL) {  // metal.rs:34-61, trowbridge_reitz.rs:16-20
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        b->c1 = tex_eval(sc, m.tex[1], si.uv);
+        if (m.const_alpha >= 0.0f) b->p0 = m.const_alpha;
+        else {
+            float r = tex_eval(sc, m.tex[2], si.uv).r;
+            if (m.remap) r = roughness_to_alpha(r);
+            b->p0 = fmaxf(r, 0.001f);
+        }
+    } else {  // glossy.rs:32-58 (alpha = roughness^2)
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        if (m.const_alpha >= 0.0f) b->p0 = m.const_alpha;
+        else {
+            float r = tex_eval(sc, m.tex[1], si.uv).r;
+            if (m.remap) r = roughness_to_alpha(r);
+            b->p0 = fmaxf(r * r, 0.001f);
+        }
+    }
+}
+
+// Light::sample_li for the four light kinds (lights/*.rs). Returns false when no visibility test exists.
+struct LightSample {
+    V3 l;
+    RGB li;
+    float pdf;
+    bool has_vis;
+    Ray vis;
+    int vis_light;
+};
+__device__ __forceinline__ void sample_light(const yk_light& L, int index, const Surface& si, V2 u, LightSample* s) {
+    s->vis_light = -1;
+    s->pdf = 1.0f;
+    s->has_vis = true;
+    const RGB I = rgb(L.i[0], L.i[1], L.i[2]);
+    const V3 lp = mk(L.p[0], L.p[1], L.p[2]);
+    if (L.kind == YK_LIGHT_POINT) {  // point_light.rs:27-49
+        const V3 to = lp - si.p;
+        const float d2 = dot0(to, to);
+        s->li = I / d2;
+        s->l = to / sqrtf(d2);
+        s->vis = spawn_ray_to(si.p, si.n, lp);
+    } else if (L.kind == YK_LIGHT_SPOT) {  // spot_light.rs:38-80
+        const V3 to = lp - si.p;
+        const float d2 = dot0(to, to);
+        s->l = to / sqrtf(d2);
+        const float ct = unit(xf_vec(L.world_to_light, -s->l)).z;
+        float fall;
+        if (ct < L.cos_total_width) fall = 0.0f;
+        else if (ct > L.cos_falloff_start) fall = 1.0f;
+        else {
+            const float dl = (ct - L.cos_total_width) / (L.cos_falloff_start - L.cos_total_width);
+            fall = (dl * dl) * (dl * dl);
+        }
+        s->li = I * fall / d2;
+        s->has_vis = !black(s->li);
+        s->vis = spawn_ray_to(si.p, si.n, lp);
+    } else if (L.kind == YK_LIGHT_RECT) {  // rectangular_light.rs:46-72
+        const V3 p = xf_point(L.sample_to_world, mk(u.x, 0.0f, u.y));
+        const V3 n = xf_normal(L.sample_to_world_inv, mk(0.0f, -1.0f, 0.0f));
+        const V3 wi = unit(p - si.p);
+        const float c = dotn(n, -wi);
+        s->li = c > 0.0f ? I : gray(0.0f);
+        s->l = wi;
+        s->vis = spawn_ray_to(si.p, si.n, p);
+        s->vis_light = index;
+        const V3 dp = si.p - p;
+        s->pdf = dot0(dp, dp) / (fabsf(c) * L.area);
+    } else {  // distant_light.rs:24-43
+        s->li = I;
+        s->l = lp;
+        s->vis = spawn_ray_to(si.p, si.n, si.p + lp * 10000.0f);
+    }
+}
+
+// ---- shading: one kernel instance per material kind ----------------------------------------------------
+// Covers Material::compute_scattering_functions, the light fold (path.rs:102-119 / whitted.rs:109-126), the
+// emitted term, BSDF sampling + throughput update + Russian roulette (path.rs:121-171), and the specular
+// recursion of whitted.rs:132-170 flattened onto a per-sample DFS stack (children inherit weight * f * |cos|).
+// Radiance is not summed here: shadow rays are queued and k_resolve adds the unoccluded terms in light order.
+__device__ __forceinline__ uint32_t shadow_slot(bool pred, uint32_t* counter) {
+    const unsigned active = __activemask();
+    const unsigned votes = __ballot_sync(active, pred);
+    if (votes == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(votes) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(votes));
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(votes & ((1u << lane) - 1u));
+}
+
+template <uint32_t KIND>
+__global__ void __launch_bounds__(kShadeThreads) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
+                                                          const uint32_t* n_ptr) {
+    const uint32_t n = *n_ptr;
+    const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        if (i >= n) continue;
+        const uint32_t path = queue[i];
+        const float4 ro = w.ray_o[path], rd = w.ray_d[path];
+        const V3 o = f4v(ro), d = f4v(rd);
+        Surface si;
+        uint32_t mat_index;
+        make_surface(sc, w.hit[path].y, o, d, &si, &mat_index);
+        Bsdf bsdf;
+        make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
+
+        const Job job = bt.jobs[path % bt.n_jobs];
+        SamplerState smp;
+        smp.rng.state = w.rng_state[path];
+        smp.rng.inc = w.rng_inc[path];
+        smp.dim = w.dim[path];
+        smp.px = job.x;
+        smp.py = job.y;
+        smp.index = job.sample_begin + bt.sample_off + path / bt.n_jobs;
+
+        const float4 beta4 = w.beta[path];
+        RGB beta = rgb(beta4.x, beta4.y, beta4.z);
+        const uint32_t flags = __float_as_uint(beta4.w);
+        const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
+        const bool was_specular = (flags & kFlagSpecular) != 0;
+
+        // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
+        for (uint32_t k = 0; k < sc.n_lights; ++k) {
+            const V2 u = smp.get_2d(cfg.sampler);
+            LightSample ls;
+            sample_light(sc.lights[k], (int)k, si, u, &ls);
+            RGB c = gray(0.0f);
+            bool need_shadow = false;
+            if (!black(ls.li)) {
+                const RGB f = bsdf.f(si.wo, ls.l);
+                if (ls.has_vis && !black(f)) {
+                    c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
+                    need_shadow = true;
+                }
+            }
+            const uint32_t ref = k * w.cap + path;
+            w.contrib[ref] = make_float4(c.r, c.g, c.b, need_shadow ? 1.0f : 0.0f);
+            const uint32_t slot = shadow_slot(need_shadow, &w.counters->shadow);
+            if (need_shadow) {
+                w.sh_o[slot] = make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, ls.vis.t_max);
+                w.sh_d[slot] = make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, __int_as_float(ls.vis_light));
+                w.sh_ref[slot] = ref;
+            }
+        }
+
+        // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
+        RGB le = gray(0.0f);
+        if (si.area_light >= 0 && dotn(si.n, si.wo) > 0.0f) {
+            const yk_light& al = sc.lights[si.area_light];
+            le = rgb(al.i[0], al.i[1], al.i[2]);
+        }
+        const bool add_le = depth == 0 || was_specular;
+
+        bool alive = false;
+        uint32_t new_flags = 0;
+        if (cfg.integrator == YK_INTEGRATOR_PATH) {
+            // path.rs:121-129 — beta multiplies the emitted term here and again in the resolve (reference quirk)
+            const RGB extra = add_le ? beta * le : gray(0.0f);
+            w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, 0.0f);
+            w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
+            const Bsdf::Sample s = bsdf.sample_f(si.wo, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137
+            if (!(black(s.f) || s.pdf == 0.0f)) {
+                alive = true;
+                const bool spec = (s.type & BX_SPECULAR) != 0;
+                beta = beta * (s.f * fabsf(dotn(s.wi, si.sh_n)) / s.pdf);
+                const Ray nr = spawn_ray(si.p, si.n, s.wi);
+                w.ray_o[path] = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
+                w.ray_d[path] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+                if (depth > 3) {  // Russian roulette, path.rs:163-169
+                    const float q = fmaxf(1.0f - beta.g, 0.05f);
+                    if (smp.get_1d(cfg.sampler) < q) alive = false;
+                    else beta = beta * (gray(1.0f) / (1.0f - q));
+                }
+                const uint32_t bounces = depth + 1;
+                if (bounces >= cfg.max_depth) alive = false;
+                new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u);
+            }
+            w.beta[path] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | (alive ? kFlagAlive : 0u)));
+        } else {
+            // whitted.rs:128-170
+            const RGB extra = add_le ? le : gray(0.0f);
+            w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, 0.0f);
+            w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+            StackEntry child[2];
+            int n_child = 0;
+            if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
+                const uint32_t wants[2] = {BX_SPECULAR | BX_REFLECTION, BX_SPECULAR | BX_TRANSMISSION};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const Bsdf::Sample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, wants[c]);
+                    if (s.type == 0u) continue;  // BxdfType::NONE: no ray, no radiance
+                    const Ray nr = spawn_ray(si.p, si.n, s.wi);
+                    StackEntry e;
+                    e.o = nr.o;
+                    e.d = nr.d;
+                    e.weight = beta * s.f * fabsf(dotn(s.wi, si.sh_n));
+                    e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u);
+                    child[n_child++] = e;
+                }
+            }
+            if (n_child == 2) stack_push(w, path, child[1]);  // transmission waits until the reflection subtree is done
+            if (n_child >= 1) {
+                const StackEntry& e = child[0];
+                w.ray_o[path] = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+                w.ray_d[path] = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+                w.beta[path] = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive));
+            } else if (!stack_pop(w, path)) {
+                w.beta[path] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(flags & ~kFlagAlive));
+            }
+        }
+        w.rng_state[path] = smp.rng.state;
+        w.dim[path] = smp.dim;
+    }
+}
+
+// ---- resolve: fold the unoccluded light terms in light order, add the emitted term, clamp, accumulate ----
+// (path.rs:113-129, whitted.rs:120-130) and compact the surviving paths into the next active queue.
+__global__ void k_resolve(Wave w, RenderCfg cfg, uint32_t* q_next) {
+    const uint32_t n0 = w.counters->mat[0], n1 = w.counters->mat[1], n2 = w.counters->mat[2], n3 = w.counters->mat[3];
+    const uint32_t total = n0 + n1 + n2 + n3;
+    const uint32_t rounds = (total + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        bool alive = false;
+        uint32_t path = 0;
+        if (i < total) {
+            uint32_t k = 0, j = i;
+            if (j >= n0) { j -= n0; k = 1; if (j >= n1) { j -= n1; k = 2; if (j >= n2) { j -= n2; k = 3; } } }
+            path = w.q_mat[(size_t)k * w.cap + j];
+            RGB radiance = gray(0.0f);
+            for (uint32_t l = 0; l < w.n_lights; ++l) {
+                const float4 c = w.contrib[l * w.cap + path];
+                if (c.w != 0.0f) radiance = radiance + rgb(c.x, c.y, c.z);
+            }
+            const float4 pe = w.pend_extra[path], pb = w.pend_beta[path];
+            radiance = radiance + rgb(pe.x, pe.y, pe.z);
+            if (pb.w != 0.0f) radiance = rgb(fminf(radiance.r, cfg.clamp), fminf(radiance.g, cfg.clamp), fminf(radiance.b, cfg.clamp));
+            float4 L = w.L[path];
+            L.x = L.x + pb.x * radiance.r;
+            L.y = L.y + pb.y * radiance.g;
+            L.z = L.z + pb.z * radiance.b;
+            w.L[path] = L;
+            alive = (__float_as_uint(w.beta[path].w) & kFlagAlive) != 0;
+        }
+        queue_push(alive, path, q_next, &w.counters->next);
+    }
+}
+
+// ---- debug integrators (bvh_heatmap.rs, geometry_normals.rs, shading_normals.rs, shading_uvs.rs) --------
+__global__ void k_debug_shade(DevScene sc, Wave w, RenderCfg cfg, uint32_t n) {
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= n) return;
+    const uint2 h = w.hit[path];
+    RGB c = gray(0.0f);
+    if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
+        const uint2 cnt = w.bvh_counts[path];
+        c = rgb((float)cnt.x, (float)cnt.y, h.y != kMiss ? (float)cnt.y : 0.0f);
+    } else if (h.y != kMiss) {
+        Surface si;
+        uint32_t m;
+        make_surface(sc, h.y, f4v(w.ray_o[path]), f4v(w.ray_d[path]), &si, &m);
+        if (cfg.integrator == YK_INTEGRATOR_GEOMETRY_NORMALS) c = rgb(si.n.x, si.n.y, si.n.z) / 2.0f + gray(0.5f);
+        else if (cfg.integrator == YK_INTEGRATOR_SHADING_NORMALS) c = rgb(si.sh_n.x, si.sh_n.y, si.sh_n.z) / 2.0f + gray(0.5f);
+        else c = rgb(si.uv.x, si.uv.y, 0.0f);
+    }
+    w.L[path] = make_float4(c.r, c.g, c.b, 0.0f);
+}
+
+// ---- film --------------------------------------------------------------------------------------------
+// `color += li` over ascending sample index (integrators/mod.rs:172), carried across batches in `accum`.
+__global__ void k_film_accumulate(Wave w, Batch bt, float* accum, uint32_t res_x) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= bt.n_jobs) return;
+    const Job job = bt.jobs[j];
+    float* a = accum + ((size_t)job.y * res_x + job.x) * 3;
+    float r = a[0], g = a[1], b = a[2];
+    for (uint32_t s = 0; s < bt.n_samples; ++s) {
+        const float4 L = w.L[(size_t)s * bt.n_jobs + j];
+        r = r + L.x; g = g + L.y; b = b + L.z;
+    }
+    a[0] = r; a[1] = g; a[2] = b;
+}
+// `color /= sample_count` + Film::update_tile overwrite (integrators/mod.rs:175-182, film.rs:274-279)
+__global__ void k_film_store(const Job* jobs, uint32_t n_jobs, const float* accum, float* film, uint32_t res_x, float spp) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const Job job = jobs[j];
+    const size_t p = ((size_t)job.y * res_x + job.x) * 3;
+    film[p] = accum[p] / spp;
+    film[p + 1] = accum[p + 1] / spp;
+    film[p + 2] = accum[p + 2] / spp;
+}
+// Accumulating film: `*fc += c` per tile sample (film.rs:260-272); tiles of different samples may overlap.
+__global__ void k_film_add(Wave w, Batch bt, float* film, uint32_t res_x) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bt.n_paths) return;
+    const Job job = bt.jobs[i % bt.n_jobs];
+    const float4 L = w.L[i];
+    float* f = film + ((size_t)job.y * res_x + job.x) * 3;
+    atomicAdd(f, L.x); atomicAdd(f + 1, L.y); atomicAdd(f + 2, L.z);
+}
+__global__ void k_zero_jobs(const Job* jobs, uint32_t n_jobs, float* accum, uint32_t res_x) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const size_t p = ((size_t)jobs[j].y * res_x + jobs[j].x) * 3;
+    accum[p] = 0.0f; accum[p + 1] = 0.0f; accum[p + 2] = 0.0f;
+}
+__global__ void k_fill_i32(int32_t* p, size_t n, int32_t v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// Host side: context, scene upload, wavefront driver.
+// =====================================================================================================
+struct yk_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    Wave wave{};
+    std::vector<void*> wave_allocs;
+    uint32_t wave_cap = 0, wave_lights = 0, wave_stack = 0;
+    Counters* h_counters = nullptr;  // pinned
+    Totals* h_totals = nullptr;      // pinned
+    Job* d_jobs = nullptr;
+    size_t jobs_cap = 0;
+    float* d_accum = nullptr;
+    float* d_film = nullptr;
+    int32_t* d_hit_ids = nullptr;
+    size_t film_cap = 0;
+    int occ_trace_closest = 0, occ_trace_any = 0;
+};
+
+struct yk_scene {
+    yk_context* ctx = nullptr;
+    DevScene dev{};
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(std::vector<void*>& bag, T** out, size_t count) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    bag.push_back(p);
+    *out = (T*)p;
+    return YK_OK;
+}
+template <class T>
+int dev_upload(std::vector<void*>& bag, const T** out, const T* src, size_t count) {
+    T* p = nullptr;
+    int rc = dev_alloc(bag, &p, count);
+    if (rc != YK_OK) return rc;
+    if (count) CUDA_TRY(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = p;
+    return YK_OK;
+}
+void free_bag(std::vector<void*>& bag) {
+    for (void* p : bag) cudaFree(p);
+    bag.clear();
+}
+
+// trowbridge_reitz.rs:22-30 on the host (libm logf, as the reference's f32::ln)
+float host_roughness_to_alpha(float r) {
+    const float x = logf(fmaxf(r, 0.001f));
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+int ensure_wave(yk_context* c, uint32_t cap, uint32_t n_lights, uint32_t stack_entries) {
+    if (c->wave_cap == cap && c->wave_lights == n_lights && c->wave_stack == stack_entries) return YK_OK;
+    free_bag(c->wave_allocs);
+    c->wave_cap = 0;
+    Wave w{};
+    w.cap = cap;
+    w.n_lights = n_lights;
+    w.stack_entries = stack_entries;
+    std::vector<void*>& bag = c->wave_allocs;
+    const size_t nl = std::max<uint32_t>(n_lights, 1);
+    int rc = YK_OK;
+#define WAVE_ALLOC(field, count) \
+    if ((rc = dev_alloc(bag, &w.field, (size_t)(count))) != YK_OK) { free_bag(bag); return rc; }
+    WAVE_ALLOC(ray_o, cap) WAVE_ALLOC(ray_d, cap) WAVE_ALLOC(hit, cap) WAVE_ALLOC(bvh_counts, cap)
+    WAVE_ALLOC(rng_state, cap) WAVE_ALLOC(rng_inc, cap) WAVE_ALLOC(dim, cap) WAVE_ALLOC(beta, cap) WAVE_ALLOC(L, cap)
+    WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap) WAVE_ALLOC(contrib, cap * nl)
+    WAVE_ALLOC(sh_o, cap * nl) WAVE_ALLOC(sh_d, cap * nl) WAVE_ALLOC(sh_ref, cap * nl)
+    WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap)
+    WAVE_ALLOC(counters, 1) WAVE_ALLOC(totals, 1)
+    if (stack_entries) {
+        WAVE_ALLOC(stack, (size_t)stack_entries * cap * 3)
+        WAVE_ALLOC(stack_top, cap)
+    }
+#undef WAVE_ALLOC
+    c->wave = w;
+    c->wave_cap = cap;
+    c->wave_lights = n_lights;
+    c->wave_stack = stack_entries;
+    return YK_OK;
+}
+
+struct Timers {
+    double closest = 0, any = 0, shade = 0;
+    uint64_t launches = 0, closest_launches = 0;
+};
+
+int grid_for(uint32_t n, int threads, int max_blocks) {
+    const uint32_t need = (n + threads - 1) / threads;
+    return (int)std::max<uint32_t>(1u, std::min<uint32_t>(need, (uint32_t)max_blocks));
+}
+
+// One batch: raygen, the bounce loop, and the per-batch film step.
+int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Batch& bt, bool accumulate_film, float* d_film,
+              yk_stats* st, Timers* tm) {
+    cudaStream_t s = c->stream;
+    Wave& w = c->wave;
+    const int T = 256;
+    k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt);
+    tm->launches += 1;
+    const bool debug = cfg.integrator >= YK_INTEGRATOR_BVH_INTERSECTIONS;
+    const int trace_blocks_closest = c->sm_count * std::max(1, c->occ_trace_closest);
+    const int trace_blocks_any = c->sm_count * std::max(1, c->occ_trace_any);
+    const int wide_blocks = c->sm_count * 16;
+    uint32_t n_active = bt.n_paths;
+    if (cfg.integrator == YK_INTEGRATOR_PATH && cfg.max_depth == 0) n_active = 0;
+    uint32_t* q_cur = nullptr;
+    int flip = 0;
+    for (uint32_t iter = 0; n_active > 0; ++iter) {
+        CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(Counters), s));
+        CUDA_TRY(cudaEventRecord(c->ev[0], s));
+        k_trace<false><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
+            sc->dev, w, q_cur, nullptr, n_active, &w.counters->work_closest,
+            cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS ? 1 : 0);
+        CUDA_TRY(cudaEventRecord(c->ev[1], s));
+        tm->launches += 1;
+        tm->closest_launches += 1;
+        st->ray_count += n_active;
+        if (debug) {
+            k_debug_shade<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, n_active);
+            tm->launches += 1;
+            if (cfg.hit_ids || true) {
+                // primary-hit digest / id image for the debug integrators too
+                uint32_t* q_next = w.q_active[flip];
+                k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, nullptr, n_active, 2, q_next);
+                tm->launches += 1;
+            }
+            CUDA_TRY(cudaStreamSynchronize(s));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+            tm->closest += ms;
+            break;
+        }
+        uint32_t* q_next = w.q_active[flip];
+        k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, nullptr, n_active, iter == 0 ? 1 : 0, q_next);
+        CUDA_TRY(cudaEventRecord(c->ev[2], s));
+        const int sg = grid_for(n_active, kShadeThreads, wide_blocks);
+        k_shade<YK_MAT_MATTE><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)0 * w.cap, &w.counters->mat[0]);
+        k_shade<YK_MAT_GLASS><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)1 * w.cap, &w.counters->mat[1]);
+        k_shade<YK_MAT_METAL><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)2 * w.cap, &w.counters->mat[2]);
+        k_shade<YK_MAT_GLOSSY><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)3 * w.cap, &w.counters->mat[3]);
+        CUDA_TRY(cudaEventRecord(c->ev[3], s));
+        if (w.n_lights) {
+            k_trace<true><<<grid_for(n_active * w.n_lights, kTraceThreads, trace_blocks_any), kTraceThreads, 0, s>>>(
+                sc->dev, w, nullptr, &w.counters->shadow, 0, &w.counters->work_any, 0);
+            tm->launches += 1;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev[4], s));
+        k_resolve<<<grid_for(n_active, T, wide_blocks), T, 0, s>>>(w, cfg, q_next);
+        tm->launches += 6;
+        CUDA_TRY(cudaMemcpyAsync(c->h_counters, w.counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaGetLastError());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); tm->closest += ms;
+        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); tm->shade += ms;
+        cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); tm->any += ms;
+        st->shadow_rays += c->h_counters->shadow;
+        n_active = c->h_counters->next;
+        q_cur = q_next;
+        flip ^= 1;
+        if (iter > (1u << 20)) return yk_set_error(YK_ERR_INVALID, "yk_render: bounce loop did not terminate");
+    }
+    if (accumulate_film) {
+        k_film_add<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, bt, d_film, cfg.res_x);
+    } else {
+        k_film_accumulate<<<(bt.n_jobs + T - 1) / T, T, 0, s>>>(w, bt, c->d_accum, cfg.res_x);
+    }
+    tm->launches += 1;
+    return YK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yk_context_create(int device_id, yk_context** out) {
+    if (!out) return yk_set_error(YK_ERR_INVALID, "yk_context_create: null output");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return yk_set_error(YK_ERR_CUDA, std::string("yk_context_create: no CUDA device (") + cudaGetErrorString(e) +
+                                             "); this backend has no CPU fallback");
+    if (device_id < 0 || device_id >= n_dev) return yk_set_error(YK_ERR_INVALID, "yk_context_create: device id out of range");
+    CUDA_TRY(cudaSetDevice(device_id));
+    auto* c = new yk_context();
+    c->device = device_id;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_counters, sizeof(Counters)));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_totals, sizeof(Totals)));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace<false>, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace<true>, kTraceThreads, 0));
+    *out = c;
+    return YK_OK;
+}
+
+void yk_context_destroy(yk_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_bag(c->wave_allocs);
+    cudaFree(c->d_jobs);
+    cudaFree(c->d_accum);
+    cudaFree(c->d_film);
+    cudaFree(c->d_hit_ids);
+    cudaFreeHost(c->h_counters);
+    cudaFreeHost(c->h_totals);
+    for (auto& ev : c->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* yk_context_stream(yk_context* c) { return c ? (void*)c->stream : nullptr; }
+
+int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
+    if (!c || !d || !out) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: null argument");
+    if (!d->n_nodes || !d->nodes || !d->n_tris || !d->tri_vertices || !d->tri_orig_id || !d->tri_material || !d->tri_area_light ||
+        !d->tri_flags)
+        return yk_set_error(YK_ERR_INVALID, "yk_scene_create: missing node / triangle arrays");
+    if (d->n_lights > (uint32_t)kMaxLights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 16 lights");
+    if (d->n_materials > 0xffffffu) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: too many materials");
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto sc = std::make_unique<yk_scene>();
+    sc->ctx = c;
+    int rc;
+    // Nodes: two 16-byte words so a visit is two LDG.128 (one 32-byte sector).
+    std::vector<float4> nodes((size_t)d->n_nodes * 2);
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+        const yk_bvh_node& n = d->nodes[i];
+        uint32_t meta = n.is_leaf ? (kMetaLeaf | n.shape_count) : ((uint32_t)n.split_axis << 16);
+        if (!n.is_leaf && n.offset >= d->n_nodes) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: child index out of range");
+        if (n.is_leaf && (uint64_t)n.offset + n.shape_count > d->n_tris)
+            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: leaf range out of range");
+        float fo, fm;
+        std::memcpy(&fo, &n.offset, 4);
+        std::memcpy(&fm, &meta, 4);
+        nodes[2 * i] = make_float4(n.p_min[0], n.p_min[1], n.p_min[2], fo);
+        nodes[2 * i + 1] = make_float4(n.p_max[0], n.p_max[1], n.p_max[2], fm);
+    }
+    // Triangles: three 16-byte words (vertices pre-gathered in leaf order; w lanes carry the per-triangle ids).
+    std::vector<float4> tris((size_t)d->n_tris * 3);
+    for (uint32_t i = 0; i < d->n_tris; ++i) {
+        const float* v = d->tri_vertices + (size_t)i * 9;
+        if (d->tri_material[i] >= d->n_materials) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: material index out of range");
+        if (d->tri_area_light[i] >= (int32_t)d->n_lights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: area light out of range");
+        uint32_t packed = d->tri_material[i] | ((uint32_t)d->tri_flags[i] << 24);
+        if ((d->tri_flags[i] & YK_TRI_HAS_NORMALS) && !d->tri_normals) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: normals flagged but absent");
+        if ((d->tri_flags[i] & YK_TRI_HAS_UVS) && !d->tri_uvs) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: uvs flagged but absent");
+        float fa, fp, fi;
+        std::memcpy(&fa, &d->tri_area_light[i], 4);
+        std::memcpy(&fp, &packed, 4);
+        std::memcpy(&fi, &d->tri_orig_id[i], 4);
+        tris[3 * i] = make_float4(v[0], v[1], v[2], fa);
+        tris[3 * i + 1] = make_float4(v[3], v[4], v[5], fp);
+        tris[3 * i + 2] = make_float4(v[6], v[7], v[8], fi);
+    }
+    if ((rc = dev_upload(sc->allocs, &sc->dev.nodes, nodes.data(), nodes.size())) != YK_OK) return rc;
+    if ((rc = dev_upload(sc->allocs, &sc->dev.tris, tris.data(), tris.size())) != YK_OK) return rc;
+    if (d->tri_normals && (rc = dev_upload(sc->allocs, &sc->dev.normals, d->tri_normals, (size_t)d->n_tris * 9)) != YK_OK) return rc;
+    if (d->tri_uvs && (rc = dev_upload(sc->allocs, &sc->dev.uvs, d->tri_uvs, (size_t)d->n_tris * 6)) != YK_OK) return rc;
+
+    std::vector<DevTexture> tex(d->n_textures);
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const yk_texture_desc& t = d->textures[i];
+        DevTexture dt{};
+        dt.kind = t.kind;
+        dt.width = t.width;
+        dt.height = t.height;
+        std::memcpy(dt.value, t.value, 12);
+        if (t.kind == YK_TEX_IMAGE) {
+            if (!t.texels || !t.width || !t.height) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: empty image texture");
+            if ((rc = dev_upload(sc->allocs, &dt.texels, t.texels, (size_t)t.width * t.height * 3)) != YK_OK) return rc;
+        } else if (t.kind != YK_TEX_CONSTANT) {
+            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: unknown texture kind");
+        }
+        tex[i] = dt;
+    }
+    std::vector<DevMaterial> mats(d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const yk_material_desc& m = d->materials[i];
+        if (m.kind > YK_MAT_GLOSSY) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: unknown material kind");
+        const int n_tex = m.kind == YK_MAT_METAL ? 3 : 2;
+        for (int k = 0; k < n_tex; ++k)
+            if (m.tex[k] < 0 || (uint32_t)m.tex[k] >= d->n_textures)
+                return yk_set_error(YK_ERR_INVALID, "yk_scene_create: texture index out of range");
+        DevMaterial dm{};
+        dm.kind = m.kind;
+        std::memcpy(dm.tex, m.tex, 12);
+        dm.eta = m.eta;
+        dm.remap = m.remap_roughness;
+        dm.const_alpha = -1.0f;
+        if (m.kind == YK_MAT_METAL || m.kind == YK_MAT_GLOSSY) {
+            const yk_texture_desc& rt = d->textures[m.tex[m.kind == YK_MAT_METAL ? 2 : 1]];
+            if (rt.kind == YK_TEX_CONSTANT) {  // metal.rs:41-45 / glossy.rs:39-49 + trowbridge_reitz.rs:16-20
+                float r = rt.value[0];
+                if (m.remap_roughness) r = host_roughness_to_alpha(r);
+                dm.const_alpha = fmaxf(m.kind == YK_MAT_GLOSSY ? r * r : r, 0.001f);
+            }
+        }
+        mats[i] = dm;
+    }
+    for (uint32_t i = 0; i < d->n_lights; ++i)
+        if (d->lights[i].kind > YK_LIGHT_DISTANT) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: unknown light kind");
+    for (uint32_t i = 0; i < d->n_tris; ++i)
+        if (d->tri_area_light[i] >= 0 && d->lights[d->tri_area_light[i]].kind != YK_LIGHT_RECT)
+            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: area light must be rectangular");
+    if ((rc = dev_upload(sc->allocs, &sc->dev.textures, tex.data(), tex.size())) != YK_OK) return rc;
+    if ((rc = dev_upload(sc->allocs, &sc->dev.materials, mats.data(), mats.size())) != YK_OK) return rc;
+    if ((rc = dev_upload(sc->allocs, &sc->dev.lights, d->lights, d->n_lights)) != YK_OK) return rc;
+    sc->dev.n_lights = d->n_lights;
+    sc->dev.n_tris = d->n_tris;
+    sc->dev.n_nodes = d->n_nodes;
+    std::memcpy(sc->dev.background, d->background, 12);
+    *out = sc.release();
+    return YK_OK;
+}
+
+void yk_scene_destroy(yk_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    free_bag(s->allocs);
+    delete s;
+}
+
+int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_film_settings* fs, const yk_sampler* sm,
+              const yk_integrator* in, const yk_tile* tiles, uint32_t n_tiles, const yk_render_opts* opts, float* film_rgb,
+              yk_stats* stats) {
+    const auto wall0 = std::chrono::steady_clock::now();
+    if (!c || !sc || !cam || !fs || !sm || !in || !film_rgb) return yk_set_error(YK_ERR_INVALID, "yk_render: null argument");
+    if (sc->ctx != c) return yk_set_error(YK_ERR_INVALID, "yk_render: scene belongs to another context");
+    if (!fs->res_x || !fs->res_y || fs->res_x > 0xffffu || fs->res_y > 0xffffu)
+        return yk_set_error(YK_ERR_INVALID, "yk_render: film resolution must fit u16 (integrators/mod.rs:140-141)");
+    if (in->kind > YK_INTEGRATOR_SHADING_UVS) return yk_set_error(YK_ERR_INVALID, "yk_render: unknown integrator");
+    if (sm->kind > YK_SAMPLER_STRATIFIED) return yk_set_error(YK_ERR_INVALID, "yk_render: unknown sampler");
+    const uint32_t spp = sm->kind == YK_SAMPLER_UNIFORM ? sm->nx : sm->nx * sm->ny;
+    if (spp == 0 || spp > 0x10000u) return yk_set_error(YK_ERR_INVALID, "yk_render: samples per pixel must be in 1..65536");
+    if (in->max_depth > 255) return yk_set_error(YK_ERR_INVALID, "yk_render: max_depth above 255");
+    if (in->kind == YK_INTEGRATOR_WHITTED && in->max_depth > 24)
+        return yk_set_error(YK_ERR_INVALID, "yk_render: whitted max_depth above 24 is not supported");
+    if (n_tiles && !tiles) return yk_set_error(YK_ERR_INVALID, "yk_render: null tile list");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t flags = opts ? opts->flags : 0u;
+    const bool on_device = (flags & YK_RENDER_FILM_ON_DEVICE) != 0;
+    const bool accumulate = fs->accumulate != 0;
+
+    // Pixel jobs in tile order, row-major inside a tile (Bounds2 iteration, math/bounds.rs:102-126).
+    std::vector<Job> jobs;
+    size_t area = 0;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const yk_tile& tl = tiles[t];
+        if (tl.x0 >= tl.x1 || tl.y0 >= tl.y1 || tl.x1 > fs->res_x || tl.y1 > fs->res_y)
+            return yk_set_error(YK_ERR_INVALID, "yk_render: tile outside the film (film.rs:224-231)");
+        area += (size_t)(tl.x1 - tl.x0) * (tl.y1 - tl.y0);
+    }
+    jobs.reserve(area);
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const yk_tile& tl = tiles[t];
+        for (uint32_t y = tl.y0; y < tl.y1; ++y)
+            for (uint32_t x = tl.x0; x < tl.x1; ++x) jobs.push_back(Job{(uint16_t)x, (uint16_t)y, accumulate ? tl.sample : 0u});
+    }
+    const size_t n_pixels = (size_t)fs->res_x * fs->res_y;
+    const uint32_t samples_per_job = accumulate ? 1u : spp;
+
+    RenderCfg cfg{};
+    cfg.sampler = SamplerCfg{sm->kind, sm->nx, sm->kind == YK_SAMPLER_UNIFORM ? 1u : sm->ny, sm->jitter, sm->seed};
+    cfg.integrator = in->kind;
+    cfg.max_depth = in->max_depth;
+    cfg.has_clamp = in->has_clamp;
+    cfg.clamp = in->indirect_clamp;
+    std::memcpy(cfg.c2w, cam->camera_to_world, 64);
+    std::memcpy(cfg.r2c, cam->raster_to_camera, 64);
+    cfg.res_x = fs->res_x;
+    cfg.res_y = fs->res_y;
+    cfg.aux_sample = opts ? opts->aux_sample : 0u;
+
+    // Device film / accumulators.
+    if (c->film_cap < n_pixels) {
+        cudaFree(c->d_accum); cudaFree(c->d_film); cudaFree(c->d_hit_ids);
+        c->d_accum = nullptr; c->d_film = nullptr; c->d_hit_ids = nullptr;
+        c->film_cap = 0;
+        CUDA_TRY(cudaMalloc((void**)&c->d_accum, n_pixels * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&c->d_film, n_pixels * 3 * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&c->d_hit_ids, n_pixels * sizeof(int32_t)));
+        c->film_cap = n_pixels;
+    }
+    float* d_film = on_device ? film_rgb : c->d_film;
+    const bool full_cover = !accumulate && area == n_pixels;
+    if (!on_device) {
+        if (full_cover) CUDA_TRY(cudaMemsetAsync(d_film, 0, n_pixels * 3 * sizeof(float), s));
+        else CUDA_TRY(cudaMemcpyAsync(d_film, film_rgb, n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    int32_t* d_ids = nullptr;
+    if (opts && opts->hit_ids) {
+        d_ids = on_device ? opts->hit_ids : c->d_hit_ids;
+        k_fill_i32<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s>>>(d_ids, n_pixels, -1);
+    }
+    cfg.hit_ids = d_ids;
+
+    yk_stats st{};
+    Timers tm;
+    CUDA_TRY(cudaEventRecord(c->ev[6], s));
+    if (!jobs.empty()) {
+        if (c->jobs_cap < jobs.size()) {
+            cudaFree(c->d_jobs);
+            c->d_jobs = nullptr;
+            c->jobs_cap = 0;
+            CUDA_TRY(cudaMalloc((void**)&c->d_jobs, jobs.size() * sizeof(Job)));
+            c->jobs_cap = jobs.size();
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->d_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, s));
+        // Wavefront capacity: paths in flight per batch.
+        uint32_t cap = opts && opts->wavefront_paths ? opts->wavefront_paths : (1u << 22);
+        const uint64_t total_paths = (uint64_t)jobs.size() * samples_per_job;
+        if (cap > total_paths) cap = (uint32_t)total_paths;
+        cap = std::max(cap, 32u);
+        const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
+        int rc = ensure_wave(c, cap, sc->dev.n_lights, stack_entries);
+        if (rc != YK_OK) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->wave.totals, 0, sizeof(Totals), s));
+        if (!accumulate) {
+            const unsigned g = (unsigned)((jobs.size() + 255) / 256);
+            k_zero_jobs<<<g, 256, 0, s>>>(c->d_jobs, (uint32_t)jobs.size(), c->d_accum, fs->res_x);
+        }
+        // Samples of one pixel per batch: enough to amortise per-batch fixed costs, few enough that many pixels
+        // (>= 64 Ki when available) share a batch.
+        uint32_t m = std::min(samples_per_job, 64u);
+        while (m > 1 && (uint64_t)m * std::min<uint64_t>(jobs.size(), 65536) > cap) m >>= 1;
+        const uint32_t jobs_per_batch = std::max(1u, cap / m);
+        uint64_t done = 0;
+        for (size_t j0 = 0; j0 < jobs.size(); j0 += jobs_per_batch) {
+            const uint32_t nj = (uint32_t)std::min<size_t>(jobs_per_batch, jobs.size() - j0);
+            for (uint32_t s0 = 0; s0 < samples_per_job; s0 += m) {
+                Batch bt;
+                bt.jobs = c->d_jobs + j0;
+                bt.n_jobs = nj;
+                bt.sample_off = s0;
+                bt.n_samples = std::min(m, samples_per_job - s0);
+                bt.n_paths = nj * bt.n_samples;
+                rc = run_batch(c, sc, cfg, bt, accumulate, d_film, &st, &tm);
+                if (rc != YK_OK) return rc;
+                done += bt.n_paths;
+                if (opts && opts->progress && opts->progress(opts->progress_user, done, total_paths)) {
+                    cudaStreamSynchronize(s);
+                    return yk_set_error(YK_ERR_CANCELLED, "yk_render: cancelled by the progress callback");
+                }
+            }
+        }
+        if (!accumulate) {
+            const unsigned g = (unsigned)((jobs.size() + 255) / 256);
+            k_film_store<<<g, 256, 0, s>>>(c->d_jobs, (uint32_t)jobs.size(), c->d_accum, d_film, fs->res_x, (float)spp);
+            tm.launches += 1;
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->h_totals, c->wave.totals, sizeof(Totals), cudaMemcpyDeviceToHost, s));
+        st.samples = total_paths;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[7], s));
+    if (!on_device) {
+        CUDA_TRY(cudaMemcpyAsync(film_rgb, d_film, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (opts && opts->hit_ids)
+            CUDA_TRY(cudaMemcpyAsync(opts->hit_ids, d_ids, n_pixels * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaGetLastError());
+    if (stats) {
+        if (!jobs.empty()) {
+            st.closest_nodes = c->h_totals->closest_nodes;
+            st.closest_tris = c->h_totals->closest_tris;
+            st.any_nodes = c->h_totals->any_nodes;
+            st.any_tris = c->h_totals->any_tris;
+            st.primary_hit_hash = c->h_totals->hit_hash;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+        st.device_ms = ms;
+        st.trace_closest_ms = tm.closest;
+        st.trace_any_ms = tm.any;
+        st.shade_ms = tm.shade;
+        st.kernel_launches = tm.launches;
+        st.trace_closest_launches = tm.closest_launches;
+        st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+        *stats = st;
+    }
+    return YK_OK;
+}
+
+}  // extern "C"
