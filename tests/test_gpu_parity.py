@@ -1,0 +1,154 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Gates: BVH-intersection counter images and primary-hit triangle ids bit-exact; radiance within
+per-image relative RMSE <= 1e-3 (FMA-free on both sides; residual differences: sin/cos/log implementations and the
+top-down weighting of the Whitted tree); closest-hit ray counts within 0.1 %.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_rmse
+from yuki_b200 import api, desc as D, scenes
+
+pytestmark = pytest.mark.gpu
+
+RMSE_TOL = 1e-3
+
+
+def _both(gpu_ctx, oracle, xf, scene, cam, film, sampler, integ, **kw):
+    dev = api.Scene(gpu_ctx, scene)
+    r = api.Renderer(gpu_ctx).render(dev, cam, film, sampler, integ, want_hit_ids=True, **kw)
+    osc = oracle.OracleScene(scene)
+    o_img, o_ids, o_st = osc.render(cam, film, sampler, integ, want_hit_ids=True)
+    dev.close()
+    return r, o_img, o_ids, o_st
+
+
+@pytest.mark.parametrize("split", [D.SPLIT_SAH, D.SPLIT_MIDDLE, D.SPLIT_EQUAL_COUNTS])
+def test_bvh_intersections_bit_exact(gpu_ctx, oracle, xf, split):
+    scene, cam = scenes.heightfield(xf, 96, 96, seed=3, split_method=split)
+    film = D.FilmSettings((160, 120), 16)
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.uniform(1), D.IntegratorType.bvh_intersections())
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+    assert r.stats.closest_nodes == o_st.closest_nodes == int(o_img[..., 0].sum())
+    assert r.stats.closest_tris == o_st.closest_tris
+    assert r.stats.primary_hit_hash == o_st.primary_hit_hash
+    assert r.stats.ray_count == o_st.ray_count == 160 * 120
+
+
+@pytest.mark.parametrize("kind", [D.INTEGRATOR_GEOMETRY_NORMALS, D.INTEGRATOR_SHADING_NORMALS, D.INTEGRATOR_SHADING_UVS])
+def test_debug_integrators_bit_exact(gpu_ctx, oracle, xf, kind):
+    scene, cam = scenes.material_room(xf)
+    film = D.FilmSettings((96, 64), 16)
+    r, o_img, o_ids, _ = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.debug(kind))
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+
+
+def test_whitted_cornell_point_light(gpu_ctx, oracle, xf):
+    scene, cam = scenes.cornell(xf, light="point", tall_box="glass")
+    film = D.FilmSettings((128, 128), 16)
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(3))
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert r.stats.primary_hit_hash == o_st.primary_hit_hash
+    assert abs(int(r.stats.ray_count) - int(o_st.ray_count)) <= 1e-3 * o_st.ray_count
+    assert rel_rmse(r.film, o_img) <= RMSE_TOL
+
+
+def test_whitted_deep_recursion(gpu_ctx, oracle, xf):
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    film = D.FilmSettings((96, 96), 32)
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(6))
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert abs(int(r.stats.ray_count) - int(o_st.ray_count)) <= 1e-3 * o_st.ray_count
+    assert rel_rmse(r.film, o_img) <= RMSE_TOL
+
+
+@pytest.mark.parametrize("sampler", [D.SamplerType.stratified(4, 4), D.SamplerType.uniform(8), D.SamplerType.stratified(3, 2, jitter=False)])
+def test_path_cornell_area_light(gpu_ctx, oracle, xf, sampler):
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass", textured_back_wall=True)
+    film = D.FilmSettings((128, 128), 16)
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, sampler, D.IntegratorType.path(8))
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert r.stats.primary_hit_hash == o_st.primary_hit_hash
+    assert abs(int(r.stats.ray_count) - int(o_st.ray_count)) <= 1e-3 * o_st.ray_count
+    assert abs(int(r.stats.shadow_rays) - int(o_st.shadow_rays)) <= 1e-3 * o_st.shadow_rays
+    assert rel_rmse(r.film, o_img) <= RMSE_TOL
+
+
+def test_path_material_room_all_materials_and_lights(gpu_ctx, oracle, xf):
+    scene, cam = scenes.material_room(xf)
+    film = D.FilmSettings((160, 90), 16)
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert abs(int(r.stats.ray_count) - int(o_st.ray_count)) <= 1e-3 * o_st.ray_count
+    assert rel_rmse(r.film, o_img) <= RMSE_TOL
+
+
+def test_path_indirect_clamp(gpu_ctx, oracle, xf):
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    film = D.FilmSettings((64, 64), 16)
+    r, o_img, _, _ = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(4, 4), D.IntegratorType.path(6, indirect_clamp=2.0))
+    assert rel_rmse(r.film, o_img) <= RMSE_TOL
+
+
+def test_small_wavefront_batches_match_single_batch(gpu_ctx, xf):
+    """Batching is invisible: many small batches give the same film bits as one large batch."""
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    film = D.FilmSettings((64, 48), 16)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    a = rn.render(dev, cam, film, D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
+    b = rn.render(dev, cam, film, D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), wavefront_paths=4096)
+    assert np.array_equal(a.film.view(np.uint32), b.film.view(np.uint32))
+    assert a.stats.ray_count == b.stats.ray_count
+
+
+def test_tile_subset_and_ragged_film(gpu_ctx, oracle, xf):
+    """Film not a multiple of the tile size, and only every other spiral tile rendered (a 2-rank share)."""
+    scene, cam = scenes.cornell(xf, light="point", tall_box="matte")
+    film = D.FilmSettings((70, 50), 16)
+    tiles = api.film_tiles(film)[::2]
+    dev = api.Scene(gpu_ctx, scene)
+    r = api.Renderer(gpu_ctx).render(dev, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(3), tiles=tiles)
+    o_img, _, _ = oracle.OracleScene(scene).render(cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(3), tiles=tiles)
+    covered = np.zeros((50, 70), bool)
+    for t in tiles:
+        covered[t["y0"]:t["y1"], t["x0"]:t["x1"]] = True
+    assert np.all(r.film[~covered] == 0.0)
+    assert rel_rmse(r.film, o_img) <= RMSE_TOL
+
+
+def test_accumulate_mode_sums_samples(gpu_ctx, oracle, xf):
+    """film.rs:260-272: accumulating tiles add one sample each; the sum over samples / spp equals the averaged render."""
+    scene, cam = scenes.cornell(xf, light="point", tall_box="matte")
+    film = D.FilmSettings((48, 48), 16)
+    acc = D.FilmSettings((48, 48), 16, accumulate=True)
+    smp = D.SamplerType.stratified(2, 2)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    avg = rn.render(dev, cam, film, smp, D.IntegratorType.whitted(3)).film
+    tiles = api.film_tiles(film)
+    out = np.zeros((48, 48, 3), np.float32)
+    for s in range(4):
+        t = tiles.copy()
+        t["sample"] = s
+        rn.render(dev, cam, acc, smp, D.IntegratorType.whitted(3), tiles=t, film_out=out)
+    assert np.allclose(out / 4.0, avg, rtol=1e-5, atol=1e-6)
+
+
+def test_empty_tile_list_and_bad_arguments(gpu_ctx, xf):
+    from yuki_b200 import capi
+    scene, cam = scenes.cornell(xf, light="point", tall_box=None)
+    film = D.FilmSettings((32, 32), 16)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    r = rn.render(dev, cam, film, D.SamplerType.uniform(1), D.IntegratorType.whitted(3), tiles=np.zeros(0, capi.TILE_DTYPE))
+    assert r.stats.samples == 0 and np.all(r.film == 0)
+    bad = np.zeros(1, capi.TILE_DTYPE)
+    bad[0] = (0, 0, 64, 16, 0, 0, 0)
+    with pytest.raises(capi.YukiGpuError):
+        rn.render(dev, cam, film, D.SamplerType.uniform(1), D.IntegratorType.whitted(3), tiles=bad)
+    with pytest.raises(capi.YukiGpuError):
+        rn.render(dev, cam, film, D.SamplerType.uniform(0), D.IntegratorType.whitted(3))

@@ -784,6 +784,7 @@ struct yk_context {
 
 struct yk_scene {
     yk_context* ctx = nullptr;
+    int device = 0;
     DevScene dev{};
     std::vector<void*> allocs;
 };
@@ -995,6 +996,7 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     CUDA_TRY(cudaSetDevice(c->device));
     auto sc = std::make_unique<yk_scene>();
     sc->ctx = c;
+    sc->device = c->device;
     int rc;
     // Nodes: two 16-byte words so a visit is two LDG.128 (one 32-byte sector).
     std::vector<float4> nodes((size_t)d->n_nodes * 2);
@@ -1090,7 +1092,7 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
 
 void yk_scene_destroy(yk_scene* s) {
     if (!s) return;
-    cudaSetDevice(s->ctx->device);
+    cudaSetDevice(s->device);
     free_bag(s->allocs);
     delete s;
 }
@@ -1112,6 +1114,7 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         return yk_set_error(YK_ERR_INVALID, "yk_render: whitted max_depth above 24 is not supported");
     if (n_tiles && !tiles) return yk_set_error(YK_ERR_INVALID, "yk_render: null tile list");
     CUDA_TRY(cudaSetDevice(c->device));
+    (void)cudaGetLastError();  // do not inherit a stale error from an unrelated earlier call
     cudaStream_t s = c->stream;
     const uint32_t flags = opts ? opts->flags : 0u;
     const bool on_device = (flags & YK_RENDER_FILM_ON_DEVICE) != 0;

@@ -2,12 +2,13 @@
 // interaction set-up, BSDFs and lights. Everything here is evaluated with the reference's operation
 // order; the translation unit is compiled with --fmad=false (Rust never contracts to FMA) and IEEE
 // division / square root, so primary-hit ids and BVH counters are bit-exact against the CPU path.
-// sin/cos go through f64 (correctly rounded to f32 in all but ~1e-9 of cases) to stay as close as possible to
-// the libm results the reference gets from f32::sin/cos.
+// sin/cos restate glibc's sinf/cosf bit for bit (yk_libm.h): those are the libm results the reference gets from
+// f32::sin/cos, and a 1-ulp difference there is enough to flip a shadow-ray decision a few bounces later.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "yk_libm.h"
 #include "yuki_gpu.h"
 
 #define YK_DEV __device__ __forceinline__
@@ -49,8 +50,8 @@ YK_DEV float comp(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
 YK_DEV V3 flip_toward(V3 n, V3 v) { return dotn(n, v) < 0.0f ? -n : n; }    // Normal::faceforward_v
 YK_DEV V3 flip_toward_n(V3 n, V3 m) { return dot0(n, m) < 0.0f ? -n : n; }  // Normal::faceforward_n
 YK_DEV float clamp01ish(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }  // f32::clamp
-YK_DEV float sin_f32(float x) { return (float)sin((double)x); }
-YK_DEV float cos_f32(float x) { return (float)cos((double)x); }
+YK_DEV float sin_f32(float x) { return yklibm::sinf_glibc(x); }
+YK_DEV float cos_f32(float x) { return yklibm::cosf_glibc(x); }
 
 // math/mod.rs:26-34, including the reference's un-rooted divisor in the else branch.
 YK_DEV void frame_from(V3 v, V3* a, V3* b) {
