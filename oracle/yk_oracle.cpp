@@ -128,7 +128,7 @@ int yko_render(const yko_scene* sc, const yko_camera_params* cp, const yko_film_
     } else {
         tl = film_tiles(fs->res_x, fs->res_y, fs->tile_dim);
     }
-    RenderTotals t = render(sc->s, cam, sampler, integ, fs->res_x, fs->res_y, fs->accumulate != 0, tl, n_threads,
+    RenderTotals t = render(sc->s, cam, sampler, integ, fs->res_x, fs->res_y, fs->accumulate != 0, tiles == nullptr, tl, n_threads,
                             {film, hit_ids, aux_sample});
     if (stats) {
         stats->ray_count = t.ray_count; stats->shadow_rays = t.shadow_rays; stats->samples = t.samples;

@@ -264,12 +264,13 @@ inline uint64_t render_tile(const Scene& scene, const Camera& cam, const Sampler
 }
 
 // Tile-queue worker model: render_manager.rs:78,135-143 + render_worker.rs:172-198 + film.rs:210-282.
-// `tiles` is the caller's tile list (normally film_tiles(); a multi-rank caller passes its share).
+// `tiles_in` is the tile list; with `replicate_samples` the manager's accumulate-mode replication (one copy of
+// every tile per sample index) is applied, otherwise the caller's list (with its own `sample` fields) is used as is.
 inline RenderTotals render(const Scene& scene, const Camera& cam, const Sampler& sampler, const Integrator& integ,
-                           uint32_t res_x, uint32_t res_y, bool accumulate, const std::vector<FilmTile>& tiles_in,
-                           uint32_t n_threads, RenderOutputs out) {
+                           uint32_t res_x, uint32_t /*res_y*/, bool accumulate, bool replicate_samples,
+                           const std::vector<FilmTile>& tiles_in, uint32_t n_threads, RenderOutputs out) {
     std::deque<FilmTile> queue(tiles_in.begin(), tiles_in.end());
-    if (accumulate) {  // render_manager.rs:135-143
+    if (accumulate && replicate_samples) {  // render_manager.rs:135-143
         std::vector<FilmTile> cur(tiles_in.begin(), tiles_in.end());
         for (uint32_t s = 1; s < sampler.samples_per_pixel(); ++s)
             for (auto& t : cur) {

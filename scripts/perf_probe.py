@@ -1,0 +1,36 @@
+"""Quick throughput probe of the wavefront renderer (not the bench contract)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from yuki_b200 import api, desc as D, scenes, transforms as xf
+
+def probe(name, scene, cam, film, sampler, integ, reps=2, **kw):
+    ctx = api.Context(0)
+    t0 = time.time(); dev = api.Scene(ctx, scene); t_scene = time.time() - t0
+    rn = api.Renderer(ctx)
+    for i in range(reps):
+        r = rn.render(dev, cam, film, sampler, integ, **kw)
+    st = r.stats
+    s = st.device_ms / 1e3
+    bytes_closest = 32 * st.closest_nodes + 36 * st.closest_tris
+    print(f"{name}: scene {t_scene:.2f}s tris {dev.host.n_tris} nodes {dev.host.n_nodes} | {st.samples/s/1e6:.1f} Msamples/s "
+          f"{st.ray_count/s/1e6:.1f} Mrays/s(closest) {(st.ray_count+st.shadow_rays)/s/1e6:.1f} Mrays/s(total) | device {st.device_ms:.1f} ms "
+          f"closest {st.trace_closest_ms:.1f} any {st.trace_any_ms:.1f} shade {st.shade_ms:.1f} | launches {st.kernel_launches} | "
+          f"closest roofline {bytes_closest/ (st.trace_closest_ms/1e3) /1e9:.0f} GB/s nodes/ray {st.closest_nodes/max(st.ray_count,1):.1f}", flush=True)
+    dev.close(); ctx.close()
+
+which = sys.argv[1] if len(sys.argv) > 1 else "cornell"
+if which in ("cornell", "all"):
+    s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+    probe("cornell 1024^2 path8 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
+    probe("cornell 1024^2 path8 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8), reps=1)
+    probe("cornell 512^2 whitted3 16spp", s, c, D.FilmSettings((512, 512), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(3))
+if which in ("hf", "all"):
+    for sm in (D.SPLIT_SAH, D.SPLIT_MIDDLE, D.SPLIT_EQUAL_COUNTS):
+        s, c = scenes.heightfield(xf, 708, 708, split_method=sm)
+        probe(f"heightfield 1M split{sm} bvh 1920x1080", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.uniform(1), D.IntegratorType.bvh_intersections())
+    s, c = scenes.heightfield(xf, 708, 708)
+    probe("heightfield 1M path8 1920x1080 4spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8))
+if which in ("room", "all"):
+    s, c = scenes.material_room(xf)
+    probe("room 1080p path8 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
