@@ -152,3 +152,58 @@ def test_empty_tile_list_and_bad_arguments(gpu_ctx, xf):
         rn.render(dev, cam, film, D.SamplerType.uniform(1), D.IntegratorType.whitted(3), tiles=bad)
     with pytest.raises(capi.YukiGpuError):
         rn.render(dev, cam, film, D.SamplerType.uniform(0), D.IntegratorType.whitted(3))
+
+
+def test_gpu_matches_committed_golden_fixtures(gpu_ctx, xf):
+    """The GPU box has no reference checkout: compare against tests/golden/oracle_renders.json (made by
+    tests/golden/make_golden.py). Path / debug integrators are bit-identical; Whitted is compared through its mean (its
+    recursion is evaluated top-down with pre-multiplied weights, a documented rounding difference)."""
+    import hashlib
+    import json
+    from test_oracle_render import GOLDEN, golden_cases
+    want = json.load(open(GOLDEN))
+    for name, (scene, cam, film, smp, integ) in golden_cases(xf).items():
+        dev = api.Scene(gpu_ctx, scene)
+        r = api.Renderer(gpu_ctx).render(dev, cam, film, smp, integ, want_hit_ids=True)
+        dev.close()
+        g = want[name]
+        assert hashlib.sha256(r.hit_ids.tobytes()).hexdigest() == g["ids_sha256"], name
+        assert r.stats.primary_hit_hash == g["primary_hit_hash"] and r.stats.ray_count == g["ray_count"], name
+        assert r.stats.closest_nodes == g["closest_nodes"] and r.stats.shadow_rays == g["shadow_rays"], name
+        if integ.kind == D.INTEGRATOR_WHITTED:
+            assert abs(float(np.mean(r.film, dtype=np.float64)) - g["film_mean"]) <= 1e-6 * g["film_mean"], name
+        else:
+            assert hashlib.sha256(r.film.tobytes()).hexdigest() == g["film_sha256"], name
+
+
+def test_path_is_bit_identical_to_the_oracle(gpu_ctx, oracle, xf):
+    """Stronger than the RMSE gate: with un-fused IEEE arithmetic and glibc-exact sinf/cosf the Path film has no
+    differing bit, for every material and light kind."""
+    for scene, cam, film in [(*scenes.material_room(xf), D.FilmSettings((96, 54), 16)),
+                             (*scenes.cornell(xf, light="rect", tall_box="glass", textured_back_wall=True), D.FilmSettings((64, 64), 16))]:
+        r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(3, 3), D.IntegratorType.path(8))
+        assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+        assert r.stats.ray_count == o_st.ray_count and r.stats.shadow_rays == o_st.shadow_rays
+        assert r.stats.any_nodes == o_st.any_nodes and r.stats.any_tris == o_st.any_tris
+
+
+def test_round_trip_properties_at_full_size(gpu_ctx, xf):
+    """Size-independent properties on the benchmark-size film (the oracle would take minutes here): rendering the two
+    interleaved halves of the tile list separately and summing equals rendering all tiles; re-rendering is idempotent;
+    every pixel is finite and non-negative."""
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    film = D.FilmSettings((1024, 1024), 16)
+    smp, integ = D.SamplerType.stratified(2, 2), D.IntegratorType.path(8)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    tiles = api.film_tiles(film)
+    full = rn.render(dev, cam, film, smp, integ)
+    again = rn.render(dev, cam, film, smp, integ)
+    a = rn.render(dev, cam, film, smp, integ, tiles=tiles[0::2])
+    b = rn.render(dev, cam, film, smp, integ, tiles=tiles[1::2])
+    assert np.array_equal(full.film.view(np.uint32), again.film.view(np.uint32))
+    assert np.array_equal((a.film + b.film).view(np.uint32), full.film.view(np.uint32))
+    assert a.stats.ray_count + b.stats.ray_count == full.stats.ray_count
+    assert np.isfinite(full.film).all() and (full.film >= 0).all()
+    assert full.stats.samples == 1024 * 1024 * 4
+    dev.close()

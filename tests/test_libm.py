@@ -1,0 +1,37 @@
+"""yk_libm.h restates glibc's sinf/cosf; on this host it must be bit-identical to the libm the oracle calls."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SRC = r'''
+#include <cstdio>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include "yk_libm.h"
+int main() {
+    uint64_t bad = 0, n = 0;
+    for (uint32_t u = 0x30000000u; u < 0x42f00000u; u += 61) for (int sg = 0; sg < 2; ++sg) {
+        uint32_t b = u | (sg ? 0x80000000u : 0u); float x; memcpy(&x, &b, 4);
+        float a = sinf(x), c = cosf(x), a2 = yklibm::sinf_glibc(x), c2 = yklibm::cosf_glibc(x);
+        bad += memcmp(&a, &a2, 4) != 0; bad += memcmp(&c, &c2, 4) != 0; ++n;
+    }
+    float specials[] = {0.0f, -0.0f, 1e-30f, 0.78539816f, 0.78539822f, 1.5707964f, 3.1415927f, 6.2831855f, 119.99f};
+    for (float x : specials) { float a = sinf(x), a2 = yklibm::sinf_glibc(x), c = cosf(x), c2 = yklibm::cosf_glibc(x);
+        bad += memcmp(&a, &a2, 4) != 0; bad += memcmp(&c, &c2, 4) != 0; }
+    printf("%llu %llu\n", (unsigned long long)n, (unsigned long long)bad);
+    return bad != 0;
+}
+'''
+
+
+def test_sinf_cosf_bit_identical_to_host_libm(tmp_path):
+    src = tmp_path / "t.cpp"
+    src.write_text(SRC)
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "yuki_b200", "csrc"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    n, bad = out.stdout.split()
+    assert out.returncode == 0 and int(bad) == 0 and int(n) > 10_000_000, out.stdout

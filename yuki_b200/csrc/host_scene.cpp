@@ -251,6 +251,9 @@ int yk_camera_make(const yk_camera_params* p, uint32_t res_x, uint32_t res_y, yk
         xf_compose(xf_scaling(fx, fy, 1.0f),
                    xf_compose(xf_scaling(1.0f / (hi_x - lo_x), 1.0f / (lo_y - hi_y), 1.0f), xf_translate(mk3(-lo_x, -hi_y, 0.0f))));
     const xform raster_to_cam = xf_compose(xf_flip(cam_to_screen), xf_flip(screen_to_raster));
+    for (int i = 0; i < 16; ++i)  // Matrix4x4::new debug-asserts !has_nans (matrix.rs:23-27), e.g. target == position
+        if (c2w.m.e[i] != c2w.m.e[i] || raster_to_cam.m.e[i] != raster_to_cam.m.e[i])
+            return yk_set_error(YK_ERR_SINGULAR, "yk_camera_make: camera matrices contain NaN (degenerate look_at / fov)");
     std::memcpy(out->camera_to_world, c2w.m.e, 64);
     std::memcpy(out->raster_to_camera, raster_to_cam.m.e, 64);
     return YK_OK;
