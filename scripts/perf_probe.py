@@ -20,10 +20,16 @@ def probe(name, scene, cam, film, sampler, integ, reps=2, **kw):
     dev.close(); ctx.close()
 
 which = sys.argv[1] if len(sys.argv) > 1 else "cornell"
+if which == "cornell16":  # one short render for ncu captures
+    s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+    probe("cornell 1024^2 path8 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=1)
+if which == "hf4":
+    s, c = scenes.heightfield(xf, 708, 708)
+    probe("heightfield 1M path8 1920x1080 4spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8), reps=1)
 if which in ("cornell", "all"):
     s, c = scenes.cornell(xf, light="rect", tall_box="glass")
     probe("cornell 1024^2 path8 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
-    probe("cornell 1024^2 path8 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8), reps=1)
+    probe("cornell 1024^2 path8 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8))
     probe("cornell 512^2 whitted3 16spp", s, c, D.FilmSettings((512, 512), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(3))
 if which in ("hf", "all"):
     for sm in (D.SPLIT_SAH, D.SPLIT_MIDDLE, D.SPLIT_EQUAL_COUNTS):

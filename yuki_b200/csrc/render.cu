@@ -57,7 +57,7 @@ struct DevMaterial {
 };
 struct DevScene {
     const float4* nodes;   // 2 x float4 per node: (p_min, offset) (p_max, meta)
-    const float4* tris;    // 3 x float4 per triangle: (v0, area_light) (v1, material | flags<<24) (v2, orig_id)
+    const float4* tris;    // 3 x float4 per triangle: (x0 x1 x2, area_light) (y0 y1 y2, material | flags<<24) (z0 z1 z2, orig_id)
     const float* normals;  // 9 per triangle or null
     const float* uvs;      // 6 per triangle or null
     const DevTexture* textures;
@@ -66,7 +66,7 @@ struct DevScene {
     uint32_t n_lights, n_tris, n_nodes;
     float background[3];
 };
-constexpr uint32_t kMetaLeaf = 0x80000000u;  // meta: leaf bit | axis << 16 | shape_count
+constexpr uint32_t kMetaLeaf = 0x80000000u;  // meta: leaf -> leaf bit | shape_count; interior -> 1 << split_axis
 
 // ---- per-iteration device counters ----------------------------------------------------------------
 struct Counters {
@@ -150,6 +150,35 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
 }
+// Block-aggregated append to one of NQ queues: one global atomic per queue per block (same-address atomics were the
+// bottleneck of classify / resolve with one atomic per warp, profiles/r01). `key` in [0, NQ) selects the queue, any
+// other value appends nothing. Must be reached by every thread of the block (blockDim.x <= 256).
+template <int NQ>
+__device__ __forceinline__ void block_scatter(int key, uint32_t value, uint32_t* const (&queues)[NQ], uint32_t* const (&counters)[NQ]) {
+    __shared__ uint32_t s_cnt[8][NQ];
+    __shared__ uint32_t s_base[NQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    uint32_t my_rank = 0;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        const unsigned votes = __ballot_sync(0xffffffffu, key == k);
+        if (key == k) my_rank = __popc(votes & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[warp][k] = __popc(votes);
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        uint32_t total = 0;
+        for (int wi = 0; wi < n_warps; ++wi) {
+            const uint32_t c = s_cnt[wi][threadIdx.x];
+            s_cnt[wi][threadIdx.x] = total;  // exclusive prefix over the block's warps
+            total += c;
+        }
+        s_base[threadIdx.x] = total ? atomicAdd(counters[threadIdx.x], total) : 0u;
+    }
+    __syncthreads();
+    if (key >= 0 && key < NQ) queues[key][s_base[key] + s_cnt[warp][key] + my_rank] = value;
+    __syncthreads();  // the shared arrays are reused by the next call
+}
 __device__ __forceinline__ unsigned long long mix_hit(uint32_t x, uint32_t y, uint32_t sample, uint32_t id) {
     unsigned long long h = ((unsigned long long)x << 48) ^ ((unsigned long long)y << 32) ^ ((unsigned long long)sample << 8) ^
                            (unsigned long long)id * 0x9E3779B97F4A7C15ULL;
@@ -182,86 +211,211 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
 }
 
 // ---- BVH traversal (bvh.rs:160-302, math/bounds.rs:176-215, shapes/triangle.rs:49-139) --------------
-// Persistent warps pull 32 rays at a time from a global cursor. One ray per lane, per-lane 64-entry stack.
-template <bool ANY>
+// Persistent warps, one ray per lane. The kernel is issue-bound on small scenes and latency-bound on large ones
+// (profiles/r01), so the design goal is: few instructions per step, and as many lanes as possible per instruction.
+//  * Two phases per warp: box steps (N) and triangle steps (T). A lane that reaches a leaf parks until the warp
+//    serves leaves; the warp keeps stepping boxes while at least kNodePhaseMin lanes want to, then drains every
+//    parked leaf. A lane never walks past its own leaf, so each ray performs exactly the reference's sequence of
+//    box and triangle tests (the counters are bit-exact). Policy chosen with scripts/sim_warp.py.
+//  * Finished lanes are refilled from the ray queue once fewer than kRefillBelow lanes are live; a warp reserves
+//    kChunk rays from the global cursor at a time.
+//  * Both steps are branch-free apart from the rare f64 edge-function fallback. The traversal stack lives in shared
+//    memory as s_stack[depth][thread] (conflict-free for any mix of depths); entries beyond kShortStack spill to
+//    local memory, up to the reference's 64.
+//  * Triangles are stored transposed (x0 x1 x2 | y0 y1 y2 | z0 z1 z2), so the watertight test's axis permutation is
+//    three index offsets instead of 18 selects.
+constexpr uint32_t kNoNode = 0xffffffffu;
+constexpr uint32_t kChunk = 64;
+constexpr int kRefillBelow = 22;
+constexpr int kNodePhaseMin = 14;
+constexpr int kShortStack = 48;
+
+template <bool ANY, bool COUNTS>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, Wave w, const uint32_t* queue, const uint32_t* n_ptr,
-                                                          uint32_t n_fixed, uint32_t* cursor, int write_counts) {
+                                                          uint32_t n_fixed, uint32_t* cursor) {
+    __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
+    uint32_t deep[kStackDepth + 1 - kShortStack];
     const uint32_t n = n_ptr ? *n_ptr : n_fixed;
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long sum_nodes = 0, sum_tris = 0;
-    uint32_t stack[kStackDepth];
+
+    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
+    bool exhausted = false;                  // warp-uniform: the global cursor ran past n
+
+    // per-lane ray state
+    bool live = false;
+    uint32_t slot = 0, path = 0;
+    float ox = 0, oy = 0, oz = 0, ix = 0, iy = 0, iz = 0, t_max = 0, hit_t = 0;
+    float okx = 0, oky = 0, okz = 0, sx = 0, sy = 0, sz = 0;  // watertight test: permuted origin, shear
+    uint32_t kx = 0, ky = 0, kz = 0, neg_mask = 0;
+    int target_light = -1;
+    uint32_t cur = kNoNode, sp = kTraceThreads, n_tests = 0, n_hits = 0, n_tris = 0, hit_tri = kMiss;
+    uint32_t leaf_pos = 0, leaf_end = 0;
+    bool occluded = false;
+
+    // `sp` is the lane's stack pointer in words: depth * kTraceThreads. Entry 0 is a kNoNode sentinel (popping it ends
+    // the ray), entries 1..kShortStack-1 live in shared memory, deeper ones in local memory.
+    uint32_t* const lane_stack = &s_stack[0][tid];
+    lane_stack[0] = kNoNode;
+    constexpr uint32_t kSpBase = kTraceThreads;  // empty stack: just the sentinel
+    auto push = [&](uint32_t v) {
+        const uint32_t depth = sp / kTraceThreads;
+        if (depth < (uint32_t)kShortStack) lane_stack[sp] = v;
+        else deep[depth - kShortStack] = v;
+        sp += kTraceThreads;
+    };
+    auto pop = [&]() -> uint32_t {
+        sp -= kTraceThreads;
+        const uint32_t depth = sp / kTraceThreads;
+        return depth < (uint32_t)kShortStack ? lane_stack[sp] : deep[depth - kShortStack];
+    };
+
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t slot = base + lane;
-        if (slot < n) {
-            const uint32_t path = ANY ? slot : (queue ? queue[slot] : slot);
-            const float4 ro = ANY ? w.sh_o[slot] : w.ray_o[path];
-            const float4 rd = ANY ? w.sh_d[slot] : w.ray_d[path];
-            const V3 o = f4v(ro), d = f4v(rd);
-            float t_max = ro.w;
-            const int target_light = ANY ? __float_as_int(rd.w) : -1;
-            const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
-            const bool neg[3] = {ix < 0.0f, iy < 0.0f, iz < 0.0f};
-            TriRay tr;
-            tr.setup(d);
-            uint32_t cur = 0, sp = 0, n_tests = 0, n_hits = 0, n_tris = 0, hit_tri = kMiss;
-            float hit_t = 0.0f;
-            bool occluded = false;
+        // ---- refill idle lanes -----------------------------------------------------------------------
+        const unsigned idle = __ballot_sync(0xffffffffu, !live);
+        if (idle && !exhausted) {
+            if (chunk_next >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, kChunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = base;
+                chunk_end = base + kChunk < n ? base + kChunk : n;
+                if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; }
+            }
+            if (!exhausted) {
+                const uint32_t mine = chunk_next + __popc(idle & lt_mask);
+                if (!live && mine < chunk_end) {
+                    slot = mine;
+                    path = ANY ? slot : (queue ? queue[slot] : slot);
+                    const float4 ro = ANY ? w.sh_o[slot] : w.ray_o[path];
+                    const float4 rd = ANY ? w.sh_d[slot] : w.ray_d[path];
+                    ox = ro.x; oy = ro.y; oz = ro.z;
+                    t_max = ro.w;
+                    target_light = ANY ? __float_as_int(rd.w) : -1;
+                    ix = 1.0f / rd.x; iy = 1.0f / rd.y; iz = 1.0f / rd.z;  // bvh.rs:164
+                    neg_mask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
+                    // triangle.rs:58-80: permutation and shear depend on the ray only
+                    const float ax = fabsf(rd.x), ay = fabsf(rd.y), az = fabsf(rd.z);
+                    kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);  // Vec3::max_dimension, math/vector.rs:188-202
+                    kx = kz < 2u ? kz + 1u : 0u;
+                    ky = kx < 2u ? kx + 1u : 0u;
+                    const float dkx = kx == 0 ? rd.x : (kx == 1 ? rd.y : rd.z), dky = ky == 0 ? rd.x : (ky == 1 ? rd.y : rd.z);
+                    const float dkz = kz == 0 ? rd.x : (kz == 1 ? rd.y : rd.z);
+                    sx = -dkx / dkz; sy = -dky / dkz;
+                    sz = kz == 0 ? ix : (kz == 1 ? iy : iz);  // 1.0 / d[kz]: the same IEEE division as above
+                    okx = kx == 0 ? ox : (kx == 1 ? oy : oz);
+                    oky = ky == 0 ? ox : (ky == 1 ? oy : oz);
+                    okz = kz == 0 ? ox : (kz == 1 ? oy : oz);
+                    cur = 0; sp = kSpBase; n_tests = 0; n_hits = 0; n_tris = 0; hit_tri = kMiss; hit_t = 0.0f;
+                    leaf_pos = leaf_end = 0; occluded = false;
+                    live = true;
+                }
+                const uint32_t taken = chunk_next + __popc(idle);
+                chunk_next = taken < chunk_end ? taken : chunk_end;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, live) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- trace until too few lanes are live -----------------------------------------------------------
+        for (;;) {
+            // N: box steps while enough lanes want one (or nothing else can run)
             for (;;) {
-                const float4 n0 = __ldg(&sc.nodes[2 * cur]);
-                const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
-                n_tests += 1;
-                // slab test: (bound - o) * inv_dir, NaN-ignoring min/max exactly like f32::min/max
-                const float t0x = (n0.x - o.x) * ix, t0y = (n0.y - o.y) * iy, t0z = (n0.z - o.z) * iz;
-                const float t1x = (n1.x - o.x) * ix, t1y = (n1.y - o.y) * iy, t1z = (n1.z - o.z) * iz;
-                const float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
-                const float tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), t_max);
-                bool pop = true;
-                if (tmin <= tmax) {
-                    n_hits += 1;
+                const bool want_n = cur != kNoNode;
+                const int n_n = __popc(__ballot_sync(0xffffffffu, want_n));
+                if (n_n == 0) break;
+                if (n_n < kNodePhaseMin && __ballot_sync(0xffffffffu, live && !want_n)) break;
+                if (want_n) {
+                    const float4 n0 = __ldg(&sc.nodes[2 * cur]);
+                    const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
+                    n_tests += 1;
+                    // slab test: (bound - o) * inv_dir, NaN-ignoring min/max exactly like f32::min/max
+                    const float t0x = (n0.x - ox) * ix, t0y = (n0.y - oy) * iy, t0z = (n0.z - oz) * iz;
+                    const float t1x = (n1.x - ox) * ix, t1y = (n1.y - oy) * iy, t1z = (n1.z - oz) * iz;
+                    const float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
+                    const float tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), t_max);
                     const uint32_t offset = __float_as_uint(n0.w), meta = __float_as_uint(n1.w);
-                    if (!(meta & kMetaLeaf)) {
-                        const uint32_t axis = (meta >> 16) & 3u;
-                        if (neg[axis]) { stack[sp++] = cur + 1; cur = offset; }
-                        else { stack[sp++] = offset; cur = cur + 1; }
-                        pop = false;
+                    const bool hit = tmin <= tmax;
+                    const bool leaf = (meta & kMetaLeaf) != 0;
+                    const bool neg = (meta & neg_mask) != 0;  // interior meta = 1 << split_axis
+                    const uint32_t next = cur + 1;
+                    if (COUNTS) n_hits += hit ? 1u : 0u;
+                    if (sp >= (uint32_t)kShortStack * kTraceThreads) {  // cold: the stack continues in local memory
+                        if (hit && !leaf) { push(neg ? next : offset); cur = neg ? offset : next; }
+                        else if (hit) { leaf_pos = offset; leaf_end = offset + (meta & 0xffffu); cur = kNoNode; }
+                        else cur = pop();
                     } else {
-                        const uint32_t count = meta & 0xffffu;
-                        for (uint32_t s = offset; s < offset + count; ++s) {
-                            const float4 a = __ldg(&sc.tris[3 * s]);
-                            const float4 b = __ldg(&sc.tris[3 * s + 1]);
-                            const float4 c = __ldg(&sc.tris[3 * s + 2]);
-                            n_tris += 1;
-                            TriHit h;
-                            if (tri_test(tr, o, t_max, f4v(a), f4v(b), f4v(c), &h)) {
-                                if (ANY) {
-                                    // bvh.rs:269-280: the target light's own emissive triangles do not occlude
-                                    const int tri_light = __float_as_int(a.w);
-                                    if (!(target_light >= 0 && tri_light >= 0 && tri_light == target_light)) { occluded = true; break; }
-                                } else {
-                                    hit_tri = s; hit_t = h.t; t_max = h.t;  // later equal-t hit replaces (bvh.rs:204-207)
-                                }
-                            }
-                        }
-                        if (ANY && occluded) break;
+                        // three disjoint predicated updates; the stack bottom holds a kNoNode sentinel, so a pop needs no
+                        // emptiness test
+                        if (hit && !leaf) { lane_stack[sp] = neg ? next : offset; sp += kTraceThreads; cur = neg ? offset : next; }
+                        if (!hit) { sp -= kTraceThreads; cur = lane_stack[sp]; }
+                        if (hit && leaf) { leaf_pos = offset; leaf_end = offset + (meta & 0xffffu); cur = kNoNode; }
                     }
                 }
-                if (pop) {
-                    if (sp == 0) break;
-                    cur = stack[--sp];
+            }
+            // T: drain the parked leaves, one triangle per lane per step, in stored order
+            while (__ballot_sync(0xffffffffu, leaf_pos < leaf_end)) {
+                if (leaf_pos < leaf_end) {
+                    const uint32_t s = leaf_pos++;
+                    const float4 A = __ldg(&sc.tris[3 * s + kx]);
+                    const float4 B = __ldg(&sc.tris[3 * s + ky]);
+                    const float4 C = __ldg(&sc.tris[3 * s + kz]);
+                    n_tris += 1;
+                    // shapes/triangle.rs:62-130 on the permuted, origin-relative vertices
+                    float ax = A.x - okx, bx = A.y - okx, cx = A.z - okx;
+                    float ay = B.x - oky, by = B.y - oky, cy = B.z - oky;
+                    const float az = C.x - okz, bz = C.y - okz, cz = C.z - okz;
+                    ax += sx * az; ay += sy * az;
+                    bx += sx * bz; by += sy * bz;
+                    cx += sx * cz; cy += sy * cz;
+                    float e0 = bx * cy - by * cx;
+                    float e1 = cx * ay - cy * ax;
+                    float e2 = ax * by - ay * bx;
+                    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {  // f64 fallback, :98-105
+                        e0 = (float)((double)bx * (double)cy - (double)by * (double)cx);
+                        e1 = (float)((double)cx * (double)ay - (double)cy * (double)ax);
+                        e2 = (float)((double)ax * (double)by - (double)ay * (double)bx);
+                    }
+                    const float det = e0 + e1 + e2;
+                    const float t_scaled = e0 * (az * sz) + e1 * (bz * sz) + e2 * (cz * sz);
+                    const float lim = t_max * det;
+                    const bool mixed = (e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f);
+                    const bool out_neg = det < 0.0f && (t_scaled >= 0.0f || t_scaled < lim);
+                    const bool out_pos = det > 0.0f && (t_scaled <= 0.0f || t_scaled > lim);
+                    const bool tri_hit = !mixed && det != 0.0f && !out_neg && !out_pos;
+                    if (tri_hit) {
+                        if (ANY) {
+                            // bvh.rs:269-280: the target light's own emissive triangles do not occlude
+                            const int tri_light = __float_as_int(kx == 0 ? A.w : (ky == 0 ? B.w : C.w));
+                            if (!(target_light >= 0 && tri_light >= 0 && tri_light == target_light)) {
+                                occluded = true;
+                                leaf_pos = leaf_end;
+                                sp = kSpBase;
+                            }
+                        } else {
+                            const float inv_det = 1.0f / det;
+                            hit_tri = s; hit_t = t_scaled * inv_det; t_max = hit_t;  // later equal-t hit replaces (bvh.rs:204-207)
+                        }
+                    }
+                    if (leaf_pos == leaf_end) cur = pop();
                 }
             }
-            if (ANY) {
-                if (occluded) w.contrib[w.sh_ref[slot]].w = 0.0f;
-            } else {
-                w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
-                if (write_counts) w.bvh_counts[path] = make_uint2(n_tests, n_hits);
+            // retire finished rays
+            if (live && cur == kNoNode) {
+                if (ANY) {
+                    if (occluded) w.contrib[w.sh_ref[slot]].w = 0.0f;
+                } else {
+                    w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
+                    if (COUNTS) w.bvh_counts[path] = make_uint2(n_tests, n_hits);
+                }
+                sum_nodes += n_tests;
+                sum_tris += n_tris;
+                live = false;
             }
-            sum_nodes += n_tests;
-            sum_tris += n_tris;
+            const int busy = __popc(__ballot_sync(0xffffffffu, live));
+            if (busy == 0 || (!exhausted && busy < kRefillBelow)) break;
         }
     }
     sum_nodes = warp_sum(sum_nodes);
@@ -333,9 +487,9 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
             if (cfg.hit_ids && sample == cfg.aux_sample) cfg.hit_ids[(size_t)job.y * cfg.res_x + job.x] = (int32_t)orig;
         }
     }
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k) queue_push(valid && kind == k, path, w.q_mat + (size_t)k * w.cap, &w.counters->mat[k]);
-    queue_push(requeue, path, q_next, &w.counters->next);
+    uint32_t* const queues[5] = {w.q_mat, w.q_mat + (size_t)w.cap, w.q_mat + (size_t)2 * w.cap, w.q_mat + (size_t)3 * w.cap, q_next};
+    uint32_t* const counters[5] = {&w.counters->mat[0], &w.counters->mat[1], &w.counters->mat[2], &w.counters->mat[3], &w.counters->next};
+    block_scatter<5>(!valid ? -1 : (requeue ? 4 : (kind < 4 ? (int)kind : -1)), path, queues, counters);
     if (first_iteration) {
         hh = warp_sum(hh);
         if ((threadIdx.x & 31) == 0 && hh) atomicAdd(&w.totals->hit_hash, hh);
@@ -345,7 +499,7 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
 // ---- surface set-up: Triangle::intersect's SurfaceInteraction part (triangle.rs:141-226) ----------------
 __device__ __forceinline__ void make_surface(const DevScene& sc, uint32_t tri, V3 o, V3 d, Surface* si, uint32_t* material) {
     const float4 a4 = __ldg(&sc.tris[3 * tri]), b4 = __ldg(&sc.tris[3 * tri + 1]), c4 = __ldg(&sc.tris[3 * tri + 2]);
-    const V3 p0 = f4v(a4), p1 = f4v(b4), p2 = f4v(c4);
+    const V3 p0 = mk(a4.x, b4.x, c4.x), p1 = mk(a4.y, b4.y, c4.y), p2 = mk(a4.z, b4.z, c4.z);  // stored transposed
     const uint32_t packed = __float_as_uint(b4.w);
     const uint32_t flags = packed >> 24;
     *material = packed & 0xffffffu;
@@ -690,7 +844,9 @@ __global__ void k_resolve(Wave w, RenderCfg cfg, uint32_t* q_next) {
             w.L[path] = L;
             alive = (__float_as_uint(w.beta[path].w) & kFlagAlive) != 0;
         }
-        queue_push(alive, path, q_next, &w.counters->next);
+        uint32_t* const queues[1] = {q_next};
+        uint32_t* const counters[1] = {&w.counters->next};
+        block_scatter<1>(alive ? 0 : -1, path, queues, counters);
     }
 }
 
@@ -879,9 +1035,12 @@ int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Bat
     for (uint32_t iter = 0; n_active > 0; ++iter) {
         CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(Counters), s));
         CUDA_TRY(cudaEventRecord(c->ev[0], s));
-        k_trace<false><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
-            sc->dev, w, q_cur, nullptr, n_active, &w.counters->work_closest,
-            cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS ? 1 : 0);
+        if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS)
+            k_trace<false, true><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
+                sc->dev, w, q_cur, nullptr, n_active, &w.counters->work_closest);
+        else
+            k_trace<false, false><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
+                sc->dev, w, q_cur, nullptr, n_active, &w.counters->work_closest);
         CUDA_TRY(cudaEventRecord(c->ev[1], s));
         tm->launches += 1;
         tm->closest_launches += 1;
@@ -911,8 +1070,8 @@ int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Bat
         k_shade<YK_MAT_GLOSSY><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)3 * w.cap, &w.counters->mat[3]);
         CUDA_TRY(cudaEventRecord(c->ev[3], s));
         if (w.n_lights) {
-            k_trace<true><<<grid_for(n_active * w.n_lights, kTraceThreads, trace_blocks_any), kTraceThreads, 0, s>>>(
-                sc->dev, w, nullptr, &w.counters->shadow, 0, &w.counters->work_any, 0);
+            k_trace<true, false><<<grid_for(n_active * w.n_lights, kTraceThreads, trace_blocks_any), kTraceThreads, 0, s>>>(
+                sc->dev, w, nullptr, &w.counters->shadow, 0, &w.counters->work_any);
             tm->launches += 1;
         }
         CUDA_TRY(cudaEventRecord(c->ev[4], s));
@@ -962,8 +1121,8 @@ int yk_context_create(int device_id, yk_context** out) {
     for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMallocHost((void**)&c->h_counters, sizeof(Counters)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_totals, sizeof(Totals)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace<false>, kTraceThreads, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace<true>, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace<false, false>, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace<true, false>, kTraceThreads, 0));
     *out = c;
     return YK_OK;
 }
@@ -1002,7 +1161,8 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     std::vector<float4> nodes((size_t)d->n_nodes * 2);
     for (uint32_t i = 0; i < d->n_nodes; ++i) {
         const yk_bvh_node& n = d->nodes[i];
-        uint32_t meta = n.is_leaf ? (kMetaLeaf | n.shape_count) : ((uint32_t)n.split_axis << 16);
+        if (!n.is_leaf && n.split_axis > 2) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: split axis out of range");
+        uint32_t meta = n.is_leaf ? (kMetaLeaf | n.shape_count) : (1u << n.split_axis);
         if (!n.is_leaf && n.offset >= d->n_nodes) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: child index out of range");
         if (n.is_leaf && (uint64_t)n.offset + n.shape_count > d->n_tris)
             return yk_set_error(YK_ERR_INVALID, "yk_scene_create: leaf range out of range");
@@ -1012,7 +1172,8 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
         nodes[2 * i] = make_float4(n.p_min[0], n.p_min[1], n.p_min[2], fo);
         nodes[2 * i + 1] = make_float4(n.p_max[0], n.p_max[1], n.p_max[2], fm);
     }
-    // Triangles: three 16-byte words (vertices pre-gathered in leaf order; w lanes carry the per-triangle ids).
+    // Triangles: three 16-byte words, vertices pre-gathered in leaf order and transposed (x0 x1 x2 | y0 y1 y2 | z0 z1 z2);
+    // the w lanes carry the per-triangle ids.
     std::vector<float4> tris((size_t)d->n_tris * 3);
     for (uint32_t i = 0; i < d->n_tris; ++i) {
         const float* v = d->tri_vertices + (size_t)i * 9;
@@ -1025,9 +1186,9 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
         std::memcpy(&fa, &d->tri_area_light[i], 4);
         std::memcpy(&fp, &packed, 4);
         std::memcpy(&fi, &d->tri_orig_id[i], 4);
-        tris[3 * i] = make_float4(v[0], v[1], v[2], fa);
-        tris[3 * i + 1] = make_float4(v[3], v[4], v[5], fp);
-        tris[3 * i + 2] = make_float4(v[6], v[7], v[8], fi);
+        tris[3 * i] = make_float4(v[0], v[3], v[6], fa);
+        tris[3 * i + 1] = make_float4(v[1], v[4], v[7], fp);
+        tris[3 * i + 2] = make_float4(v[2], v[5], v[8], fi);
     }
     if ((rc = dev_upload(sc->allocs, &sc->dev.nodes, nodes.data(), nodes.size())) != YK_OK) return rc;
     if ((rc = dev_upload(sc->allocs, &sc->dev.tris, tris.data(), tris.size())) != YK_OK) return rc;
