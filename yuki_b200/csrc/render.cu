@@ -71,18 +71,23 @@ constexpr uint32_t kMetaLeaf = 0x80000000u;  // meta: leaf -> leaf bit | shape_c
 // ---- per-iteration device counters ----------------------------------------------------------------
 struct Counters {
     uint32_t mat[4];       // material queue lengths
-    uint32_t shadow;       // shadow queue length
     uint32_t next;         // next active queue length
     uint32_t work_closest; // dynamic ray fetch cursors
-    uint32_t work_any;
+    uint32_t work_shadow;
+    uint32_t _pad;
 };
 struct Totals {
     unsigned long long closest_nodes, closest_tris, any_nodes, any_tris, hit_hash, shadow_rays;
 };
 
-struct Job {  // one pixel's share of the batch
+struct JobIn {  // as uploaded by the host: one pixel's share of the batch
     uint16_t x, y;
     uint32_t sample_begin;
+};
+struct Job {  // + the pixel's PCG stream, (SipHash13(x, y) << 1) | 1 (uniform.rs:77-81): one hash per pixel, not per sample
+    uint16_t x, y;
+    uint32_t sample_begin;
+    unsigned long long rng_inc;
 };
 // Path i of a batch is sample (sample_begin + sample_off + i / n_jobs) of pixel jobs[i % n_jobs]: a warp holds
 // 32 neighbouring pixels of one tile row at the same sample index.
@@ -92,6 +97,9 @@ struct Batch {
 };
 
 // ---- wavefront state (SoA, capacity `cap` paths) --------------------------------------------------
+// Per bounce a path touches: ray (32 B) + hit (8 B) in the traversal; ray, hit, rng state (8 B), beta (16 B) in
+// shading, which writes the next ray / beta / rng state, the pending radiance terms (32 B) and 40 B per light that
+// needs a shadow ray; the shadow kernel reads those back and does the one read-modify-write of L.
 struct Wave {
     uint32_t cap, n_lights, stack_entries;
     float4* ray_o;   // o.xyz, t_max
@@ -99,16 +107,13 @@ struct Wave {
     uint2* hit;      // t bits, triangle index (kMiss = none)
     uint2* bvh_counts;  // BVHIntersections: tests, hits
     unsigned long long* rng_state;
-    unsigned long long* rng_inc;
-    uint32_t* dim;
-    float4* beta;    // throughput (path) / node weight (whitted); w = flags
+    float4* beta;    // throughput (path) / node weight (whitted); w = flags | sampler dimension << kDimShift
     float4* L;       // accumulated radiance
-    float4* pend_beta;   // weight to apply to this bounce's radiance
-    float4* pend_extra;  // emitted term of this bounce
-    float4* contrib;     // cap * n_lights: (f*li*cos/pdf, visible flag)
-    float4* sh_o;        // shadow rays: o.xyz, t_max
-    float4* sh_d;        // d.xyz, area light id (int bits)
-    uint32_t* sh_ref;    // index into contrib
+    float4* pend_beta;   // weight to apply to this bounce's radiance; w = clamp flag
+    float4* pend_extra;  // emitted term of this bounce; w = bit mask of the lights whose shadow ray must be traced
+    float4* lt_o;        // cap * n_lights: shadow ray o.xyz | contribution.r   (contribution = f * li * cos / pdf)
+    float4* lt_d;        //                 shadow ray d.xyz | contribution.g
+    float2* lt_c;        //                 contribution.b   | area light id of the sampled light (int bits, -1 = none)
     float4* stack;       // whitted: stack_entries * cap * 3 float4
     uint32_t* stack_top; // whitted
     uint32_t* q_active[2];
@@ -120,6 +125,8 @@ struct Wave {
 constexpr uint32_t kFlagSpecular = 0x100u;   // path: specular_bounce / whitted: is_specular
 constexpr uint32_t kFlagAlive = 0x200u;
 constexpr uint32_t kDepthMask = 0xffu;       // path: bounces / whitted: depth
+constexpr uint32_t kDimShift = 10;           // sampler dimension (stratified.rs:40) in the upper 22 bits
+constexpr uint32_t kFlagMask = (1u << kDimShift) - 1u;
 
 struct RenderCfg {
     SamplerCfg sampler;
@@ -186,6 +193,17 @@ __device__ __forceinline__ unsigned long long mix_hit(uint32_t x, uint32_t y, ui
     return h;
 }
 
+// ---- per-pixel sampler stream: hash_values!(pixel.x, pixel.y) (uniform.rs:77, stratified.rs:95) ----------------
+__global__ void k_jobs_prepare(const JobIn* in, Job* out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const JobIn j = in[i];
+    Job o;
+    o.x = j.x; o.y = j.y; o.sample_begin = j.sample_begin;
+    o.rng_inc = (hash_pixel(j.x, j.y) << 1) | 1ULL;
+    out[i] = o;
+}
+
 // ---- raygen: Integrator::render loop head (integrators/mod.rs:145-169) -----------------------------
 __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +211,7 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
     const Job job = bt.jobs[i % bt.n_jobs];
     const uint32_t sample = job.sample_begin + bt.sample_off + i / bt.n_jobs;
     SamplerState s;
-    s.start(cfg.sampler, job.x, job.y, sample);
+    s.start(cfg.sampler, job.x, job.y, sample, job.rng_inc);
     const V2 j = s.get_2d(cfg.sampler);
     // Camera::ray, camera.rs:105-114
     const V3 p_cam = xf_point(cfg.r2c, mk((float)job.x + j.x, (float)job.y + j.y, 0.0f));
@@ -203,15 +221,13 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
     w.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
     w.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
     w.rng_state[i] = s.rng.state;
-    w.rng_inc[i] = s.rng.inc;
-    w.dim[i] = s.dim;
-    w.beta[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(kFlagAlive));
+    w.beta[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(kFlagAlive | (s.dim << kDimShift)));
     w.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (w.stack_top) w.stack_top[i] = 0;
 }
 
 // ---- BVH traversal (bvh.rs:160-302, math/bounds.rs:176-215, shapes/triangle.rs:49-139) --------------
-// Persistent warps, one ray per lane. The kernel is issue-bound on small scenes and latency-bound on large ones
+// Persistent warps, one ray per lane. The kernels are issue-bound on small scenes and latency-bound on large ones
 // (profiles/r01), so the design goal is: few instructions per step, and as many lanes as possible per instruction.
 //  * Two phases per warp: box steps (N) and triangle steps (T). A lane that reaches a leaf parks until the warp
 //    serves leaves; the warp keeps stepping boxes while at least kNodePhaseMin lanes want to, then drains every
@@ -220,8 +236,8 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
 //  * Finished lanes are refilled from the ray queue once fewer than kRefillBelow lanes are live; a warp reserves
 //    kChunk rays from the global cursor at a time.
 //  * Both steps are branch-free apart from the rare f64 edge-function fallback. The traversal stack lives in shared
-//    memory as s_stack[depth][thread] (conflict-free for any mix of depths); entries beyond kShortStack spill to
-//    local memory, up to the reference's 64.
+//    memory as s_stack[depth][thread] (conflict-free for any mix of depths) above a kNoNode sentinel, so a pop needs no
+//    emptiness test; entries beyond kShortStack spill to local memory, up to the reference's 64.
 //  * Triangles are stored transposed (x0 x1 x2 | y0 y1 y2 | z0 z1 z2), so the watertight test's axis permutation is
 //    three index offsets instead of 18 selects.
 constexpr uint32_t kNoNode = 0xffffffffu;
@@ -229,47 +245,157 @@ constexpr uint32_t kChunk = 64;
 constexpr int kRefillBelow = 22;
 constexpr int kNodePhaseMin = 14;
 constexpr int kShortStack = 48;
+constexpr uint32_t kSpBase = kTraceThreads;  // stack pointer (in words, depth * kTraceThreads) of an empty stack
 
-template <bool ANY, bool COUNTS>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, Wave w, const uint32_t* queue, const uint32_t* n_ptr,
-                                                          uint32_t n_fixed, uint32_t* cursor) {
-    __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
-    uint32_t deep[kStackDepth + 1 - kShortStack];
-    const uint32_t n = n_ptr ? *n_ptr : n_fixed;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned long long sum_nodes = 0, sum_tris = 0;
+struct TraceLane {
+    float ox, oy, oz, ix, iy, iz, t_max;
+    float okx, oky, okz, sx, sy, sz;  // watertight test: permuted origin, shear
+    uint32_t kx, ky, kz, neg_mask;
+    uint32_t cur, sp, leaf_pos, leaf_end;
+    uint32_t n_tests, n_hits, n_tris;
 
-    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
-    bool exhausted = false;                  // warp-uniform: the global cursor ran past n
-
-    // per-lane ray state
-    bool live = false;
-    uint32_t slot = 0, path = 0;
-    float ox = 0, oy = 0, oz = 0, ix = 0, iy = 0, iz = 0, t_max = 0, hit_t = 0;
-    float okx = 0, oky = 0, okz = 0, sx = 0, sy = 0, sz = 0;  // watertight test: permuted origin, shear
-    uint32_t kx = 0, ky = 0, kz = 0, neg_mask = 0;
-    int target_light = -1;
-    uint32_t cur = kNoNode, sp = kTraceThreads, n_tests = 0, n_hits = 0, n_tris = 0, hit_tri = kMiss;
-    uint32_t leaf_pos = 0, leaf_end = 0;
-    bool occluded = false;
-
-    // `sp` is the lane's stack pointer in words: depth * kTraceThreads. Entry 0 is a kNoNode sentinel (popping it ends
-    // the ray), entries 1..kShortStack-1 live in shared memory, deeper ones in local memory.
-    uint32_t* const lane_stack = &s_stack[0][tid];
-    lane_stack[0] = kNoNode;
-    constexpr uint32_t kSpBase = kTraceThreads;  // empty stack: just the sentinel
-    auto push = [&](uint32_t v) {
+    __device__ __forceinline__ void idle() {
+        cur = kNoNode; sp = kSpBase; leaf_pos = leaf_end = 0; n_tests = n_hits = n_tris = 0;
+        ox = oy = oz = ix = iy = iz = t_max = okx = oky = okz = sx = sy = sz = 0.0f;
+        kx = ky = kz = neg_mask = 0;
+    }
+    __device__ __forceinline__ void start(float o_x, float o_y, float o_z, float d_x, float d_y, float d_z, float tmax) {
+        ox = o_x; oy = o_y; oz = o_z;
+        t_max = tmax;
+        ix = 1.0f / d_x; iy = 1.0f / d_y; iz = 1.0f / d_z;  // bvh.rs:164
+        neg_mask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
+        // triangle.rs:58-80: permutation and shear depend on the ray only
+        const float ax = fabsf(d_x), ay = fabsf(d_y), az = fabsf(d_z);
+        kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);  // Vec3::max_dimension, math/vector.rs:188-202
+        kx = kz < 2u ? kz + 1u : 0u;
+        ky = kx < 2u ? kx + 1u : 0u;
+        const float dkx = kx == 0 ? d_x : (kx == 1 ? d_y : d_z), dky = ky == 0 ? d_x : (ky == 1 ? d_y : d_z);
+        const float dkz = kz == 0 ? d_x : (kz == 1 ? d_y : d_z);
+        sx = -dkx / dkz; sy = -dky / dkz;
+        sz = kz == 0 ? ix : (kz == 1 ? iy : iz);  // 1.0 / d[kz]: the same IEEE division as above
+        okx = kx == 0 ? ox : (kx == 1 ? oy : oz);
+        oky = ky == 0 ? ox : (ky == 1 ? oy : oz);
+        okz = kz == 0 ? ox : (kz == 1 ? oy : oz);
+        cur = 0; sp = kSpBase; n_tests = 0; n_hits = 0; n_tris = 0;
+        leaf_pos = leaf_end = 0;
+    }
+    __device__ __forceinline__ bool wants_box() const { return cur != kNoNode; }
+    __device__ __forceinline__ bool wants_tri() const { return leaf_pos < leaf_end; }
+    __device__ __forceinline__ void push(uint32_t* lane_stack, uint32_t* deep, uint32_t v) {
         const uint32_t depth = sp / kTraceThreads;
         if (depth < (uint32_t)kShortStack) lane_stack[sp] = v;
         else deep[depth - kShortStack] = v;
         sp += kTraceThreads;
-    };
-    auto pop = [&]() -> uint32_t {
+    }
+    __device__ __forceinline__ uint32_t pop(const uint32_t* lane_stack, const uint32_t* deep) {
         sp -= kTraceThreads;
         const uint32_t depth = sp / kTraceThreads;
         return depth < (uint32_t)kShortStack ? lane_stack[sp] : deep[depth - kShortStack];
-    };
+    }
+    // One box test (bvh.rs:176-199, math/bounds.rs:176-215).
+    template <bool COUNTS>
+    __device__ __forceinline__ void box_step(const DevScene& sc, uint32_t* lane_stack, uint32_t* deep) {
+        const float4 n0 = __ldg(&sc.nodes[2 * cur]);
+        const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
+        n_tests += 1;
+        // slab test: (bound - o) * inv_dir, NaN-ignoring min/max exactly like f32::min/max
+        const float t0x = (n0.x - ox) * ix, t0y = (n0.y - oy) * iy, t0z = (n0.z - oz) * iz;
+        const float t1x = (n1.x - ox) * ix, t1y = (n1.y - oy) * iy, t1z = (n1.z - oz) * iz;
+        const float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
+        const float tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), t_max);
+        const uint32_t offset = __float_as_uint(n0.w), meta = __float_as_uint(n1.w);
+        const bool hit = tmin <= tmax;
+        const bool leaf = (meta & kMetaLeaf) != 0;
+        const bool neg = (meta & neg_mask) != 0;  // interior meta = 1 << split_axis
+        const uint32_t next = cur + 1;
+        if (COUNTS) n_hits += hit ? 1u : 0u;
+        if (sp >= (uint32_t)kShortStack * kTraceThreads) {  // cold: the stack continues in local memory
+            if (hit && !leaf) { push(lane_stack, deep, neg ? next : offset); cur = neg ? offset : next; }
+            else if (hit) { leaf_pos = offset; leaf_end = offset + (meta & 0xffffu); cur = kNoNode; }
+            else cur = pop(lane_stack, deep);
+        } else {
+            // three disjoint predicated updates
+            if (hit && !leaf) { lane_stack[sp] = neg ? next : offset; sp += kTraceThreads; cur = neg ? offset : next; }  // far child waits
+            if (!hit) { sp -= kTraceThreads; cur = lane_stack[sp]; }
+            if (hit && leaf) { leaf_pos = offset; leaf_end = offset + (meta & 0xffffu); cur = kNoNode; }
+        }
+    }
+    // One triangle test of the parked leaf (shapes/triangle.rs:62-130 on the permuted, origin-relative vertices).
+    // Returns true on a hit with t in (0, t_max]; the caller decides what a hit means and then calls leaf_done().
+    __device__ __forceinline__ bool tri_step(const DevScene& sc, uint32_t* tri, float* t_scaled_out, float* det_out, int* area_light) {
+        const uint32_t s = leaf_pos++;
+        const float4 A = __ldg(&sc.tris[3 * s + kx]);
+        const float4 B = __ldg(&sc.tris[3 * s + ky]);
+        const float4 C = __ldg(&sc.tris[3 * s + kz]);
+        n_tris += 1;
+        float ax = A.x - okx, bx = A.y - okx, cx = A.z - okx;
+        float ay = B.x - oky, by = B.y - oky, cy = B.z - oky;
+        const float az = C.x - okz, bz = C.y - okz, cz = C.z - okz;
+        ax += sx * az; ay += sy * az;
+        bx += sx * bz; by += sy * bz;
+        cx += sx * cz; cy += sy * cz;
+        float e0 = bx * cy - by * cx;
+        float e1 = cx * ay - cy * ax;
+        float e2 = ax * by - ay * bx;
+        if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {  // f64 fallback, :98-105
+            e0 = (float)((double)bx * (double)cy - (double)by * (double)cx);
+            e1 = (float)((double)cx * (double)ay - (double)cy * (double)ax);
+            e2 = (float)((double)ax * (double)by - (double)ay * (double)bx);
+        }
+        const float det = e0 + e1 + e2;
+        const float t_scaled = e0 * (az * sz) + e1 * (bz * sz) + e2 * (cz * sz);
+        const float lim = t_max * det;
+        const bool mixed = (e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f);
+        const bool out_neg = det < 0.0f && (t_scaled >= 0.0f || t_scaled < lim);
+        const bool out_pos = det > 0.0f && (t_scaled <= 0.0f || t_scaled > lim);
+        *tri = s;
+        *t_scaled_out = t_scaled;
+        *det_out = det;
+        *area_light = __float_as_int(kx == 0 ? A.w : (ky == 0 ? B.w : C.w));
+        return !mixed && det != 0.0f && !out_neg && !out_pos;
+    }
+    __device__ __forceinline__ void leaf_done(const uint32_t* lane_stack, const uint32_t* deep) {
+        if (leaf_pos == leaf_end) cur = pop(lane_stack, deep);
+    }
+    __device__ __forceinline__ void stop() { cur = kNoNode; leaf_pos = leaf_end = 0; sp = kSpBase; }
+};
+
+// Runs box steps while enough lanes want one, then drains the parked leaves. `on_hit(tri, t_scaled, det, area_light)`
+// is called for every accepted triangle. Returns when every lane of the warp is either finished or parked nowhere.
+#define YK_TRACE_PHASES(LANE, LIVE, COUNTS, ON_HIT)                                                              \
+    for (;;) {                                                                                                    \
+        const bool want_n = (LANE).wants_box();                                                                   \
+        const int n_n = __popc(__ballot_sync(0xffffffffu, want_n));                                               \
+        if (n_n == 0) break;                                                                                      \
+        if (n_n < kNodePhaseMin && __ballot_sync(0xffffffffu, (LIVE) && !want_n)) break;                          \
+        if (want_n) (LANE).template box_step<COUNTS>(sc, lane_stack, deep);                                       \
+    }                                                                                                             \
+    while (__ballot_sync(0xffffffffu, (LANE).wants_tri())) {                                                      \
+        if ((LANE).wants_tri()) {                                                                                 \
+            uint32_t tri_; float ts_, det_; int al_;                                                              \
+            if ((LANE).tri_step(sc, &tri_, &ts_, &det_, &al_)) { ON_HIT }                                         \
+            (LANE).leaf_done(lane_stack, deep);                                                                   \
+        }                                                                                                         \
+    }
+
+// Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
+template <bool COUNTS>
+__global__ void __launch_bounds__(kTraceThreads) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, uint32_t n, uint32_t* cursor) {
+    __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
+    uint32_t deep[kStackDepth + 1 - kShortStack];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t* const lane_stack = &s_stack[0][tid];
+    lane_stack[0] = kNoNode;  // sentinel: popping it ends the ray
+    unsigned long long sum_nodes = 0, sum_tris = 0;
+    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
+    bool exhausted = false;                  // warp-uniform: the global cursor ran past n
+
+    TraceLane tl;
+    tl.idle();
+    bool live = false;
+    uint32_t path = 0, hit_tri = kMiss;
+    float hit_t = 0.0f;
 
     for (;;) {
         // ---- refill idle lanes -----------------------------------------------------------------------
@@ -286,29 +412,11 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, Wave w, co
             if (!exhausted) {
                 const uint32_t mine = chunk_next + __popc(idle & lt_mask);
                 if (!live && mine < chunk_end) {
-                    slot = mine;
-                    path = ANY ? slot : (queue ? queue[slot] : slot);
-                    const float4 ro = ANY ? w.sh_o[slot] : w.ray_o[path];
-                    const float4 rd = ANY ? w.sh_d[slot] : w.ray_d[path];
-                    ox = ro.x; oy = ro.y; oz = ro.z;
-                    t_max = ro.w;
-                    target_light = ANY ? __float_as_int(rd.w) : -1;
-                    ix = 1.0f / rd.x; iy = 1.0f / rd.y; iz = 1.0f / rd.z;  // bvh.rs:164
-                    neg_mask = (ix < 0.0f ? 1u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 4u : 0u);
-                    // triangle.rs:58-80: permutation and shear depend on the ray only
-                    const float ax = fabsf(rd.x), ay = fabsf(rd.y), az = fabsf(rd.z);
-                    kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);  // Vec3::max_dimension, math/vector.rs:188-202
-                    kx = kz < 2u ? kz + 1u : 0u;
-                    ky = kx < 2u ? kx + 1u : 0u;
-                    const float dkx = kx == 0 ? rd.x : (kx == 1 ? rd.y : rd.z), dky = ky == 0 ? rd.x : (ky == 1 ? rd.y : rd.z);
-                    const float dkz = kz == 0 ? rd.x : (kz == 1 ? rd.y : rd.z);
-                    sx = -dkx / dkz; sy = -dky / dkz;
-                    sz = kz == 0 ? ix : (kz == 1 ? iy : iz);  // 1.0 / d[kz]: the same IEEE division as above
-                    okx = kx == 0 ? ox : (kx == 1 ? oy : oz);
-                    oky = ky == 0 ? ox : (ky == 1 ? oy : oz);
-                    okz = kz == 0 ? ox : (kz == 1 ? oy : oz);
-                    cur = 0; sp = kSpBase; n_tests = 0; n_hits = 0; n_tris = 0; hit_tri = kMiss; hit_t = 0.0f;
-                    leaf_pos = leaf_end = 0; occluded = false;
+                    path = queue ? queue[mine] : mine;
+                    const float4 ro = w.ray_o[path];
+                    const float4 rd = w.ray_d[path];
+                    tl.start(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w);
+                    hit_tri = kMiss; hit_t = 0.0f;
                     live = true;
                 }
                 const uint32_t taken = chunk_next + __popc(idle);
@@ -321,97 +429,16 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, Wave w, co
         }
         // ---- trace until too few lanes are live -----------------------------------------------------------
         for (;;) {
-            // N: box steps while enough lanes want one (or nothing else can run)
-            for (;;) {
-                const bool want_n = cur != kNoNode;
-                const int n_n = __popc(__ballot_sync(0xffffffffu, want_n));
-                if (n_n == 0) break;
-                if (n_n < kNodePhaseMin && __ballot_sync(0xffffffffu, live && !want_n)) break;
-                if (want_n) {
-                    const float4 n0 = __ldg(&sc.nodes[2 * cur]);
-                    const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
-                    n_tests += 1;
-                    // slab test: (bound - o) * inv_dir, NaN-ignoring min/max exactly like f32::min/max
-                    const float t0x = (n0.x - ox) * ix, t0y = (n0.y - oy) * iy, t0z = (n0.z - oz) * iz;
-                    const float t1x = (n1.x - ox) * ix, t1y = (n1.y - oy) * iy, t1z = (n1.z - oz) * iz;
-                    const float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
-                    const float tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), t_max);
-                    const uint32_t offset = __float_as_uint(n0.w), meta = __float_as_uint(n1.w);
-                    const bool hit = tmin <= tmax;
-                    const bool leaf = (meta & kMetaLeaf) != 0;
-                    const bool neg = (meta & neg_mask) != 0;  // interior meta = 1 << split_axis
-                    const uint32_t next = cur + 1;
-                    if (COUNTS) n_hits += hit ? 1u : 0u;
-                    if (sp >= (uint32_t)kShortStack * kTraceThreads) {  // cold: the stack continues in local memory
-                        if (hit && !leaf) { push(neg ? next : offset); cur = neg ? offset : next; }
-                        else if (hit) { leaf_pos = offset; leaf_end = offset + (meta & 0xffffu); cur = kNoNode; }
-                        else cur = pop();
-                    } else {
-                        // three disjoint predicated updates; the stack bottom holds a kNoNode sentinel, so a pop needs no
-                        // emptiness test
-                        if (hit && !leaf) { lane_stack[sp] = neg ? next : offset; sp += kTraceThreads; cur = neg ? offset : next; }
-                        if (!hit) { sp -= kTraceThreads; cur = lane_stack[sp]; }
-                        if (hit && leaf) { leaf_pos = offset; leaf_end = offset + (meta & 0xffffu); cur = kNoNode; }
-                    }
-                }
-            }
-            // T: drain the parked leaves, one triangle per lane per step, in stored order
-            while (__ballot_sync(0xffffffffu, leaf_pos < leaf_end)) {
-                if (leaf_pos < leaf_end) {
-                    const uint32_t s = leaf_pos++;
-                    const float4 A = __ldg(&sc.tris[3 * s + kx]);
-                    const float4 B = __ldg(&sc.tris[3 * s + ky]);
-                    const float4 C = __ldg(&sc.tris[3 * s + kz]);
-                    n_tris += 1;
-                    // shapes/triangle.rs:62-130 on the permuted, origin-relative vertices
-                    float ax = A.x - okx, bx = A.y - okx, cx = A.z - okx;
-                    float ay = B.x - oky, by = B.y - oky, cy = B.z - oky;
-                    const float az = C.x - okz, bz = C.y - okz, cz = C.z - okz;
-                    ax += sx * az; ay += sy * az;
-                    bx += sx * bz; by += sy * bz;
-                    cx += sx * cz; cy += sy * cz;
-                    float e0 = bx * cy - by * cx;
-                    float e1 = cx * ay - cy * ax;
-                    float e2 = ax * by - ay * bx;
-                    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {  // f64 fallback, :98-105
-                        e0 = (float)((double)bx * (double)cy - (double)by * (double)cx);
-                        e1 = (float)((double)cx * (double)ay - (double)cy * (double)ax);
-                        e2 = (float)((double)ax * (double)by - (double)ay * (double)bx);
-                    }
-                    const float det = e0 + e1 + e2;
-                    const float t_scaled = e0 * (az * sz) + e1 * (bz * sz) + e2 * (cz * sz);
-                    const float lim = t_max * det;
-                    const bool mixed = (e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f);
-                    const bool out_neg = det < 0.0f && (t_scaled >= 0.0f || t_scaled < lim);
-                    const bool out_pos = det > 0.0f && (t_scaled <= 0.0f || t_scaled > lim);
-                    const bool tri_hit = !mixed && det != 0.0f && !out_neg && !out_pos;
-                    if (tri_hit) {
-                        if (ANY) {
-                            // bvh.rs:269-280: the target light's own emissive triangles do not occlude
-                            const int tri_light = __float_as_int(kx == 0 ? A.w : (ky == 0 ? B.w : C.w));
-                            if (!(target_light >= 0 && tri_light >= 0 && tri_light == target_light)) {
-                                occluded = true;
-                                leaf_pos = leaf_end;
-                                sp = kSpBase;
-                            }
-                        } else {
-                            const float inv_det = 1.0f / det;
-                            hit_tri = s; hit_t = t_scaled * inv_det; t_max = hit_t;  // later equal-t hit replaces (bvh.rs:204-207)
-                        }
-                    }
-                    if (leaf_pos == leaf_end) cur = pop();
-                }
-            }
-            // retire finished rays
-            if (live && cur == kNoNode) {
-                if (ANY) {
-                    if (occluded) w.contrib[w.sh_ref[slot]].w = 0.0f;
-                } else {
-                    w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
-                    if (COUNTS) w.bvh_counts[path] = make_uint2(n_tests, n_hits);
-                }
-                sum_nodes += n_tests;
-                sum_tris += n_tris;
+            YK_TRACE_PHASES(tl, live, COUNTS, {
+                (void)al_;
+                const float inv_det = 1.0f / det_;  // triangle.rs:133-139
+                hit_tri = tri_; hit_t = ts_ * inv_det; tl.t_max = hit_t;  // later equal-t hit replaces (bvh.rs:204-207)
+            })
+            if (live && !tl.wants_box()) {  // retire
+                w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
+                if (COUNTS) w.bvh_counts[path] = make_uint2(tl.n_tests, tl.n_hits);
+                sum_nodes += tl.n_tests;
+                sum_tris += tl.n_tris;
                 live = false;
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, live));
@@ -421,8 +448,120 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene sc, Wave w, co
     sum_nodes = warp_sum(sum_nodes);
     sum_tris = warp_sum(sum_tris);
     if (lane == 0 && (sum_nodes | sum_tris)) {
-        atomicAdd(ANY ? &w.totals->any_nodes : &w.totals->closest_nodes, sum_nodes);
-        atomicAdd(ANY ? &w.totals->any_tris : &w.totals->closest_tris, sum_tris);
+        atomicAdd(&w.totals->closest_nodes, sum_nodes);
+        atomicAdd(&w.totals->closest_tris, sum_tris);
+    }
+}
+
+// Shadow rays + radiance fold: BoundingVolumeHierarchy::any_intersect behind VisibilityTester (bvh.rs:235-302,
+// visibility.rs) for every light the shading kernel queued, then the fold body `c + f*li*cos/pdf` in light order,
+// `radiance += beta * Le`, the indirect clamp and `L += beta * radiance` (path.rs:113-129, whitted.rs:120-130).
+// One *path* per queue entry (the four material queues, concatenated); a lane traces its path's shadow rays one after
+// the other in light order, so the float sums associate exactly like the reference's fold.
+__global__ void __launch_bounds__(kTraceThreads) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, uint32_t* cursor) {
+    __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
+    uint32_t deep[kStackDepth + 1 - kShortStack];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t* const lane_stack = &s_stack[0][tid];
+    lane_stack[0] = kNoNode;
+    const uint32_t n0 = w.counters->mat[0], n1 = w.counters->mat[1], n2 = w.counters->mat[2], n3 = w.counters->mat[3];
+    const uint32_t n = n0 + n1 + n2 + n3;
+    unsigned long long sum_nodes = 0, sum_tris = 0, sum_rays = 0;
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    TraceLane tl;
+    tl.idle();
+    bool live = false;       // the lane owns a path whose fold is not finished
+    bool need_ray = false;   // ... and must load the shadow ray of the lowest light in `mask`
+    bool occluded = false;
+    uint32_t path = 0, mask = 0;
+    int target_light = -1;
+    RGB radiance = gray(0.0f), contribution = gray(0.0f);
+
+    auto finish_path = [&]() {  // path.rs:121-129
+        const float4 pe = w.pend_extra[path], pb = w.pend_beta[path];
+        RGB r = radiance + rgb(pe.x, pe.y, pe.z);
+        if (pb.w != 0.0f) r = rgb(fminf(r.r, cfg.clamp), fminf(r.g, cfg.clamp), fminf(r.b, cfg.clamp));
+        float4 L = w.L[path];
+        L.x = L.x + pb.x * r.r;
+        L.y = L.y + pb.y * r.g;
+        L.z = L.z + pb.z * r.b;
+        w.L[path] = L;
+    };
+
+    for (;;) {
+        // ---- refill: new paths for idle lanes (paths without shadow rays are folded on the spot) ------------
+        for (int round = 0; round < 4; ++round) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !live);
+            if (!idle || exhausted) break;
+            if (chunk_next >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, kChunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = base;
+                chunk_end = base + kChunk < n ? base + kChunk : n;
+                if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; break; }
+            }
+            const uint32_t mine = chunk_next + __popc(idle & lt_mask);
+            if (!live && mine < chunk_end) {
+                uint32_t k = 0, j = mine;
+                if (j >= n0) { j -= n0; k = 1; if (j >= n1) { j -= n1; k = 2; if (j >= n2) { j -= n2; k = 3; } } }
+                path = w.q_mat[(size_t)k * w.cap + j];
+                mask = __float_as_uint(w.pend_extra[path].w);
+                radiance = gray(0.0f);
+                sum_rays += __popc(mask);
+                if (mask) { live = true; need_ray = true; }
+                else finish_path();
+            }
+            const uint32_t taken = chunk_next + __popc(idle);
+            chunk_next = taken < chunk_end ? taken : chunk_end;
+        }
+        if (need_ray) {  // next light of this lane's path
+            const uint32_t k = __ffs(mask) - 1;
+            const size_t ref = (size_t)k * w.cap + path;
+            const float4 ro = w.lt_o[ref], rd = w.lt_d[ref];
+            const float2 rc = w.lt_c[ref];
+            contribution = rgb(ro.w, rd.w, rc.x);
+            target_light = __float_as_int(rc.y);
+            tl.start(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, 0.9999f);  // interaction.rs:57-58
+            occluded = false;
+            need_ray = false;
+        }
+        if (__ballot_sync(0xffffffffu, live) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        for (;;) {
+            YK_TRACE_PHASES(tl, live, false, {
+                (void)tri_; (void)ts_; (void)det_;
+                // bvh.rs:269-280: the target light's own emissive triangles do not occlude
+                if (!(target_light >= 0 && al_ >= 0 && al_ == target_light)) { occluded = true; tl.stop(); }
+            })
+            if (live && !need_ray && !tl.wants_box()) {  // this shadow ray is done
+                sum_nodes += tl.n_tests;
+                sum_tris += tl.n_tris;
+                tl.n_tests = 0; tl.n_tris = 0;
+                if (!occluded) radiance = radiance + contribution;
+                mask &= mask - 1;
+                if (mask) need_ray = true;
+                else { finish_path(); live = false; }
+            }
+            const int tracing = __popc(__ballot_sync(0xffffffffu, live && !need_ray));
+            if (tracing == 0 || tracing < kRefillBelow) {
+                // leave to reload unless nothing could be reloaded (queue exhausted and no lane waits for its next light)
+                if (tracing == 0 || !exhausted || __ballot_sync(0xffffffffu, need_ray)) break;
+            }
+        }
+    }
+    sum_nodes = warp_sum(sum_nodes);
+    sum_tris = warp_sum(sum_tris);
+    sum_rays = warp_sum(sum_rays);
+    if (lane == 0 && (sum_nodes | sum_tris | sum_rays)) {
+        atomicAdd(&w.totals->any_nodes, sum_nodes);
+        atomicAdd(&w.totals->any_tris, sum_tris);
+        atomicAdd(&w.totals->shadow_rays, sum_rays);
     }
 }
 
@@ -440,8 +579,9 @@ __device__ __forceinline__ void stack_push(const Wave& w, uint32_t path, const S
     base[2] = make_float4(e.weight.b, __uint_as_float(e.flags), 0.0f, 0.0f);
     w.stack_top[path] = top + 1;
 }
-// Pops the next pending node into the path's ray/weight slots. Returns false when the tree is done.
-__device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path) {
+// Pops the next pending node into the path's ray/weight slots (the sampler dimension `dim` carries on: the reference
+// shares one sampler through the recursion). Returns false when the tree is done.
+__device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path, uint32_t dim) {
     const uint32_t top = w.stack_top[path];
     if (top == 0) return false;
     const float4* base = w.stack + ((size_t)(top - 1) * w.cap + path) * 3;
@@ -449,14 +589,13 @@ __device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path) {
     w.stack_top[path] = top - 1;
     w.ray_o[path] = make_float4(a.x, a.y, a.z, __int_as_float(0x7f800000));
     w.ray_d[path] = make_float4(a.w, b.x, b.y, 0.0f);
-    w.beta[path] = make_float4(b.z, b.w, c.x, __uint_as_float(__float_as_uint(c.y) | kFlagAlive));
+    w.beta[path] = make_float4(b.z, b.w, c.x, __uint_as_float(__float_as_uint(c.y) | kFlagAlive | (dim << kDimShift)));
     return true;
 }
 
 // ---- classify: miss handling + compaction by material ("ray-queue sort/compaction pass") ---------------
-__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, const uint32_t* n_ptr, uint32_t n_fixed,
-                           int first_iteration, uint32_t* q_next) {
-    const uint32_t n = n_ptr ? *n_ptr : n_fixed;
+__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, uint32_t n, int first_iteration,
+                           uint32_t* q_next) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     uint32_t path = 0, kind = 4;
@@ -478,7 +617,7 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
             L.y = L.y + b.y * sc.background[1];
             L.z = L.z + b.z * sc.background[2];
             w.L[path] = L;
-            if (cfg.integrator == YK_INTEGRATOR_WHITTED) requeue = stack_pop(w, path);
+            if (cfg.integrator == YK_INTEGRATOR_WHITTED) requeue = stack_pop(w, path, __float_as_uint(b.w) >> kDimShift);
         }
         if (first_iteration) {
             const Job job = bt.jobs[path % bt.n_jobs];
@@ -676,173 +815,133 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 // Covers Material::compute_scattering_functions, the light fold (path.rs:102-119 / whitted.rs:109-126), the
 // emitted term, BSDF sampling + throughput update + Russian roulette (path.rs:121-171), and the specular
 // recursion of whitted.rs:132-170 flattened onto a per-sample DFS stack (children inherit weight * f * |cos|).
-// Radiance is not summed here: shadow rays are queued and k_resolve adds the unoccluded terms in light order.
-__device__ __forceinline__ uint32_t shadow_slot(bool pred, uint32_t* counter) {
-    const unsigned active = __activemask();
-    const unsigned votes = __ballot_sync(active, pred);
-    if (votes == 0) return 0;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(votes) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(votes));
-    base = __shfl_sync(active, base, leader);
-    return base + __popc(votes & ((1u << lane) - 1u));
-}
-
+// Radiance is not summed here: each light that needs a visibility test leaves its shadow ray and contribution in
+// lt_*, and k_trace_shadow adds the unoccluded terms in light order. Surviving paths are appended to the next
+// active queue (one atomic per block).
 template <uint32_t KIND>
 __global__ void __launch_bounds__(kShadeThreads) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
-                                                          const uint32_t* n_ptr) {
+                                                          const uint32_t* n_ptr, uint32_t* q_next) {
     const uint32_t n = *n_ptr;
     const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        if (i >= n) continue;
-        const uint32_t path = queue[i];
-        const float4 ro = w.ray_o[path], rd = w.ray_d[path];
-        const V3 o = f4v(ro), d = f4v(rd);
-        Surface si;
-        uint32_t mat_index;
-        make_surface(sc, w.hit[path].y, o, d, &si, &mat_index);
-        Bsdf bsdf;
-        make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
-
-        const Job job = bt.jobs[path % bt.n_jobs];
-        SamplerState smp;
-        smp.rng.state = w.rng_state[path];
-        smp.rng.inc = w.rng_inc[path];
-        smp.dim = w.dim[path];
-        smp.px = job.x;
-        smp.py = job.y;
-        smp.index = job.sample_begin + bt.sample_off + path / bt.n_jobs;
-
-        const float4 beta4 = w.beta[path];
-        RGB beta = rgb(beta4.x, beta4.y, beta4.z);
-        const uint32_t flags = __float_as_uint(beta4.w);
-        const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
-        const bool was_specular = (flags & kFlagSpecular) != 0;
-
-        // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
-        for (uint32_t k = 0; k < sc.n_lights; ++k) {
-            const V2 u = smp.get_2d(cfg.sampler);
-            LightSample ls;
-            sample_light(sc.lights[k], (int)k, si, u, &ls);
-            RGB c = gray(0.0f);
-            bool need_shadow = false;
-            if (!black(ls.li)) {
-                const RGB f = bsdf.f(si.wo, ls.l);
-                if (ls.has_vis && !black(f)) {
-                    c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
-                    need_shadow = true;
-                }
-            }
-            const uint32_t ref = k * w.cap + path;
-            w.contrib[ref] = make_float4(c.r, c.g, c.b, need_shadow ? 1.0f : 0.0f);
-            const uint32_t slot = shadow_slot(need_shadow, &w.counters->shadow);
-            if (need_shadow) {
-                w.sh_o[slot] = make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, ls.vis.t_max);
-                w.sh_d[slot] = make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, __int_as_float(ls.vis_light));
-                w.sh_ref[slot] = ref;
-            }
-        }
-
-        // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
-        RGB le = gray(0.0f);
-        if (si.area_light >= 0 && dotn(si.n, si.wo) > 0.0f) {
-            const yk_light& al = sc.lights[si.area_light];
-            le = rgb(al.i[0], al.i[1], al.i[2]);
-        }
-        const bool add_le = depth == 0 || was_specular;
-
-        bool alive = false;
-        uint32_t new_flags = 0;
-        if (cfg.integrator == YK_INTEGRATOR_PATH) {
-            // path.rs:121-129 — beta multiplies the emitted term here and again in the resolve (reference quirk)
-            const RGB extra = add_le ? beta * le : gray(0.0f);
-            w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, 0.0f);
-            w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
-            const Bsdf::Sample s = bsdf.sample_f(si.wo, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137
-            if (!(black(s.f) || s.pdf == 0.0f)) {
-                alive = true;
-                const bool spec = (s.type & BX_SPECULAR) != 0;
-                beta = beta * (s.f * fabsf(dotn(s.wi, si.sh_n)) / s.pdf);
-                const Ray nr = spawn_ray(si.p, si.n, s.wi);
-                w.ray_o[path] = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
-                w.ray_d[path] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
-                if (depth > 3) {  // Russian roulette, path.rs:163-169
-                    const float q = fmaxf(1.0f - beta.g, 0.05f);
-                    if (smp.get_1d(cfg.sampler) < q) alive = false;
-                    else beta = beta * (gray(1.0f) / (1.0f - q));
-                }
-                const uint32_t bounces = depth + 1;
-                if (bounces >= cfg.max_depth) alive = false;
-                new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u);
-            }
-            w.beta[path] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | (alive ? kFlagAlive : 0u)));
-        } else {
-            // whitted.rs:128-170
-            const RGB extra = add_le ? le : gray(0.0f);
-            w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, 0.0f);
-            w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, 0.0f);
-            StackEntry child[2];
-            int n_child = 0;
-            if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
-                const uint32_t wants[2] = {BX_SPECULAR | BX_REFLECTION, BX_SPECULAR | BX_TRANSMISSION};
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const Bsdf::Sample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, wants[c]);
-                    if (s.type == 0u) continue;  // BxdfType::NONE: no ray, no radiance
-                    const Ray nr = spawn_ray(si.p, si.n, s.wi);
-                    StackEntry e;
-                    e.o = nr.o;
-                    e.d = nr.d;
-                    e.weight = beta * s.f * fabsf(dotn(s.wi, si.sh_n));
-                    e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u);
-                    child[n_child++] = e;
-                }
-            }
-            if (n_child == 2) stack_push(w, path, child[1]);  // transmission waits until the reflection subtree is done
-            if (n_child >= 1) {
-                const StackEntry& e = child[0];
-                w.ray_o[path] = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
-                w.ray_d[path] = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
-                w.beta[path] = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive));
-            } else if (!stack_pop(w, path)) {
-                w.beta[path] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(flags & ~kFlagAlive));
-            }
-        }
-        w.rng_state[path] = smp.rng.state;
-        w.dim[path] = smp.dim;
-    }
-}
-
-// ---- resolve: fold the unoccluded light terms in light order, add the emitted term, clamp, accumulate ----
-// (path.rs:113-129, whitted.rs:120-130) and compact the surviving paths into the next active queue.
-__global__ void k_resolve(Wave w, RenderCfg cfg, uint32_t* q_next) {
-    const uint32_t n0 = w.counters->mat[0], n1 = w.counters->mat[1], n2 = w.counters->mat[2], n3 = w.counters->mat[3];
-    const uint32_t total = n0 + n1 + n2 + n3;
-    const uint32_t rounds = (total + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
-    for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
+        if (block_first >= n) break;  // block-uniform
+        const uint32_t i = block_first + threadIdx.x;
         bool alive = false;
         uint32_t path = 0;
-        if (i < total) {
-            uint32_t k = 0, j = i;
-            if (j >= n0) { j -= n0; k = 1; if (j >= n1) { j -= n1; k = 2; if (j >= n2) { j -= n2; k = 3; } } }
-            path = w.q_mat[(size_t)k * w.cap + j];
-            RGB radiance = gray(0.0f);
-            for (uint32_t l = 0; l < w.n_lights; ++l) {
-                const float4 c = w.contrib[l * w.cap + path];
-                if (c.w != 0.0f) radiance = radiance + rgb(c.x, c.y, c.z);
+        if (i < n) {
+            path = queue[i];
+            const float4 ro = w.ray_o[path], rd = w.ray_d[path];
+            const V3 o = f4v(ro), d = f4v(rd);
+            Surface si;
+            uint32_t mat_index;
+            make_surface(sc, w.hit[path].y, o, d, &si, &mat_index);
+            Bsdf bsdf;
+            make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
+
+            const float4 beta4 = w.beta[path];
+            RGB beta = rgb(beta4.x, beta4.y, beta4.z);
+            const uint32_t flags = __float_as_uint(beta4.w) & kFlagMask;
+            const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
+            const bool was_specular = (flags & kFlagSpecular) != 0;
+
+            const Job job = bt.jobs[path % bt.n_jobs];
+            SamplerState smp;
+            smp.rng.state = w.rng_state[path];
+            smp.rng.inc = job.rng_inc;
+            smp.dim = __float_as_uint(beta4.w) >> kDimShift;
+            smp.px = job.x;
+            smp.py = job.y;
+            smp.index = job.sample_begin + bt.sample_off + path / bt.n_jobs;
+
+            // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
+            uint32_t shadow_mask = 0;
+            for (uint32_t k = 0; k < sc.n_lights; ++k) {
+                const V2 u = smp.get_2d(cfg.sampler);
+                LightSample ls;
+                sample_light(sc.lights[k], (int)k, si, u, &ls);
+                if (!black(ls.li)) {
+                    const RGB f = bsdf.f(si.wo, ls.l);
+                    if (ls.has_vis && !black(f)) {
+                        const RGB c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
+                        const size_t ref = (size_t)k * w.cap + path;
+                        w.lt_o[ref] = make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, c.r);
+                        w.lt_d[ref] = make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, c.g);
+                        w.lt_c[ref] = make_float2(c.b, __int_as_float(ls.vis_light));
+                        shadow_mask |= 1u << k;
+                    }
+                }
             }
-            const float4 pe = w.pend_extra[path], pb = w.pend_beta[path];
-            radiance = radiance + rgb(pe.x, pe.y, pe.z);
-            if (pb.w != 0.0f) radiance = rgb(fminf(radiance.r, cfg.clamp), fminf(radiance.g, cfg.clamp), fminf(radiance.b, cfg.clamp));
-            float4 L = w.L[path];
-            L.x = L.x + pb.x * radiance.r;
-            L.y = L.y + pb.y * radiance.g;
-            L.z = L.z + pb.z * radiance.b;
-            w.L[path] = L;
-            alive = (__float_as_uint(w.beta[path].w) & kFlagAlive) != 0;
+
+            // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
+            RGB le = gray(0.0f);
+            if (si.area_light >= 0 && dotn(si.n, si.wo) > 0.0f) {
+                const yk_light& al = sc.lights[si.area_light];
+                le = rgb(al.i[0], al.i[1], al.i[2]);
+            }
+            const bool add_le = depth == 0 || was_specular;
+
+            uint32_t new_flags = 0;
+            if (cfg.integrator == YK_INTEGRATOR_PATH) {
+                // path.rs:121-129 — beta multiplies the emitted term here and again in the fold (reference quirk)
+                const RGB extra = add_le ? beta * le : gray(0.0f);
+                w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
+                w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
+                const Bsdf::Sample s = bsdf.sample_f(si.wo, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137
+                if (!(black(s.f) || s.pdf == 0.0f)) {
+                    alive = true;
+                    const bool spec = (s.type & BX_SPECULAR) != 0;
+                    beta = beta * (s.f * fabsf(dotn(s.wi, si.sh_n)) / s.pdf);
+                    const Ray nr = spawn_ray(si.p, si.n, s.wi);
+                    if (depth > 3) {  // Russian roulette, path.rs:163-169
+                        const float q = fmaxf(1.0f - beta.g, 0.05f);
+                        if (smp.get_1d(cfg.sampler) < q) alive = false;
+                        else beta = beta * (gray(1.0f) / (1.0f - q));
+                    }
+                    const uint32_t bounces = depth + 1;
+                    if (bounces >= cfg.max_depth) alive = false;
+                    new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u);
+                    if (alive) {  // a finished path's ray / throughput / sampler state is never read again
+                        w.ray_o[path] = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
+                        w.ray_d[path] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+                        w.beta[path] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
+                        w.rng_state[path] = smp.rng.state;
+                    }
+                }
+            } else {
+                // whitted.rs:128-170
+                const RGB extra = add_le ? le : gray(0.0f);
+                w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
+                w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+                StackEntry child[2];
+                int n_child = 0;
+                if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
+                    const uint32_t wants[2] = {BX_SPECULAR | BX_REFLECTION, BX_SPECULAR | BX_TRANSMISSION};
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const Bsdf::Sample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, wants[c]);
+                        if (s.type == 0u) continue;  // BxdfType::NONE: no ray, no radiance
+                        const Ray nr = spawn_ray(si.p, si.n, s.wi);
+                        StackEntry e;
+                        e.o = nr.o;
+                        e.d = nr.d;
+                        e.weight = beta * s.f * fabsf(dotn(s.wi, si.sh_n));
+                        e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u);
+                        child[n_child++] = e;
+                    }
+                }
+                if (n_child == 2) stack_push(w, path, child[1]);  // transmission waits until the reflection subtree is done
+                if (n_child >= 1) {
+                    const StackEntry& e = child[0];
+                    w.ray_o[path] = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+                    w.ray_d[path] = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+                    w.beta[path] = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
+                    alive = true;
+                } else {
+                    alive = stack_pop(w, path, smp.dim);
+                }
+                if (alive) w.rng_state[path] = smp.rng.state;
+            }
         }
         uint32_t* const queues[1] = {q_next};
         uint32_t* const counters[1] = {&w.counters->next};
@@ -930,6 +1029,7 @@ struct yk_context {
     Counters* h_counters = nullptr;  // pinned
     Totals* h_totals = nullptr;      // pinned
     Job* d_jobs = nullptr;
+    JobIn* d_jobs_in = nullptr;
     size_t jobs_cap = 0;
     float* d_accum = nullptr;
     float* d_film = nullptr;
@@ -989,9 +1089,9 @@ int ensure_wave(yk_context* c, uint32_t cap, uint32_t n_lights, uint32_t stack_e
 #define WAVE_ALLOC(field, count) \
     if ((rc = dev_alloc(bag, &w.field, (size_t)(count))) != YK_OK) { free_bag(bag); return rc; }
     WAVE_ALLOC(ray_o, cap) WAVE_ALLOC(ray_d, cap) WAVE_ALLOC(hit, cap) WAVE_ALLOC(bvh_counts, cap)
-    WAVE_ALLOC(rng_state, cap) WAVE_ALLOC(rng_inc, cap) WAVE_ALLOC(dim, cap) WAVE_ALLOC(beta, cap) WAVE_ALLOC(L, cap)
-    WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap) WAVE_ALLOC(contrib, cap * nl)
-    WAVE_ALLOC(sh_o, cap * nl) WAVE_ALLOC(sh_d, cap * nl) WAVE_ALLOC(sh_ref, cap * nl)
+    WAVE_ALLOC(rng_state, cap) WAVE_ALLOC(beta, cap) WAVE_ALLOC(L, cap)
+    WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap)
+    WAVE_ALLOC(lt_o, cap * nl) WAVE_ALLOC(lt_d, cap * nl) WAVE_ALLOC(lt_c, cap * nl)
     WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap)
     WAVE_ALLOC(counters, 1) WAVE_ALLOC(totals, 1)
     if (stack_entries) {
@@ -1026,7 +1126,7 @@ int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Bat
     tm->launches += 1;
     const bool debug = cfg.integrator >= YK_INTEGRATOR_BVH_INTERSECTIONS;
     const int trace_blocks_closest = c->sm_count * std::max(1, c->occ_trace_closest);
-    const int trace_blocks_any = c->sm_count * std::max(1, c->occ_trace_any);
+    const int trace_blocks_shadow = c->sm_count * std::max(1, c->occ_trace_any);
     const int wide_blocks = c->sm_count * 16;
     uint32_t n_active = bt.n_paths;
     if (cfg.integrator == YK_INTEGRATOR_PATH && cfg.max_depth == 0) n_active = 0;
@@ -1036,46 +1136,37 @@ int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Bat
         CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(Counters), s));
         CUDA_TRY(cudaEventRecord(c->ev[0], s));
         if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS)
-            k_trace<false, true><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
-                sc->dev, w, q_cur, nullptr, n_active, &w.counters->work_closest);
+            k_trace_closest<true><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
+                sc->dev, w, q_cur, n_active, &w.counters->work_closest);
         else
-            k_trace<false, false><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
-                sc->dev, w, q_cur, nullptr, n_active, &w.counters->work_closest);
+            k_trace_closest<false><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
+                sc->dev, w, q_cur, n_active, &w.counters->work_closest);
         CUDA_TRY(cudaEventRecord(c->ev[1], s));
         tm->launches += 1;
         tm->closest_launches += 1;
         st->ray_count += n_active;
+        uint32_t* q_next = w.q_active[flip];
         if (debug) {
             k_debug_shade<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, n_active);
-            tm->launches += 1;
-            if (cfg.hit_ids || true) {
-                // primary-hit digest / id image for the debug integrators too
-                uint32_t* q_next = w.q_active[flip];
-                k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, nullptr, n_active, 2, q_next);
-                tm->launches += 1;
-            }
+            // primary-hit digest / id image for the debug integrators too
+            k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, n_active, 2, q_next);
+            tm->launches += 2;
             CUDA_TRY(cudaStreamSynchronize(s));
             float ms = 0;
             cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
             tm->closest += ms;
             break;
         }
-        uint32_t* q_next = w.q_active[flip];
-        k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, nullptr, n_active, iter == 0 ? 1 : 0, q_next);
+        k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, n_active, iter == 0 ? 1 : 0, q_next);
         CUDA_TRY(cudaEventRecord(c->ev[2], s));
         const int sg = grid_for(n_active, kShadeThreads, wide_blocks);
-        k_shade<YK_MAT_MATTE><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)0 * w.cap, &w.counters->mat[0]);
-        k_shade<YK_MAT_GLASS><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)1 * w.cap, &w.counters->mat[1]);
-        k_shade<YK_MAT_METAL><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)2 * w.cap, &w.counters->mat[2]);
-        k_shade<YK_MAT_GLOSSY><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)3 * w.cap, &w.counters->mat[3]);
+        k_shade<YK_MAT_MATTE><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)0 * w.cap, &w.counters->mat[0], q_next);
+        k_shade<YK_MAT_GLASS><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)1 * w.cap, &w.counters->mat[1], q_next);
+        k_shade<YK_MAT_METAL><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)2 * w.cap, &w.counters->mat[2], q_next);
+        k_shade<YK_MAT_GLOSSY><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)3 * w.cap, &w.counters->mat[3], q_next);
         CUDA_TRY(cudaEventRecord(c->ev[3], s));
-        if (w.n_lights) {
-            k_trace<true, false><<<grid_for(n_active * w.n_lights, kTraceThreads, trace_blocks_any), kTraceThreads, 0, s>>>(
-                sc->dev, w, nullptr, &w.counters->shadow, 0, &w.counters->work_any);
-            tm->launches += 1;
-        }
+        k_trace_shadow<<<grid_for(n_active, kTraceThreads, trace_blocks_shadow), kTraceThreads, 0, s>>>(sc->dev, w, cfg, &w.counters->work_shadow);
         CUDA_TRY(cudaEventRecord(c->ev[4], s));
-        k_resolve<<<grid_for(n_active, T, wide_blocks), T, 0, s>>>(w, cfg, q_next);
         tm->launches += 6;
         CUDA_TRY(cudaMemcpyAsync(c->h_counters, w.counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -1084,7 +1175,6 @@ int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Bat
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); tm->closest += ms;
         cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); tm->shade += ms;
         cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); tm->any += ms;
-        st->shadow_rays += c->h_counters->shadow;
         n_active = c->h_counters->next;
         q_cur = q_next;
         flip ^= 1;
@@ -1121,8 +1211,8 @@ int yk_context_create(int device_id, yk_context** out) {
     for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMallocHost((void**)&c->h_counters, sizeof(Counters)));
     CUDA_TRY(cudaMallocHost((void**)&c->h_totals, sizeof(Totals)));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace<false, false>, kTraceThreads, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace<true, false>, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace_closest<false>, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace_shadow, kTraceThreads, 0));
     *out = c;
     return YK_OK;
 }
@@ -1133,6 +1223,7 @@ void yk_context_destroy(yk_context* c) {
     cudaStreamSynchronize(c->stream);
     free_bag(c->wave_allocs);
     cudaFree(c->d_jobs);
+    cudaFree(c->d_jobs_in);
     cudaFree(c->d_accum);
     cudaFree(c->d_film);
     cudaFree(c->d_hit_ids);
@@ -1282,7 +1373,7 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     const bool accumulate = fs->accumulate != 0;
 
     // Pixel jobs in tile order, row-major inside a tile (Bounds2 iteration, math/bounds.rs:102-126).
-    std::vector<Job> jobs;
+    std::vector<JobIn> jobs;
     size_t area = 0;
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const yk_tile& tl = tiles[t];
@@ -1294,7 +1385,7 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const yk_tile& tl = tiles[t];
         for (uint32_t y = tl.y0; y < tl.y1; ++y)
-            for (uint32_t x = tl.x0; x < tl.x1; ++x) jobs.push_back(Job{(uint16_t)x, (uint16_t)y, accumulate ? tl.sample : 0u});
+            for (uint32_t x = tl.x0; x < tl.x1; ++x) jobs.push_back(JobIn{(uint16_t)x, (uint16_t)y, accumulate ? tl.sample : 0u});
     }
     const size_t n_pixels = (size_t)fs->res_x * fs->res_y;
     const uint32_t samples_per_job = accumulate ? 1u : spp;
@@ -1340,12 +1431,17 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     if (!jobs.empty()) {
         if (c->jobs_cap < jobs.size()) {
             cudaFree(c->d_jobs);
+            cudaFree(c->d_jobs_in);
             c->d_jobs = nullptr;
+            c->d_jobs_in = nullptr;
             c->jobs_cap = 0;
             CUDA_TRY(cudaMalloc((void**)&c->d_jobs, jobs.size() * sizeof(Job)));
+            CUDA_TRY(cudaMalloc((void**)&c->d_jobs_in, jobs.size() * sizeof(JobIn)));
             c->jobs_cap = jobs.size();
         }
-        CUDA_TRY(cudaMemcpyAsync(c->d_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->d_jobs_in, jobs.data(), jobs.size() * sizeof(JobIn), cudaMemcpyHostToDevice, s));
+        k_jobs_prepare<<<(unsigned)((jobs.size() + 255) / 256), 256, 0, s>>>(c->d_jobs_in, c->d_jobs, (uint32_t)jobs.size());
+        tm.launches += 1;
         // Wavefront capacity: paths in flight per batch.
         uint32_t cap = opts && opts->wavefront_paths ? opts->wavefront_paths : (1u << 22);
         const uint64_t total_paths = (uint64_t)jobs.size() * samples_per_job;
@@ -1406,6 +1502,7 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
             st.any_nodes = c->h_totals->any_nodes;
             st.any_tris = c->h_totals->any_tris;
             st.primary_hit_hash = c->h_totals->hit_hash;
+            st.shadow_rays = c->h_totals->shadow_rays;
         }
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);

@@ -180,9 +180,11 @@ struct SamplerState {
     uint32_t px, py, index, dim;
     YK_DEV uint32_t spp(const SamplerCfg& c) const { return c.kind == YK_SAMPLER_UNIFORM ? c.nx : c.nx * c.ny; }
     // uniform.rs:72-84, stratified.rs:90-102 (always called with dimension 0 by Integrator::render)
-    YK_DEV void start(const SamplerCfg& c, uint32_t x, uint32_t y, uint32_t sample_index) {
+    // `inc` = (hash_values!(x, y) << 1) | 1, the pixel's PCG stream, hashed once per pixel (Job::rng_inc).
+    YK_DEV void start(const SamplerCfg& c, uint32_t x, uint32_t y, uint32_t sample_index, uint64_t inc) {
         px = x; py = y; index = sample_index; dim = 0;
-        rng.seed(c.seed, hash_pixel(x, y));
+        rng.inc = inc;
+        rng.state = (c.seed + inc) * kPcgMult + inc;  // Lcg64Xsh32::new
         rng.advance((uint64_t)sample_index * 65536ULL);
     }
     YK_DEV float get_1d(const SamplerCfg& c) {
