@@ -236,6 +236,9 @@ void yk_xf_vec(const yk_transform*, const float* v3, float* out3);
 void yk_xf_normal(const yk_transform*, const float* n3, float* out3);
 /* Light constructors (`new` in lights/point_light.rs, spot_light.rs, rectangular_light.rs, distant_light.rs) */
 int yk_light_make(const yk_light_desc*, yk_light* out);
+/* Diagnostic: number of numerators for which the kernels' division-by-invariant (csrc/yk_fastdiv.h; stands in for the
+   `/` and `%` of stratified.rs:127-128,177 and the batch index arithmetic) differs from n / d. Must return 0. */
+uint64_t yk_selftest_fastdiv(uint32_t d, const uint32_t* numerators, uint64_t count);
 
 #ifdef __cplusplus
 }

@@ -18,8 +18,11 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__b
         'smsp__sass_inst_executed_op_local_ld.sum', 'smsp__sass_inst_executed_op_local_st.sum',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fp64.sum','sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.sum']
 idx = {h: i for i, h in enumerate(hdr)}
+stall = [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio')]
 for r in rows[2:]:
     print('----')
     for w in want:
         if w in idx:
             print(f"{w:72s} {r[idx[w]]:>22s} {units[idx[w]]}")
+    top = sorted(((float(r[idx[n]] or 0), n) for n in stall), reverse=True)[:6]
+    print('warps stalled per issue (top): ' + ', '.join(f"{n[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]}={v:.2f}" for v, n in top))

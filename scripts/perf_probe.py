@@ -23,6 +23,13 @@ which = sys.argv[1] if len(sys.argv) > 1 else "cornell"
 if which == "cornell16":  # one short render for ncu captures
     s, c = scenes.cornell(xf, light="rect", tall_box="glass")
     probe("cornell 1024^2 path8 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=1)
+if which == "c16":
+    s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+    probe("cornell 1024^2 path8 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=3)
+if which == "capsweep":
+    s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+    for cap in (1 << 22, 1 << 21, 1 << 20, 1 << 19, 1 << 18):
+        probe(f"cornell 1024^2 path8 16spp cap {cap}", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=2, wavefront_paths=cap)
 if which == "hf4":
     s, c = scenes.heightfield(xf, 708, 708)
     probe("heightfield 1M path8 1920x1080 4spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8), reps=1)

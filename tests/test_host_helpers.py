@@ -85,3 +85,20 @@ def test_light_constructors(xf):
     assert out.area == np.float32(0.5) * np.float32(0.25)
     ld.kind = 9
     assert L.yk_light_make(C.byref(ld), C.byref(out)) == -1
+
+
+def test_division_by_invariant_matches_integer_division():
+    """csrc/yk_fastdiv.h replaces the `/` and `%` of stratified.rs:127-128,177 and the batch index arithmetic on the
+    device; it must agree with n / d for every 32-bit numerator (edge values + random draws per divisor)."""
+    from yuki_b200 import capi
+    rng = np.random.default_rng(7)
+    edge = np.array([0, 1, 2, 3, 2**16 - 1, 2**16, 2**31 - 1, 2**31, 2**31 + 1, 2**32 - 2, 2**32 - 1], dtype=np.uint64)
+    divisors = list(range(1, 70)) + [255, 256, 257, 1000, 1023, 1024, 1025, 4095, 4096, 4097, 65535, 65536, 65537, 2**20, 2**22,
+                                     2**22 + 1, 3 * 2**20 + 7, 2**31 - 1, 2**31, 2**31 + 1, 2**32 - 1]
+    divisors += [int(x) for x in rng.integers(1, 2**32, size=200, dtype=np.uint64)]
+    for d in divisors:
+        near = np.array([k * d + o for k in (1, 2, 3, 1000, (2**32 - 1) // d) for o in (-1, 0, 1)], dtype=np.int64)
+        near = near[(near >= 0) & (near < 2**32)].astype(np.uint64)
+        n = np.concatenate([edge, near, rng.integers(0, 2**32, size=20000, dtype=np.uint64)]).astype(np.uint32)
+        n = np.ascontiguousarray(n)
+        assert capi.lib().yk_selftest_fastdiv(d, n.ctypes.data, len(n)) == 0, d

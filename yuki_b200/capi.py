@@ -14,7 +14,7 @@ import numpy as np
 from . import desc as D
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyuki_gpu.so")
+LIB_PATH = os.environ.get("YUKI_GPU_LIB") or os.path.join(_HERE, "libyuki_gpu.so")  # override: A/B builds during development
 
 
 class YukiGpuError(RuntimeError):
@@ -137,7 +137,7 @@ EXPORTS = [
     "yk_last_error", "yk_context_create", "yk_context_destroy", "yk_scene_create", "yk_scene_destroy", "yk_render",
     "yk_context_stream", "yk_bvh_build", "yk_host_scene_build", "yk_host_scene_destroy", "yk_host_scene_flat", "yk_camera_make",
     "yk_film_tiles", "yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_new", "yk_xf_look_at",
-    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make",
+    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv",
 ]
 
 _lib = None
@@ -172,6 +172,8 @@ def lib():
     L.yk_camera_make.argtypes = [C.POINTER(CameraParams), u32, u32, C.POINTER(Camera)]
     L.yk_film_tiles.argtypes = [u32, u32, u32, vp, u32]
     L.yk_film_tiles.restype = u32
+    L.yk_selftest_fastdiv.argtypes = [u32, vp, C.c_uint64]
+    L.yk_selftest_fastdiv.restype = C.c_uint64
     T = C.POINTER(Transform)
     L.yk_xf_identity.argtypes = [T]
     L.yk_xf_translation.argtypes = [fp, T]

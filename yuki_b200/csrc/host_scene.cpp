@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "host_math.h"
+#include "yk_fastdiv.h"
 #include "yuki_gpu.h"
 
 namespace ykh {
@@ -320,5 +321,12 @@ void yk_xf_inverted(const yk_transform* a, yk_transform* o) { from_xform(xf_flip
 void yk_xf_point(const yk_transform* t, const float* p, float* o) { store3(apply_point(to_xform(*t).m, load3(p)), o); }
 void yk_xf_vec(const yk_transform* t, const float* v, float* o) { store3(apply_vec(to_xform(*t).m, load3(v)), o); }
 void yk_xf_normal(const yk_transform* t, const float* n, float* o) { store3(apply_normal(to_xform(*t).inv, load3(n)), o); }
+
+uint64_t yk_selftest_fastdiv(uint32_t d, const uint32_t* numerators, uint64_t count) {
+    const FastDiv f = FastDiv::make(d);
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < count; ++i) bad += f.div_host(numerators[i]) != numerators[i] / f.d;
+    return bad;
+}
 
 }  // extern "C"

@@ -32,6 +32,9 @@ constexpr int kStackDepth = 64;  // bvh.rs:172
 constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 constexpr int kShadeThreads = 128;
+#ifndef YK_SHADE_MIN_BLOCKS
+#define YK_SHADE_MIN_BLOCKS 4
+#endif
 
 #define CUDA_TRY(expr)                                                                                          \
     do {                                                                                                        \
@@ -94,6 +97,7 @@ struct Job {  // + the pixel's PCG stream, (SipHash13(x, y) << 1) | 1 (uniform.r
 struct Batch {
     const Job* jobs;
     uint32_t n_jobs, sample_off, n_samples, n_paths;
+    FastDiv div_jobs;  // by n_jobs
 };
 
 // ---- wavefront state (SoA, capacity `cap` paths) --------------------------------------------------
@@ -204,14 +208,24 @@ __global__ void k_jobs_prepare(const JobIn* in, Job* out, uint32_t n) {
     out[i] = o;
 }
 
+// hash_values!(pixel.x, pixel.y, dimension, seed) for every (dimension, pixel) of a pixel group (SamplerCfg::hash_table)
+__global__ void k_dim_hashes(const Job* jobs, uint32_t n_jobs, uint32_t n_dims, unsigned long long seed, uint32_t* out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const Job job = jobs[j];
+    for (uint32_t dim = blockIdx.y; dim < n_dims; dim += gridDim.y)
+        out[(size_t)dim * n_jobs + j] = (uint32_t)hash_pixel_dim_seed(job.x, job.y, dim, seed);
+}
+
 // ---- raygen: Integrator::render loop head (integrators/mod.rs:145-169) -----------------------------
 __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bt.n_paths) return;
-    const Job job = bt.jobs[i % bt.n_jobs];
-    const uint32_t sample = job.sample_begin + bt.sample_off + i / bt.n_jobs;
+    const uint32_t si = bt.div_jobs.div(i), ji = i - si * bt.n_jobs;
+    const Job job = bt.jobs[ji];
+    const uint32_t sample = job.sample_begin + bt.sample_off + si;
     SamplerState s;
-    s.start(cfg.sampler, job.x, job.y, sample, job.rng_inc);
+    s.start(cfg.sampler, job.x, job.y, sample, job.rng_inc, ji);
     const V2 j = s.get_2d(cfg.sampler);
     // Camera::ray, camera.rs:105-114
     const V3 p_cam = xf_point(cfg.r2c, mk((float)job.x + j.x, (float)job.y + j.y, 0.0f));
@@ -620,8 +634,9 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
             if (cfg.integrator == YK_INTEGRATOR_WHITTED) requeue = stack_pop(w, path, __float_as_uint(b.w) >> kDimShift);
         }
         if (first_iteration) {
-            const Job job = bt.jobs[path % bt.n_jobs];
-            const uint32_t sample = job.sample_begin + bt.sample_off + path / bt.n_jobs;
+            const uint32_t si = bt.div_jobs.div(path);
+            const Job job = bt.jobs[path - si * bt.n_jobs];
+            const uint32_t sample = job.sample_begin + bt.sample_off + si;
             hh = mix_hit(job.x, job.y, sample, orig);
             if (cfg.hit_ids && sample == cfg.aux_sample) cfg.hit_ids[(size_t)job.y * cfg.res_x + job.x] = (int32_t)orig;
         }
@@ -819,7 +834,7 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 // lt_*, and k_trace_shadow adds the unoccluded terms in light order. Surviving paths are appended to the next
 // active queue (one atomic per block).
 template <uint32_t KIND>
-__global__ void __launch_bounds__(kShadeThreads) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
+__global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
                                                           const uint32_t* n_ptr, uint32_t* q_next) {
     const uint32_t n = *n_ptr;
     const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
@@ -845,14 +860,16 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DevScene sc, Wave w, Re
             const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
             const bool was_specular = (flags & kFlagSpecular) != 0;
 
-            const Job job = bt.jobs[path % bt.n_jobs];
+            const uint32_t sample_i = bt.div_jobs.div(path), job_i = path - sample_i * bt.n_jobs;
+            const Job job = bt.jobs[job_i];
             SamplerState smp;
             smp.rng.state = w.rng_state[path];
             smp.rng.inc = job.rng_inc;
             smp.dim = __float_as_uint(beta4.w) >> kDimShift;
             smp.px = job.x;
             smp.py = job.y;
-            smp.index = job.sample_begin + bt.sample_off + path / bt.n_jobs;
+            smp.index = job.sample_begin + bt.sample_off + sample_i;
+            smp.job = job_i;
 
             // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
             uint32_t shadow_mask = 0;
@@ -997,7 +1014,7 @@ __global__ void k_film_store(const Job* jobs, uint32_t n_jobs, const float* accu
 __global__ void k_film_add(Wave w, Batch bt, float* film, uint32_t res_x) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bt.n_paths) return;
-    const Job job = bt.jobs[i % bt.n_jobs];
+    const Job job = bt.jobs[bt.div_jobs.mod(i)];
     const float4 L = w.L[i];
     float* f = film + ((size_t)job.y * res_x + job.x) * 3;
     atomicAdd(f, L.x); atomicAdd(f + 1, L.y); atomicAdd(f + 2, L.z);
@@ -1031,6 +1048,8 @@ struct yk_context {
     Job* d_jobs = nullptr;
     JobIn* d_jobs_in = nullptr;
     size_t jobs_cap = 0;
+    uint32_t* d_dim_hash = nullptr;  // SamplerCfg::hash_table of the current pixel group
+    size_t dim_hash_cap = 0;
     float* d_accum = nullptr;
     float* d_film = nullptr;
     int32_t* d_hit_ids = nullptr;
@@ -1224,6 +1243,7 @@ void yk_context_destroy(yk_context* c) {
     free_bag(c->wave_allocs);
     cudaFree(c->d_jobs);
     cudaFree(c->d_jobs_in);
+    cudaFree(c->d_dim_hash);
     cudaFree(c->d_accum);
     cudaFree(c->d_film);
     cudaFree(c->d_hit_ids);
@@ -1391,7 +1411,15 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     const uint32_t samples_per_job = accumulate ? 1u : spp;
 
     RenderCfg cfg{};
-    cfg.sampler = SamplerCfg{sm->kind, sm->nx, sm->kind == YK_SAMPLER_UNIFORM ? 1u : sm->ny, sm->jitter, sm->seed};
+    cfg.sampler = SamplerCfg{};
+    cfg.sampler.kind = sm->kind;
+    cfg.sampler.nx = sm->nx;
+    cfg.sampler.ny = sm->kind == YK_SAMPLER_UNIFORM ? 1u : sm->ny;
+    cfg.sampler.jitter = sm->jitter;
+    cfg.sampler.seed = sm->seed;
+    cfg.sampler.div_nx = FastDiv::make(cfg.sampler.nx);
+    cfg.sampler.div_ny = FastDiv::make(cfg.sampler.ny);
+    cfg.sampler.div_n = FastDiv::make(cfg.sampler.nx * cfg.sampler.ny);
     cfg.integrator = in->kind;
     cfg.max_depth = in->max_depth;
     cfg.has_clamp = in->has_clamp;
@@ -1463,14 +1491,38 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         uint64_t done = 0;
         for (size_t j0 = 0; j0 < jobs.size(); j0 += jobs_per_batch) {
             const uint32_t nj = (uint32_t)std::min<size_t>(jobs_per_batch, jobs.size() - j0);
+            // Stratified sampler: tabulate the (pixel, dimension) hashes of this pixel group once for all of its samples.
+            RenderCfg gcfg = cfg;
+            if (sm->kind == YK_SAMPLER_STRATIFIED) {
+                uint64_t dims = 2;
+                if (in->kind == YK_INTEGRATOR_PATH) dims = 2 + (uint64_t)in->max_depth * (2ull * sc->dev.n_lights + 3);
+                else if (in->kind == YK_INTEGRATOR_WHITTED)
+                    dims = 2 + 2ull * sc->dev.n_lights * ((1ull << std::min(in->max_depth, 8u)) - 1);
+                dims = std::min<uint64_t>(dims, std::min<uint64_t>(4096, (256ull << 20) / (4ull * nj)));  // the rest is hashed on the fly
+                const size_t need = (size_t)dims * nj;
+                if (c->dim_hash_cap < need) {
+                    cudaFree(c->d_dim_hash);
+                    c->d_dim_hash = nullptr;
+                    c->dim_hash_cap = 0;
+                    CUDA_TRY(cudaMalloc((void**)&c->d_dim_hash, need * sizeof(uint32_t)));
+                    c->dim_hash_cap = need;
+                }
+                k_dim_hashes<<<dim3((nj + 255) / 256, (unsigned)std::min<uint64_t>(dims, 64)), 256, 0, s>>>(c->d_jobs + j0, nj, (uint32_t)dims,
+                                                                                                             sm->seed, c->d_dim_hash);
+                tm.launches += 1;
+                gcfg.sampler.hash_table = c->d_dim_hash;
+                gcfg.sampler.n_hash_dims = (uint32_t)dims;
+                gcfg.sampler.hash_stride = nj;
+            }
             for (uint32_t s0 = 0; s0 < samples_per_job; s0 += m) {
                 Batch bt;
                 bt.jobs = c->d_jobs + j0;
                 bt.n_jobs = nj;
+                bt.div_jobs = FastDiv::make(nj);
                 bt.sample_off = s0;
                 bt.n_samples = std::min(m, samples_per_job - s0);
                 bt.n_paths = nj * bt.n_samples;
-                rc = run_batch(c, sc, cfg, bt, accumulate, d_film, &st, &tm);
+                rc = run_batch(c, sc, gcfg, bt, accumulate, d_film, &st, &tm);
                 if (rc != YK_OK) return rc;
                 done += bt.n_paths;
                 if (opts && opts->progress && opts->progress(opts->progress_user, done, total_paths)) {

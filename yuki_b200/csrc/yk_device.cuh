@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "yk_fastdiv.h"
 #include "yk_libm.h"
 #include "yuki_gpu.h"
 
@@ -30,12 +31,20 @@ struct RGB {
     float r, g, b;
 };
 
+// IEEE division. CUDA's correctly rounded `/` leaves its inline fast path for a subroutine whenever the numerator is
+// zero, which axis-aligned normals and single-channel colours make the common case here (profiles/r01: 11 % of the
+// shading kernel's instructions). 0 / b for finite non-zero b is a signed zero; everything else takes `/`.
+YK_DEV float fdiv(float a, float b) {
+    const uint32_t ub = __float_as_uint(b) & 0x7fffffffu;
+    if (a == 0.0f && ub - 1u < 0x7f7fffffu) return __uint_as_float((__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u);
+    return a / b;
+}
 YK_DEV V3 mk(float x, float y, float z) { return V3{x, y, z}; }
 YK_DEV V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 YK_DEV V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 YK_DEV V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
 YK_DEV V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
-YK_DEV V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+YK_DEV V3 operator/(V3 a, float s) { return {fdiv(a.x, s), fdiv(a.y, s), fdiv(a.z, s)}; }
 // Vec3::dot has a leading zero term, dot_n/dot_v do not (yuki_derive/src/impl_vec_like.rs:193-197,
 // math/vector.rs:228-230, math/normal.rs:57-59).
 YK_DEV float dot0(V3 a, V3 b) { return 0.0f + a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -65,9 +74,9 @@ YK_DEV RGB gray(float v) { return RGB{v, v, v}; }
 YK_DEV RGB operator+(RGB a, RGB b) { return {a.r + b.r, a.g + b.g, a.b + b.b}; }
 YK_DEV RGB operator-(RGB a, RGB b) { return {a.r - b.r, a.g - b.g, a.b - b.b}; }
 YK_DEV RGB operator*(RGB a, RGB b) { return {a.r * b.r, a.g * b.g, a.b * b.b}; }
-YK_DEV RGB operator/(RGB a, RGB b) { return {a.r / b.r, a.g / b.g, a.b / b.b}; }
+YK_DEV RGB operator/(RGB a, RGB b) { return {fdiv(a.r, b.r), fdiv(a.g, b.g), fdiv(a.b, b.b)}; }
 YK_DEV RGB operator*(RGB a, float s) { return {a.r * s, a.g * s, a.b * s}; }
-YK_DEV RGB operator/(RGB a, float s) { return {a.r / s, a.g / s, a.b / s}; }
+YK_DEV RGB operator/(RGB a, float s) { return {fdiv(a.r, s), fdiv(a.g, s), fdiv(a.b, s)}; }
 YK_DEV bool black(RGB a) { return a.r == 0.0f && a.g == 0.0f && a.b == 0.0f; }
 YK_DEV RGB rsqrt3(RGB a) { return {sqrtf(a.r), sqrtf(a.g), sqrtf(a.b)}; }
 
@@ -150,7 +159,8 @@ struct Pcg {
     }
     YK_DEV float next_f32() { return (float)(next() >> 8) * (1.0f / 16777216.0f); }
 };
-YK_DEV uint32_t permutation_element(uint32_t i, uint32_t l, uint32_t p) {  // stratified.rs:147-178
+YK_DEV uint32_t permutation_element(uint32_t i, const FastDiv& ld, uint32_t p) {  // stratified.rs:147-178
+    const uint32_t l = ld.d;
     uint32_t w = l - 1;
     w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
     do {
@@ -167,33 +177,41 @@ YK_DEV uint32_t permutation_element(uint32_t i, uint32_t l, uint32_t p) {  // st
         i &= w;
         i ^= i >> 5;
     } while (i >= l);
-    return (i + p) % l;
+    return ld.mod(i + p);
 }
 
 struct SamplerCfg {
     uint32_t kind, nx, ny, jitter;
     uint64_t seed;
+    FastDiv div_n, div_nx, div_ny;  // n = nx * ny
+    // hash_values!(pixel, dimension, seed) (stratified.rs:105,122) depends on neither the sample index nor the path, so
+    // the 32 bits the permutation uses are tabulated once per pixel group: hash_table[dim * hash_stride + job], dim <
+    // n_hash_dims. One SipHash per (pixel, dimension) instead of one per (pixel, dimension, sample).
+    const uint32_t* hash_table;
+    uint32_t n_hash_dims, hash_stride;
 };
 // Per-path sampler registers. `dim` is only meaningful for the stratified sampler (it keys the hash).
 struct SamplerState {
     Pcg rng;
-    uint32_t px, py, index, dim;
-    YK_DEV uint32_t spp(const SamplerCfg& c) const { return c.kind == YK_SAMPLER_UNIFORM ? c.nx : c.nx * c.ny; }
-    // uniform.rs:72-84, stratified.rs:90-102 (always called with dimension 0 by Integrator::render)
+    uint32_t px, py, index, dim, job;
+    // uniform.rs:72-84, stratified.rs:90-102 (always called with dimension 0 by Integrator::render).
     // `inc` = (hash_values!(x, y) << 1) | 1, the pixel's PCG stream, hashed once per pixel (Job::rng_inc).
-    YK_DEV void start(const SamplerCfg& c, uint32_t x, uint32_t y, uint32_t sample_index, uint64_t inc) {
-        px = x; py = y; index = sample_index; dim = 0;
+    YK_DEV void start(const SamplerCfg& c, uint32_t x, uint32_t y, uint32_t sample_index, uint64_t inc, uint32_t job_index) {
+        px = x; py = y; index = sample_index; dim = 0; job = job_index;
         rng.inc = inc;
         rng.state = (c.seed + inc) * kPcgMult + inc;  // Lcg64Xsh32::new
         rng.advance((uint64_t)sample_index * 65536ULL);
     }
+    YK_DEV uint32_t dim_hash(const SamplerCfg& c) const {
+        if (dim < c.n_hash_dims) return __ldg(&c.hash_table[(size_t)dim * c.hash_stride + job]);
+        return (uint32_t)hash_pixel_dim_seed(px, py, dim, c.seed);
+    }
     YK_DEV float get_1d(const SamplerCfg& c) {
         if (c.kind == YK_SAMPLER_UNIFORM) { dim += 1; return rng.next_f32(); }
-        const uint32_t n = c.nx * c.ny;
-        const uint32_t stratum = permutation_element(index, n, (uint32_t)hash_pixel_dim_seed(px, py, dim, c.seed));
+        const uint32_t stratum = permutation_element(index, c.div_n, dim_hash(c));
         dim += 1;
         const float delta = c.jitter ? rng.next_f32() : 0.5f;
-        return ((float)stratum + delta) / (float)n;
+        return ((float)stratum + delta) / (float)c.div_n.d;
     }
     YK_DEV V2 get_2d(const SamplerCfg& c) {
         if (c.kind == YK_SAMPLER_UNIFORM) {
@@ -202,11 +220,10 @@ struct SamplerState {
             const float y = rng.next_f32();
             return {x, y};
         }
-        const uint32_t n = c.nx * c.ny;
-        const uint32_t stratum = permutation_element(index, n, (uint32_t)hash_pixel_dim_seed(px, py, dim, c.seed));
+        const uint32_t stratum = permutation_element(index, c.div_n, dim_hash(c));
         dim += 2;
-        const uint32_t sx = stratum % c.nx;
-        const uint32_t sy = stratum / c.ny;  // reference divides by pixel_samples.y (stratified.rs:128)
+        const uint32_t sx = c.div_nx.mod(stratum);
+        const uint32_t sy = c.div_ny.div(stratum);  // reference divides by pixel_samples.y (stratified.rs:128)
         const float dx = c.jitter ? rng.next_f32() : 0.5f;
         const float dy = c.jitter ? rng.next_f32() : 0.5f;
         return {((float)sx + dx) / (float)c.nx, ((float)sy + dy) / (float)c.ny};
