@@ -14,6 +14,7 @@
 #include <chrono>
 #include <memory>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,15 +73,17 @@ struct DevScene {
 constexpr uint32_t kMetaLeaf = 0x80000000u;  // meta: leaf -> leaf bit | shape_count; interior -> 1 << split_axis
 
 // ---- per-iteration device counters ----------------------------------------------------------------
-struct Counters {
-    uint32_t mat[4];       // material queue lengths
-    uint32_t next;         // next active queue length
-    uint32_t work_closest; // dynamic ray fetch cursors
+// Queue lengths never leave the device: every kernel of a bounce reads its element count from `cur` and appends to
+// `nxt`, so a batch is one asynchronous launch sequence (no host round trip per bounce).
+struct IterCounters {
+    uint32_t n_active;      // rays of this bounce (length of the active queue)
+    uint32_t mat[4];        // material queue lengths
+    uint32_t work_closest;  // dynamic ray fetch cursors
     uint32_t work_shadow;
     uint32_t _pad;
 };
 struct Totals {
-    unsigned long long closest_nodes, closest_tris, any_nodes, any_tris, hit_hash, shadow_rays;
+    unsigned long long closest_nodes, closest_tris, any_nodes, any_tris, hit_hash, shadow_rays, closest_rays;
 };
 
 struct JobIn {  // as uploaded by the host: one pixel's share of the batch
@@ -122,7 +125,6 @@ struct Wave {
     uint32_t* stack_top; // whitted
     uint32_t* q_active[2];
     uint32_t* q_mat;     // 4 * cap
-    Counters* counters;
     Totals* totals;
 };
 // beta.w flag word
@@ -218,9 +220,10 @@ __global__ void k_dim_hashes(const Job* jobs, uint32_t n_jobs, uint32_t n_dims, 
 }
 
 // ---- raygen: Integrator::render loop head (integrators/mod.rs:145-169) -----------------------------
-__global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt) {
+__global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, IterCounters* first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bt.n_paths) return;
+    if (i == 0) first->n_active = bt.n_paths;
     const uint32_t si = bt.div_jobs.div(i), ji = i - si * bt.n_jobs;
     const Job job = bt.jobs[ji];
     const uint32_t sample = job.sample_begin + bt.sample_off + si;
@@ -394,9 +397,12 @@ struct TraceLane {
 
 // Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
 template <bool COUNTS>
-__global__ void __launch_bounds__(kTraceThreads) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, uint32_t n, uint32_t* cursor) {
+__global__ void __launch_bounds__(kTraceThreads) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, IterCounters* cur) {
     __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
     uint32_t deep[kStackDepth + 1 - kShortStack];
+    const uint32_t n = cur->n_active;
+    uint32_t* const cursor = &cur->work_closest;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&w.totals->closest_rays, (unsigned long long)n);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t* const lane_stack = &s_stack[0][tid];
@@ -472,14 +478,15 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_closest(DevScene sc, Wa
 // `radiance += beta * Le`, the indirect clamp and `L += beta * radiance` (path.rs:113-129, whitted.rs:120-130).
 // One *path* per queue entry (the four material queues, concatenated); a lane traces its path's shadow rays one after
 // the other in light order, so the float sums associate exactly like the reference's fold.
-__global__ void __launch_bounds__(kTraceThreads) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, uint32_t* cursor) {
+__global__ void __launch_bounds__(kTraceThreads) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, IterCounters* cur) {
+    uint32_t* const cursor = &cur->work_shadow;
     __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
     uint32_t deep[kStackDepth + 1 - kShortStack];
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t* const lane_stack = &s_stack[0][tid];
     lane_stack[0] = kNoNode;
-    const uint32_t n0 = w.counters->mat[0], n1 = w.counters->mat[1], n2 = w.counters->mat[2], n3 = w.counters->mat[3];
+    const uint32_t n0 = cur->mat[0], n1 = cur->mat[1], n2 = cur->mat[2], n3 = cur->mat[3];
     const uint32_t n = n0 + n1 + n2 + n3;
     unsigned long long sum_nodes = 0, sum_tris = 0, sum_rays = 0;
     uint32_t chunk_next = 0, chunk_end = 0;
@@ -608,45 +615,51 @@ __device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path, uint32_t
 }
 
 // ---- classify: miss handling + compaction by material ("ray-queue sort/compaction pass") ---------------
-__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, uint32_t n, int first_iteration,
-                           uint32_t* q_next) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
-    uint32_t path = 0, kind = 4;
-    bool requeue = false;
-    unsigned long long hh = 0;
-    if (valid) {
-        path = queue ? queue[i] : i;
-        const uint2 h = w.hit[path];
-        uint32_t orig = 0xffffffffu;
-        if (h.y != kMiss) {
-            const uint32_t m = __float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) & 0xffffffu;
-            kind = sc.materials[m].kind;
-            if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
-        } else {
-            // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
-            const float4 b = w.beta[path];
-            float4 L = w.L[path];
-            L.x = L.x + b.x * sc.background[0];
-            L.y = L.y + b.y * sc.background[1];
-            L.z = L.z + b.z * sc.background[2];
-            w.L[path] = L;
-            if (cfg.integrator == YK_INTEGRATOR_WHITTED) requeue = stack_pop(w, path, __float_as_uint(b.w) >> kDimShift);
+__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, IterCounters* cur, IterCounters* nxt,
+                           int first_iteration, uint32_t* q_next) {
+    const uint32_t n = cur->n_active;
+    const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
+        if (block_first >= n) break;  // block-uniform
+        const uint32_t i = block_first + threadIdx.x;
+        const bool valid = i < n;
+        uint32_t path = 0, kind = 4;
+        bool requeue = false;
+        unsigned long long hh = 0;
+        if (valid) {
+            path = queue ? queue[i] : i;
+            const uint2 h = w.hit[path];
+            uint32_t orig = 0xffffffffu;
+            if (h.y != kMiss) {
+                const uint32_t m = __float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) & 0xffffffu;
+                kind = sc.materials[m].kind;
+                if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
+            } else {
+                // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
+                const float4 b = w.beta[path];
+                float4 L = w.L[path];
+                L.x = L.x + b.x * sc.background[0];
+                L.y = L.y + b.y * sc.background[1];
+                L.z = L.z + b.z * sc.background[2];
+                w.L[path] = L;
+                if (cfg.integrator == YK_INTEGRATOR_WHITTED) requeue = stack_pop(w, path, __float_as_uint(b.w) >> kDimShift);
+            }
+            if (first_iteration) {
+                const uint32_t si = bt.div_jobs.div(path);
+                const Job job = bt.jobs[path - si * bt.n_jobs];
+                const uint32_t sample = job.sample_begin + bt.sample_off + si;
+                hh = mix_hit(job.x, job.y, sample, orig);
+                if (cfg.hit_ids && sample == cfg.aux_sample) cfg.hit_ids[(size_t)job.y * cfg.res_x + job.x] = (int32_t)orig;
+            }
         }
+        uint32_t* const queues[5] = {w.q_mat, w.q_mat + (size_t)w.cap, w.q_mat + (size_t)2 * w.cap, w.q_mat + (size_t)3 * w.cap, q_next};
+        uint32_t* const counters[5] = {&cur->mat[0], &cur->mat[1], &cur->mat[2], &cur->mat[3], &nxt->n_active};
+        block_scatter<5>(!valid ? -1 : (requeue ? 4 : (kind < 4 ? (int)kind : -1)), path, queues, counters);
         if (first_iteration) {
-            const uint32_t si = bt.div_jobs.div(path);
-            const Job job = bt.jobs[path - si * bt.n_jobs];
-            const uint32_t sample = job.sample_begin + bt.sample_off + si;
-            hh = mix_hit(job.x, job.y, sample, orig);
-            if (cfg.hit_ids && sample == cfg.aux_sample) cfg.hit_ids[(size_t)job.y * cfg.res_x + job.x] = (int32_t)orig;
+            hh = warp_sum(hh);
+            if ((threadIdx.x & 31) == 0 && hh) atomicAdd(&w.totals->hit_hash, hh);
         }
-    }
-    uint32_t* const queues[5] = {w.q_mat, w.q_mat + (size_t)w.cap, w.q_mat + (size_t)2 * w.cap, w.q_mat + (size_t)3 * w.cap, q_next};
-    uint32_t* const counters[5] = {&w.counters->mat[0], &w.counters->mat[1], &w.counters->mat[2], &w.counters->mat[3], &w.counters->next};
-    block_scatter<5>(!valid ? -1 : (requeue ? 4 : (kind < 4 ? (int)kind : -1)), path, queues, counters);
-    if (first_iteration) {
-        hh = warp_sum(hh);
-        if ((threadIdx.x & 31) == 0 && hh) atomicAdd(&w.totals->hit_hash, hh);
     }
 }
 
@@ -835,8 +848,8 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 // active queue (one atomic per block).
 template <uint32_t KIND>
 __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
-                                                          const uint32_t* n_ptr, uint32_t* q_next) {
-    const uint32_t n = *n_ptr;
+                                                                               IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
+    const uint32_t n = cur->mat[KIND];
     const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
@@ -961,7 +974,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             }
         }
         uint32_t* const queues[1] = {q_next};
-        uint32_t* const counters[1] = {&w.counters->next};
+        uint32_t* const counters[1] = {&nxt->n_active};
         block_scatter<1>(alive ? 0 : -1, path, queues, counters);
     }
 }
@@ -1035,31 +1048,54 @@ __global__ void k_fill_i32(int32_t* p, size_t n, int32_t v) {
 // =====================================================================================================
 // Host side: context, scene upload, wavefront driver.
 // =====================================================================================================
+constexpr int kMaxPipes = 2;   // batches in flight on separate streams (their kernels overlap on the SMs)
+constexpr int kRing = 2;       // batches queued per pipe before the host waits for the oldest
+constexpr int kTimedStages = 5;  // events per bounce: before/after closest, after classify, after shading, after shadow
+
+// One asynchronous wavefront lane: its own stream, path state, bounce counters and timing events.
+struct Pipe {
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    Wave wave{};
+    std::vector<void*> wave_allocs;
+    uint32_t wave_cap = 0, wave_lights = 0, wave_stack = 0;
+    IterCounters* d_ctr = nullptr;   // two entries, alternating per bounce
+    IterCounters* h_ctr = nullptr;   // pinned: read-back for the integrators whose bounce count is unbounded (Whitted)
+    Totals* h_totals = nullptr;      // pinned
+    uint32_t* d_dim_hash = nullptr;  // SamplerCfg::hash_table of the pipe's current pixel group
+    size_t dim_hash_cap = 0;
+    size_t hash_group = (size_t)-1;
+    struct Slot {
+        cudaEvent_t done = nullptr;
+        std::vector<cudaEvent_t> ev;  // kTimedStages per bounce
+        uint32_t n_iters = 0;
+        uint64_t n_paths = 0;
+        bool busy = false;
+    } slot[kRing];
+    uint64_t n_batches = 0;
+};
+
 struct yk_context {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
-    Wave wave{};
-    std::vector<void*> wave_allocs;
-    uint32_t wave_cap = 0, wave_lights = 0, wave_stack = 0;
-    Counters* h_counters = nullptr;  // pinned
-    Totals* h_totals = nullptr;      // pinned
+    cudaEvent_t ev[4] = {};
+    Pipe pipe[kMaxPipes];
     Job* d_jobs = nullptr;
     JobIn* d_jobs_in = nullptr;
     size_t jobs_cap = 0;
-    uint32_t* d_dim_hash = nullptr;  // SamplerCfg::hash_table of the current pixel group
-    size_t dim_hash_cap = 0;
     float* d_accum = nullptr;
     float* d_film = nullptr;
     int32_t* d_hit_ids = nullptr;
     size_t film_cap = 0;
     int occ_trace_closest = 0, occ_trace_any = 0;
+    int n_pipes = kMaxPipes;
 };
 
 struct yk_scene {
     yk_context* ctx = nullptr;
     int device = 0;
+    uint32_t material_kinds = 0;  // bit k set: some triangle's material has kind k
     DevScene dev{};
     std::vector<void*> allocs;
 };
@@ -1094,15 +1130,15 @@ float host_roughness_to_alpha(float r) {
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
-int ensure_wave(yk_context* c, uint32_t cap, uint32_t n_lights, uint32_t stack_entries) {
-    if (c->wave_cap == cap && c->wave_lights == n_lights && c->wave_stack == stack_entries) return YK_OK;
-    free_bag(c->wave_allocs);
-    c->wave_cap = 0;
+int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries) {
+    if (p->wave_cap == cap && p->wave_lights == n_lights && p->wave_stack == stack_entries) return YK_OK;
+    free_bag(p->wave_allocs);
+    p->wave_cap = 0;
     Wave w{};
     w.cap = cap;
     w.n_lights = n_lights;
     w.stack_entries = stack_entries;
-    std::vector<void*>& bag = c->wave_allocs;
+    std::vector<void*>& bag = p->wave_allocs;
     const size_t nl = std::max<uint32_t>(n_lights, 1);
     int rc = YK_OK;
 #define WAVE_ALLOC(field, count) \
@@ -1112,16 +1148,16 @@ int ensure_wave(yk_context* c, uint32_t cap, uint32_t n_lights, uint32_t stack_e
     WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap)
     WAVE_ALLOC(lt_o, cap * nl) WAVE_ALLOC(lt_d, cap * nl) WAVE_ALLOC(lt_c, cap * nl)
     WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap)
-    WAVE_ALLOC(counters, 1) WAVE_ALLOC(totals, 1)
+    WAVE_ALLOC(totals, 1)
     if (stack_entries) {
         WAVE_ALLOC(stack, (size_t)stack_entries * cap * 3)
         WAVE_ALLOC(stack_top, cap)
     }
 #undef WAVE_ALLOC
-    c->wave = w;
-    c->wave_cap = cap;
-    c->wave_lights = n_lights;
-    c->wave_stack = stack_entries;
+    p->wave = w;
+    p->wave_cap = cap;
+    p->wave_lights = n_lights;
+    p->wave_stack = stack_entries;
     return YK_OK;
 }
 
@@ -1135,69 +1171,114 @@ int grid_for(uint32_t n, int threads, int max_blocks) {
     return (int)std::max<uint32_t>(1u, std::min<uint32_t>(need, (uint32_t)max_blocks));
 }
 
-// One batch: raygen, the bounce loop, and the per-batch film step.
-int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Batch& bt, bool accumulate_film, float* d_film,
-              yk_stats* st, Timers* tm) {
-    cudaStream_t s = c->stream;
-    Wave& w = c->wave;
+// Waits for the batch in ring slot `k` of the pipe and folds its stage timings into `tm`.
+int retire_slot(Pipe* p, int k, Timers* tm, uint64_t* done_paths) {
+    Pipe::Slot& sl = p->slot[k];
+    if (!sl.busy) return YK_OK;
+    CUDA_TRY(cudaEventSynchronize(sl.done));
+    for (uint32_t i = 0; i < sl.n_iters; ++i) {
+        cudaEvent_t* e = &sl.ev[(size_t)i * kTimedStages];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e[0], e[1]); tm->closest += ms;
+        cudaEventElapsedTime(&ms, e[2], e[3]); tm->shade += ms;
+        cudaEventElapsedTime(&ms, e[3], e[4]); tm->any += ms;
+    }
+    *done_paths += sl.n_paths;
+    sl.busy = false;
+    return YK_OK;
+}
+
+// One batch on one pipe: raygen, the bounce loop, and the per-batch film step, all asynchronous on the pipe's stream.
+// Path tracing runs exactly max_depth bounces (every queue length stays on the device); Whitted's tree walk has no
+// such bound, so it reads the next bounce's ray count back once per bounce.
+int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, const Batch& bt, bool accumulate_film, float* d_film,
+              Timers* tm, uint64_t* done_paths) {
+    cudaStream_t s = p->stream;
+    Wave& w = p->wave;
+    const int k = (int)(p->n_batches % kRing);
+    int rc = retire_slot(p, k, tm, done_paths);
+    if (rc != YK_OK) return rc;
+    Pipe::Slot& sl = p->slot[k];
+    if (!sl.done) CUDA_TRY(cudaEventCreate(&sl.done));
+    sl.n_iters = 0;
+    sl.n_paths = bt.n_paths;
+    auto stage_event = [&](uint32_t iter, int stage) -> cudaEvent_t {
+        const size_t idx = (size_t)iter * kTimedStages + stage;
+        while (sl.ev.size() <= idx) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            sl.ev.push_back(e);
+        }
+        return sl.ev[idx];
+    };
+
     const int T = 256;
-    k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt);
+    CUDA_TRY(cudaMemsetAsync(p->d_ctr, 0, 2 * sizeof(IterCounters), s));
+    k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt, &p->d_ctr[0]);
     tm->launches += 1;
     const bool debug = cfg.integrator >= YK_INTEGRATOR_BVH_INTERSECTIONS;
+    const bool sync_loop = cfg.integrator == YK_INTEGRATOR_WHITTED;
     const int trace_blocks_closest = c->sm_count * std::max(1, c->occ_trace_closest);
     const int trace_blocks_shadow = c->sm_count * std::max(1, c->occ_trace_any);
     const int wide_blocks = c->sm_count * 16;
-    uint32_t n_active = bt.n_paths;
-    if (cfg.integrator == YK_INTEGRATOR_PATH && cfg.max_depth == 0) n_active = 0;
+    const int classify_blocks = grid_for(bt.n_paths, T, c->sm_count * 8);
+    const int shade_blocks = grid_for(bt.n_paths, kShadeThreads, wide_blocks);
+    const int closest_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_closest);
+    const int shadow_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_shadow);
+    uint32_t max_iters = 1;
+    if (cfg.integrator == YK_INTEGRATOR_PATH) max_iters = cfg.max_depth;
+    else if (sync_loop) max_iters = 0xffffffffu;
     uint32_t* q_cur = nullptr;
     int flip = 0;
-    for (uint32_t iter = 0; n_active > 0; ++iter) {
-        CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(Counters), s));
-        CUDA_TRY(cudaEventRecord(c->ev[0], s));
+    for (uint32_t iter = 0; iter < max_iters; ++iter) {
+        IterCounters* cur = &p->d_ctr[iter & 1];
+        IterCounters* nxt = &p->d_ctr[(iter + 1) & 1];
+        if (iter > 0) CUDA_TRY(cudaMemsetAsync(nxt, 0, sizeof(IterCounters), s));
+        CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
         if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS)
-            k_trace_closest<true><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
-                sc->dev, w, q_cur, n_active, &w.counters->work_closest);
+            k_trace_closest<true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
         else
-            k_trace_closest<false><<<grid_for(n_active, kTraceThreads, trace_blocks_closest), kTraceThreads, 0, s>>>(
-                sc->dev, w, q_cur, n_active, &w.counters->work_closest);
-        CUDA_TRY(cudaEventRecord(c->ev[1], s));
+            k_trace_closest<false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+        CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
         tm->launches += 1;
         tm->closest_launches += 1;
-        st->ray_count += n_active;
         uint32_t* q_next = w.q_active[flip];
         if (debug) {
-            k_debug_shade<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, n_active);
+            k_debug_shade<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt.n_paths);
             // primary-hit digest / id image for the debug integrators too
-            k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, n_active, 2, q_next);
+            k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, cur, nxt, 2, q_next);
             tm->launches += 2;
-            CUDA_TRY(cudaStreamSynchronize(s));
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-            tm->closest += ms;
+            for (int st = 2; st < kTimedStages; ++st) CUDA_TRY(cudaEventRecord(stage_event(iter, st), s));
+            sl.n_iters = iter + 1;
             break;
         }
-        k_classify<<<(n_active + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, n_active, iter == 0 ? 1 : 0, q_next);
-        CUDA_TRY(cudaEventRecord(c->ev[2], s));
-        const int sg = grid_for(n_active, kShadeThreads, wide_blocks);
-        k_shade<YK_MAT_MATTE><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)0 * w.cap, &w.counters->mat[0], q_next);
-        k_shade<YK_MAT_GLASS><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)1 * w.cap, &w.counters->mat[1], q_next);
-        k_shade<YK_MAT_METAL><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)2 * w.cap, &w.counters->mat[2], q_next);
-        k_shade<YK_MAT_GLOSSY><<<sg, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, w.q_mat + (size_t)3 * w.cap, &w.counters->mat[3], q_next);
-        CUDA_TRY(cudaEventRecord(c->ev[3], s));
-        k_trace_shadow<<<grid_for(n_active, kTraceThreads, trace_blocks_shadow), kTraceThreads, 0, s>>>(sc->dev, w, cfg, &w.counters->work_shadow);
-        CUDA_TRY(cudaEventRecord(c->ev[4], s));
-        tm->launches += 6;
-        CUDA_TRY(cudaMemcpyAsync(c->h_counters, w.counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        CUDA_TRY(cudaGetLastError());
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); tm->closest += ms;
-        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); tm->shade += ms;
-        cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); tm->any += ms;
-        n_active = c->h_counters->next;
+        k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, cur, nxt, iter == 0 ? 1 : 0, q_next);
+        CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
+        tm->launches += 1;
+        for (uint32_t kind = 0; kind < 4; ++kind) {
+            if (!(sc->material_kinds & (1u << kind))) continue;  // no triangle of the scene has this material kind
+            uint32_t* q = w.q_mat + (size_t)kind * w.cap;
+            switch (kind) {
+                case YK_MAT_MATTE: k_shade<YK_MAT_MATTE><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
+                case YK_MAT_GLASS: k_shade<YK_MAT_GLASS><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
+                case YK_MAT_METAL: k_shade<YK_MAT_METAL><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
+                default: k_shade<YK_MAT_GLOSSY><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
+            }
+            tm->launches += 1;
+        }
+        CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
+        k_trace_shadow<<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
+        CUDA_TRY(cudaEventRecord(stage_event(iter, 4), s));
+        tm->launches += 1;
+        sl.n_iters = iter + 1;
         q_cur = q_next;
         flip ^= 1;
-        if (iter > (1u << 20)) return yk_set_error(YK_ERR_INVALID, "yk_render: bounce loop did not terminate");
+        if (sync_loop) {
+            CUDA_TRY(cudaMemcpyAsync(p->h_ctr, nxt, sizeof(IterCounters), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (p->h_ctr->n_active == 0) break;
+            if (iter > (1u << 20)) return yk_set_error(YK_ERR_INVALID, "yk_render: bounce loop did not terminate");
+        }
     }
     if (accumulate_film) {
         k_film_add<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, bt, d_film, cfg.res_x);
@@ -1205,6 +1286,10 @@ int run_batch(yk_context* c, const yk_scene* sc, const RenderCfg& cfg, const Bat
         k_film_accumulate<<<(bt.n_jobs + T - 1) / T, T, 0, s>>>(w, bt, c->d_accum, cfg.res_x);
     }
     tm->launches += 1;
+    CUDA_TRY(cudaEventRecord(sl.done, s));
+    CUDA_TRY(cudaGetLastError());
+    sl.busy = true;
+    p->n_batches += 1;
     return YK_OK;
 }
 
@@ -1227,9 +1312,23 @@ int yk_context_create(int device_id, yk_context** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
-    CUDA_TRY(cudaMallocHost((void**)&c->h_counters, sizeof(Counters)));
-    CUDA_TRY(cudaMallocHost((void**)&c->h_totals, sizeof(Totals)));
+    for (auto& ev : c->ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventDestroy(c->ev[2]));
+    CUDA_TRY(cudaEventDestroy(c->ev[3]));
+    CUDA_TRY(cudaEventCreate(&c->ev[2]));  // timing pair around the whole render
+    CUDA_TRY(cudaEventCreate(&c->ev[3]));
+    if (const char* np = getenv("YK_PIPES")) c->n_pipes = std::max(1, std::min(kMaxPipes, atoi(np)));
+    for (int i = 0; i < kMaxPipes; ++i) {
+        Pipe& p = c->pipe[i];
+        if (i == 0) p.stream = c->stream;
+        else {
+            CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+            p.owns_stream = true;
+        }
+        CUDA_TRY(cudaMalloc((void**)&p.d_ctr, 2 * sizeof(IterCounters)));
+        CUDA_TRY(cudaMallocHost((void**)&p.h_ctr, sizeof(IterCounters)));
+        CUDA_TRY(cudaMallocHost((void**)&p.h_totals, sizeof(Totals)));
+    }
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace_closest<false>, kTraceThreads, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace_shadow, kTraceThreads, 0));
     *out = c;
@@ -1239,16 +1338,24 @@ int yk_context_create(int device_id, yk_context** out) {
 void yk_context_destroy(yk_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    free_bag(c->wave_allocs);
+    cudaDeviceSynchronize();
+    for (Pipe& p : c->pipe) {
+        free_bag(p.wave_allocs);
+        cudaFree(p.d_ctr);
+        cudaFree(p.d_dim_hash);
+        cudaFreeHost(p.h_ctr);
+        cudaFreeHost(p.h_totals);
+        for (auto& sl : p.slot) {
+            if (sl.done) cudaEventDestroy(sl.done);
+            for (cudaEvent_t e : sl.ev) cudaEventDestroy(e);
+        }
+        if (p.owns_stream) cudaStreamDestroy(p.stream);
+    }
     cudaFree(c->d_jobs);
     cudaFree(c->d_jobs_in);
-    cudaFree(c->d_dim_hash);
     cudaFree(c->d_accum);
     cudaFree(c->d_film);
     cudaFree(c->d_hit_ids);
-    cudaFreeHost(c->h_counters);
-    cudaFreeHost(c->h_totals);
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1289,6 +1396,7 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     for (uint32_t i = 0; i < d->n_tris; ++i) {
         const float* v = d->tri_vertices + (size_t)i * 9;
         if (d->tri_material[i] >= d->n_materials) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: material index out of range");
+        if (d->materials[d->tri_material[i]].kind <= YK_MAT_GLOSSY) sc->material_kinds |= 1u << d->materials[d->tri_material[i]].kind;
         if (d->tri_area_light[i] >= (int32_t)d->n_lights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: area light out of range");
         uint32_t packed = d->tri_material[i] | ((uint32_t)d->tri_flags[i] << 24);
         if ((d->tri_flags[i] & YK_TRI_HAS_NORMALS) && !d->tri_normals) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: normals flagged but absent");
@@ -1455,7 +1563,8 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
 
     yk_stats st{};
     Timers tm;
-    CUDA_TRY(cudaEventRecord(c->ev[6], s));
+    Totals totals{};
+    CUDA_TRY(cudaEventRecord(c->ev[2], s));
     if (!jobs.empty()) {
         if (c->jobs_cap < jobs.size()) {
             cudaFree(c->d_jobs);
@@ -1475,71 +1584,105 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         const uint64_t total_paths = (uint64_t)jobs.size() * samples_per_job;
         if (cap > total_paths) cap = (uint32_t)total_paths;
         cap = std::max(cap, 32u);
-        const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
-        int rc = ensure_wave(c, cap, sc->dev.n_lights, stack_entries);
-        if (rc != YK_OK) return rc;
-        CUDA_TRY(cudaMemsetAsync(c->wave.totals, 0, sizeof(Totals), s));
-        if (!accumulate) {
-            const unsigned g = (unsigned)((jobs.size() + 255) / 256);
-            k_zero_jobs<<<g, 256, 0, s>>>(c->d_jobs, (uint32_t)jobs.size(), c->d_accum, fs->res_x);
-        }
         // Samples of one pixel per batch: enough to amortise per-batch fixed costs, few enough that many pixels
         // (>= 64 Ki when available) share a batch.
         uint32_t m = std::min(samples_per_job, 64u);
         while (m > 1 && (uint64_t)m * std::min<uint64_t>(jobs.size(), 65536) > cap) m >>= 1;
-        const uint32_t jobs_per_batch = std::max(1u, cap / m);
+        uint32_t jobs_per_batch = std::max(1u, cap / m);
+        // Pipes: pixel groups alternate between the streams, so one group's latency-bound shading overlaps the other's
+        // issue-bound traversal. A pixel's samples stay on one pipe, in order (the film sum is order-dependent).
+        // The accumulating film adds with atomics across tiles, so it keeps to one stream.
+        int n_pipes = accumulate ? 1 : c->n_pipes;
+        if (n_pipes > 1 && jobs.size() <= jobs_per_batch) {  // one group only: split it if that leaves decent batches
+            if ((uint64_t)(jobs.size() / 2) * m >= (1u << 20)) jobs_per_batch = (uint32_t)((jobs.size() + 1) / 2);
+            else n_pipes = 1;
+        }
+        const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
+        const uint32_t wave_cap = (uint32_t)std::min<uint64_t>(cap, (uint64_t)jobs_per_batch * m);
+        int rc = YK_OK;
+        if (!accumulate) {
+            const unsigned g = (unsigned)((jobs.size() + 255) / 256);
+            k_zero_jobs<<<g, 256, 0, s>>>(c->d_jobs, (uint32_t)jobs.size(), c->d_accum, fs->res_x);
+            tm.launches += 1;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev[0], s));
+        for (int pi = 0; pi < n_pipes; ++pi) {
+            Pipe& p = c->pipe[pi];
+            if ((rc = ensure_wave(&p, wave_cap, sc->dev.n_lights, stack_entries)) != YK_OK) return rc;
+            if (pi > 0) CUDA_TRY(cudaStreamWaitEvent(p.stream, c->ev[0], 0));
+            CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), p.stream));
+            p.hash_group = (size_t)-1;
+        }
+        const size_t n_groups = (jobs.size() + jobs_per_batch - 1) / jobs_per_batch;
         uint64_t done = 0;
-        for (size_t j0 = 0; j0 < jobs.size(); j0 += jobs_per_batch) {
-            const uint32_t nj = (uint32_t)std::min<size_t>(jobs_per_batch, jobs.size() - j0);
-            // Stratified sampler: tabulate the (pixel, dimension) hashes of this pixel group once for all of its samples.
-            RenderCfg gcfg = cfg;
-            if (sm->kind == YK_SAMPLER_STRATIFIED) {
-                uint64_t dims = 2;
-                if (in->kind == YK_INTEGRATOR_PATH) dims = 2 + (uint64_t)in->max_depth * (2ull * sc->dev.n_lights + 3);
-                else if (in->kind == YK_INTEGRATOR_WHITTED)
-                    dims = 2 + 2ull * sc->dev.n_lights * ((1ull << std::min(in->max_depth, 8u)) - 1);
-                dims = std::min<uint64_t>(dims, std::min<uint64_t>(4096, (256ull << 20) / (4ull * nj)));  // the rest is hashed on the fly
-                const size_t need = (size_t)dims * nj;
-                if (c->dim_hash_cap < need) {
-                    cudaFree(c->d_dim_hash);
-                    c->d_dim_hash = nullptr;
-                    c->dim_hash_cap = 0;
-                    CUDA_TRY(cudaMalloc((void**)&c->d_dim_hash, need * sizeof(uint32_t)));
-                    c->dim_hash_cap = need;
-                }
-                k_dim_hashes<<<dim3((nj + 255) / 256, (unsigned)std::min<uint64_t>(dims, 64)), 256, 0, s>>>(c->d_jobs + j0, nj, (uint32_t)dims,
-                                                                                                             sm->seed, c->d_dim_hash);
-                tm.launches += 1;
-                gcfg.sampler.hash_table = c->d_dim_hash;
-                gcfg.sampler.n_hash_dims = (uint32_t)dims;
-                gcfg.sampler.hash_stride = nj;
-            }
-            for (uint32_t s0 = 0; s0 < samples_per_job; s0 += m) {
-                Batch bt;
-                bt.jobs = c->d_jobs + j0;
-                bt.n_jobs = nj;
-                bt.div_jobs = FastDiv::make(nj);
-                bt.sample_off = s0;
-                bt.n_samples = std::min(m, samples_per_job - s0);
-                bt.n_paths = nj * bt.n_samples;
-                rc = run_batch(c, sc, gcfg, bt, accumulate, d_film, &st, &tm);
-                if (rc != YK_OK) return rc;
-                done += bt.n_paths;
-                if (opts && opts->progress && opts->progress(opts->progress_user, done, total_paths)) {
-                    cudaStreamSynchronize(s);
-                    return yk_set_error(YK_ERR_CANCELLED, "yk_render: cancelled by the progress callback");
+        bool cancelled = false;
+        for (size_t g0 = 0; g0 < n_groups && !cancelled; g0 += n_pipes) {
+            for (uint32_t s0 = 0; s0 < samples_per_job && !cancelled; s0 += m) {
+                for (int pi = 0; pi < n_pipes && g0 + pi < n_groups && !cancelled; ++pi) {
+                    Pipe& p = c->pipe[pi];
+                    const size_t group = g0 + pi, j0 = group * jobs_per_batch;
+                    const uint32_t nj = (uint32_t)std::min<size_t>(jobs_per_batch, jobs.size() - j0);
+                    RenderCfg gcfg = cfg;
+                    if (sm->kind == YK_SAMPLER_STRATIFIED) {
+                        // tabulate the (pixel, dimension) hashes of this pixel group once for all of its samples
+                        uint64_t dims = 2;
+                        if (in->kind == YK_INTEGRATOR_PATH) dims = 2 + (uint64_t)in->max_depth * (2ull * sc->dev.n_lights + 3);
+                        else if (in->kind == YK_INTEGRATOR_WHITTED)
+                            dims = 2 + 2ull * sc->dev.n_lights * ((1ull << std::min(in->max_depth, 8u)) - 1);
+                        dims = std::min<uint64_t>(dims, std::min<uint64_t>(4096, (256ull << 20) / (4ull * nj)));  // the rest is hashed on the fly
+                        if (p.hash_group != group) {
+                            const size_t need = (size_t)dims * nj;
+                            if (p.dim_hash_cap < need) {
+                                CUDA_TRY(cudaStreamSynchronize(p.stream));
+                                cudaFree(p.d_dim_hash);
+                                p.d_dim_hash = nullptr;
+                                p.dim_hash_cap = 0;
+                                CUDA_TRY(cudaMalloc((void**)&p.d_dim_hash, need * sizeof(uint32_t)));
+                                p.dim_hash_cap = need;
+                            }
+                            k_dim_hashes<<<dim3((nj + 255) / 256, (unsigned)std::min<uint64_t>(dims, 64)), 256, 0, p.stream>>>(
+                                c->d_jobs + j0, nj, (uint32_t)dims, sm->seed, p.d_dim_hash);
+                            tm.launches += 1;
+                            p.hash_group = group;
+                        }
+                        gcfg.sampler.hash_table = p.d_dim_hash;
+                        gcfg.sampler.n_hash_dims = (uint32_t)dims;
+                        gcfg.sampler.hash_stride = nj;
+                    }
+                    Batch bt;
+                    bt.jobs = c->d_jobs + j0;
+                    bt.n_jobs = nj;
+                    bt.div_jobs = FastDiv::make(nj);
+                    bt.sample_off = s0;
+                    bt.n_samples = std::min(m, samples_per_job - s0);
+                    bt.n_paths = nj * bt.n_samples;
+                    rc = run_batch(c, &p, sc, gcfg, bt, accumulate, d_film, &tm, &done);
+                    if (rc != YK_OK) { cudaDeviceSynchronize(); return rc; }
+                    if (opts && opts->progress && opts->progress(opts->progress_user, done, total_paths)) cancelled = true;
                 }
             }
         }
+        for (int pi = 0; pi < n_pipes; ++pi) {
+            Pipe& p = c->pipe[pi];
+            CUDA_TRY(cudaMemcpyAsync(p.h_totals, p.wave.totals, sizeof(Totals), cudaMemcpyDeviceToHost, p.stream));
+            for (int k = 0; k < kRing; ++k)
+                if ((rc = retire_slot(&p, k, &tm, &done)) != YK_OK) return rc;
+            CUDA_TRY(cudaStreamSynchronize(p.stream));
+            const Totals& t = *p.h_totals;
+            totals.closest_nodes += t.closest_nodes; totals.closest_tris += t.closest_tris;
+            totals.any_nodes += t.any_nodes; totals.any_tris += t.any_tris;
+            totals.hit_hash += t.hit_hash; totals.shadow_rays += t.shadow_rays; totals.closest_rays += t.closest_rays;
+        }
+        if (cancelled) return yk_set_error(YK_ERR_CANCELLED, "yk_render: cancelled by the progress callback");
+        if (opts && opts->progress) opts->progress(opts->progress_user, done, total_paths);
         if (!accumulate) {
             const unsigned g = (unsigned)((jobs.size() + 255) / 256);
             k_film_store<<<g, 256, 0, s>>>(c->d_jobs, (uint32_t)jobs.size(), c->d_accum, d_film, fs->res_x, (float)spp);
             tm.launches += 1;
         }
-        CUDA_TRY(cudaMemcpyAsync(c->h_totals, c->wave.totals, sizeof(Totals), cudaMemcpyDeviceToHost, s));
         st.samples = total_paths;
     }
-    CUDA_TRY(cudaEventRecord(c->ev[7], s));
+    CUDA_TRY(cudaEventRecord(c->ev[3], s));
     if (!on_device) {
         CUDA_TRY(cudaMemcpyAsync(film_rgb, d_film, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (opts && opts->hit_ids)
@@ -1548,16 +1691,15 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     if (stats) {
-        if (!jobs.empty()) {
-            st.closest_nodes = c->h_totals->closest_nodes;
-            st.closest_tris = c->h_totals->closest_tris;
-            st.any_nodes = c->h_totals->any_nodes;
-            st.any_tris = c->h_totals->any_tris;
-            st.primary_hit_hash = c->h_totals->hit_hash;
-            st.shadow_rays = c->h_totals->shadow_rays;
-        }
+        st.closest_nodes = totals.closest_nodes;
+        st.closest_tris = totals.closest_tris;
+        st.any_nodes = totals.any_nodes;
+        st.any_tris = totals.any_tris;
+        st.primary_hit_hash = totals.hit_hash;
+        st.shadow_rays = totals.shadow_rays;
+        st.ray_count = totals.closest_rays;
         float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
         st.device_ms = ms;
         st.trace_closest_ms = tm.closest;
         st.trace_any_ms = tm.any;
