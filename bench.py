@@ -34,7 +34,7 @@ WORKLOAD = "cornell-box 1024x1024, Path max_depth 8 (Russian roulette after 3 bo
 RES = (1024, 1024)
 SPP_NX = SPP_NY = 32
 MAX_DEPTH = 8
-CPU_SAMPLE_SPP = 4  # bounded CPU sample: sample indices 0..3 of every pixel (accumulate-mode tiles)
+CPU_SAMPLE_SPP = 32  # bounded CPU sample: sample indices 0..31 of every pixel (accumulate-mode tiles), ~10 s on 15 host threads
 
 
 def workload(xf):
@@ -44,6 +44,19 @@ def workload(xf):
     sampler = D.SamplerType.stratified(SPP_NX, SPP_NY, jitter=True)
     integ = D.IntegratorType.path(MAX_DEPTH)
     return scene, cam, film, sampler, integ
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this command (profiles/<round>/traffic.json, written by scripts/ncu_traffic.py). None when absent."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for rnd in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        f = os.path.join(pdir, rnd, "traffic.json")
+        if os.path.exists(f):
+            with open(f) as fh:
+                best = json.load(fh)
+    return best
 
 
 def peaks():
@@ -244,6 +257,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
+        traffic = ncu_traffic()
         alg_bytes = 32 * agg["closest_nodes"] + 36 * agg["closest_tris"]
         launches = max(agg["trace_closest_launches"], 1)
         t_closest = max(agg["trace_closest_ms"], 1e-9) / 1e3
@@ -253,15 +267,17 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tile_dim": 16, "partition": f"spiral tiles interleaved over {world} rank(s)",
-                       "l2": "256 MB L2 flush between steps; wavefront state (~0.7 GB/batch) exceeds the 126 MB L2, the 37-node scene is cache-resident by nature"},
+                       "l2": "256 MB L2 flush between steps; wavefront state (~0.6 GB/batch) exceeds the 126 MB L2, the 37-node scene is cache-resident by nature",
+                       "wavefront": "4 Mi paths per batch, queue lengths on the device (no host sync per bounce)"},
             "mrays_per_s": float(counts[0].item()) / (ms_total / 1e3) / 1e6,
             "mrays_per_s_total": float((counts[0] + counts[1]).item()) / (ms_total / 1e3) / 1e6,
             "gpu_launches": int(counts[2].item()),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "includes": "yk_scene_create + yk_render with host film (pinned staging inside the library)"},
-            "roofline": {"bound": "hbm", "kernel": "k_trace<false> (trace_closest)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / launches, "avg_launch_ms": 1e3 * t_closest / launches,
                          "launches": launches, "share_of_step": agg["trace_closest_ms"] / ms_total,
                          "note": "rank 0; 32 B per node visit + 36 B per triangle test (SURVEY.md §8d); the 37-node scene is L1/L2-resident, so achieved can exceed the HBM peak"},

@@ -144,7 +144,7 @@ class Renderer:
     def render(self, scene: Scene, camera_params: D.CameraParameters, film: D.FilmSettings, sampler: D.SamplerType,
                integrator: D.IntegratorType, tiles: Optional[np.ndarray] = None, want_hit_ids: bool = False,
                aux_sample: int = 0, wavefront_paths: int = 0, film_out: Optional[np.ndarray] = None,
-               device_film_ptr: Optional[int] = None, progress=None) -> RenderResult:
+               device_film_ptr: Optional[int] = None, progress=None, pipes: int = 0) -> RenderResult:
         cam = make_camera(camera_params, film)
         if tiles is None:
             tiles = film_tiles(film)
@@ -153,6 +153,7 @@ class Renderer:
         opts = capi.RenderOpts()
         opts.wavefront_paths = wavefront_paths
         opts.aux_sample = aux_sample
+        opts.pipes = pipes
         hit_ids = None
         if device_film_ptr is not None:
             opts.flags |= capi.RENDER_FILM_ON_DEVICE

@@ -116,7 +116,7 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64)
 
 class RenderOpts(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("wavefront_paths", C.c_uint32), ("hit_ids", C.c_void_p), ("aux_sample", C.c_uint32),
-                ("_pad", C.c_uint32), ("progress", PROGRESS_FN), ("progress_user", C.c_void_p)]
+                ("pipes", C.c_uint32), ("progress", PROGRESS_FN), ("progress_user", C.c_void_p)]
 
 
 class Stats(C.Structure):

@@ -1089,7 +1089,7 @@ struct yk_context {
     int32_t* d_hit_ids = nullptr;
     size_t film_cap = 0;
     int occ_trace_closest = 0, occ_trace_any = 0;
-    int n_pipes = kMaxPipes;
+    int n_pipes_env = 0;  // YK_PIPES override (development)
 };
 
 struct yk_scene {
@@ -1317,7 +1317,7 @@ int yk_context_create(int device_id, yk_context** out) {
     CUDA_TRY(cudaEventDestroy(c->ev[3]));
     CUDA_TRY(cudaEventCreate(&c->ev[2]));  // timing pair around the whole render
     CUDA_TRY(cudaEventCreate(&c->ev[3]));
-    if (const char* np = getenv("YK_PIPES")) c->n_pipes = std::max(1, std::min(kMaxPipes, atoi(np)));
+    if (const char* np = getenv("YK_PIPES")) c->n_pipes_env = std::max(1, std::min(kMaxPipes, atoi(np)));
     for (int i = 0; i < kMaxPipes; ++i) {
         Pipe& p = c->pipe[i];
         if (i == 0) p.stream = c->stream;
@@ -1592,7 +1592,13 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         // Pipes: pixel groups alternate between the streams, so one group's latency-bound shading overlaps the other's
         // issue-bound traversal. A pixel's samples stay on one pipe, in order (the film sum is order-dependent).
         // The accumulating film adds with atomics across tiles, so it keeps to one stream.
-        int n_pipes = accumulate ? 1 : c->n_pipes;
+        // Default: a second pipe only where a bounce is many small launches (several material kinds / lights), measured
+        // +17 % on the config-4 room and +5 % on the Cornell box (profiles/r01); YK_PIPES / opts->pipes override.
+        int n_pipes = c->n_pipes_env > 0 ? c->n_pipes_env
+                                         : ((__builtin_popcount(sc->material_kinds) + (int)sc->dev.n_lights >= 5) ? 2 : 1);
+        if (opts && opts->pipes) n_pipes = (int)opts->pipes;
+        n_pipes = std::max(1, std::min(kMaxPipes, n_pipes));
+        if (accumulate) n_pipes = 1;
         if (n_pipes > 1 && jobs.size() <= jobs_per_batch) {  // one group only: split it if that leaves decent batches
             if ((uint64_t)(jobs.size() / 2) * m >= (1u << 20)) jobs_per_batch = (uint32_t)((jobs.size() + 1) / 2);
             else n_pipes = 1;
