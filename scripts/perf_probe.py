@@ -30,6 +30,15 @@ if which == "capsweep":
     s, c = scenes.cornell(xf, light="rect", tall_box="glass")
     for cap in (1 << 22, 1 << 21, 1 << 20, 1 << 19, 1 << 18):
         probe(f"cornell 1024^2 path8 16spp cap {cap}", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=2, wavefront_paths=cap)
+if which == "terrain":
+    import time as _t
+    t0 = _t.time(); s, c = scenes.terrain_room(xf); print(f"terrain scene desc {_t.time()-t0:.1f}s", flush=True)
+    probe("terrain 10M path8 3840x2160 4spp", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8), reps=2)
+    probe("terrain 10M bvh-intersections 3840x2160", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.uniform(1), D.IntegratorType.bvh_intersections(), reps=2)
+if which == "hf16":
+    s, c = scenes.heightfield(xf, 708, 708)
+    probe("heightfield 1M path8 1920x1080 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=2)
+    probe("heightfield 1M bvh 1920x1080 uniform 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.uniform(16), D.IntegratorType.bvh_intersections(), reps=2)
 if which == "hf4":
     s, c = scenes.heightfield(xf, 708, 708)
     probe("heightfield 1M path8 1920x1080 4spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8), reps=1)

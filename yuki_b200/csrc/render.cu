@@ -259,9 +259,18 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, IterCounters* first) {
 //    three index offsets instead of 18 selects.
 constexpr uint32_t kNoNode = 0xffffffffu;
 constexpr uint32_t kChunk = 64;
-constexpr int kRefillBelow = 22;
-constexpr int kNodePhaseMin = 14;
-constexpr int kShortStack = 48;
+#ifndef YK_REFILL_BELOW
+#define YK_REFILL_BELOW 22
+#endif
+#ifndef YK_NODE_PHASE_MIN
+#define YK_NODE_PHASE_MIN 14
+#endif
+constexpr int kRefillBelow = YK_REFILL_BELOW;
+constexpr int kNodePhaseMin = YK_NODE_PHASE_MIN;
+#ifndef YK_SHORT_STACK
+#define YK_SHORT_STACK 24
+#endif
+constexpr int kShortStack = YK_SHORT_STACK;
 constexpr uint32_t kSpBase = kTraceThreads;  // stack pointer (in words, depth * kTraceThreads) of an empty stack
 
 struct TraceLane {
