@@ -236,6 +236,20 @@ void yk_xf_vec(const yk_transform*, const float* v3, float* out3);
 void yk_xf_normal(const yk_transform*, const float* n3, float* out3);
 /* Light constructors (`new` in lights/point_light.rs, spot_light.rs, rectangular_light.rs, distant_light.rs) */
 int yk_light_make(const yk_light_desc*, yk_light* out);
+/* PLY mesh file -> vertex / index arrays: what scene/ply.rs:19-156 takes from a file (vertex x y z [nx ny nz] [u v]
+ * as float properties, faces as int/uint lists, fan-triangulated). ASCII and both binary byte orders. The arrays stay
+ * owned by the handle. The fit-to-unit transform and the Scene::ply defaults are applied by the caller. */
+typedef struct yk_ply yk_ply;
+typedef struct {
+    uint32_t n_points, n_indices;
+    const float* points;      /* n_points * 3 */
+    const float* normals;     /* n_points * 3 or NULL */
+    const float* uvs;         /* n_points * 2 or NULL */
+    const uint32_t* indices;  /* n_indices = 3 * triangles */
+} yk_ply_data;
+int yk_ply_load(const char* path, yk_ply** out);
+void yk_ply_view(const yk_ply*, yk_ply_data* out);
+void yk_ply_destroy(yk_ply*);
 /* Diagnostic: number of numerators for which the kernels' division-by-invariant (csrc/yk_fastdiv.h; stands in for the
    `/` and `%` of stratified.rs:127-128,177 and the batch index arithmetic) differs from n / d. Must return 0. */
 uint64_t yk_selftest_fastdiv(uint32_t d, const uint32_t* numerators, uint64_t count);

@@ -115,6 +115,22 @@ def film_tiles(film: D.FilmSettings) -> np.ndarray:
     return out
 
 
+def load_ply(path: str):
+    """scene/ply.rs `load` up to the index buffer: returns (points (N,3), indices (T*3,), normals (N,3)|None, uvs (N,2)|None)."""
+    h = C.c_void_p()
+    capi.check(capi.lib().yk_ply_load(str(path).encode(), C.byref(h)))
+    try:
+        v = capi.PlyData()
+        capi.lib().yk_ply_view(h, C.byref(v))
+        pts = np.ctypeslib.as_array(v.points, shape=(v.n_points, 3)).copy() if v.n_points else np.zeros((0, 3), np.float32)
+        idx = np.ctypeslib.as_array(v.indices, shape=(v.n_indices,)).copy() if v.n_indices else np.zeros((0,), np.uint32)
+        nrm = np.ctypeslib.as_array(v.normals, shape=(v.n_points, 3)).copy() if v.normals and v.n_points else None
+        uvs = np.ctypeslib.as_array(v.uvs, shape=(v.n_points, 2)).copy() if v.uvs and v.n_points else None
+    finally:
+        capi.lib().yk_ply_destroy(h)
+    return pts, idx, nrm, uvs
+
+
 def bvh_build(tri_vertices: np.ndarray, max_shapes_in_node=1, split_method=D.SPLIT_SAH):
     """BoundingVolumeHierarchy::new over world-space triangles (T,3,3) -> (nodes, order)."""
     v = np.ascontiguousarray(tri_vertices, np.float32).reshape(-1, 9)

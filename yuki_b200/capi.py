@@ -114,6 +114,11 @@ class SceneDescFlat(C.Structure):
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64)
 
 
+class PlyData(C.Structure):
+    _fields_ = [("n_points", C.c_uint32), ("n_indices", C.c_uint32), ("points", C.POINTER(C.c_float)),
+                ("normals", C.POINTER(C.c_float)), ("uvs", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_uint32))]
+
+
 class RenderOpts(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("wavefront_paths", C.c_uint32), ("hit_ids", C.c_void_p), ("aux_sample", C.c_uint32),
                 ("pipes", C.c_uint32), ("progress", PROGRESS_FN), ("progress_user", C.c_void_p)]
@@ -137,7 +142,7 @@ EXPORTS = [
     "yk_last_error", "yk_context_create", "yk_context_destroy", "yk_scene_create", "yk_scene_destroy", "yk_render",
     "yk_context_stream", "yk_bvh_build", "yk_host_scene_build", "yk_host_scene_destroy", "yk_host_scene_flat", "yk_camera_make",
     "yk_film_tiles", "yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_new", "yk_xf_look_at",
-    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv",
+    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy",
 ]
 
 _lib = None
@@ -172,6 +177,11 @@ def lib():
     L.yk_camera_make.argtypes = [C.POINTER(CameraParams), u32, u32, C.POINTER(Camera)]
     L.yk_film_tiles.argtypes = [u32, u32, u32, vp, u32]
     L.yk_film_tiles.restype = u32
+    L.yk_ply_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.yk_ply_view.argtypes = [vp, C.POINTER(PlyData)]
+    L.yk_ply_view.restype = None
+    L.yk_ply_destroy.argtypes = [vp]
+    L.yk_ply_destroy.restype = None
     L.yk_selftest_fastdiv.argtypes = [u32, vp, C.c_uint64]
     L.yk_selftest_fastdiv.restype = C.c_uint64
     T = C.POINTER(Transform)

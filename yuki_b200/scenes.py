@@ -155,6 +155,59 @@ def heightfield(xf, nx=708, nz=708, seed=1, split_method=D.SPLIT_SAH, max_shapes
     return s, cam
 
 
+def ply(xf, path, split_method=D.SPLIT_SAH, max_shapes_in_node=1):
+    """`Scene::ply` (scene/mod.rs:99-150) on a PLY file: the mesh scaled to fit 2 units around the origin
+    (scene/ply.rs:99-108), white Matte, point light (5,5,0) I=600, camera (2,2,2) -> origin, fov X 40."""
+    from . import api
+    pts, idx, nrm, uvs = api.load_ply(path)
+    s = D.SceneDesc(split_method=split_method, max_shapes_in_node=max_shapes_in_node)
+    white = s.add_material(D.Material(D.MAT_MATTE, (s.add_texture(D.Texture.constant(1.0)), s.add_texture(D.Texture.constant(0.0)))))
+    s.meshes.append(D.Mesh(fit_to_unit(xf, pts), pts, idx, white, normals=nrm, uvs=uvs))
+    s.lights.append(D.Light(D.LIGHT_POINT, xf.translation((5.0, 5.0, 0.0)), (600.0, 600.0, 600.0)))
+    cam = D.CameraParameters((2.0, 2.0, 2.0), (0.0, 0.0, 0.0), fov_axis=D.FOV_X, fov_deg=40.0)
+    return s, cam
+
+
+def write_ply(path, points, indices, normals=None, uvs=None, fmt="binary_little_endian", quads=False):
+    """Test / tooling helper: writes a mesh the way the reference's inputs look (vertex x y z [nx ny nz] [u v] float,
+    face list uchar int vertex_indices). `quads=True` merges consecutive triangle pairs (a b c)(a c d) into 4-gons."""
+    points = np.asarray(points, np.float32)
+    idx = np.asarray(indices, np.uint32).reshape(-1, 3)
+    faces = [list(t) for t in idx]
+    if quads:
+        faces = []
+        k = 0
+        while k < len(idx):
+            if k + 1 < len(idx) and idx[k][0] == idx[k + 1][0] and idx[k][2] == idx[k + 1][1]:
+                faces.append([idx[k][0], idx[k][1], idx[k][2], idx[k + 1][2]])
+                k += 2
+            else:
+                faces.append(list(idx[k]))
+                k += 1
+    cols = [points]
+    names = ["x", "y", "z"]
+    if normals is not None:
+        cols.append(np.asarray(normals, np.float32)); names += ["nx", "ny", "nz"]
+    if uvs is not None:
+        cols.append(np.asarray(uvs, np.float32)); names += ["u", "v"]
+    verts = np.concatenate(cols, axis=1).astype(np.float32)
+    header = ["ply", f"format {fmt} 1.0", "comment yuki_b200 test mesh", f"element vertex {len(verts)}"]
+    header += [f"property float {n}" for n in names]
+    header += [f"element face {len(faces)}", "property list uchar int vertex_indices", "end_header"]
+    with open(path, "wb") as f:
+        f.write(("\n".join(header) + "\n").encode())
+        if fmt == "ascii":
+            for v in verts:
+                f.write((" ".join(repr(float(x)) for x in v) + "\n").encode())
+            for fc in faces:
+                f.write((str(len(fc)) + " " + " ".join(str(int(i)) for i in fc) + "\n").encode())
+        else:
+            e = "<" if fmt == "binary_little_endian" else ">"
+            f.write(verts.astype(e + "f4").tobytes())
+            for fc in faces:
+                f.write(np.uint8(len(fc)).tobytes() + np.asarray(fc, e + "i4").tobytes())
+
+
 def _box(lo, hi):
     x0, y0, z0 = lo
     x1, y1, z1 = hi
