@@ -236,6 +236,19 @@ void yk_xf_vec(const yk_transform*, const float* v3, float* out3);
 void yk_xf_normal(const yk_transform*, const float* n3, float* out3);
 /* Light constructors (`new` in lights/point_light.rs, spot_light.rs, rectangular_light.rs, distant_light.rs) */
 int yk_light_make(const yk_light_desc*, yk_light* out);
+/* ---- after the path: film output ---------------------------------------------------------------- */
+/* app/util.rs:89-110 `write_exr`: the film as an OpenEXR file with float R, G, B channels (uncompressed scanlines). */
+int yk_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgb);
+/* app/renderpasses/tonemap.rs:318-399: divide by the tile's sample count (accumulating films; `tile_samples` may be
+ * NULL), exposure, ACES filmic fit, clamp to [0,1]. Host buffers; runs on the context's GPU. */
+int yk_tonemap_filmic(yk_context*, const float* film_rgb, uint32_t res_x, uint32_t res_y, const float* tile_samples, uint32_t n_tiles,
+                      uint32_t tile_dim, float exposure, float* out_rgb);
+/* app/renderpasses/tonemap.rs:401-432, 447-472: blue->green->red heat map of one channel (0 R, 1 G, 2 B, 3 luminance;
+ * as in the shader, channel 0 displays luminance). auto_range != 0: [min,max] come from `find_min_max` over the film and
+ * are written back; otherwise the given values are used. */
+int yk_heatmap(yk_context*, const float* film_rgb, uint32_t res_x, uint32_t res_y, uint32_t channel, int auto_range, float* min_val,
+               float* max_val, float* out_rgb);
+
 /* PLY mesh file -> vertex / index arrays: what scene/ply.rs:19-156 takes from a file (vertex x y z [nx ny nz] [u v]
  * as float properties, faces as int/uint lists, fan-triangulated). ASCII and both binary byte orders. The arrays stay
  * owned by the handle. The fit-to-unit transform and the Scene::ply defaults are applied by the caller. */

@@ -207,3 +207,67 @@ def test_round_trip_properties_at_full_size(gpu_ctx, xf):
     assert np.isfinite(full.film).all() and (full.film >= 0).all()
     assert full.stats.samples == 1024 * 1024 * 4
     dev.close()
+
+
+def test_async_renderer_launch_check_status_kill(gpu_ctx, xf):
+    """renderer/mod.rs:53-177: launch() returns at once, check_status() reports progress and then Finished{ray_count},
+    kill() stops a running task; the film equals the blocking render's."""
+    import time
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    fs = D.FilmSettings((96, 96), 16)
+    smp, integ = D.SamplerType.stratified(4, 4), D.IntegratorType.path(6)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    ref = rn.render(dev, cam, fs, smp, integ)
+    film = api.Film(fs)
+    rn.launch(dev, cam, film, smp, integ)
+    assert rn.is_active()
+    finished, deadline = None, time.time() + 60
+    while finished is None and time.time() < deadline:
+        st = rn.check_status()
+        if isinstance(st, api.RenderFinished):
+            finished = st
+        elif isinstance(st, api.RenderProgress):
+            assert 0 <= st.tiles_done <= st.tiles_total == 36
+        time.sleep(0.001)
+    assert finished is not None and not rn.is_active()
+    assert finished.ray_count == ref.stats.ray_count
+    assert np.array_equal(film.pixels.view(np.uint32), ref.film.view(np.uint32)) and film.dirty
+    # a long render is cut short by kill() (polled between wavefront batches)
+    big = D.FilmSettings((512, 512), 16)
+    film2 = api.Film(big)
+    t0 = time.time()
+    rn.launch(dev, cam, film2, D.SamplerType.stratified(32, 32), D.IntegratorType.path(8), wavefront_paths=1 << 18)
+    time.sleep(0.05)
+    rn.kill()
+    assert not rn.is_active() and rn.check_status() is None
+    assert time.time() - t0 < 20.0
+
+
+def test_accumulating_launch_counts_samples_and_matches_the_mean(gpu_ctx, xf):
+    """render_manager.rs:135-143 + film.rs:260-272: an accumulating launch renders one tile list per sample index and adds
+    them in order; pixels / samples[tile] is then bit-identical to the averaging render (same ascending-sample sums)."""
+    import time
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    fs = D.FilmSettings((80, 48), 16)
+    acc = D.FilmSettings((80, 48), 16, accumulate=True)
+    smp, integ = D.SamplerType.stratified(3, 3), D.IntegratorType.path(5)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    ref = rn.render(dev, cam, fs, smp, integ).film
+    film = api.Film(acc)
+    rn.launch(dev, cam, film, smp, integ)
+    deadline = time.time() + 60
+    while rn.is_active() and time.time() < deadline:
+        rn.check_status()
+        time.sleep(0.001)
+    assert not rn.is_active() and rn.last_error is None
+    assert np.all(film.samples == 9)
+    mean = (film.pixels / np.float32(9.0)).astype(np.float32)
+    assert np.array_equal(mean.view(np.uint32), ref.view(np.uint32))
+    # a single forced sample (force_single_sample, sampling/mod.rs:21-42) adds exactly one more
+    rn.launch(dev, cam, film, smp, integ, force_single_sample=True)
+    while rn.is_active() and time.time() < deadline:
+        rn.check_status()
+        time.sleep(0.001)
+    assert np.all(film.samples == 10)

@@ -8,6 +8,9 @@ only marshals descriptors. It fails loudly when the CUDA library or a GPU is mis
 from __future__ import annotations
 
 import ctypes as C
+import threading
+import time
+from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
@@ -115,6 +118,39 @@ def film_tiles(film: D.FilmSettings) -> np.ndarray:
     return out
 
 
+def write_exr(path: str, film: np.ndarray):
+    """app/util.rs `write_exr`: film (H, W, 3) f32 -> OpenEXR with float R, G, B channels."""
+    film = np.ascontiguousarray(film, np.float32)
+    assert film.ndim == 3 and film.shape[2] == 3
+    capi.check(capi.lib().yk_write_exr(str(path).encode(), film.shape[1], film.shape[0], capi.fptr(film)))
+
+
+def tonemap_filmic(ctx: Context, film: np.ndarray, exposure: float = 1.0, tile_samples: Optional[np.ndarray] = None,
+                   tile_dim: int = 16) -> np.ndarray:
+    """ToneMapType::Filmic (app/renderpasses/tonemap.rs:318-399). `tile_samples[flat_tile]` = Film::samples (film.rs:74)."""
+    film = np.ascontiguousarray(film, np.float32)
+    out = np.empty_like(film)
+    ts, n_tiles = None, 0
+    if tile_samples is not None:
+        ts = np.ascontiguousarray(tile_samples, np.float32).reshape(-1)
+        n_tiles = len(ts)
+    capi.check(capi.lib().yk_tonemap_filmic(ctx._h, capi.fptr(film), film.shape[1], film.shape[0], capi.fptr(ts) if ts is not None else None,
+                                             n_tiles, tile_dim, float(exposure), capi.fptr(out)))
+    return out
+
+
+def heatmap(ctx: Context, film: np.ndarray, channel: int = 0, value_range=None):
+    """ToneMapType::Heatmap (app/renderpasses/tonemap.rs:401-432); value_range None = `find_min_max` (:447-472).
+    Returns (image, (min, max))."""
+    film = np.ascontiguousarray(film, np.float32)
+    out = np.empty_like(film)
+    lo = C.c_float(0.0 if value_range is None else value_range[0])
+    hi = C.c_float(0.0 if value_range is None else value_range[1])
+    capi.check(capi.lib().yk_heatmap(ctx._h, capi.fptr(film), film.shape[1], film.shape[0], int(channel), 1 if value_range is None else 0,
+                                     C.byref(lo), C.byref(hi), capi.fptr(out)))
+    return out, (lo.value, hi.value)
+
+
 def load_ply(path: str):
     """scene/ply.rs `load` up to the index buffer: returns (points (N,3), indices (T*3,), normals (N,3)|None, uvs (N,2)|None)."""
     h = C.c_void_p()
@@ -143,6 +179,39 @@ def bvh_build(tri_vertices: np.ndarray, max_shapes_in_node=1, split_method=D.SPL
     return nodes[: n_nodes.value].copy(), order
 
 
+class Film:
+    """`Film` (film.rs:60-101): RGB f32 pixels, row-major, plus — for accumulating renders — the per-tile sample counts
+    the tone-map pass divides by (`samples[tile.index]`, film.rs:74, 270)."""
+
+    def __init__(self, settings: D.FilmSettings):
+        self.settings = settings
+        w, h = int(settings.res[0]), int(settings.res[1])
+        self.pixels = np.zeros((h, w, 3), np.float32)
+        n_tiles = ((w + settings.tile_dim - 1) // settings.tile_dim) * ((h + settings.tile_dim - 1) // settings.tile_dim)
+        self.samples = np.zeros(n_tiles, np.uint16) if settings.accumulate else None
+        self.dirty = False
+
+    def clear(self):
+        self.pixels[...] = 0.0
+        if self.samples is not None:
+            self.samples[...] = 0
+        self.dirty = True
+
+
+@dataclass
+class RenderProgress:        # RenderStatus::Progress, renderer/mod.rs:21-28
+    active_threads: int
+    tiles_done: int
+    tiles_total: int
+    approx_remaining_s: float
+    current_rays_per_s: float
+
+
+@dataclass
+class RenderFinished:        # RenderStatus::Finished, renderer/mod.rs:29-31
+    ray_count: int
+
+
 class RenderResult:
     def __init__(self, film, hit_ids, stats):
         self.film = film
@@ -156,6 +225,99 @@ class Renderer:
 
     def __init__(self, ctx: Context):
         self.ctx = ctx
+        self._thread = None
+        self._lock = threading.Lock()
+        self._kill = False
+        self._render_id = 0
+        self._messages = []
+        self._in_progress = False
+        self.last_result = None
+        self.last_error = None
+
+    # ---- the reference's asynchronous surface: launch / check_status / kill (renderer/mod.rs:53-177) ----
+    def is_active(self) -> bool:
+        return self._in_progress
+
+    def launch(self, scene: Scene, camera_params: D.CameraParameters, film: Film, sampler: D.SamplerType, integrator: D.IntegratorType,
+               film_settings: Optional[D.FilmSettings] = None, force_single_sample: bool = False, **render_kw):
+        """Starts a render into `film` on a background thread, overriding a running one (renderer/mod.rs:131-177).
+        Accumulating film settings render one tile list per sample index, in order (render_manager.rs:135-143) and add
+        into the film; otherwise the film's tiles are overwritten with the per-pixel mean."""
+        self.kill()
+        fs = film_settings or film.settings
+        assert tuple(fs.res) == tuple(film.settings.res), "Film does not match settings"   # film.rs:421
+        if force_single_sample:   # SamplerType::instantiate(force_single_sample), sampling/mod.rs:21-42
+            sampler = D.SamplerType(kind=sampler.kind, nx=1, ny=1, jitter=sampler.jitter, seed=sampler.seed)
+        base = film_tiles(fs)
+        if fs.accumulate:
+            tiles = []
+            for smp in range(sampler.samples_per_pixel()):
+                t = base.copy()
+                t["sample"] = smp
+                tiles.append(t)
+            tiles = np.concatenate(tiles)
+        else:
+            tiles = base
+        self._render_id += 1
+        rid = self._render_id
+        self._kill = False
+        self._in_progress = True
+        self.last_result = None
+        self.last_error = None
+        t0 = time.perf_counter()
+
+        def progress(done, total):
+            now = time.perf_counter() - t0
+            frac = done / max(total, 1)
+            with self._lock:
+                if rid == self._render_id:
+                    self._messages.append(RenderProgress(1, int(frac * len(tiles)), len(tiles),
+                                                         (now / frac - now) if frac > 0 else float("inf"),
+                                                         0.0))
+            return self._kill
+
+        def work():
+            try:
+                res = self.render(scene, camera_params, fs, sampler, integrator, tiles=tiles, film_out=film.pixels, progress=progress,
+                                  **render_kw)
+                if fs.accumulate and film.samples is not None:
+                    np.add.at(film.samples, tiles["index"], 1)   # samples[tile.index] += 1, film.rs:270
+                film.dirty = True
+                with self._lock:
+                    if rid == self._render_id:
+                        self.last_result = res
+                        self._messages.append(RenderFinished(int(res.stats.ray_count)))
+            except capi.YukiGpuError as e:
+                with self._lock:
+                    if rid == self._render_id and e.code != capi.ERR_CANCELLED:
+                        self.last_error = e
+                        self._messages.append(RenderFinished(0))
+
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def check_status(self):
+        """Latest `RenderProgress`, or `RenderFinished` once the task is done; None when nothing new (renderer/mod.rs:61-120)."""
+        ret = None
+        if self._in_progress:
+            with self._lock:
+                msgs, self._messages = self._messages, []
+            for m in msgs:
+                ret = m
+                if isinstance(m, RenderFinished):
+                    self._in_progress = False
+                    break
+        return ret
+
+    def kill(self):
+        """Stops the running task (polled between wavefront batches) and joins the worker (renderer/mod.rs:122-128)."""
+        if self._thread is not None:
+            self._kill = True
+            self._thread.join()
+            self._thread = None
+        with self._lock:
+            self._messages = []
+        self._in_progress = False
 
     def render(self, scene: Scene, camera_params: D.CameraParameters, film: D.FilmSettings, sampler: D.SamplerType,
                integrator: D.IntegratorType, tiles: Optional[np.ndarray] = None, want_hit_ids: bool = False,

@@ -17,6 +17,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("YUKI_GPU_LIB") or os.path.join(_HERE, "libyuki_gpu.so")  # override: A/B builds during development
 
 
+ERR_CANCELLED = -5  # YK_ERR_CANCELLED
+
+
 class YukiGpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"yuki_gpu error {code}: {msg}")
@@ -142,7 +145,7 @@ EXPORTS = [
     "yk_last_error", "yk_context_create", "yk_context_destroy", "yk_scene_create", "yk_scene_destroy", "yk_render",
     "yk_context_stream", "yk_bvh_build", "yk_host_scene_build", "yk_host_scene_destroy", "yk_host_scene_flat", "yk_camera_make",
     "yk_film_tiles", "yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_new", "yk_xf_look_at",
-    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy",
+    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy", "yk_write_exr", "yk_tonemap_filmic", "yk_heatmap",
 ]
 
 _lib = None
@@ -177,6 +180,9 @@ def lib():
     L.yk_camera_make.argtypes = [C.POINTER(CameraParams), u32, u32, C.POINTER(Camera)]
     L.yk_film_tiles.argtypes = [u32, u32, u32, vp, u32]
     L.yk_film_tiles.restype = u32
+    L.yk_write_exr.argtypes = [C.c_char_p, u32, u32, fp]
+    L.yk_tonemap_filmic.argtypes = [vp, fp, u32, u32, fp, u32, u32, C.c_float, fp]
+    L.yk_heatmap.argtypes = [vp, fp, u32, u32, u32, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), fp]
     L.yk_ply_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.yk_ply_view.argtypes = [vp, C.POINTER(PlyData)]
     L.yk_ply_view.restype = None

@@ -1628,15 +1628,36 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
             CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), p.stream));
             p.hash_group = (size_t)-1;
         }
-        const size_t n_groups = (jobs.size() + jobs_per_batch - 1) / jobs_per_batch;
+        // Pixel groups: consecutive runs of at most jobs_per_batch jobs. The accumulating film adds every batch into the
+        // film in stream order, so a group never spans a change of `tile.sample`: within one sample index the reference's
+        // tiles are disjoint, each pixel appears once per batch and the per-pixel sum runs in tile-list order exactly
+        // like the reference's `*fc += c` (film.rs:260-272).
+        std::vector<std::pair<size_t, uint32_t>> groups;  // (first job, job count)
+        {
+            size_t seg_begin = 0;
+            auto flush = [&](size_t seg_end) {
+                for (size_t j = seg_begin; j < seg_end; j += jobs_per_batch)
+                    groups.emplace_back(j, (uint32_t)std::min<size_t>(jobs_per_batch, seg_end - j));
+                seg_begin = seg_end;
+            };
+            if (accumulate) {
+                size_t j = 0;
+                for (uint32_t t = 0; t < n_tiles; ++t) {
+                    if (t > 0 && tiles[t].sample != tiles[t - 1].sample) flush(j);
+                    j += (size_t)(tiles[t].x1 - tiles[t].x0) * (tiles[t].y1 - tiles[t].y0);
+                }
+            }
+            flush(jobs.size());
+        }
+        const size_t n_groups = groups.size();
         uint64_t done = 0;
         bool cancelled = false;
         for (size_t g0 = 0; g0 < n_groups && !cancelled; g0 += n_pipes) {
             for (uint32_t s0 = 0; s0 < samples_per_job && !cancelled; s0 += m) {
                 for (int pi = 0; pi < n_pipes && g0 + pi < n_groups && !cancelled; ++pi) {
                     Pipe& p = c->pipe[pi];
-                    const size_t group = g0 + pi, j0 = group * jobs_per_batch;
-                    const uint32_t nj = (uint32_t)std::min<size_t>(jobs_per_batch, jobs.size() - j0);
+                    const size_t group = g0 + pi, j0 = groups[group].first;
+                    const uint32_t nj = groups[group].second;
                     RenderCfg gcfg = cfg;
                     if (sm->kind == YK_SAMPLER_STRATIFIED) {
                         // tabulate the (pixel, dimension) hashes of this pixel group once for all of its samples
