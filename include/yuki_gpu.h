@@ -107,6 +107,12 @@ typedef struct {                   /* shapes/mesh.rs:8-18 + the per-Triangle mat
     int32_t area_light;            /* index of a rect light in `lights`, or -1 */
 } yk_mesh_desc;
 
+typedef struct {                   /* Sphere::new, shapes/sphere.rs:23-33 */
+    yk_transform object_to_world;
+    float radius;
+    int32_t material;
+} yk_sphere_desc;
+
 typedef struct {                   /* scene/mod.rs:41-49 + SceneLoadSettings :25-39 */
     uint32_t n_meshes, n_textures, n_materials, n_lights;
     const yk_mesh_desc* meshes;
@@ -116,6 +122,8 @@ typedef struct {                   /* scene/mod.rs:41-49 + SceneLoadSettings :25
     float background[3];
     uint32_t max_shapes_in_node;   /* default 1 */
     uint32_t split_method;         /* yk_split_method, default SAH */
+    uint32_t n_spheres;            /* shapes are the meshes' triangles in order, then the spheres (scene/mod.rs:497) */
+    const yk_sphere_desc* spheres;
 } yk_host_scene_desc;
 
 /* ---- scene description, device level (flattened; what the FFI crate passes) ---------------- */
@@ -133,6 +141,14 @@ typedef struct {                   /* light with its constructor already evaluat
 #define YK_TRI_SWAPS_HANDEDNESS 1u
 #define YK_TRI_HAS_NORMALS 2u
 #define YK_TRI_HAS_UVS 4u
+#define YK_TRI_IS_SPHERE 8u        /* the leaf slot is a sphere: tri_sphere[i] indexes `spheres`, the vertex slot is unused */
+
+typedef struct {                   /* shapes/sphere.rs:15-21 with both transforms evaluated */
+    float object_to_world[16];
+    float world_to_object[16];
+    float radius;
+    uint32_t swaps_handedness;     /* Transform::swaps_handedness, math/transform.rs:84-90 */
+} yk_sphere;
 
 typedef struct {
     uint32_t n_nodes;
@@ -150,6 +166,9 @@ typedef struct {
     const yk_material_desc* materials;
     const yk_light* lights;
     float background[3];
+    uint32_t n_spheres;             /* shapes/sphere.rs; 0 for triangle-only scenes */
+    const yk_sphere* spheres;
+    const int32_t* tri_sphere;      /* NULL, or per leaf slot: index into `spheres`, -1 for triangles */
 } yk_scene_desc;
 
 /* ---- render options / statistics ------------------------------------------------------------ */

@@ -91,6 +91,19 @@ yko_scene* yko_scene_create(const yko_host_scene_desc* d) {
         for (uint32_t v0 = 0; v0 + 2 < md.n_indices; v0 += 3)
             s.shapes.push_back({i, {md.indices[v0], md.indices[v0 + 1], md.indices[v0 + 2]}, md.material, md.area_light, orig++});
     }
+    for (uint32_t k = 0; k < d->n_spheres; ++k) {  // Sphere::new, shapes/sphere.rs:23-33
+        const yko_sphere_desc& sd = d->spheres[k];
+        Sphere sp;
+        sp.object_to_world = to_xf(sd.object_to_world);
+        sp.world_to_object = xf_inverted(sp.object_to_world);
+        sp.radius = sd.radius;
+        sp.material = sd.material;
+        sp.transform_swaps_handedness = xf_swaps_handedness(sp.object_to_world);
+        s.spheres.push_back(sp);
+        Triangle shape{0, {0, 0, 0}, sd.material, -1, orig++};
+        shape.sphere = (int32_t)k;
+        s.shapes.push_back(shape);
+    }
     s.background = {d->background[0], d->background[1], d->background[2]};
     s.max_shapes_in_node = d->max_shapes_in_node;
     s.split_method = (SplitMethod)d->split_method;

@@ -54,6 +54,12 @@ typedef struct {
 } yko_mesh_desc;
 
 typedef struct {
+    yko_transform object_to_world;
+    float radius;
+    int32_t material;
+} yko_sphere_desc;
+
+typedef struct {
     uint32_t n_meshes, n_textures, n_materials, n_lights;
     const yko_mesh_desc* meshes;
     const yko_texture_desc* textures;
@@ -62,6 +68,8 @@ typedef struct {
     float background[3];
     uint32_t max_shapes_in_node;
     uint32_t split_method;    /* 0 SAH, 1 Middle, 2 EqualCounts */
+    uint32_t n_spheres;       /* shapes = the meshes' triangles in order, then the spheres (scene/mod.rs:497) */
+    const yko_sphere_desc* spheres;
 } yko_host_scene_desc;
 
 typedef struct { float position[3]; float target[3]; float up[3]; uint32_t fov_axis; float fov_deg; } yko_camera_params;

@@ -51,12 +51,23 @@ struct Mesh {
     bool transform_swaps_handedness;
 };
 
+// One entry of the reference's `Vec<Arc<dyn Shape>>`: a mesh triangle (shapes/triangle.rs) or, when `sphere >= 0`, a
+// sphere (shapes/sphere.rs).
 struct Triangle {
     uint32_t mesh;
     uint32_t v[3];
     int32_t material;
     int32_t area_light;  // index into lights or -1
     uint32_t orig_id;    // index in the un-reordered shape list
+    int32_t sphere = -1; // index into Scene::spheres
+};
+
+// shapes/sphere.rs:15-33
+struct Sphere {
+    Transform object_to_world, world_to_object;
+    float radius;
+    int32_t material;
+    bool transform_swaps_handedness;
 };
 
 // interaction.rs:84-94
@@ -103,6 +114,7 @@ struct IntersectionResult {
 struct Scene {
     std::vector<Mesh> meshes;
     std::vector<Triangle> shapes;  // BVH (leaf) order after build
+    std::vector<Sphere> spheres;
     std::vector<BVHNode> nodes;
     std::vector<Texture> textures;
     std::vector<Material> materials;
@@ -111,14 +123,20 @@ struct Scene {
     uint32_t max_shapes_in_node = 1;
     SplitMethod split_method = SPLIT_SAH;
 
-    // shapes/triangle.rs:229-235
+    // shapes/triangle.rs:229-235, shapes/sphere.rs:121-123
     Bounds3 world_bound(const Triangle& t) const {
+        if (t.sphere >= 0) {
+            const Sphere& sp = spheres[t.sphere];
+            const float r = sp.radius;
+            return xf_bounds(sp.object_to_world, Bounds3{{-r, -r, -r}, {r, r, r}});
+        }
         const Mesh& m = meshes[t.mesh];
         return union_p(bounds_new(m.points[t.v[0]], m.points[t.v[1]]), m.points[t.v[2]]);
     }
 
     bool triangle_intersect(const Triangle& tri, const Ray& ray, float* t_out, SurfaceInteraction* si,
                             bool want_si) const;
+    bool sphere_intersect(const Sphere& sp, const Ray& ray, float* t_out, SurfaceInteraction* si, bool want_si) const;
     bool build_bvh();
     IntersectionResult intersect(Ray ray, TraversalStats* ts) const;
     bool any_intersect(const Ray& ray, int32_t area_light, TraversalStats* ts) const;
@@ -128,9 +146,67 @@ struct Scene {
     }
 };
 
+// shapes/sphere.rs:36-119
+inline bool Scene::sphere_intersect(const Sphere& sp, const Ray& ray, float* t_out, SurfaceInteraction* si, bool want_si) const {
+    const Ray r = xf_ray(sp.world_to_object, ray);
+    const float a = r.d.x * r.d.x + r.d.y * r.d.y + r.d.z * r.d.z;
+    const float b = 2.0f * (r.d.x * r.o.x + r.d.y * r.o.y + r.d.z * r.o.z);
+    const float c = r.o.x * r.o.x + r.o.y * r.o.y + r.o.z * r.o.z - sp.radius * sp.radius;
+    const float discrim = b * b - 4.0f * a * c;
+    if (discrim < 0.0f) return false;
+    const float rd = std::sqrt(discrim);
+    const float q = b < 0.0f ? -0.5f * (b - rd) : -0.5f * (b + rd);
+    float t0 = q / a, t1 = c / q;
+    if (t0 > t1) std::swap(t0, t1);
+    if (t0 > r.t_max || t1 <= 0.0f) return false;
+    float t = t0;
+    if (t <= 0.0f) {
+        t = t1;
+        if (t > r.t_max) return false;
+    }
+    *t_out = t;
+    if (!want_si) return true;
+    V3 p = r.o + r.d * t;
+    p = p * (sp.radius / len(p - v3(0, 0, 0)));
+    if (p.x == 0.0f && p.y == 0.0f) p.x = 1e-5f * sp.radius;
+    const float kPiF = 3.14159274101257324f;
+    float phi = std::atan2(p.y, p.x);
+    if (phi < 0.0f) phi += 2.0f * kPiF;
+    const float phi_max = 2.0f * kPiF, theta_min = kPiF, theta_max = 0.0f;
+    const float u = phi / phi_max;
+    const float cz = p.z / sp.radius;
+    const float theta = std::acos(cz < -1.0f ? -1.0f : (cz > 1.0f ? 1.0f : cz));
+    const float v = (theta - theta_min) / (theta_max - theta_min);
+    const float z_radius = std::sqrt(p.x * p.x + p.y * p.y);
+    const float inv_z_radius = 1.0f / z_radius;
+    const float cos_phi = p.x * inv_z_radius, sin_phi = p.y * inv_z_radius;
+    const V3 dpdu = v3(-phi_max * p.y, phi_max * p.x, 0.0f);
+    const V3 dpdv = v3(p.z * cos_phi, p.z * sin_phi, -sp.radius * std::sin(theta)) * (theta_max - theta_min);
+    // SurfaceInteraction::new (interaction.rs:95-124) in object space ...
+    V3 n = normalized(cross(dpdu, dpdv));
+    if (sp.transform_swaps_handedness) n = -n;
+    // ... then &object_to_world * si (interaction.rs:141-164); note wo = -ray.d of the WORLD ray goes through the transform
+    const Transform& o2w = sp.object_to_world;
+    const V3 n_w = normalized(xf_normal(o2w, n));
+    V3 sh_n = normalized(xf_normal(o2w, n));
+    sh_n = faceforward_n(sh_n, n_w);
+    si->p = xf_point(o2w, p);
+    si->n = n_w;
+    si->uv = {u, v};
+    si->dpdu = xf_vec(o2w, dpdu);
+    si->dpdv = xf_vec(o2w, dpdv);
+    si->wo = normalized(xf_vec(o2w, -ray.d));
+    si->sh_n = faceforward_n(sh_n, n_w);
+    si->sh_dpdu = xf_vec(o2w, dpdu);
+    si->sh_dpdv = xf_vec(o2w, dpdv);
+    si->area_light = -1;
+    return true;
+}
+
 // shapes/triangle.rs:49-227
 inline bool Scene::triangle_intersect(const Triangle& tri, const Ray& ray, float* t_out, SurfaceInteraction* si,
                                       bool want_si) const {
+    if (tri.sphere >= 0) return sphere_intersect(spheres[tri.sphere], ray, t_out, si, want_si);
     const Mesh& mesh = meshes[tri.mesh];
     V3 p0 = mesh.points[tri.v[0]], p1 = mesh.points[tri.v[1]], p2 = mesh.points[tri.v[2]];
 

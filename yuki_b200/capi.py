@@ -91,11 +91,20 @@ class MeshDesc(C.Structure):
                 ("indices", C.POINTER(C.c_uint32)), ("material", C.c_int32), ("area_light", C.c_int32)]
 
 
+class SphereDesc(C.Structure):
+    _fields_ = [("object_to_world", Transform), ("radius", C.c_float), ("material", C.c_int32)]
+
+
 class HostSceneDesc(C.Structure):
     _fields_ = [("n_meshes", C.c_uint32), ("n_textures", C.c_uint32), ("n_materials", C.c_uint32), ("n_lights", C.c_uint32),
                 ("meshes", C.POINTER(MeshDesc)), ("textures", C.POINTER(TextureDesc)), ("materials", C.POINTER(MaterialDesc)),
                 ("lights", C.POINTER(LightDesc)), ("background", C.c_float * 3), ("max_shapes_in_node", C.c_uint32),
-                ("split_method", C.c_uint32)]
+                ("split_method", C.c_uint32), ("n_spheres", C.c_uint32), ("spheres", C.POINTER(SphereDesc))]
+
+
+class SphereDev(C.Structure):
+    _fields_ = [("object_to_world", C.c_float * 16), ("world_to_object", C.c_float * 16), ("radius", C.c_float),
+                ("swaps_handedness", C.c_uint32)]
 
 
 class LightDev(C.Structure):
@@ -111,7 +120,8 @@ class SceneDescFlat(C.Structure):
                 ("tri_area_light", C.POINTER(C.c_int32)), ("tri_flags", C.POINTER(C.c_uint8)),
                 ("n_textures", C.c_uint32), ("n_materials", C.c_uint32), ("n_lights", C.c_uint32),
                 ("textures", C.POINTER(TextureDesc)), ("materials", C.POINTER(MaterialDesc)), ("lights", C.POINTER(LightDev)),
-                ("background", C.c_float * 3)]
+                ("background", C.c_float * 3), ("n_spheres", C.c_uint32), ("spheres", C.POINTER(SphereDev)),
+                ("tri_sphere", C.POINTER(C.c_int32))]
 
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64)
@@ -238,7 +248,7 @@ def build_host_scene_desc(scene: D.SceneDesc, S=None):
     """SceneDesc -> (HostSceneDesc, keepalive). `S` lets the oracle binding reuse this with its own
     (layout-identical) struct classes."""
     S = S or {"host": HostSceneDesc, "mesh": MeshDesc, "tex": TextureDesc, "mat": MaterialDesc, "light": LightDesc,
-              "xf": Transform}
+              "xf": Transform, "sphere": SphereDesc}
     keep = []
     meshes = (S["mesh"] * max(len(scene.meshes), 1))()
     for i, m in enumerate(scene.meshes):
@@ -295,6 +305,14 @@ def build_host_scene_desc(scene: D.SceneDesc, S=None):
     hd = S["host"]()
     hd.n_meshes, hd.n_textures, hd.n_materials, hd.n_lights = len(scene.meshes), len(scene.textures), len(scene.materials), len(scene.lights)
     hd.meshes, hd.textures, hd.materials, hd.lights = meshes, texs, mats, lights
+    spheres = (S["sphere"] * max(len(scene.spheres), 1))()
+    for i, sp in enumerate(scene.spheres):
+        spheres[i].object_to_world = to_c_transform(sp.object_to_world, S["xf"])
+        spheres[i].radius = float(sp.radius)
+        spheres[i].material = int(sp.material)
+    hd.n_spheres = len(scene.spheres)
+    hd.spheres = spheres
+    keep.append(spheres)
     hd.background = f3(scene.background)
     hd.max_shapes_in_node = scene.max_shapes_in_node
     hd.split_method = scene.split_method

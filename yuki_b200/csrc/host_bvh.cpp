@@ -214,10 +214,32 @@ static uint32_t tree_height(const yk_bvh_node* nodes, uint32_t n_nodes) {
     return best;
 }
 
+int bvh_build_boxes(const float* boxes6, uint32_t n, uint32_t max_shapes_in_node, uint32_t split_method, std::vector<yk_bvh_node>* nodes,
+                    std::vector<uint32_t>* order, const char** why);
+
 int bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
               std::vector<yk_bvh_node>* nodes, std::vector<uint32_t>* order, const char** why) {
     if (!tri_vertices || n_tris == 0) {
         *why = "yk_bvh_build: empty triangle list";
+        return YK_ERR_INVALID;
+    }
+    std::vector<float> boxes((size_t)n_tris * 6);
+    for (uint32_t i = 0; i < n_tris; ++i) {
+        const float* v = tri_vertices + (size_t)i * 9;
+        // Triangle::world_bound (triangle.rs:229-235): Bounds3::new(p0, p1).union_p(p2)
+        box3 b{min3(load3(v), load3(v + 3)), max3(load3(v), load3(v + 3))};
+        b = grow(b, load3(v + 6));
+        store3(b.lo, &boxes[(size_t)i * 6]);
+        store3(b.hi, &boxes[(size_t)i * 6 + 3]);
+    }
+    return bvh_build_boxes(boxes.data(), n_tris, max_shapes_in_node, split_method, nodes, order, why);
+}
+
+// The build only sees world bounds (Shape::world_bound, shapes/mod.rs:33): `boxes6` = (p_min, p_max) per shape.
+int bvh_build_boxes(const float* boxes6, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
+                    std::vector<yk_bvh_node>* nodes, std::vector<uint32_t>* order, const char** why) {
+    if (!boxes6 || n_tris == 0) {
+        *why = "yk_bvh_build: empty shape list";
         return YK_ERR_INVALID;
     }
     if (split_method > YK_SPLIT_EQUAL_COUNTS) {
@@ -226,10 +248,7 @@ int bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in
     }
     std::vector<Prim> prims(n_tris);
     for (uint32_t i = 0; i < n_tris; ++i) {
-        const float* v = tri_vertices + (size_t)i * 9;
-        // Triangle::world_bound (triangle.rs:229-235): Bounds3::new(p0, p1).union_p(p2)
-        box3 b{min3(load3(v), load3(v + 3)), max3(load3(v), load3(v + 3))};
-        b = grow(b, load3(v + 6));
+        const box3 b{load3(boxes6 + (size_t)i * 6), load3(boxes6 + (size_t)i * 6 + 3)};
         prims[i] = {i, b, add(b.lo, divs(sub(b.hi, b.lo), 0.5f))};
     }
     Builder bld;

@@ -14,6 +14,8 @@
 namespace ykh {
 int bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
               std::vector<yk_bvh_node>* nodes, std::vector<uint32_t>* order, const char** why);
+int bvh_build_boxes(const float* boxes6, uint32_t n, uint32_t max_shapes_in_node, uint32_t split_method, std::vector<yk_bvh_node>* nodes,
+                    std::vector<uint32_t>* order, const char** why);
 }
 
 // ---- error channel (shared with the device side) ------------------------------------------------
@@ -48,6 +50,8 @@ struct yk_host_scene {
     std::vector<yk_material_desc> materials;
     std::vector<yk_light> lights;
     float background[3];
+    std::vector<yk_sphere> spheres;
+    std::vector<int32_t> tri_sphere;  // empty when the scene has no sphere
 };
 
 extern "C" {
@@ -149,11 +153,51 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
             flags.push_back(fl);
         }
     }
+    // World bounds of every shape: triangles (triangle.rs:229-235), then the spheres (sphere.rs:121-123,
+    // Transform * Bounds3 = union of the eight transformed corners, math/transform.rs:186-201).
+    const uint32_t n_mesh_tris = (uint32_t)mats.size();
+    std::vector<float> boxes((size_t)(n_mesh_tris + d->n_spheres) * 6);
+    for (uint32_t i = 0; i < n_mesh_tris; ++i) {
+        const float* v = &verts[(size_t)i * 9];
+        box3 b{min3(load3(v), load3(v + 3)), max3(load3(v), load3(v + 3))};
+        b = grow(b, load3(v + 6));
+        store3(b.lo, &boxes[(size_t)i * 6]);
+        store3(b.hi, &boxes[(size_t)i * 6 + 3]);
+    }
+    std::vector<int32_t> sphere_of(n_mesh_tris, -1);
+    for (uint32_t k = 0; k < d->n_spheres; ++k) {
+        const yk_sphere_desc& sd = d->spheres[k];
+        if (!d->spheres || sd.material < 0 || (uint32_t)sd.material >= d->n_materials)
+            return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: sphere material index out of range");
+        const xform o2w = to_xform(sd.object_to_world);
+        yk_sphere sp{};
+        std::memcpy(sp.object_to_world, o2w.m.e, 64);
+        std::memcpy(sp.world_to_object, o2w.inv.e, 64);
+        sp.radius = sd.radius;
+        sp.swaps_handedness = flips_handedness(o2w.m) ? 1u : 0u;
+        hs->spheres.push_back(sp);
+        const float r = sd.radius;
+        const f3 mi = mk3(-r, -r, -r), ma = mk3(r, r, r);
+        const f3 corners[8] = {mi, mk3(ma.x, mi.y, mi.z), mk3(mi.x, ma.y, mi.z), mk3(mi.x, mi.y, ma.z),
+                               mk3(ma.x, ma.y, mi.z), mk3(ma.x, mi.y, ma.z), mk3(mi.x, ma.y, ma.z), ma};
+        box3 b{mk3(3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f), mk3(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f)};
+        for (const f3& cnr : corners) b = grow(b, apply_point(o2w.m, cnr));
+        store3(b.lo, &boxes[(size_t)(n_mesh_tris + k) * 6]);
+        store3(b.hi, &boxes[(size_t)(n_mesh_tris + k) * 6 + 3]);
+        // the shape slot: no vertices, the sphere's material, no area light (Sphere::new takes none)
+        verts.insert(verts.end(), 9, 0.0f);
+        if (any_normals) norms.insert(norms.end(), 9, 0.0f);
+        if (any_uvs) uvs.insert(uvs.end(), 6, 0.0f);
+        mats.push_back((uint32_t)sd.material);
+        alights.push_back(-1);
+        flags.push_back((uint8_t)(YK_TRI_IS_SPHERE | (sp.swaps_handedness ? YK_TRI_SWAPS_HANDEDNESS : 0u)));
+        sphere_of.push_back((int32_t)k);
+    }
     const uint32_t n_tris = (uint32_t)mats.size();
     std::vector<uint32_t> order;
     const char* why = "";
-    int rc = bvh_build(verts.data(), n_tris, d->max_shapes_in_node ? d->max_shapes_in_node : 1u, d->split_method, &hs->nodes,
-                       &order, &why);
+    int rc = bvh_build_boxes(boxes.data(), n_tris, d->max_shapes_in_node ? d->max_shapes_in_node : 1u, d->split_method, &hs->nodes,
+                             &order, &why);
     if (rc != YK_OK) return yk_set_error(rc, why);
 
     // Gather into leaf order.
@@ -172,6 +216,10 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
         hs->tri_material[i] = mats[s];
         hs->tri_area_light[i] = alights[s];
         hs->tri_flags[i] = flags[s];
+    }
+    if (d->n_spheres) {
+        hs->tri_sphere.resize(n_tris);
+        for (uint32_t i = 0; i < n_tris; ++i) hs->tri_sphere[i] = sphere_of[order[i]];
     }
 
     hs->texel_storage.resize(d->n_textures);
@@ -212,6 +260,9 @@ void yk_host_scene_flat(const yk_host_scene* hs, yk_scene_desc* o) {
     o->tri_material = hs->tri_material.data();
     o->tri_area_light = hs->tri_area_light.data();
     o->tri_flags = hs->tri_flags.data();
+    o->n_spheres = (uint32_t)hs->spheres.size();
+    o->spheres = hs->spheres.empty() ? nullptr : hs->spheres.data();
+    o->tri_sphere = hs->tri_sphere.empty() ? nullptr : hs->tri_sphere.data();
     o->n_textures = (uint32_t)hs->textures.size();
     o->n_materials = (uint32_t)hs->materials.size();
     o->n_lights = (uint32_t)hs->lights.size();

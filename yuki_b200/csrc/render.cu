@@ -14,6 +14,7 @@
 #include <chrono>
 #include <memory>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -67,6 +68,8 @@ struct DevScene {
     const DevTexture* textures;
     const DevMaterial* materials;
     const yk_light* lights;
+    const yk_sphere* spheres;  // sphere slots of `tris`: vertex lanes are NaN (so the triangle test "accepts" them and the
+                               // rare hit path takes over), row 0's w = -2 - sphere index
     uint32_t n_lights, n_tris, n_nodes;
     float background[3];
 };
@@ -273,6 +276,13 @@ constexpr int kNodePhaseMin = YK_NODE_PHASE_MIN;
 constexpr int kShortStack = YK_SHORT_STACK;
 constexpr uint32_t kSpBase = kTraceThreads;  // stack pointer (in words, depth * kTraceThreads) of an empty stack
 
+// Sphere slots are rare: the test lives behind a real call so that it costs the traversal loops no registers.
+__device__ __noinline__ bool sphere_slot_test(const yk_sphere* spheres, int tag, float ox, float oy, float oz, float4 rd, float t_max,
+                                              float* t_out) {
+    V3 o_s, d_s;
+    return sphere_test(spheres[-2 - tag], mk(ox, oy, oz), f4v(rd), t_max, t_out, &o_s, &d_s);
+}
+
 struct TraceLane {
     float ox, oy, oz, ix, iy, iz, t_max;
     float okx, oky, okz, sx, sy, sz;  // watertight test: permuted origin, shear
@@ -283,6 +293,7 @@ struct TraceLane {
     __device__ __forceinline__ void idle() {
         cur = kNoNode; sp = kSpBase; leaf_pos = leaf_end = 0; n_tests = n_hits = n_tris = 0;
         ox = oy = oz = ix = iy = iz = t_max = okx = oky = okz = sx = sy = sz = 0.0f;
+
         kx = ky = kz = neg_mask = 0;
     }
     __device__ __forceinline__ void start(float o_x, float o_y, float o_z, float d_x, float d_y, float d_z, float tmax) {
@@ -405,8 +416,8 @@ struct TraceLane {
     }
 
 // Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
-template <bool COUNTS>
-__global__ void __launch_bounds__(kTraceThreads) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, IterCounters* cur) {
+template <bool COUNTS, bool SPHERES>
+__global__ void __launch_bounds__(kTraceThreads, 8) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, IterCounters* cur) {
     __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
     uint32_t deep[kStackDepth + 1 - kShortStack];
     const uint32_t n = cur->n_active;
@@ -459,9 +470,16 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_closest(DevScene sc, Wa
         // ---- trace until too few lanes are live -----------------------------------------------------------
         for (;;) {
             YK_TRACE_PHASES(tl, live, COUNTS, {
-                (void)al_;
-                const float inv_det = 1.0f / det_;  // triangle.rs:133-139
-                hit_tri = tri_; hit_t = ts_ * inv_det; tl.t_max = hit_t;  // later equal-t hit replaces (bvh.rs:204-207)
+                if (SPHERES && det_ != det_) {  // a sphere slot (NaN vertex lanes): shapes/sphere.rs:36-77
+                    float t_s;
+                    /* the direction is not kept in registers: re-read it on this rare path */
+                    if (sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.ray_d[path], tl.t_max, &t_s)) {
+                        hit_tri = tri_; hit_t = t_s; tl.t_max = t_s;
+                    }
+                } else {
+                    const float inv_det = 1.0f / det_;  // triangle.rs:133-139
+                    hit_tri = tri_; hit_t = ts_ * inv_det; tl.t_max = hit_t;  // later equal-t hit replaces (bvh.rs:204-207)
+                }
             })
             if (live && !tl.wants_box()) {  // retire
                 w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
@@ -487,7 +505,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_closest(DevScene sc, Wa
 // `radiance += beta * Le`, the indirect clamp and `L += beta * radiance` (path.rs:113-129, whitted.rs:120-130).
 // One *path* per queue entry (the four material queues, concatenated); a lane traces its path's shadow rays one after
 // the other in light order, so the float sums associate exactly like the reference's fold.
-__global__ void __launch_bounds__(kTraceThreads) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, IterCounters* cur) {
+template <bool SPHERES>
+__global__ void __launch_bounds__(kTraceThreads, 7) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, IterCounters* cur) {
     uint32_t* const cursor = &cur->work_shadow;
     __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
     uint32_t deep[kStackDepth + 1 - kShortStack];
@@ -565,9 +584,16 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_shadow(DevScene sc, Wav
         }
         for (;;) {
             YK_TRACE_PHASES(tl, live, false, {
-                (void)tri_; (void)ts_; (void)det_;
-                // bvh.rs:269-280: the target light's own emissive triangles do not occlude
-                if (!(target_light >= 0 && al_ >= 0 && al_ == target_light)) { occluded = true; tl.stop(); }
+                (void)tri_; (void)ts_;
+                bool blocks = true;
+                if (SPHERES && det_ != det_) {  // sphere slot: run the real test; spheres carry no area light
+                    float t_s;
+                    blocks = sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.lt_d[(size_t)(__ffs(mask) - 1) * w.cap + path],
+                                              tl.t_max, &t_s);
+                } else if (target_light >= 0 && al_ >= 0 && al_ == target_light) {
+                    blocks = false;  // bvh.rs:269-280: the target light's own emissive triangles do not occlude
+                }
+                if (blocks) { occluded = true; tl.stop(); }
             })
             if (live && !need_ray && !tl.wants_box()) {  // this shadow ray is done
                 sum_nodes += tl.n_tests;
@@ -644,7 +670,7 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
                 const uint32_t m = __float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) & 0xffffffu;
                 kind = sc.materials[m].kind;
                 if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
-            } else {
+            } else if (first_iteration != 2) {  // (2 = debug integrators: their li() returns no background)
                 // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
                 const float4 b = w.beta[path];
                 float4 L = w.L[path];
@@ -679,6 +705,10 @@ __device__ __forceinline__ void make_surface(const DevScene& sc, uint32_t tri, V
     const uint32_t packed = __float_as_uint(b4.w);
     const uint32_t flags = packed >> 24;
     *material = packed & 0xffffffu;
+    if (flags & YK_TRI_IS_SPHERE) {
+        sphere_surface(sc.spheres[-2 - __float_as_int(a4.w)], o, d, si);
+        return;
+    }
     // Barycentrics: re-run the (deterministic) triangle test that the traversal accepted.
     TriRay tr;
     tr.setup(d);
@@ -914,7 +944,10 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
 
             // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
             RGB le = gray(0.0f);
-            if (si.area_light >= 0 && dotn(si.n, si.wo) > 0.0f) {
+            // The integrators pass -ray.d here and (Path) to sample_f, but si.wo to Bsdf::f; the two differ for spheres, whose
+            // si.wo went through object_to_world once more (sphere.rs:116, interaction.rs:155).
+            const V3 wo_ray = -d;
+            if (si.area_light >= 0 && dotn(si.n, wo_ray) > 0.0f) {
                 const yk_light& al = sc.lights[si.area_light];
                 le = rgb(al.i[0], al.i[1], al.i[2]);
             }
@@ -926,7 +959,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                 const RGB extra = add_le ? beta * le : gray(0.0f);
                 w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
                 w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
-                const Bsdf::Sample s = bsdf.sample_f(si.wo, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137
+                const Bsdf::Sample s = bsdf.sample_f(wo_ray, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137 (wo = -ray.d)
                 if (!(black(s.f) || s.pdf == 0.0f)) {
                     alive = true;
                     const bool spec = (s.type & BX_SPECULAR) != 0;
@@ -1244,10 +1277,14 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         IterCounters* nxt = &p->d_ctr[(iter + 1) & 1];
         if (iter > 0) CUDA_TRY(cudaMemsetAsync(nxt, 0, sizeof(IterCounters), s));
         CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
-        if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS)
-            k_trace_closest<true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
-        else
-            k_trace_closest<false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+        const bool spheres = sc->dev.spheres != nullptr;  // scenes without spheres run instantiations without the sphere path
+        if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
+            if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+            else k_trace_closest<true, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+        } else {
+            if (spheres) k_trace_closest<false, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+            else k_trace_closest<false, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+        }
         CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
         tm->launches += 1;
         tm->closest_launches += 1;
@@ -1276,7 +1313,8 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             tm->launches += 1;
         }
         CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
-        k_trace_shadow<<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
+        if (spheres) k_trace_shadow<true><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
+        else k_trace_shadow<false><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
         CUDA_TRY(cudaEventRecord(stage_event(iter, 4), s));
         tm->launches += 1;
         sl.n_iters = iter + 1;
@@ -1338,8 +1376,8 @@ int yk_context_create(int device_id, yk_context** out) {
         CUDA_TRY(cudaMallocHost((void**)&p.h_ctr, sizeof(IterCounters)));
         CUDA_TRY(cudaMallocHost((void**)&p.h_totals, sizeof(Totals)));
     }
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace_closest<false>, kTraceThreads, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace_shadow, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace_closest<false, false>, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace_shadow<false>, kTraceThreads, 0));
     *out = c;
     return YK_OK;
 }
@@ -1410,6 +1448,21 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
         uint32_t packed = d->tri_material[i] | ((uint32_t)d->tri_flags[i] << 24);
         if ((d->tri_flags[i] & YK_TRI_HAS_NORMALS) && !d->tri_normals) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: normals flagged but absent");
         if ((d->tri_flags[i] & YK_TRI_HAS_UVS) && !d->tri_uvs) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: uvs flagged but absent");
+        const bool is_sphere = (d->tri_flags[i] & YK_TRI_IS_SPHERE) != 0;
+        if (is_sphere && (!d->tri_sphere || !d->spheres || d->tri_sphere[i] < 0 || (uint32_t)d->tri_sphere[i] >= d->n_spheres))
+            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: sphere slot without a valid sphere index");
+        if (is_sphere) {  // NaN vertex lanes + (-2 - sphere index) where triangles keep their area light
+            const float qnan = std::nanf("");
+            const int32_t tag = -2 - d->tri_sphere[i];
+            float ft, fp2, fi2;
+            std::memcpy(&ft, &tag, 4);
+            std::memcpy(&fp2, &packed, 4);
+            std::memcpy(&fi2, &d->tri_orig_id[i], 4);
+            tris[3 * i] = make_float4(qnan, qnan, qnan, ft);
+            tris[3 * i + 1] = make_float4(qnan, qnan, qnan, fp2);
+            tris[3 * i + 2] = make_float4(qnan, qnan, qnan, fi2);
+            continue;
+        }
         float fa, fp, fi;
         std::memcpy(&fa, &d->tri_area_light[i], 4);
         std::memcpy(&fp, &packed, 4);
@@ -1471,6 +1524,7 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     if ((rc = dev_upload(sc->allocs, &sc->dev.textures, tex.data(), tex.size())) != YK_OK) return rc;
     if ((rc = dev_upload(sc->allocs, &sc->dev.materials, mats.data(), mats.size())) != YK_OK) return rc;
     if ((rc = dev_upload(sc->allocs, &sc->dev.lights, d->lights, d->n_lights)) != YK_OK) return rc;
+    if (d->n_spheres && (rc = dev_upload(sc->allocs, &sc->dev.spheres, d->spheres, d->n_spheres)) != YK_OK) return rc;
     sc->dev.n_lights = d->n_lights;
     sc->dev.n_tris = d->n_tris;
     sc->dev.n_nodes = d->n_nodes;

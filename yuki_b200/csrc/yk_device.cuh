@@ -315,6 +315,66 @@ struct Surface {
     int area_light;
 };
 
+// ---- sphere (shapes/sphere.rs:36-119) -----------------------------------------------------------------
+// The quadratic of :40-77 in the sphere's object space. Returns the hit distance and the object-space ray.
+YK_DEV bool sphere_test(const yk_sphere& sp, V3 o_w, V3 d_w, float t_max, float* t_out, V3* o_obj, V3* d_obj) {
+    const V3 o = xf_point(sp.world_to_object, o_w), d = xf_vec(sp.world_to_object, d_w);  // &world_to_object * ray, transform.rs:171-177
+    const float a = d.x * d.x + d.y * d.y + d.z * d.z;
+    const float b = 2.0f * (d.x * o.x + d.y * o.y + d.z * o.z);
+    const float c = o.x * o.x + o.y * o.y + o.z * o.z - sp.radius * sp.radius;
+    const float discrim = b * b - 4.0f * a * c;
+    if (discrim < 0.0f) return false;
+    const float rd = sqrtf(discrim);
+    const float q = b < 0.0f ? -0.5f * (b - rd) : -0.5f * (b + rd);
+    float t0 = q / a, t1 = c / q;
+    if (t0 > t1) { const float tmp = t0; t0 = t1; t1 = tmp; }
+    if (t0 > t_max || t1 <= 0.0f) return false;
+    float t = t0;
+    if (t <= 0.0f) {
+        t = t1;
+        if (t > t_max) return false;
+    }
+    *t_out = t;
+    *o_obj = o;
+    *d_obj = d;
+    return true;
+}
+// Surface interaction of a sphere hit (:79-117) moved to world space by `&object_to_world * SurfaceInteraction`
+// (interaction.rs:141-164). atan2 / acos are CUDA's, not glibc's: uv and the shading frame can differ from the CPU
+// path in the last bits (radiance tolerance); the hit itself uses only + - * / sqrt and is exact.
+YK_DEV void sphere_surface(const yk_sphere& sp, V3 o_w, V3 d_w, Surface* si) {
+    float t = 0.0f;
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+    sphere_test(sp, o_w, d_w, __int_as_float(0x7f800000), &t, &o, &d);
+    V3 p = o + d * t;
+    p = p * (sp.radius / length(p - mk(0.0f, 0.0f, 0.0f)));
+    if (p.x == 0.0f && p.y == 0.0f) p.x = 1e-5f * sp.radius;
+    float phi = atan2f(p.y, p.x);
+    if (phi < 0.0f) phi += 2.0f * kPi;
+    const float phi_max = 2.0f * kPi, theta_min = kPi, theta_max = 0.0f;
+    const float u = phi / phi_max;
+    const float theta = acosf(clamp01ish(p.z / sp.radius, -1.0f, 1.0f));
+    const float v = (theta - theta_min) / (theta_max - theta_min);
+    const float z_radius = sqrtf(p.x * p.x + p.y * p.y);
+    const float inv_z_radius = 1.0f / z_radius;
+    const float cos_phi = p.x * inv_z_radius, sin_phi = p.y * inv_z_radius;
+    const V3 dpdu = mk(-phi_max * p.y, phi_max * p.x, 0.0f);
+    const V3 dpdv = mk(p.z * cos_phi, p.z * sin_phi, -sp.radius * sin_f32(theta)) * (theta_max - theta_min);
+    V3 n = unit(cross64(dpdu, dpdv));  // SurfaceInteraction::new, interaction.rs:105-113
+    if (sp.swaps_handedness) n = -n;
+    // &object_to_world * si
+    const V3 n_w = unit(xf_normal(sp.world_to_object, n));
+    V3 sh_n = unit(xf_normal(sp.world_to_object, n));
+    sh_n = flip_toward_n(sh_n, n_w);
+    si->p = xf_point(sp.object_to_world, p);
+    si->n = n_w;
+    si->uv = {u, v};
+    si->wo = unit(xf_vec(sp.object_to_world, -d_w));  // the world-space -ray.d goes through the transform again (sphere.rs:116)
+    si->sh_n = flip_toward_n(sh_n, n_w);
+    si->sh_dpdu = xf_vec(sp.object_to_world, dpdu);
+    si->area_light = -1;
+}
+
 // ---- BSDF -----------------------------------------------------------------------------------------
 enum : uint32_t { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16, BX_ALL = 31 };
 

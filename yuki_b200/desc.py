@@ -79,8 +79,16 @@ class Mesh:
 
 
 @dataclass
+class Sphere:                               # Sphere::new, shapes/sphere.rs:23-33
+    object_to_world: Transform
+    radius: float
+    material: int
+
+
+@dataclass
 class SceneDesc:
     meshes: List[Mesh] = field(default_factory=list)
+    spheres: List[Sphere] = field(default_factory=list)   # shapes = mesh triangles in order, then the spheres
     textures: List[Texture] = field(default_factory=list)
     materials: List[Material] = field(default_factory=list)
     lights: List[Light] = field(default_factory=list)

@@ -34,8 +34,10 @@ def checker_texture(size=256, cells=8, a=(0.8, 0.8, 0.8), b=(0.2, 0.3, 0.7)) -> 
     return img
 
 
-def cornell(xf, light="rect", tall_box="glass", textured_back_wall=False, split_method=D.SPLIT_SAH, max_shapes_in_node=1):
-    """Cornell box in metres, camera looking down -z (scene/mod.rs:154-531)."""
+def cornell(xf, light="rect", tall_box="glass", textured_back_wall=False, split_method=D.SPLIT_SAH, max_shapes_in_node=1,
+            sphere=False):
+    """Cornell box in metres, camera looking down -z (scene/mod.rs:154-531). `sphere=True` adds the copper sphere of
+    scene/mod.rs:497-501 (with `split_method=D.SPLIT_MIDDLE` this is `Scene::cornell()` up to the missing back-wall PNG)."""
     LEFT, RIGHT, BOTTOM, TOP, FRONT, BACK = F(555.0), F(0.0), F(0.0), F(550.0), F(0.0), F(560.0)
     X_CENTER = (LEFT + RIGHT) / F(2.0)
     Z_CENTER = (FRONT + BACK) / F(2.0)
@@ -109,6 +111,11 @@ def cornell(xf, light="rect", tall_box="glass", textured_back_wall=False, split_
         add([(423.0, 330.0, 247.0), (265.0, 330.0, 296.0), (314.0, 330.0, 456.0), (472.0, 330.0, 406.0), (423.0, 0.0, 247.0),
              (472.0, 0.0, 406.0), (314.0, 0.0, 456.0), (265.0, 0.0, 296.0)],
             (0, 1, 2, 0, 2, 3, 4, 0, 3, 4, 3, 5, 5, 3, 2, 5, 2, 6, 6, 2, 1, 6, 1, 7, 7, 1, 0, 7, 0, 4), box_mat)
+    if sphere:  # scene/mod.rs:214-223, 497-501
+        copper = s.add_material(D.Material(D.MAT_METAL, (s.add_texture(D.Texture.constant(0.27105, 0.67693, 1.31640)),
+                                                         s.add_texture(D.Texture.constant(3.60920, 2.62480, 2.29210)),
+                                                         s.add_texture(D.Texture.constant(0.01))), remap_roughness=True))
+        s.spheres.append(D.Sphere(xf.translation((0.186, 0.082, -0.168)), 0.082, copper))
     cam = D.CameraParameters((0.278, 0.273, 0.800), (0.278, 0.273, -0.260), fov_axis=D.FOV_X, fov_deg=40.0)
     return s, cam
 
