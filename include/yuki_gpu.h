@@ -122,8 +122,10 @@ typedef struct {                   /* scene/mod.rs:41-49 + SceneLoadSettings :25
     float background[3];
     uint32_t max_shapes_in_node;   /* default 1 */
     uint32_t split_method;         /* yk_split_method, default SAH */
-    uint32_t n_spheres;            /* shapes are the meshes' triangles in order, then the spheres (scene/mod.rs:497) */
+    uint32_t n_spheres;            /* shapes are the meshes' triangles in order, then the spheres (scene/mod.rs:497) ... */
     const yk_sphere_desc* spheres;
+    uint32_t n_objects;            /* ... unless `objects` gives the declaration order: mesh index, or -1 - sphere index */
+    const int32_t* objects;        /* (file order of the pbrt loader, pbrt/mod.rs:797-809); NULL = meshes then spheres */
 } yk_host_scene_desc;
 
 /* ---- scene description, device level (flattened; what the FFI crate passes) ---------------- */
@@ -267,6 +269,19 @@ int yk_tonemap_filmic(yk_context*, const float* film_rgb, uint32_t res_x, uint32
  * are written back; otherwise the given values are used. */
 int yk_heatmap(yk_context*, const float* film_rgb, uint32_t res_x, uint32_t res_y, uint32_t channel, int auto_range, float* min_val,
                float* max_val, float* out_rgb);
+
+/* pbrt-v3 scene file -> host scene description, camera parameters and film resolution: the subset and defaults of
+ * scene/pbrt/{lexer,mod,param_set,cie}.rs (see csrc/host_pbrt.cpp for the directive list and the kept quirks).
+ * The result's pointers stay owned by the handle. */
+typedef struct yk_pbrt_scene yk_pbrt_scene;
+typedef struct {
+    yk_host_scene_desc scene;
+    yk_camera_params camera;
+    uint32_t res_x, res_y;
+} yk_pbrt_result;
+int yk_pbrt_load(const char* path, uint32_t max_shapes_in_node, uint32_t split_method, yk_pbrt_scene** out);
+const yk_pbrt_result* yk_pbrt_view(const yk_pbrt_scene*);
+void yk_pbrt_destroy(yk_pbrt_scene*);
 
 /* PLY mesh file -> vertex / index arrays: what scene/ply.rs:19-156 takes from a file (vertex x y z [nx ny nz] [u v]
  * as float properties, faces as int/uint lists, fan-triangulated). ASCII and both binary byte orders. The arrays stay

@@ -72,7 +72,7 @@ yko_scene* yko_scene_create(const yko_host_scene_desc* d) {
         s.lights.push_back(L);
     }
     uint32_t orig = 0;
-    for (uint32_t i = 0; i < d->n_meshes; ++i) {
+    auto add_mesh = [&](uint32_t i) {
         const yko_mesh_desc& md = d->meshes[i];
         Transform o2w = to_xf(md.object_to_world);
         Mesh mesh;
@@ -88,10 +88,11 @@ yko_scene* yko_scene_create(const yko_host_scene_desc* d) {
         }
         mesh.transform_swaps_handedness = xf_swaps_handedness(o2w);
         s.meshes.push_back(std::move(mesh));
+        const uint32_t mesh_index = (uint32_t)s.meshes.size() - 1;
         for (uint32_t v0 = 0; v0 + 2 < md.n_indices; v0 += 3)
-            s.shapes.push_back({i, {md.indices[v0], md.indices[v0 + 1], md.indices[v0 + 2]}, md.material, md.area_light, orig++});
-    }
-    for (uint32_t k = 0; k < d->n_spheres; ++k) {  // Sphere::new, shapes/sphere.rs:23-33
+            s.shapes.push_back({mesh_index, {md.indices[v0], md.indices[v0 + 1], md.indices[v0 + 2]}, md.material, md.area_light, orig++});
+    };
+    auto add_sphere = [&](uint32_t k) {  // Sphere::new, shapes/sphere.rs:23-33
         const yko_sphere_desc& sd = d->spheres[k];
         Sphere sp;
         sp.object_to_world = to_xf(sd.object_to_world);
@@ -101,8 +102,17 @@ yko_scene* yko_scene_create(const yko_host_scene_desc* d) {
         sp.transform_swaps_handedness = xf_swaps_handedness(sp.object_to_world);
         s.spheres.push_back(sp);
         Triangle shape{0, {0, 0, 0}, sd.material, -1, orig++};
-        shape.sphere = (int32_t)k;
+        shape.sphere = (int32_t)s.spheres.size() - 1;
         s.shapes.push_back(shape);
+    };
+    if (d->objects) {  // declaration order of a loaded file (pbrt/mod.rs:797-809)
+        for (uint32_t i = 0; i < d->n_objects; ++i) {
+            if (d->objects[i] >= 0) add_mesh((uint32_t)d->objects[i]);
+            else add_sphere((uint32_t)(-1 - d->objects[i]));
+        }
+    } else {  // meshes, then spheres (scene/mod.rs:497)
+        for (uint32_t i = 0; i < d->n_meshes; ++i) add_mesh(i);
+        for (uint32_t k = 0; k < d->n_spheres; ++k) add_sphere(k);
     }
     s.background = {d->background[0], d->background[1], d->background[2]};
     s.max_shapes_in_node = d->max_shapes_in_node;

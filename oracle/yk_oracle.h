@@ -68,8 +68,10 @@ typedef struct {
     float background[3];
     uint32_t max_shapes_in_node;
     uint32_t split_method;    /* 0 SAH, 1 Middle, 2 EqualCounts */
-    uint32_t n_spheres;       /* shapes = the meshes' triangles in order, then the spheres (scene/mod.rs:497) */
+    uint32_t n_spheres;       /* shapes = the meshes' triangles in order, then the spheres (scene/mod.rs:497) ... */
     const yko_sphere_desc* spheres;
+    uint32_t n_objects;       /* ... unless `objects` lists the declaration order: mesh index, or -1 - sphere index */
+    const int32_t* objects;
 } yko_host_scene_desc;
 
 typedef struct { float position[3]; float target[3]; float up[3]; uint32_t fov_axis; float fov_deg; } yko_camera_params;

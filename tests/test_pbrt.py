@@ -1,0 +1,240 @@
+"""pbrt-v3 subset loader (csrc/host_pbrt.cpp) against the rules of yuki/src/scene/pbrt/{lexer,mod,param_set,cie}.rs: a
+generated Cornell-box file must load to exactly the programmatic scene (config 1), and the loader's defaults / quirks
+are checked one by one."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from yuki_b200 import api, capi, desc as D, scenes, transforms as xf
+
+F = np.float32
+
+
+def fmt(v):
+    return " ".join(repr(float(x)) for x in np.asarray(v, np.float32).reshape(-1))
+
+
+def cornell_pbrt(tmp_path, sphere=False, with_ply=False):
+    """The Cornell box of scenes.cornell(light='point', tall_box='matte') written as a pbrt-v3 file of the accepted subset."""
+    ref, cam = scenes.cornell(xf, light="point", tall_box="matte", sphere=sphere)
+    lines = ["# generated Cornell box", f"LookAt {fmt(cam.position)}  {fmt(cam.target)}  0 1 0",
+             f'Camera "perspective" "float fov" [{cam.fov_deg!r}]', 'Film "image" "integer xresolution" [96] "integer yresolution" [96]',
+             'Sampler "halton" "integer pixelsamples" 16', 'Integrator "path" "integer maxdepth" [ 5 ]', "WorldBegin",
+             f'LightSource "point" "rgb I" [{fmt(ref.lights[0].intensity)}] "point from" [0.2775 0.54 -0.28]']
+    for k, m in enumerate(ref.meshes):
+        kd = ref.textures[ref.materials[m.material].tex[0]].value
+        lines += ["AttributeBegin", f'  Material "matte" "rgb Kd" [{fmt(kd)}]', "  Scale 0.001 0.001 0.001", "  Scale 1 1 -1"]
+        if with_ply and k == 0:
+            scenes.write_ply(tmp_path / "floor.ply", m.points, m.indices, fmt="binary_little_endian")
+            lines.append('  Shape "plymesh" "string filename" "floor.ply"')
+        else:
+            uv = "" if m.uvs is None else f' "float uv" [{fmt(m.uvs)}]'
+            lines.append(f'  Shape "trianglemesh" "integer indices" [{" ".join(str(int(i)) for i in m.indices)}] "point P" [{fmt(m.points)}]{uv}')
+        lines.append("AttributeEnd")
+    if sphere:
+        lines += ["AttributeBegin", '  Material "metal"', "  Translate 0.186 0.082 -0.168", '  Shape "sphere" "float radius" 0.082', "AttributeEnd"]
+    lines.append("WorldEnd")
+    path = tmp_path / "cornell.pbrt"
+    path.write_text("\n".join(lines) + "\n")
+    return path, ref, cam
+
+
+def same_host_scene(a: D.SceneDesc, b: D.SceneDesc):
+    ha, hb = api.HostScene(a), api.HostScene(b)
+    assert ha.n_nodes == hb.n_nodes and ha.n_tris == hb.n_tris
+    assert ha.nodes().tobytes() == hb.nodes().tobytes()
+    assert np.array_equal(ha.order(), hb.order())
+    assert np.array_equal(ha.tri_vertices().view(np.uint32), hb.tri_vertices().view(np.uint32))
+
+
+@pytest.mark.parametrize("with_ply", [False, True])
+def test_cornell_file_loads_to_the_programmatic_scene(tmp_path, with_ply):
+    path, ref, cam = cornell_pbrt(tmp_path, with_ply=with_ply)
+    sc, lcam, film = api.load_pbrt(path)
+    assert film.res == (96, 96) and film.tile_dim == 16
+    f32 = lambda t: tuple(float(F(v)) for v in t)
+    assert lcam.position == f32(cam.position) and lcam.target == f32(cam.target) and lcam.up == (0.0, 1.0, 0.0)
+    assert lcam.fov_deg == cam.fov_deg and lcam.fov_axis == D.FOV_X      # square film -> FoV::X (mod.rs:827-835)
+    assert len(sc.lights) == 1 and sc.lights[0].kind == D.LIGHT_POINT and sc.background == (0.0, 0.0, 0.0)
+    assert sc.objects == list(range(len(ref.meshes)))
+    same_host_scene(sc, ref)
+    for m, r in zip(sc.meshes, ref.meshes):
+        assert sc.textures[sc.materials[m.material].tex[0]].value == ref.textures[ref.materials[r.material].tex[0]].value
+        assert (m.uvs is None) == (r.uvs is None)
+
+
+def test_sphere_and_declaration_order(tmp_path):
+    path, ref, _ = cornell_pbrt(tmp_path, sphere=True)
+    sc, _, _ = api.load_pbrt(path, split_method=D.SPLIT_MIDDLE)
+    assert sc.objects[-1] == -1 and len(sc.spheres) == 1 and sc.spheres[0].radius == float(F(0.082))
+    m = sc.materials[sc.spheres[0].material]
+    assert m.kind == D.MAT_METAL and m.remap_roughness            # metal defaults: copper eta/k, roughness 0.01, remap
+    eta = sc.textures[m.tex[0]].value
+    # pbrt's copper table through the reference's Riemann sum, which is not normalised by the integral of y(lambda)
+    # (mod.rs:1000-1016): about 100x pbrt's own (0.2004, 0.9240, 1.1022) — kept, it is what the reference computes
+    np.testing.assert_allclose(eta, (7.3587, 86.1807, 155.2710), rtol=1e-4)
+    assert sc.textures[m.tex[2]].value[0] == float(F(0.01))
+    ref.split_method = D.SPLIT_MIDDLE
+    same_host_scene(sc, ref)
+    # a sphere declared between two meshes keeps its place in the shape list
+    (tmp_path / "mid.pbrt").write_text('WorldBegin\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\n'
+                                       'Shape "sphere"\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 1 1 0 1 0 1 1]\nWorldEnd\n')
+    sc2, _, _ = api.load_pbrt(tmp_path / "mid.pbrt")
+    assert sc2.objects == [0, -1, 1] and sc2.spheres[0].radius == 1.0
+    hs = api.HostScene(sc2)
+    assert sorted(hs.order().tolist()) == [0, 1, 2]
+
+
+def test_defaults_and_quirks(tmp_path):
+    f = tmp_path / "q.pbrt"
+    f.write_text('''
+Film "image" "integer xresolution" [200] "integer yresolution" [100]   # wide film -> vertical fov
+Camera "perspective"
+LightSource "infinite"
+LightSource "distant" "point from" [0 1 0] "point to" [0 0 0] "rgb L" [2 2 2]
+LightSource "point" "rgb I" [0 0 0]          # black: dropped
+LightSource "spot"                           # not implemented: skipped
+AreaLightSource "diffuse" "rgb L" [1 1 1]    # ignored
+MakeNamedMaterial "shiny" "string type" "glossy" "rgb Rs" [.2 .3 .4] "float roughness" .25
+WorldBegin
+Material "matte" "float sigma" 30
+Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 1 0]
+TransformBegin
+  Translate 5 0 0
+  NamedMaterial "shiny"
+TransformEnd                                  # quirk: pops the graphics state (none pushed), keeps the translation
+Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 1 0]
+AttributeBegin
+  Material "plastic"                         # unsupported -> grey matte
+  Shape "trianglemesh" "integer indices" [0 1] "point P" [0 0 0 1 0 0]     # < 3 indices: skipped
+  Shape "cylinder"                           # unsupported shape: skipped
+  Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 1 0] "normal N" [0 0 1 0 0 1 0 0 1]
+AttributeEnd
+NamedMaterial "missing"                       # unknown name -> default material
+Material "glass" "float eta" 1.33
+Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 1 0]
+WorldEnd
+''')
+    sc, cam, film = api.load_pbrt(f)
+    assert film.res == (200, 100) and cam.fov_axis == D.FOV_Y and cam.fov_deg == 45.0
+    assert cam.position == (0.0, 0.0, 0.0) and cam.up == (0.0, 1.0, 0.0)
+    assert sc.background == (1.0, 1.0, 1.0)
+    assert [l.kind for l in sc.lights] == [D.LIGHT_DISTANT] and sc.lights[0].direction == (0.0, 1.0, 0.0)
+    assert len(sc.meshes) == 4
+    mats = [sc.materials[m.material] for m in sc.meshes]
+    rad = F(np.pi) / F(180.0)
+    assert mats[0].kind == D.MAT_MATTE and sc.textures[mats[0].tex[1]].value[0] == float((F(30.0) * rad) * rad)   # sigma: to_radians twice
+    assert sc.textures[mats[0].tex[0]].value == (0.5, 0.5, 0.5)
+    assert mats[1].kind == D.MAT_GLOSSY and not mats[1].remap_roughness and sc.textures[mats[1].tex[1]].value[0] == 0.25
+    assert sc.meshes[1].object_to_world.m[3] == 5.0          # the translation survived TransformEnd
+    assert mats[2].kind == D.MAT_MATTE and sc.textures[mats[2].tex[0]].value == (0.5, 0.5, 0.5) and sc.meshes[2].normals is not None
+    assert sc.meshes[2].object_to_world.m[3] == 5.0          # AttributeBegin saved it, AttributeEnd restored the same
+    assert mats[3].kind == D.MAT_GLASS and abs(mats[3].eta - 1.33) < 1e-6
+
+
+def test_spectrum_parameter_uses_the_cie_fits(tmp_path):
+    from oracle import post  # noqa: F401  (numpy restatement style: float32 throughout)
+    lam = np.array([400, 500, 600, 700], np.float32)
+    val = np.array([0.1, 0.9, 0.5, 0.2], np.float32)
+
+    def g(l, c, a, b):
+        t = (l - F(c)) * (F(a) if l < F(c) else F(b))
+        return np.exp(F(-0.5) * t * t, dtype=np.float32)
+    x = y = z = F(0.0)
+    for l, s in zip(lam, val):
+        x += (F(0.362) * g(l, 442.0, 0.0624, 0.0374) + F(1.056) * g(l, 599.8, 0.0264, 0.0323) - F(0.065) * g(l, 501.1, 0.0490, 0.0382)) * s
+        y += (F(0.821) * g(l, 568.8, 0.0213, 0.0247) + F(0.286) * g(l, 530.9, 0.0613, 0.0322)) * s
+        z += (F(1.217) * g(l, 437.0, 0.0845, 0.0278) + F(0.681) * g(l, 459.0, 0.0385, 0.0725)) * s
+    k = (lam[-1] - lam[0]) / F(4.0)
+    x, y, z = x * k, y * k, z * k
+    want = (F(3.240479) * x - F(1.537150) * y - F(0.498535) * z, F(-0.969256) * x + F(1.875991) * y + F(0.041556) * z,
+            F(0.055648) * x - F(0.204043) * y + F(1.057311) * z)
+    (tmp_path / "kd.spd").write_text("# lambda value\n400 0.1\n500 0.9 # inline comment\n600 0.5\n700 0.2\n")
+    for spec in ('"spectrum Kd" [400 0.1 500 0.9 600 0.5 700 0.2]', '"spectrum Kd" "kd.spd"'):
+        f = tmp_path / "s.pbrt"
+        f.write_text(f'WorldBegin\nMaterial "matte" {spec}\nShape "sphere"\nWorldEnd\n')
+        sc, _, _ = api.load_pbrt(f)
+        got = sc.textures[sc.materials[sc.spheres[0].material].tex[0]].value
+        np.testing.assert_allclose(got, [float(v) for v in want], rtol=2e-6, atol=1e-7)
+
+
+def _png(path, img, depth=8, alpha=False):
+    h, w, _ = img.shape
+    dt = ">u2" if depth == 16 else "u1"
+    px = img.astype(dt)
+    if alpha:
+        px = np.concatenate([px, np.full((h, w, 1), 65535 if depth == 16 else 255, dt)], axis=2).astype(dt)
+    raw = b"".join(b"\x00" + px[y].tobytes() for y in range(h))
+
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body) & 0xffffffff)
+    path.write_bytes(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, 6 if alpha else 2, 0, 0, 0)) +
+                     chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+@pytest.mark.parametrize("depth,alpha", [(8, False), (8, True), (16, False), (16, True)])
+def test_imagemap_texture_png(tmp_path, depth, alpha):
+    rng = np.random.default_rng(depth + alpha)
+    img = rng.integers(0, 2 ** depth, (5, 7, 3))
+    _png(tmp_path / "t.png", img, depth, alpha)
+    f = tmp_path / "t.pbrt"
+    f.write_text('Texture "wall" "spectrum" "imagemap" "string filename" "t.png"\nTexture "bump" "float" "imagemap" "string filename" "nope.png"\n'
+                 'WorldBegin\nMaterial "matte" "texture Kd" "wall"\nShape "sphere"\nWorldEnd\n')
+    sc, _, _ = api.load_pbrt(f)
+    t = sc.textures[sc.materials[sc.spheres[0].material].tex[0]]
+    assert t.kind == D.TEX_IMAGE and t.image.shape == (5, 7, 3)
+    want = img.astype(np.float32) / np.float32(2 ** depth - 1)       # image_texture.rs:9-36: u8 / 255, u16 / 65535
+    assert np.array_equal(t.image.view(np.uint32), want.astype(np.float32).view(np.uint32))
+
+
+@pytest.mark.parametrize("body,needle", [
+    ('Camera "orthographic"\n', "Only perspective camera is supported"),
+    ('WorldBegin\nObjectBegin "x"\n', "UnimplementedToken"),
+    ('Transform [1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1]\n', "UnimplementedToken"),
+    ('WorldBegin\nMaterial "matte" "texture Kd" "nope"\n', "Texture 'nope' not found"),
+    ('WorldBegin\nShape "sphere" "float radius" [1\n', "UnexpectedToken"),
+    ('WorldBegin\nShape "sphere" "vector3 v" [1 2 3]\n', "UnknownParamType"),
+    ('WorldBegin\nFoo\n', "UnknownIdentifier"),
+    ('WorldBegin\nScale 1 2 x3 \n', "UnknownIdentifier"),
+    ('WorldBegin\nScale 1 2 3.4.5 \n', "InvalidNumber"),
+    ('WorldBegin\nShape "sphere\n', "UnterminatedString"),
+    ('Include "missing.pbrt"\n', "could not open"),
+    ('MakeNamedMaterial "a" "string kind" "matte"\n', "UnknownParamType"),
+])
+def test_rejected_files(tmp_path, body, needle):
+    f = tmp_path / "bad.pbrt"
+    f.write_text(body)
+    with pytest.raises(capi.YukiGpuError) as e:
+        api.load_pbrt(f)
+    assert needle in str(e.value)
+
+
+def test_include_and_number_forms(tmp_path):
+    (tmp_path / "geo.pbrt").write_text('Shape "trianglemesh" "integer indices" [0 1 2]"point P"[-.5 0 0 5e-1 0 0 0 1.5 0]\n')
+    f = tmp_path / "main.pbrt"
+    f.write_text('WorldBegin\nRotate 90 0 0 1\nInclude "geo.pbrt"\nShape "sphere" "float radius" 2\nWorldEnd\n')
+    sc, _, _ = api.load_pbrt(f)
+    assert sc.objects == [0, -1] and sc.spheres[0].radius == 2.0
+    assert sc.meshes[0].points.tolist() == [[-0.5, 0.0, 0.0], [0.5, 0.0, 0.0], [0.0, 1.5, 0.0]]
+    r = xf.rotation(float(F(90.0) * (F(np.pi) / F(180.0))), (0.0, 0.0, 1.0))
+    assert np.array_equal(sc.meshes[0].object_to_world.m.view(np.uint32), np.asarray(r.m, np.float32).view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_render_of_the_loaded_cornell_file(tmp_path):
+    """Config 1 end to end: pbrt file -> loader -> CUDA Whitted render == the programmatic scene's render, bit for bit, and
+    within the radiance gate of the oracle rendering the loaded description."""
+    from conftest import rel_rmse
+    from oracle import oracle as O
+    path, ref, _ = cornell_pbrt(tmp_path, sphere=False, with_ply=True)
+    sc, cam, film = api.load_pbrt(path)
+    smp, integ = D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(3)
+    ctx = api.Context(0)
+    a = api.Renderer(ctx).render(api.Scene(ctx, sc), cam, film, smp, integ, want_hit_ids=True)
+    b = api.Renderer(ctx).render(api.Scene(ctx, ref), cam, film, smp, integ, want_hit_ids=True)
+    assert np.array_equal(a.hit_ids, b.hit_ids) and np.array_equal(a.film.view(np.uint32), b.film.view(np.uint32))
+    o_img, o_ids, _ = O.OracleScene(sc).render(cam, film, smp, integ, want_hit_ids=True)
+    assert np.array_equal(a.hit_ids, o_ids) and rel_rmse(a.film, o_img) <= 1e-3
+    ctx.close()

@@ -151,6 +151,58 @@ def heatmap(ctx: Context, film: np.ndarray, channel: int = 0, value_range=None):
     return out, (lo.value, hi.value)
 
 
+def load_pbrt(path: str, max_shapes_in_node: int = 1, split_method: int = D.SPLIT_SAH):
+    """scene/pbrt/mod.rs `load`: pbrt-v3 file -> (SceneDesc, CameraParameters, FilmSettings), parsed by the C++ loader
+    (csrc/host_pbrt.cpp). The description is copied out of the loader's storage, so it feeds the CUDA backend and the
+    test oracle exactly like the programmatic scenes."""
+    h = C.c_void_p()
+    capi.check(capi.lib().yk_pbrt_load(str(path).encode(), int(max_shapes_in_node), int(split_method), C.byref(h)))
+    try:
+        r = capi.lib().yk_pbrt_view(h).contents
+        hd = r.scene
+
+        def xf(t):
+            return D.Transform(np.array(t.m[:], np.float32), np.array(t.m_inv[:], np.float32))
+
+        def arr(ptr, n, cols, dtype=np.float32):
+            if not ptr or n == 0:
+                return None
+            return np.ctypeslib.as_array(ptr, shape=(n * cols,)).astype(dtype).reshape((n, cols) if cols > 1 else (n,)).copy()
+
+        sc = D.SceneDesc(split_method=int(hd.split_method), max_shapes_in_node=int(hd.max_shapes_in_node),
+                         background=tuple(float(v) for v in hd.background))
+        for i in range(hd.n_textures):
+            t = hd.textures[i]
+            if t.kind == D.TEX_IMAGE:
+                img = np.ctypeslib.as_array(t.texels, shape=(t.height, t.width, 3)).copy()
+                sc.textures.append(D.Texture(D.TEX_IMAGE, (0.0, 0.0, 0.0), img))
+            else:
+                sc.textures.append(D.Texture(D.TEX_CONSTANT, tuple(float(v) for v in t.value)))
+        for i in range(hd.n_materials):
+            m = hd.materials[i]
+            sc.materials.append(D.Material(int(m.kind), tuple(int(v) for v in m.tex), eta=float(m.eta), remap_roughness=bool(m.remap_roughness)))
+        for i in range(hd.n_lights):
+            l = hd.lights[i]
+            sc.lights.append(D.Light(int(l.kind), xf(l.light_to_world), tuple(float(v) for v in l.intensity), float(l.total_width_deg),
+                                     float(l.falloff_start_deg), tuple(float(v) for v in l.size), tuple(float(v) for v in l.direction)))
+        for i in range(hd.n_meshes):
+            m = hd.meshes[i]
+            pts = arr(m.points, m.n_points, 3)
+            sc.meshes.append(D.Mesh(xf(m.object_to_world), pts if pts is not None else np.zeros((0, 3), np.float32),
+                                    arr(m.indices, m.n_indices, 1, np.uint32), int(m.material), normals=arr(m.normals, m.n_points, 3),
+                                    uvs=arr(m.uvs, m.n_points, 2), area_light=int(m.area_light)))
+        for i in range(hd.n_spheres):
+            sp = hd.spheres[i]
+            sc.spheres.append(D.Sphere(xf(sp.object_to_world), float(sp.radius), int(sp.material)))
+        sc.objects = [int(hd.objects[i]) for i in range(hd.n_objects)]
+        cam = D.CameraParameters(tuple(float(v) for v in r.camera.position), tuple(float(v) for v in r.camera.target),
+                                 tuple(float(v) for v in r.camera.up), int(r.camera.fov_axis), float(r.camera.fov_deg))
+        film = D.FilmSettings((int(r.res_x), int(r.res_y)), 16)
+    finally:
+        capi.lib().yk_pbrt_destroy(h)
+    return sc, cam, film
+
+
 def load_ply(path: str):
     """scene/ply.rs `load` up to the index buffer: returns (points (N,3), indices (T*3,), normals (N,3)|None, uvs (N,2)|None)."""
     h = C.c_void_p()

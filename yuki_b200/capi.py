@@ -99,7 +99,12 @@ class HostSceneDesc(C.Structure):
     _fields_ = [("n_meshes", C.c_uint32), ("n_textures", C.c_uint32), ("n_materials", C.c_uint32), ("n_lights", C.c_uint32),
                 ("meshes", C.POINTER(MeshDesc)), ("textures", C.POINTER(TextureDesc)), ("materials", C.POINTER(MaterialDesc)),
                 ("lights", C.POINTER(LightDesc)), ("background", C.c_float * 3), ("max_shapes_in_node", C.c_uint32),
-                ("split_method", C.c_uint32), ("n_spheres", C.c_uint32), ("spheres", C.POINTER(SphereDesc))]
+                ("split_method", C.c_uint32), ("n_spheres", C.c_uint32), ("spheres", C.POINTER(SphereDesc)),
+                ("n_objects", C.c_uint32), ("objects", C.POINTER(C.c_int32))]
+
+
+class PbrtResult(C.Structure):
+    _fields_ = [("scene", HostSceneDesc), ("camera", CameraParams), ("res_x", C.c_uint32), ("res_y", C.c_uint32)]
 
 
 class SphereDev(C.Structure):
@@ -155,7 +160,7 @@ EXPORTS = [
     "yk_last_error", "yk_context_create", "yk_context_destroy", "yk_scene_create", "yk_scene_destroy", "yk_render",
     "yk_context_stream", "yk_bvh_build", "yk_host_scene_build", "yk_host_scene_destroy", "yk_host_scene_flat", "yk_camera_make",
     "yk_film_tiles", "yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_new", "yk_xf_look_at",
-    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy", "yk_write_exr", "yk_tonemap_filmic", "yk_heatmap",
+    "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy", "yk_write_exr", "yk_tonemap_filmic", "yk_heatmap", "yk_pbrt_load", "yk_pbrt_view", "yk_pbrt_destroy",
 ]
 
 _lib = None
@@ -193,6 +198,11 @@ def lib():
     L.yk_write_exr.argtypes = [C.c_char_p, u32, u32, fp]
     L.yk_tonemap_filmic.argtypes = [vp, fp, u32, u32, fp, u32, u32, C.c_float, fp]
     L.yk_heatmap.argtypes = [vp, fp, u32, u32, u32, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), fp]
+    L.yk_pbrt_load.argtypes = [C.c_char_p, u32, u32, C.POINTER(vp)]
+    L.yk_pbrt_view.argtypes = [vp]
+    L.yk_pbrt_view.restype = C.POINTER(PbrtResult)
+    L.yk_pbrt_destroy.argtypes = [vp]
+    L.yk_pbrt_destroy.restype = None
     L.yk_ply_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.yk_ply_view.argtypes = [vp, C.POINTER(PlyData)]
     L.yk_ply_view.restype = None
@@ -313,6 +323,11 @@ def build_host_scene_desc(scene: D.SceneDesc, S=None):
     hd.n_spheres = len(scene.spheres)
     hd.spheres = spheres
     keep.append(spheres)
+    if scene.objects is not None:
+        objs = np.ascontiguousarray(scene.objects, np.int32)
+        keep.append(objs)
+        hd.n_objects = len(objs)
+        hd.objects = objs.ctypes.data_as(C.POINTER(C.c_int32))
     hd.background = f3(scene.background)
     hd.max_shapes_in_node = scene.max_shapes_in_node
     hd.split_method = scene.split_method

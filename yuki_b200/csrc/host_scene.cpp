@@ -116,7 +116,10 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
         any_normals |= d->meshes[mi].normals != nullptr;
         any_uvs |= d->meshes[mi].uvs != nullptr;
     }
-    for (uint32_t mi = 0; mi < d->n_meshes; ++mi) {
+    std::vector<float> boxes;         // world bounds per shape, in shape-list order
+    std::vector<int32_t> sphere_of;   // sphere index per shape, -1 for triangles
+    // Mesh::new + Triangle::new: one shape per index triplet (mesh.rs:21-43, triangle.rs:229-235 for the bounds)
+    auto add_mesh = [&](uint32_t mi) -> int {
         const yk_mesh_desc& m = d->meshes[mi];
         if (m.material < 0 || (uint32_t)m.material >= d->n_materials)
             return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: mesh material index out of range");
@@ -148,26 +151,24 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
                     uvs.push_back(m.uvs ? m.uvs[2 * vi + 1] : 0.0f);
                 }
             }
+            const float* v = &verts[verts.size() - 9];
+            box3 b{min3(load3(v), load3(v + 3)), max3(load3(v), load3(v + 3))};
+            b = grow(b, load3(v + 6));
+            float bb[6];
+            store3(b.lo, bb); store3(b.hi, bb + 3);
+            boxes.insert(boxes.end(), bb, bb + 6);
             mats.push_back((uint32_t)m.material);
             alights.push_back(m.area_light);
             flags.push_back(fl);
+            sphere_of.push_back(-1);
         }
-    }
-    // World bounds of every shape: triangles (triangle.rs:229-235), then the spheres (sphere.rs:121-123,
-    // Transform * Bounds3 = union of the eight transformed corners, math/transform.rs:186-201).
-    const uint32_t n_mesh_tris = (uint32_t)mats.size();
-    std::vector<float> boxes((size_t)(n_mesh_tris + d->n_spheres) * 6);
-    for (uint32_t i = 0; i < n_mesh_tris; ++i) {
-        const float* v = &verts[(size_t)i * 9];
-        box3 b{min3(load3(v), load3(v + 3)), max3(load3(v), load3(v + 3))};
-        b = grow(b, load3(v + 6));
-        store3(b.lo, &boxes[(size_t)i * 6]);
-        store3(b.hi, &boxes[(size_t)i * 6 + 3]);
-    }
-    std::vector<int32_t> sphere_of(n_mesh_tris, -1);
-    for (uint32_t k = 0; k < d->n_spheres; ++k) {
+        return YK_OK;
+    };
+    // Sphere::new (sphere.rs:23-33); bounds = object_to_world * [-r, r]^3 as the union of the eight transformed corners
+    // (sphere.rs:121-123, math/transform.rs:186-201)
+    auto add_sphere = [&](uint32_t k) -> int {
         const yk_sphere_desc& sd = d->spheres[k];
-        if (!d->spheres || sd.material < 0 || (uint32_t)sd.material >= d->n_materials)
+        if (sd.material < 0 || (uint32_t)sd.material >= d->n_materials)
             return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: sphere material index out of range");
         const xform o2w = to_xform(sd.object_to_world);
         yk_sphere sp{};
@@ -182,8 +183,9 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
                                mk3(ma.x, ma.y, mi.z), mk3(ma.x, mi.y, ma.z), mk3(mi.x, ma.y, ma.z), ma};
         box3 b{mk3(3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f), mk3(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f)};
         for (const f3& cnr : corners) b = grow(b, apply_point(o2w.m, cnr));
-        store3(b.lo, &boxes[(size_t)(n_mesh_tris + k) * 6]);
-        store3(b.hi, &boxes[(size_t)(n_mesh_tris + k) * 6 + 3]);
+        float bb[6];
+        store3(b.lo, bb); store3(b.hi, bb + 3);
+        boxes.insert(boxes.end(), bb, bb + 6);
         // the shape slot: no vertices, the sphere's material, no area light (Sphere::new takes none)
         verts.insert(verts.end(), 9, 0.0f);
         if (any_normals) norms.insert(norms.end(), 9, 0.0f);
@@ -191,12 +193,28 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
         mats.push_back((uint32_t)sd.material);
         alights.push_back(-1);
         flags.push_back((uint8_t)(YK_TRI_IS_SPHERE | (sp.swaps_handedness ? YK_TRI_SWAPS_HANDEDNESS : 0u)));
-        sphere_of.push_back((int32_t)k);
+        sphere_of.push_back((int32_t)hs->spheres.size() - 1);
+        return YK_OK;
+    };
+    if (d->n_spheres && !d->spheres) return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: null sphere list");
+    int rc = YK_OK;
+    if (d->objects) {  // the loader's declaration order (pbrt/mod.rs:797-809)
+        for (uint32_t i = 0; i < d->n_objects; ++i) {
+            const int32_t o = d->objects[i];
+            if (o >= 0 ? (uint32_t)o >= d->n_meshes : (uint32_t)(-1 - o) >= d->n_spheres)
+                return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: object index out of range");
+            if ((rc = o >= 0 ? add_mesh((uint32_t)o) : add_sphere((uint32_t)(-1 - o))) != YK_OK) return rc;
+        }
+    } else {  // meshes, then spheres (scene/mod.rs:497)
+        for (uint32_t mi = 0; mi < d->n_meshes; ++mi)
+            if ((rc = add_mesh(mi)) != YK_OK) return rc;
+        for (uint32_t k = 0; k < d->n_spheres; ++k)
+            if ((rc = add_sphere(k)) != YK_OK) return rc;
     }
     const uint32_t n_tris = (uint32_t)mats.size();
     std::vector<uint32_t> order;
     const char* why = "";
-    int rc = bvh_build_boxes(boxes.data(), n_tris, d->max_shapes_in_node ? d->max_shapes_in_node : 1u, d->split_method, &hs->nodes,
+    rc = bvh_build_boxes(boxes.data(), n_tris, d->max_shapes_in_node ? d->max_shapes_in_node : 1u, d->split_method, &hs->nodes,
                              &order, &why);
     if (rc != YK_OK) return yk_set_error(rc, why);
 
@@ -217,7 +235,7 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
         hs->tri_area_light[i] = alights[s];
         hs->tri_flags[i] = flags[s];
     }
-    if (d->n_spheres) {
+    if (!hs->spheres.empty()) {
         hs->tri_sphere.resize(n_tris);
         for (uint32_t i = 0; i < n_tris; ++i) hs->tri_sphere[i] = sphere_of[order[i]];
     }

@@ -88,7 +88,8 @@ class Sphere:                               # Sphere::new, shapes/sphere.rs:23-3
 @dataclass
 class SceneDesc:
     meshes: List[Mesh] = field(default_factory=list)
-    spheres: List[Sphere] = field(default_factory=list)   # shapes = mesh triangles in order, then the spheres
+    spheres: List[Sphere] = field(default_factory=list)   # shapes = mesh triangles in order, then the spheres ...
+    objects: Optional[List[int]] = None     # ... unless given: declaration order, mesh index or -1 - sphere index
     textures: List[Texture] = field(default_factory=list)
     materials: List[Material] = field(default_factory=list)
     lights: List[Light] = field(default_factory=list)
