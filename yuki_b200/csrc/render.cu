@@ -127,7 +127,8 @@ struct Wave {
     float4* stack;       // whitted: stack_entries * cap * 3 float4
     uint32_t* stack_top; // whitted
     uint32_t* q_active[2];
-    uint32_t* q_mat;     // 4 * cap
+    uint32_t* q_mat;     // 4 * cap: paths per material kind
+    uint32_t* q_mat_tri; // 4 * cap: the hit slot of each entry, so shading starts its triangle fetch without the hit[] gather
     Totals* totals;
 };
 // beta.w flag word
@@ -169,8 +170,9 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // Block-aggregated append to one of NQ queues: one global atomic per queue per block (same-address atomics were the
 // bottleneck of classify / resolve with one atomic per warp, profiles/r01). `key` in [0, NQ) selects the queue, any
 // other value appends nothing. Must be reached by every thread of the block (blockDim.x <= 256).
+// Returns the slot the value was written to (undefined when nothing was appended).
 template <int NQ>
-__device__ __forceinline__ void block_scatter(int key, uint32_t value, uint32_t* const (&queues)[NQ], uint32_t* const (&counters)[NQ]) {
+__device__ __forceinline__ uint32_t block_scatter(int key, uint32_t value, uint32_t* const (&queues)[NQ], uint32_t* const (&counters)[NQ]) {
     __shared__ uint32_t s_cnt[8][NQ];
     __shared__ uint32_t s_base[NQ];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
@@ -192,8 +194,13 @@ __device__ __forceinline__ void block_scatter(int key, uint32_t value, uint32_t*
         s_base[threadIdx.x] = total ? atomicAdd(counters[threadIdx.x], total) : 0u;
     }
     __syncthreads();
-    if (key >= 0 && key < NQ) queues[key][s_base[key] + s_cnt[warp][key] + my_rank] = value;
+    uint32_t pos = 0;
+    if (key >= 0 && key < NQ) {
+        pos = s_base[key] + s_cnt[warp][key] + my_rank;
+        queues[key][pos] = value;
+    }
     __syncthreads();  // the shared arrays are reused by the next call
+    return pos;
 }
 __device__ __forceinline__ unsigned long long mix_hit(uint32_t x, uint32_t y, uint32_t sample, uint32_t id) {
     unsigned long long h = ((unsigned long long)x << 48) ^ ((unsigned long long)y << 32) ^ ((unsigned long long)sample << 8) ^
@@ -699,12 +706,13 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
         if (block_first >= n) break;  // block-uniform
         const uint32_t i = block_first + threadIdx.x;
         const bool valid = i < n;
-        uint32_t path = 0, kind = 4;
+        uint32_t path = 0, kind = 4, hit_slot = kMiss;
         bool requeue = false;
         unsigned long long hh = 0;
         if (valid) {
             path = queue ? queue[i] : i;
             const uint2 h = w.hit[path];
+            hit_slot = h.y;
             uint32_t orig = 0xffffffffu;
             if (h.y != kMiss) {
                 const uint32_t m = __float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) & 0xffffffu;
@@ -730,7 +738,9 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
         }
         uint32_t* const queues[5] = {w.q_mat, w.q_mat + (size_t)w.cap, w.q_mat + (size_t)2 * w.cap, w.q_mat + (size_t)3 * w.cap, q_next};
         uint32_t* const counters[5] = {&cur->mat[0], &cur->mat[1], &cur->mat[2], &cur->mat[3], &nxt->n_active};
-        block_scatter<5>(!valid ? -1 : (requeue ? 4 : (kind < 4 ? (int)kind : -1)), path, queues, counters);
+        const int key = !valid ? -1 : (requeue ? 4 : (kind < 4 ? (int)kind : -1));
+        const uint32_t pos = block_scatter<5>(key, path, queues, counters);
+        if (key >= 0 && key < 4) w.q_mat_tri[(size_t)key * w.cap + pos] = hit_slot;
         if (first_iteration) {
             hh = warp_sum(hh);
             if ((threadIdx.x & 31) == 0 && hh) atomicAdd(&w.totals->hit_hash, hh);
@@ -927,7 +937,8 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 // active queue (one atomic per block).
 template <uint32_t KIND>
 __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
-                                                                               IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
+                                                                               const uint32_t* queue_tri, IterCounters* cur, IterCounters* nxt,
+                                                                               uint32_t* q_next) {
     const uint32_t n = cur->mat[KIND];
     const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t r = 0; r < rounds; ++r) {
@@ -938,11 +949,12 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         uint32_t path = 0;
         if (i < n) {
             path = queue[i];
+            const uint32_t hit_slot = queue_tri[i];
             const float4 ro = w.ray_o[path], rd = w.ray_d[path];
             const V3 o = f4v(ro), d = f4v(rd);
             Surface si;
             uint32_t mat_index;
-            make_surface(sc, w.hit[path].y, o, d, &si, &mat_index);
+            make_surface(sc, hit_slot, o, d, &si, &mat_index);
             Bsdf bsdf;
             make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
 
@@ -1229,7 +1241,7 @@ int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries
     WAVE_ALLOC(rng_state, cap) WAVE_ALLOC(beta, cap) WAVE_ALLOC(L, cap)
     WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap)
     WAVE_ALLOC(lt_o, cap * nl) WAVE_ALLOC(lt_d, cap * nl) WAVE_ALLOC(lt_c, cap * nl)
-    WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap)
+    WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap) WAVE_ALLOC(q_mat_tri, (size_t)4 * cap)
     WAVE_ALLOC(totals, 1)
     if (stack_entries) {
         WAVE_ALLOC(stack, (size_t)stack_entries * cap * 3)
@@ -1344,11 +1356,12 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         for (uint32_t kind = 0; kind < 4; ++kind) {
             if (!(sc->material_kinds & (1u << kind))) continue;  // no triangle of the scene has this material kind
             uint32_t* q = w.q_mat + (size_t)kind * w.cap;
+            uint32_t* qt = w.q_mat_tri + (size_t)kind * w.cap;
             switch (kind) {
-                case YK_MAT_MATTE: k_shade<YK_MAT_MATTE><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
-                case YK_MAT_GLASS: k_shade<YK_MAT_GLASS><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
-                case YK_MAT_METAL: k_shade<YK_MAT_METAL><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
-                default: k_shade<YK_MAT_GLOSSY><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, cur, nxt, q_next); break;
+                case YK_MAT_MATTE: k_shade<YK_MAT_MATTE><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
+                case YK_MAT_GLASS: k_shade<YK_MAT_GLASS><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
+                case YK_MAT_METAL: k_shade<YK_MAT_METAL><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
+                default: k_shade<YK_MAT_GLOSSY><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
             }
             tm->launches += 1;
         }
