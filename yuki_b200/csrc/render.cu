@@ -35,7 +35,7 @@ constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 constexpr int kShadeThreads = 128;
 #ifndef YK_SHADE_MIN_BLOCKS
-#define YK_SHADE_MIN_BLOCKS 4
+#define YK_SHADE_MIN_BLOCKS 8
 #endif
 
 #define CUDA_TRY(expr)                                                                                          \
