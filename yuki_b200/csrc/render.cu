@@ -34,6 +34,12 @@ constexpr int kStackDepth = 64;  // bvh.rs:172
 constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 constexpr int kShadeThreads = 128;
+#ifndef YK_TRACE_MIN_BLOCKS
+#define YK_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef YK_SHADOW_MIN_BLOCKS
+#define YK_SHADOW_MIN_BLOCKS 8
+#endif
 #ifndef YK_SHADE_MIN_BLOCKS
 #define YK_SHADE_MIN_BLOCKS 8
 #endif
@@ -464,7 +470,7 @@ struct TraceLane {
 
 // Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
 template <bool COUNTS, bool SPHERES>
-__global__ void __launch_bounds__(kTraceThreads, 8) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, IterCounters* cur) {
+__global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, IterCounters* cur) {
     __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
     uint32_t deep[kStackDepth + 1 - kShortStack];
     const uint32_t n = cur->n_active;
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(kTraceThreads, 8) k_trace_closest(DevScene sc,
 // One *path* per queue entry (the four material queues, concatenated); a lane traces its path's shadow rays one after
 // the other in light order, so the float sums associate exactly like the reference's fold.
 template <bool SPHERES>
-__global__ void __launch_bounds__(kTraceThreads, 7) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, IterCounters* cur) {
+__global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, IterCounters* cur) {
     uint32_t* const cursor = &cur->work_shadow;
     __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
     uint32_t deep[kStackDepth + 1 - kShortStack];
