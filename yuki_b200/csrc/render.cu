@@ -125,6 +125,10 @@ struct Wave {
     unsigned long long* rng_state;
     float4* beta;    // throughput (path) / node weight (whitted); w = flags | sampler dimension << kDimShift
     float4* L;       // accumulated radiance
+    // The five arrays below are the shading kernels' hand-over to the shadow kernel. They are indexed by the *shading
+    // position* g (position in the concatenation of this bounce's four material queues), not by path: the shading
+    // kernels write them fully coalesced and the shadow kernel streams them with no dependent gather.
+    uint32_t* sh_path;   // path of shading position g
     float4* pend_beta;   // weight to apply to this bounce's radiance; w = clamp flag
     float4* pend_extra;  // emitted term of this bounce; w = bit mask of the lights whose shadow ray must be traced
     float4* lt_o;        // cap * n_lights: shadow ray o.xyz | contribution.r   (contribution = f * li * cos / pdf)
@@ -578,12 +582,12 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
     bool live = false;       // the lane owns a path whose fold is not finished
     bool need_ray = false;   // ... and must load the shadow ray of the lowest light in `mask`
     bool occluded = false;
-    uint32_t path = 0, mask = 0;
+    uint32_t path = 0, pos = 0, mask = 0;  // pos: the path's shading position (index of the hand-over arrays)
     int target_light = -1;
     RGB radiance = gray(0.0f), contribution = gray(0.0f);
 
     auto finish_path = [&]() {  // path.rs:121-129
-        const float4 pe = w.pend_extra[path], pb = w.pend_beta[path];
+        const float4 pe = w.pend_extra[pos], pb = w.pend_beta[pos];
         RGB r = radiance + rgb(pe.x, pe.y, pe.z);
         if (pb.w != 0.0f) r = rgb(fminf(r.r, cfg.clamp), fminf(r.g, cfg.clamp), fminf(r.b, cfg.clamp));
         float4 L = w.L[path];
@@ -608,10 +612,9 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             }
             const uint32_t mine = chunk_next + __popc(idle & lt_mask);
             if (!live && mine < chunk_end) {
-                uint32_t k = 0, j = mine;
-                if (j >= n0) { j -= n0; k = 1; if (j >= n1) { j -= n1; k = 2; if (j >= n2) { j -= n2; k = 3; } } }
-                path = w.q_mat[(size_t)k * w.cap + j];
-                mask = __float_as_uint(w.pend_extra[path].w);
+                pos = mine;
+                path = w.sh_path[pos];
+                mask = __float_as_uint(w.pend_extra[pos].w);
                 radiance = gray(0.0f);
                 sum_rays += __popc(mask);
                 if (mask) { live = true; need_ray = true; }
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
         }
         if (need_ray) {  // next light of this lane's path
             const uint32_t k = __ffs(mask) - 1;
-            const size_t ref = (size_t)k * w.cap + path;
+            const size_t ref = (size_t)k * w.cap + pos;
             const float4 ro = w.lt_o[ref], rd = w.lt_d[ref];
             const float2 rc = w.lt_c[ref];
             contribution = rgb(ro.w, rd.w, rc.x);
@@ -641,7 +644,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
                 bool blocks = true;
                 if (SPHERES && det_ != det_) {  // sphere slot: run the real test; spheres carry no area light
                     float t_s;
-                    blocks = sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.lt_d[(size_t)(__ffs(mask) - 1) * w.cap + path],
+                    blocks = sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.lt_d[(size_t)(__ffs(mask) - 1) * w.cap + pos],
                                               tl.t_max, &t_s);
                 } else if (target_light >= 0 && al_ >= 0 && al_ == target_light) {
                     blocks = false;  // bvh.rs:269-280: the target light's own emissive triangles do not occlude
@@ -946,6 +949,9 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                                                                                const uint32_t* queue_tri, IterCounters* cur, IterCounters* nxt,
                                                                                uint32_t* q_next) {
     const uint32_t n = cur->mat[KIND];
+    uint32_t g_base = 0;  // shading position of this kind's first queue entry (classify has finished: the counts are final)
+#pragma unroll
+    for (uint32_t k = 0; k < KIND; ++k) g_base += cur->mat[k];
     const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
@@ -955,6 +961,8 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         uint32_t path = 0;
         if (i < n) {
             path = queue[i];
+            const uint32_t g = g_base + i;
+            w.sh_path[g] = path;
             const uint32_t hit_slot = queue_tri[i];
             const float4 ro = w.ray_o[path], rd = w.ray_d[path];
             const V3 o = f4v(ro), d = f4v(rd);
@@ -991,7 +999,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     const RGB f = bsdf.f(si.wo, ls.l);
                     if (ls.has_vis && !black(f)) {
                         const RGB c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
-                        const size_t ref = (size_t)k * w.cap + path;
+                        const size_t ref = (size_t)k * w.cap + g;
                         w.lt_o[ref] = make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, c.r);
                         w.lt_d[ref] = make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, c.g);
                         w.lt_c[ref] = make_float2(c.b, __int_as_float(ls.vis_light));
@@ -1015,8 +1023,8 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             if (cfg.integrator == YK_INTEGRATOR_PATH) {
                 // path.rs:121-129 — beta multiplies the emitted term here and again in the fold (reference quirk)
                 const RGB extra = add_le ? beta * le : gray(0.0f);
-                w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
-                w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
+                w.pend_extra[g] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
+                w.pend_beta[g] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
                 const Bsdf::Sample s = bsdf.sample_f(wo_ray, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137 (wo = -ray.d)
                 if (!(black(s.f) || s.pdf == 0.0f)) {
                     alive = true;
@@ -1041,8 +1049,8 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             } else {
                 // whitted.rs:128-170
                 const RGB extra = add_le ? le : gray(0.0f);
-                w.pend_extra[path] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
-                w.pend_beta[path] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+                w.pend_extra[g] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
+                w.pend_beta[g] = make_float4(beta.r, beta.g, beta.b, 0.0f);
                 StackEntry child[2];
                 int n_child = 0;
                 if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
@@ -1245,7 +1253,7 @@ int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries
     if ((rc = dev_alloc(bag, &w.field, (size_t)(count))) != YK_OK) { free_bag(bag); return rc; }
     WAVE_ALLOC(ray_o, cap) WAVE_ALLOC(ray_d, cap) WAVE_ALLOC(hit, cap) WAVE_ALLOC(bvh_counts, cap)
     WAVE_ALLOC(rng_state, cap) WAVE_ALLOC(beta, cap) WAVE_ALLOC(L, cap)
-    WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap)
+    WAVE_ALLOC(sh_path, cap) WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap)
     WAVE_ALLOC(lt_o, cap * nl) WAVE_ALLOC(lt_d, cap * nl) WAVE_ALLOC(lt_c, cap * nl)
     WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap) WAVE_ALLOC(q_mat_tri, (size_t)4 * cap)
     WAVE_ALLOC(totals, 1)
