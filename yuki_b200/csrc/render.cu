@@ -118,12 +118,17 @@ struct Batch {
 // needs a shadow ray; the shadow kernel reads those back and does the one read-modify-write of L.
 struct Wave {
     uint32_t cap, n_lights, stack_entries;
-    float4* ray_o;   // o.xyz, t_max
-    float4* ray_d;   // d.xyz, -
-    uint2* hit;      // t bits, triangle index (kMiss = none)
+    // Per-bounce path state, streamed: bounce b reads st[b & 1] at the ray's queue slot and the shading kernels write the
+    // survivors' state to st[(b + 1) & 1] at their position in the next queue. Every kernel therefore reads and writes
+    // dense, (near-)coalesced arrays; nothing is gathered through a path index except L and the Whitted stack.
+    struct Stream {
+        float4* ray_o;   // o.xyz, t_max
+        float4* ray_d;   // d.xyz, -
+        float4* beta;    // throughput (path) / node weight (whitted); w = flags | sampler dimension << kDimShift
+        unsigned long long* rng;
+    } st[2];
+    uint2* hit;         // per queue slot: t bits, shape slot (kMiss = none)
     uint2* bvh_counts;  // BVHIntersections: tests, hits
-    unsigned long long* rng_state;
-    float4* beta;    // throughput (path) / node weight (whitted); w = flags | sampler dimension << kDimShift
     float4* L;       // accumulated radiance
     // The five arrays below are the shading kernels' hand-over to the shadow kernel. They are indexed by the *shading
     // position* g (position in the concatenation of this bounce's four material queues), not by path: the shading
@@ -138,7 +143,8 @@ struct Wave {
     uint32_t* stack_top; // whitted
     uint32_t* q_active[2];
     uint32_t* q_mat;     // 4 * cap: paths per material kind
-    uint32_t* q_mat_tri; // 4 * cap: the hit slot of each entry, so shading starts its triangle fetch without the hit[] gather
+    uint32_t* q_mat_tri; // 4 * cap: the hit shape slot of each entry
+    uint32_t* q_mat_slot; // 4 * cap: the entry's slot in this bounce's active queue (index of st[] / hit[])
     Totals* totals;
 };
 // beta.w flag word
@@ -255,10 +261,10 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, IterCounters* first) {
     const V3 d_cam = unit(p_cam);
     const V3 o = xf_point(cfg.c2w, mk(0.0f, 0.0f, 0.0f));
     const V3 d = xf_vec(cfg.c2w, d_cam);
-    w.ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
-    w.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
-    w.rng_state[i] = s.rng.state;
-    w.beta[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(kFlagAlive | (s.dim << kDimShift)));
+    w.st[0].ray_o[i] = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
+    w.st[0].ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    w.st[0].rng[i] = s.rng.state;
+    w.st[0].beta[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(kFlagAlive | (s.dim << kDimShift)));
     w.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (w.stack_top) w.stack_top[i] = 0;
 }
@@ -474,7 +480,7 @@ struct TraceLane {
 
 // Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
 template <bool COUNTS, bool SPHERES>
-__global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_closest(DevScene sc, Wave w, const uint32_t* queue, IterCounters* cur) {
+__global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_closest(DevScene sc, Wave w, int b, IterCounters* cur) {
     __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
     uint32_t deep[kStackDepth + 1 - kShortStack];
     const uint32_t n = cur->n_active;
@@ -509,9 +515,9 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
             if (!exhausted) {
                 const uint32_t mine = chunk_next + __popc(idle & lt_mask);
                 if (!live && mine < chunk_end) {
-                    path = queue ? queue[mine] : mine;
-                    const float4 ro = w.ray_o[path];
-                    const float4 rd = w.ray_d[path];
+                    path = mine;  // the queue slot: rays, hits and counters of a bounce are all in queue order
+                    const float4 ro = w.st[b].ray_o[path];
+                    const float4 rd = w.st[b].ray_d[path];
                     tl.start(sbase, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w);
                     hit_tri = kMiss; hit_t = 0.0f;
                     live = true;
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
                 if (SPHERES && det_ != det_) {  // a sphere slot (NaN vertex lanes): shapes/sphere.rs:36-77
                     float t_s;
                     /* the direction is not kept in registers: re-read it on this rare path */
-                    if (sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.ray_d[path], tl.t_max, &t_s)) {
+                    if (sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.st[b].ray_d[path], tl.t_max, &t_s)) {
                         hit_tri = tri_; hit_t = t_s; tl.t_max = t_s;
                     }
                 } else {
@@ -691,23 +697,31 @@ __device__ __forceinline__ void stack_push(const Wave& w, uint32_t path, const S
     base[2] = make_float4(e.weight.b, __uint_as_float(e.flags), 0.0f, 0.0f);
     w.stack_top[path] = top + 1;
 }
-// Pops the next pending node into the path's ray/weight slots (the sampler dimension `dim` carries on: the reference
-// shares one sampler through the recursion). Returns false when the tree is done.
-__device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path, uint32_t dim) {
+// Pops the next pending node of the path's tree. Returns false when the tree is done.
+__device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path, StackEntry* e) {
     const uint32_t top = w.stack_top[path];
     if (top == 0) return false;
     const float4* base = w.stack + ((size_t)(top - 1) * w.cap + path) * 3;
     const float4 a = base[0], b = base[1], c = base[2];
     w.stack_top[path] = top - 1;
-    w.ray_o[path] = make_float4(a.x, a.y, a.z, __int_as_float(0x7f800000));
-    w.ray_d[path] = make_float4(a.w, b.x, b.y, 0.0f);
-    w.beta[path] = make_float4(b.z, b.w, c.x, __uint_as_float(__float_as_uint(c.y) | kFlagAlive | (dim << kDimShift)));
+    e->o = mk(a.x, a.y, a.z);
+    e->d = mk(a.w, b.x, b.y);
+    e->weight = rgb(b.z, b.w, c.x);
+    e->flags = __float_as_uint(c.y);
     return true;
+}
+// Writes a tree node as the path's next ray (the sampler dimension `dim` carries on: the reference shares one sampler
+// through the recursion).
+__device__ __forceinline__ void stream_node(const Wave::Stream& st, uint32_t pos, const StackEntry& e, uint32_t dim, unsigned long long rng) {
+    st.ray_o[pos] = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+    st.ray_d[pos] = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+    st.beta[pos] = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (dim << kDimShift)));
+    st.rng[pos] = rng;
 }
 
 // ---- classify: miss handling + compaction by material ("ray-queue sort/compaction pass") ---------------
-__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, IterCounters* cur, IterCounters* nxt,
-                           int first_iteration, uint32_t* q_next) {
+__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, int b, IterCounters* cur,
+                           IterCounters* nxt, int first_iteration, uint32_t* q_next) {
     const uint32_t n = cur->n_active;
     const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t r = 0; r < rounds; ++r) {
@@ -717,10 +731,12 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
         const bool valid = i < n;
         uint32_t path = 0, kind = 4, hit_slot = kMiss;
         bool requeue = false;
+        StackEntry node{};
+        uint32_t node_dim = 0;
         unsigned long long hh = 0;
         if (valid) {
             path = queue ? queue[i] : i;
-            const uint2 h = w.hit[path];
+            const uint2 h = w.hit[i];
             hit_slot = h.y;
             uint32_t orig = 0xffffffffu;
             if (h.y != kMiss) {
@@ -729,13 +745,16 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
                 if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
             } else if (first_iteration != 2) {  // (2 = debug integrators: their li() returns no background)
                 // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
-                const float4 b = w.beta[path];
+                const float4 bw = w.st[b].beta[i];
                 float4 L = w.L[path];
-                L.x = L.x + b.x * sc.background[0];
-                L.y = L.y + b.y * sc.background[1];
-                L.z = L.z + b.z * sc.background[2];
+                L.x = L.x + bw.x * sc.background[0];
+                L.y = L.y + bw.y * sc.background[1];
+                L.z = L.z + bw.z * sc.background[2];
                 w.L[path] = L;
-                if (cfg.integrator == YK_INTEGRATOR_WHITTED) requeue = stack_pop(w, path, __float_as_uint(b.w) >> kDimShift);
+                if (cfg.integrator == YK_INTEGRATOR_WHITTED) {
+                    node_dim = __float_as_uint(bw.w) >> kDimShift;
+                    requeue = stack_pop(w, path, &node);
+                }
             }
             if (first_iteration) {
                 const uint32_t si = bt.div_jobs.div(path);
@@ -749,7 +768,12 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
         uint32_t* const counters[5] = {&cur->mat[0], &cur->mat[1], &cur->mat[2], &cur->mat[3], &nxt->n_active};
         const int key = !valid ? -1 : (requeue ? 4 : (kind < 4 ? (int)kind : -1));
         const uint32_t pos = block_scatter<5>(key, path, queues, counters);
-        if (key >= 0 && key < 4) w.q_mat_tri[(size_t)key * w.cap + pos] = hit_slot;
+        if (key >= 0 && key < 4) {
+            w.q_mat_tri[(size_t)key * w.cap + pos] = hit_slot;
+            w.q_mat_slot[(size_t)key * w.cap + pos] = i;
+        } else if (key == 4) {
+            stream_node(w.st[b ^ 1], pos, node, node_dim, w.st[b].rng[i]);
+        }
         if (first_iteration) {
             hh = warp_sum(hh);
             if ((threadIdx.x & 31) == 0 && hh) atomicAdd(&w.totals->hit_hash, hh);
@@ -946,8 +970,8 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 // active queue (one atomic per block).
 template <uint32_t KIND>
 __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
-                                                                               const uint32_t* queue_tri, IterCounters* cur, IterCounters* nxt,
-                                                                               uint32_t* q_next) {
+                                                                               const uint32_t* queue_tri, const uint32_t* queue_slot, int b,
+                                                                               IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
     const uint32_t n = cur->mat[KIND];
     uint32_t g_base = 0;  // shading position of this kind's first queue entry (classify has finished: the counts are final)
 #pragma unroll
@@ -959,12 +983,15 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         const uint32_t i = block_first + threadIdx.x;
         bool alive = false;
         uint32_t path = 0;
+        // the survivor's state for the next bounce, written after the compaction assigns its position
+        float4 nx_o = make_float4(0, 0, 0, 0), nx_d = make_float4(0, 0, 0, 0), nx_beta = make_float4(0, 0, 0, 0);
+        unsigned long long nx_rng = 0;
         if (i < n) {
             path = queue[i];
             const uint32_t g = g_base + i;
             w.sh_path[g] = path;
-            const uint32_t hit_slot = queue_tri[i];
-            const float4 ro = w.ray_o[path], rd = w.ray_d[path];
+            const uint32_t hit_slot = queue_tri[i], slot = queue_slot[i];
+            const float4 ro = w.st[b].ray_o[slot], rd = w.st[b].ray_d[slot];
             const V3 o = f4v(ro), d = f4v(rd);
             Surface si;
             uint32_t mat_index;
@@ -972,7 +999,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             Bsdf bsdf;
             make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
 
-            const float4 beta4 = w.beta[path];
+            const float4 beta4 = w.st[b].beta[slot];
             RGB beta = rgb(beta4.x, beta4.y, beta4.z);
             const uint32_t flags = __float_as_uint(beta4.w) & kFlagMask;
             const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
@@ -981,7 +1008,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             const uint32_t sample_i = bt.div_jobs.div(path), job_i = path - sample_i * bt.n_jobs;
             const Job job = bt.jobs[job_i];
             SamplerState smp;
-            smp.rng.state = w.rng_state[path];
+            smp.rng.state = w.st[b].rng[slot];
             smp.rng.inc = job.rng_inc;
             smp.dim = __float_as_uint(beta4.w) >> kDimShift;
             smp.px = job.x;
@@ -1039,12 +1066,9 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     const uint32_t bounces = depth + 1;
                     if (bounces >= cfg.max_depth) alive = false;
                     new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u);
-                    if (alive) {  // a finished path's ray / throughput / sampler state is never read again
-                        w.ray_o[path] = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
-                        w.ray_d[path] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
-                        w.beta[path] = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
-                        w.rng_state[path] = smp.rng.state;
-                    }
+                    nx_o = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
+                    nx_d = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+                    nx_beta = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
                 }
             } else {
                 // whitted.rs:128-170
@@ -1069,21 +1093,24 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     }
                 }
                 if (n_child == 2) stack_push(w, path, child[1]);  // transmission waits until the reflection subtree is done
-                if (n_child >= 1) {
-                    const StackEntry& e = child[0];
-                    w.ray_o[path] = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
-                    w.ray_d[path] = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
-                    w.beta[path] = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
-                    alive = true;
-                } else {
-                    alive = stack_pop(w, path, smp.dim);
-                }
-                if (alive) w.rng_state[path] = smp.rng.state;
+                StackEntry e = child[0];
+                alive = n_child >= 1 || stack_pop(w, path, &e);
+                nx_o = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+                nx_d = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+                nx_beta = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
             }
+            nx_rng = smp.rng.state;
         }
         uint32_t* const queues[1] = {q_next};
         uint32_t* const counters[1] = {&nxt->n_active};
-        block_scatter<1>(alive ? 0 : -1, path, queues, counters);
+        const uint32_t npos = block_scatter<1>(alive ? 0 : -1, path, queues, counters);
+        if (alive) {  // a finished path's ray / throughput / sampler state is never read again
+            const Wave::Stream& out = w.st[b ^ 1];
+            out.ray_o[npos] = nx_o;
+            out.ray_d[npos] = nx_d;
+            out.beta[npos] = nx_beta;
+            out.rng[npos] = nx_rng;
+        }
     }
 }
 
@@ -1099,7 +1126,7 @@ __global__ void k_debug_shade(DevScene sc, Wave w, RenderCfg cfg, uint32_t n) {
     } else if (h.y != kMiss) {
         Surface si;
         uint32_t m;
-        make_surface(sc, h.y, f4v(w.ray_o[path]), f4v(w.ray_d[path]), &si, &m);
+        make_surface(sc, h.y, f4v(w.st[0].ray_o[path]), f4v(w.st[0].ray_d[path]), &si, &m);  // first bounce: slot == path
         if (cfg.integrator == YK_INTEGRATOR_GEOMETRY_NORMALS) c = rgb(si.n.x, si.n.y, si.n.z) / 2.0f + gray(0.5f);
         else if (cfg.integrator == YK_INTEGRATOR_SHADING_NORMALS) c = rgb(si.sh_n.x, si.sh_n.y, si.sh_n.z) / 2.0f + gray(0.5f);
         else c = rgb(si.uv.x, si.uv.y, 0.0f);
@@ -1251,11 +1278,13 @@ int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries
     int rc = YK_OK;
 #define WAVE_ALLOC(field, count) \
     if ((rc = dev_alloc(bag, &w.field, (size_t)(count))) != YK_OK) { free_bag(bag); return rc; }
-    WAVE_ALLOC(ray_o, cap) WAVE_ALLOC(ray_d, cap) WAVE_ALLOC(hit, cap) WAVE_ALLOC(bvh_counts, cap)
-    WAVE_ALLOC(rng_state, cap) WAVE_ALLOC(beta, cap) WAVE_ALLOC(L, cap)
+    for (int k = 0; k < 2; ++k) {
+        WAVE_ALLOC(st[k].ray_o, cap) WAVE_ALLOC(st[k].ray_d, cap) WAVE_ALLOC(st[k].beta, cap) WAVE_ALLOC(st[k].rng, cap)
+    }
+    WAVE_ALLOC(hit, cap) WAVE_ALLOC(bvh_counts, cap) WAVE_ALLOC(L, cap)
     WAVE_ALLOC(sh_path, cap) WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap)
     WAVE_ALLOC(lt_o, cap * nl) WAVE_ALLOC(lt_d, cap * nl) WAVE_ALLOC(lt_c, cap * nl)
-    WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap) WAVE_ALLOC(q_mat_tri, (size_t)4 * cap)
+    WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap) WAVE_ALLOC(q_mat_tri, (size_t)4 * cap) WAVE_ALLOC(q_mat_slot, (size_t)4 * cap)
     WAVE_ALLOC(totals, 1)
     if (stack_entries) {
         WAVE_ALLOC(stack, (size_t)stack_entries * cap * 3)
@@ -1339,17 +1368,18 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
     uint32_t* q_cur = nullptr;
     int flip = 0;
     for (uint32_t iter = 0; iter < max_iters; ++iter) {
+        const int b = (int)(iter & 1);  // this bounce reads stream b and writes stream b ^ 1
         IterCounters* cur = &p->d_ctr[iter & 1];
         IterCounters* nxt = &p->d_ctr[(iter + 1) & 1];
         if (iter > 0) CUDA_TRY(cudaMemsetAsync(nxt, 0, sizeof(IterCounters), s));
         CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
         const bool spheres = sc->dev.spheres != nullptr;  // scenes without spheres run instantiations without the sphere path
         if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
-            if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
-            else k_trace_closest<true, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+            if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
+            else k_trace_closest<true, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
         } else {
-            if (spheres) k_trace_closest<false, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
-            else k_trace_closest<false, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, q_cur, cur);
+            if (spheres) k_trace_closest<false, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
+            else k_trace_closest<false, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
         }
         CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
         tm->launches += 1;
@@ -1358,24 +1388,25 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         if (debug) {
             k_debug_shade<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt.n_paths);
             // primary-hit digest / id image for the debug integrators too
-            k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, cur, nxt, 2, q_next);
+            k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, 2, q_next);
             tm->launches += 2;
             for (int st = 2; st < kTimedStages; ++st) CUDA_TRY(cudaEventRecord(stage_event(iter, st), s));
             sl.n_iters = iter + 1;
             break;
         }
-        k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, cur, nxt, iter == 0 ? 1 : 0, q_next);
+        k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
         CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
         tm->launches += 1;
         for (uint32_t kind = 0; kind < 4; ++kind) {
             if (!(sc->material_kinds & (1u << kind))) continue;  // no triangle of the scene has this material kind
             uint32_t* q = w.q_mat + (size_t)kind * w.cap;
             uint32_t* qt = w.q_mat_tri + (size_t)kind * w.cap;
+            uint32_t* qs = w.q_mat_slot + (size_t)kind * w.cap;
             switch (kind) {
-                case YK_MAT_MATTE: k_shade<YK_MAT_MATTE><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
-                case YK_MAT_GLASS: k_shade<YK_MAT_GLASS><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
-                case YK_MAT_METAL: k_shade<YK_MAT_METAL><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
-                default: k_shade<YK_MAT_GLOSSY><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, cur, nxt, q_next); break;
+                case YK_MAT_MATTE: k_shade<YK_MAT_MATTE><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
+                case YK_MAT_GLASS: k_shade<YK_MAT_GLASS><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
+                case YK_MAT_METAL: k_shade<YK_MAT_METAL><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
+                default: k_shade<YK_MAT_GLOSSY><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
             }
             tm->launches += 1;
         }
