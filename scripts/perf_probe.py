@@ -56,3 +56,12 @@ if which in ("hf", "all"):
 if which in ("room", "all"):
     s, c = scenes.material_room(xf)
     probe("room 1080p path8 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
+if which == "ab":  # one line per scene class, for A/B builds (YUKI_GPU_LIB=...)
+    s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+    probe("cornell 1024^2 path8 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8))
+    s, c = scenes.material_room(xf)
+    probe("room 1080p path8 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
+    s, c = scenes.heightfield(xf, 708, 708)
+    probe("heightfield 1M path8 1920x1080 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=2)
+    s, c = scenes.terrain_room(xf)
+    probe("terrain 10M path8 3840x2160 4spp", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8), reps=2)

@@ -271,3 +271,48 @@ def test_accumulating_launch_counts_samples_and_matches_the_mean(gpu_ctx, xf):
         rn.check_status()
         time.sleep(0.001)
     assert np.all(film.samples == 10)
+
+
+@pytest.mark.parametrize("split,max_shapes", [(D.SPLIT_EQUAL_COUNTS, 40), (D.SPLIT_MIDDLE, 40), (D.SPLIT_SAH, 7), (D.SPLIT_EQUAL_COUNTS, 60000)])
+def test_leaf_sizes_counters_and_path_bit_exact(gpu_ctx, oracle, xf, split, max_shapes):
+    """Leaves of many shapes: above 16 shapes the device leaf refs go through the leaf table instead of the packed form
+    (DESIGN.md §3); with max_shapes above the triangle count the root itself is a leaf (no interior record at all).
+    Counter images, hit ids, shadow-ray counters and the Path film stay bit-exact."""
+    scene, cam = scenes.heightfield(xf, 40, 40, seed=5, split_method=split, max_shapes_in_node=max_shapes)
+    film = D.FilmSettings((96, 72), 16)
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.uniform(1), D.IntegratorType.bvh_intersections())
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+    assert r.stats.closest_nodes == o_st.closest_nodes and r.stats.closest_tris == o_st.closest_tris
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.path(5))
+    assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+    assert r.stats.closest_nodes == o_st.closest_nodes and r.stats.closest_tris == o_st.closest_tris
+    assert r.stats.any_nodes == o_st.any_nodes and r.stats.any_tris == o_st.any_tris and r.stats.shadow_rays == o_st.shadow_rays
+
+
+def test_deep_traversal_stack_spills_bit_exact(gpu_ctx, oracle, xf):
+    """A degenerate (list-like) hierarchy drives the traversal stack beyond its shared-memory levels into the spill
+    arrays: Middle splits of a geometrically graded strip of tilted quads give a one-sided tree, and rays along the strip
+    pass through every nested box (up to 69 passed box tests per ray, > 30 pending far children)."""
+    import numpy as np_
+    n = 60
+    xs = np_.concatenate([[0.0], np_.cumsum(1.7 ** np_.arange(n))]).astype(np_.float32)
+    xs = xs / xs[-1] * 8.0 - 4.0
+    pts, idx = [], []
+    for i in range(n):
+        b = len(pts)
+        pts += [(xs[i], -0.5, 0.0), (xs[i + 1], -0.5, 0.0), (xs[i + 1], 0.5, 1.0), (xs[i], 0.5, 1.0)]
+        idx += [b, b + 1, b + 2, b, b + 2, b + 3]
+    s = D.SceneDesc(split_method=D.SPLIT_MIDDLE, max_shapes_in_node=1)
+    m = s.add_material(D.Material(D.MAT_MATTE, (s.add_texture(D.Texture.constant(0.7, 0.6, 0.5)), s.add_texture(D.Texture.constant(0.0)))))
+    s.meshes.append(D.Mesh(xf.identity(), np_.asarray(pts, np_.float32), np_.asarray(idx, np_.uint32), m))
+    s.lights.append(D.Light(D.LIGHT_POINT, xf.translation((-6.0, 0.3, 0.2)), (30.0, 30.0, 30.0)))
+    cam = D.CameraParameters((-6.0, 0.1, 0.45), (4.0, 0.1, 0.5), fov_axis=D.FOV_X, fov_deg=12.0)  # looks along the strip
+    film = D.FilmSettings((80, 60), 16)
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, s, cam, film, D.SamplerType.uniform(1), D.IntegratorType.bvh_intersections())
+    assert np.array_equal(r.hit_ids, o_ids)
+    assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+    assert o_img[..., 1].max() > 40
+    r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, s, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.path(4))
+    assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+    assert r.stats.any_nodes == o_st.any_nodes and r.stats.closest_nodes == o_st.closest_nodes

@@ -67,7 +67,12 @@ struct DevMaterial {
     uint32_t _pad;
 };
 struct DevScene {
-    const float4* nodes;   // 2 x float4 per node: (p_min, offset) (p_max, meta)
+    // One 64-byte record per *interior* node holding the boxes of its two children:
+    //   (p_min child0, ref0) (p_max child0, -) (p_min child1, ref1) (p_max child1, -)
+    // child0 = the node after its parent in the reference's pre-order array, child1 = second_child_index (bvh.rs:396-419).
+    // A visit loads both boxes with one request; leaves have no record of their own (their shape range is in the ref).
+    const float4* nodes2;
+    const uint2* leaf_table;  // null: leaf refs are packed (count - 1) << 27 | first; else ref = index of (first, count)
     const float4* tris;    // 3 x float4 per triangle: (x0 x1 x2, area_light) (y0 y1 y2, material | flags<<24) (z0 z1 z2, orig_id)
     const float* normals;  // 9 per triangle or null
     const float* uvs;      // 6 per triangle or null
@@ -78,8 +83,14 @@ struct DevScene {
                                // rare hit path takes over), row 0's w = -2 - sphere index
     uint32_t n_lights, n_tris, n_nodes;
     float background[3];
+    float root_min[3], root_max[3];  // the root's own box (tested once per ray)
+    uint32_t root_ref;
 };
-constexpr uint32_t kMetaLeaf = 0x80000000u;  // meta: leaf -> leaf bit | shape_count; interior -> 1 << split_axis
+// Child refs: interior = kRefInterior | split_axis << 29 | record index (the axis picks the near child before the record is
+// loaded); leaf = bit 31 clear, see leaf_table. kNoNode (all ones) is the stack sentinel / "no node".
+constexpr uint32_t kRefInterior = 0x80000000u;
+constexpr uint32_t kRefIndexMask = 0x1fffffffu;
+constexpr uint32_t kLeafFirstBits = 27;
 
 // ---- per-iteration device counters ----------------------------------------------------------------
 // Queue lengths never leave the device: every kernel of a bounce reads its element count from `cur` and appends to
@@ -294,16 +305,24 @@ constexpr uint32_t kChunk = 64;
 constexpr int kRefillBelow = YK_REFILL_BELOW;
 constexpr int kNodePhaseMin = YK_NODE_PHASE_MIN;
 #ifndef YK_SHORT_STACK
-#define YK_SHORT_STACK 24
+#define YK_SHORT_STACK 16
 #endif
 constexpr int kShortStack = YK_SHORT_STACK;
-constexpr uint32_t kStackStride = kTraceThreads * 4;  // bytes between two levels of one lane's stack: s_stack[depth][thread]
+// s_stack[depth][thread] = (child ref, key = the child's clamped slab entry distance): one 64-bit access per push / pop,
+// conflict-free for any mix of depths (a half-warp's 16 entries cover the 32 banks)
+constexpr uint32_t kStackStride = kTraceThreads * 8;  // bytes between two levels of one lane's stack
+constexpr int kDeepStack = kStackDepth + 1 - kShortStack;
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void lds_entry(uint32_t addr, uint32_t* ref, float* key) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(*ref), "=f"(*key) : "r"(addr));
+}
+__device__ __forceinline__ void sts_entry(uint32_t addr, uint32_t ref, float key) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ref), "f"(key) : "memory");
+}
 
 // Sphere slots are rare: the test lives behind a real call so that it costs the traversal loops no registers.
 __device__ __noinline__ bool sphere_slot_test(const yk_sphere* spheres, int tag, float ox, float oy, float oz, float4 rd, float t_max,
@@ -312,20 +331,61 @@ __device__ __noinline__ bool sphere_slot_test(const yk_sphere* spheres, int tag,
     return sphere_test(spheres[-2 - tag], mk(ox, oy, oz), f4v(rd), t_max, t_out, &o_s, &d_s);
 }
 
+// Traversal state of one ray. The walk performs exactly the reference's sequence of box and shape tests, but is
+// organised around the 64-byte two-child records:
+//  * entering an interior node loads both children's boxes at once and slab-tests both. The near child (by the ray's
+//    sign on the split axis, bvh.rs:186-194) is tested against the current t_max, as the reference does next. The far
+//    child's test happens later in the reference, with whatever t_max is current *then* — but the slab arithmetic does
+//    not depend on t_max except through the final `min(.., t_max)`, so the far child's clamped entry distance is kept
+//    as the stack entry's `key` and the deferred test is `key <= t_max` at pop time: no memory access for a popped
+//    node that misses, and only nodes whose box test passes are ever loaded (half the dependent loads of a one-node-
+//    per-visit walk). A far child that can never pass (entry beyond its own exit) gets a NaN key.
+//  * counters: the closest-hit walk always drains its stack, so both tests of a record are counted when it is loaded
+//    and never-passing far children are not pushed; the any-hit walk ends early, so it counts a far child's test when
+//    it is popped (or tested on the spot) and pushes NaN-key entries too.
 struct TraceLane {
     float ox, oy, oz, ix, iy, iz, t_max;
     float okx, oky, okz, sx, sy, sz;  // watertight test: permuted origin, shear
     uint32_t kx, ky, kz, neg_mask;
-    uint32_t cur, leaf_pos, leaf_end;
-    uint32_t sp;  // shared-memory byte address of the lane's next free stack entry (level 0 holds the kNoNode sentinel)
-    uint32_t n_tests, n_hits, n_tris;
+    uint32_t cur;  // interior ref to enter next, or kNoNode
+    uint32_t leaf_pos, leaf_end;
+    uint32_t sp;  // shared-memory byte address of the lane's next free stack entry (level 0 holds the sentinel)
+    uint32_t n_tests, n_tris;  // running totals of the lane (all of its rays): box tests, shape tests
+    uint32_t n_hits;           // passed box tests of the current ray (COUNTS only)
 
     __device__ __forceinline__ void idle(uint32_t sbase) {
         cur = kNoNode; sp = sbase + kStackStride; leaf_pos = leaf_end = 0; n_tests = n_hits = n_tris = 0;
         ox = oy = oz = ix = iy = iz = t_max = okx = oky = okz = sx = sy = sz = 0.0f;
         kx = ky = kz = neg_mask = 0;
     }
-    __device__ __forceinline__ void start(uint32_t sbase, float o_x, float o_y, float o_z, float d_x, float d_y, float d_z, float tmax) {
+    // Slab distances of one box (math/bounds.rs:176-215): lo = max(max_comp(min(t0, t1)), 0), hi = min_comp(max(t0, t1));
+    // the reference's test is lo <= min(hi, t_max). NaN-ignoring min/max exactly like f32::min/max.
+    __device__ __forceinline__ void slab(float ax, float ay, float az, float bx, float by, float bz, float* lo, float* hi) const {
+        const float t0x = (ax - ox) * ix, t0y = (ay - oy) * iy, t0z = (az - oz) * iz;
+        const float t1x = (bx - ox) * ix, t1y = (by - oy) * iy, t1z = (bz - oz) * iz;
+        *lo = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
+        *hi = fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z)));
+    }
+    // Makes `ref` the lane's next piece of work: an interior node to enter, or a leaf to park. Select-only (no branch
+    // but the warp-uniform leaf-table one).
+    template <bool GENERIC>
+    __device__ __forceinline__ void enter(const DevScene& sc, uint32_t ref) {
+        const bool interior = (int32_t)ref < 0;  // (the sentinel kNoNode counts as interior and ends the ray)
+        cur = interior ? ref : kNoNode;
+        uint32_t first, count;
+        if (GENERIC && sc.leaf_table) {
+            const uint2 l = interior ? make_uint2(0u, 0u) : __ldg(&sc.leaf_table[ref]);
+            first = l.x; count = l.y;
+        } else {
+            first = ref & ((1u << kLeafFirstBits) - 1u);
+            count = (ref >> kLeafFirstBits) + 1u;
+        }
+        leaf_pos = interior ? leaf_pos : first;
+        leaf_end = interior ? leaf_end : first + count;
+    }
+    template <bool COUNTS, bool GENERIC>
+    __device__ __forceinline__ void start(const DevScene& sc, uint32_t sbase, float o_x, float o_y, float o_z, float d_x, float d_y, float d_z,
+                                          float tmax) {
         ox = o_x; oy = o_y; oz = o_z;
         t_max = tmax;
         ix = 1.0f / d_x; iy = 1.0f / d_y; iz = 1.0f / d_z;  // bvh.rs:164
@@ -342,73 +402,96 @@ struct TraceLane {
         okx = kx == 0 ? ox : (kx == 1 ? oy : oz);
         oky = ky == 0 ? ox : (ky == 1 ? oy : oz);
         okz = kz == 0 ? ox : (kz == 1 ? oy : oz);
-        cur = 0; sp = sbase + kStackStride; n_tests = 0; n_hits = 0; n_tris = 0;
+        sp = sbase + kStackStride; n_tests += 1; n_hits = 0;
         leaf_pos = leaf_end = 0;
+        cur = kNoNode;
+        // the root's own box (bvh.rs:176-179 on node 0)
+        float lo, hi;
+        slab(sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], &lo, &hi);
+        if (lo <= fminf(hi, t_max)) {
+            if (COUNTS) n_hits = 1;
+            enter<GENERIC>(sc, sc.root_ref);
+        }
     }
     __device__ __forceinline__ bool wants_box() const { return cur != kNoNode; }
     __device__ __forceinline__ bool wants_tri() const { return leaf_pos < leaf_end; }
-    __device__ __forceinline__ void push(uint32_t sbase, uint32_t* deep, uint32_t v) {
-        const uint32_t depth = (sp - sbase) / kStackStride;
-        if (depth < (uint32_t)kShortStack) sts_u32(sp, v);
-        else deep[depth - kShortStack] = v;
+    __device__ __forceinline__ void push(uint32_t sbase, uint32_t* deep_ref, float* deep_key, uint32_t ref, float key) {
+        if (sp < sbase + (uint32_t)kShortStack * kStackStride) {
+            sts_entry(sp, ref, key);
+        } else {  // cold: the stack continues in local memory, up to the reference's 64 entries
+            const uint32_t depth = (sp - sbase) / kStackStride - kShortStack;
+            deep_ref[depth] = ref;
+            deep_key[depth] = key;
+        }
         sp += kStackStride;
     }
-    __device__ __forceinline__ uint32_t pop(uint32_t sbase, const uint32_t* deep) {
-        sp -= kStackStride;
-        const uint32_t depth = (sp - sbase) / kStackStride;
-        return depth < (uint32_t)kShortStack ? lds_u32(sp) : deep[depth - kShortStack];
-    }
-    // One box test (bvh.rs:176-199, math/bounds.rs:176-215).
-    template <bool COUNTS>
-    __device__ __forceinline__ void box_step(const DevScene& sc, uint32_t sbase, uint32_t* deep) {
-        const float4 n0 = __ldg(&sc.nodes[2 * cur]);
-        const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
-        n_tests += 1;
-        // slab test: (bound - o) * inv_dir, NaN-ignoring min/max exactly like f32::min/max
-        const float t0x = (n0.x - ox) * ix, t0y = (n0.y - oy) * iy, t0z = (n0.z - oz) * iz;
-        const float t1x = (n1.x - ox) * ix, t1y = (n1.y - oy) * iy, t1z = (n1.z - oz) * iz;
-        const float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
-        const float tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), t_max);
-        const uint32_t offset = __float_as_uint(n0.w), meta = __float_as_uint(n1.w);
-        const uint32_t next = cur + 1;
-        if (COUNTS) n_hits += tmin <= tmax ? 1u : 0u;
-        if (sp >= sbase + (uint32_t)kShortStack * kStackStride) {  // cold: the stack continues in local memory
-            const bool hit = tmin <= tmax, leaf = (meta & kMetaLeaf) != 0, neg = (meta & neg_mask) != 0;
-            if (hit && !leaf) { push(sbase, deep, neg ? next : offset); cur = neg ? offset : next; }
-            else if (hit) { leaf_pos = offset; leaf_end = offset + (meta & 0xffffu); cur = kNoNode; }
-            else cur = pop(sbase, deep);
+    // Pops until an entry passes its deferred box test (the sentinel's key 0 always does). Returns its ref.
+    template <bool COUNTS, bool ANYHIT>
+    __device__ __forceinline__ uint32_t pop_passing(uint32_t sbase, const uint32_t* deep_ref, const float* deep_key) {
+        uint32_t ref;
+        float key;
+        if (sp > sbase + (uint32_t)kShortStack * kStackStride) {  // cold: the top of the stack is in local memory
+            do {
+                sp -= kStackStride;
+                if (sp < sbase + (uint32_t)kShortStack * kStackStride) {
+                    lds_entry(sp, &ref, &key);
+                } else {
+                    const uint32_t depth = (sp - sbase) / kStackStride - kShortStack;
+                    ref = deep_ref[depth];
+                    key = deep_key[depth];
+                }
+                if (ANYHIT) n_tests += ref != kNoNode ? 1u : 0u;
+            } while (!(key <= t_max));
         } else {
-            // Hit an interior node: the far child waits on the stack, descend into the near one (by the ray's sign on the
-            // split axis; interior meta = 1 << axis). Hit a leaf: park it. Miss: pop (the sentinel ends the ray).
-            // Written as predicated PTX: the compiler's version of the same three updates cost ~10 more instructions.
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p_hit, p_leaf, p_neg, p_in, p_lh, p_ms;\n\t"
-                ".reg .u32 t, near, far;\n\t"
-                "setp.le.f32 p_hit, %4, %5;\n\t"
-                "setp.lt.s32 p_leaf, %6, 0;\n\t"
-                "and.b32 t, %6, %7;\n\t"
-                "setp.ne.u32 p_neg, t, 0;\n\t"
-                "and.pred p_in, p_hit, !p_leaf;\n\t"
-                "and.pred p_lh, p_hit, p_leaf;\n\t"
-                "not.pred p_ms, p_hit;\n\t"
-                "selp.u32 near, %8, %9, p_neg;\n\t"
-                "selp.u32 far, %9, %8, p_neg;\n\t"
-                "@p_in st.shared.u32 [%1], far;\n\t"
-                "@p_in add.u32 %1, %1, 512;\n\t"
-                "@p_in mov.u32 %0, near;\n\t"
-                "@p_ms sub.u32 %1, %1, 512;\n\t"
-                "@p_ms ld.shared.u32 %0, [%1];\n\t"
-                "and.b32 t, %6, 0xffff;\n\t"
-                "@p_lh mov.u32 %2, %8;\n\t"
-                "@p_lh add.u32 %3, %8, t;\n\t"
-                "@p_lh mov.u32 %0, 0xffffffff;\n\t"
-                "}"
-                : "+r"(cur), "+r"(sp), "+r"(leaf_pos), "+r"(leaf_end)
-                : "f"(tmin), "f"(tmax), "r"(meta), "r"(neg_mask), "r"(offset), "r"(next)
-                : "memory");
-            static_assert(kStackStride == 512, "the stride is spelled out in the PTX above");
+            do {
+                sp -= kStackStride;
+                lds_entry(sp, &ref, &key);
+                if (ANYHIT) n_tests += ref != kNoNode ? 1u : 0u;
+            } while (!(key <= t_max));
         }
+        if (COUNTS) n_hits += ref != kNoNode ? 1u : 0u;
+        return ref;
+    }
+    // Enters the interior node `cur`: the box tests of its two children (bvh.rs:176-199, math/bounds.rs:176-215).
+    template <bool COUNTS, bool ANYHIT, bool GENERIC>
+    __device__ __forceinline__ void box_step(const DevScene& sc, uint32_t sbase, uint32_t* deep_ref, float* deep_key) {
+        // near child first: the second child when the ray is negative on the split axis (bvh.rs:186-194)
+        const uint32_t neg = (neg_mask >> ((cur >> 29) & 3u)) & 1u;
+        const float4* rec = sc.nodes2 + 4 * (size_t)(cur & kRefIndexMask);
+        const float4* near = rec + 2 * neg;
+        const float4* far = rec + 2 * (neg ^ 1u);
+        const float4 n0 = __ldg(near), n1 = __ldg(near + 1);
+        const float4 f0 = __ldg(far), f1 = __ldg(far + 1);
+        float lo_n, hi_n, lo_f, hi_f;
+        slab(n0.x, n0.y, n0.z, n1.x, n1.y, n1.z, &lo_n, &hi_n);
+        slab(f0.x, f0.y, f0.z, f1.x, f1.y, f1.z, &lo_f, &hi_f);
+        const uint32_t ref_n = __float_as_uint(n0.w), ref_f = __float_as_uint(f0.w);
+        const bool hit_n = lo_n <= fminf(hi_n, t_max);
+        const bool ok_f = !(lo_f > hi_f);  // can the far child pass at all? (a NaN hi is ignored by the reference's min)
+        const float key_f = ok_f ? lo_f : __int_as_float(0x7fc00000);
+        // near missed: nothing happens before the far child's test, t_max is what the pop would see
+        const bool hit_f = !hit_n && key_f <= t_max;
+        n_tests += (ANYHIT && hit_n) ? 1u : 2u;
+        if (COUNTS) n_hits += (hit_n || hit_f) ? 1u : 0u;
+        const bool do_push = hit_n && (ANYHIT || ok_f);
+        uint32_t take = hit_n ? ref_n : ref_f;
+        if (sp >= sbase + (uint32_t)kShortStack * kStackStride) {  // cold: the stack continues in local memory
+            if (do_push) push(sbase, deep_ref, deep_key, ref_f, key_f);
+            if (!(hit_n || hit_f)) take = pop_passing<COUNTS, ANYHIT>(sbase, deep_ref, deep_key);
+        } else {
+            if (do_push) sts_entry(sp, ref_f, key_f);
+            sp += do_push ? kStackStride : 0u;
+            if (!(hit_n || hit_f)) {
+                float key;
+                do {
+                    sp -= kStackStride;
+                    lds_entry(sp, &take, &key);
+                    if (ANYHIT) n_tests += take != kNoNode ? 1u : 0u;
+                } while (!(key <= t_max));
+                if (COUNTS) n_hits += take != kNoNode ? 1u : 0u;
+            }
+        }
+        enter<GENERIC>(sc, take);
     }
     // One triangle test of the parked leaf (shapes/triangle.rs:62-130 on the permuted, origin-relative vertices).
     // Returns true on a hit with t in (0, t_max]; the caller decides what a hit means and then calls leaf_done().
@@ -444,8 +527,9 @@ struct TraceLane {
         *area_light = __float_as_int(kx == 0 ? A.w : (ky == 0 ? B.w : C.w));
         return !mixed && det != 0.0f && !out_neg && !out_pos;
     }
-    __device__ __forceinline__ void leaf_done(uint32_t sbase, const uint32_t* deep) {
-        if (leaf_pos == leaf_end) cur = pop(sbase, deep);
+    template <bool COUNTS, bool ANYHIT, bool GENERIC>
+    __device__ __forceinline__ void leaf_done(const DevScene& sc, uint32_t sbase, const uint32_t* deep_ref, const float* deep_key) {
+        if (leaf_pos == leaf_end) enter<GENERIC>(sc, pop_passing<COUNTS, ANYHIT>(sbase, deep_ref, deep_key));
     }
     // ends the ray: the next pop (leaf_done) takes the sentinel
     __device__ __forceinline__ void stop(uint32_t sbase) { cur = kNoNode; leaf_pos = leaf_end = 0; sp = sbase + kStackStride; }
@@ -459,38 +543,38 @@ struct TraceLane {
 #ifndef YK_BOX_STEPS_PER_VOTE
 #define YK_BOX_STEPS_PER_VOTE 3
 #endif
-#define YK_TRACE_PHASES(LANE, LIVE, COUNTS, ON_HIT)                                                              \
+#define YK_TRACE_PHASES(LANE, LIVE, COUNTS, ANYHIT, GENERIC, ON_HIT)                                             \
     for (;;) {                                                                                                    \
         const bool want_n = (LANE).wants_box();                                                                   \
         const int n_n = __popc(__ballot_sync(0xffffffffu, want_n));                                               \
         if (n_n == 0) break;                                                                                      \
         if (n_n < kNodePhaseMin && __ballot_sync(0xffffffffu, (LIVE) && !want_n)) break;                          \
-        if (want_n) (LANE).template box_step<COUNTS>(sc, sbase, deep);                                            \
-        if (YK_BOX_STEPS_PER_VOTE > 1 && (LANE).wants_box()) (LANE).template box_step<COUNTS>(sc, sbase, deep);   \
-        if (YK_BOX_STEPS_PER_VOTE > 2 && (LANE).wants_box()) (LANE).template box_step<COUNTS>(sc, sbase, deep);   \
-        if (YK_BOX_STEPS_PER_VOTE > 3 && (LANE).wants_box()) (LANE).template box_step<COUNTS>(sc, sbase, deep);   \
+        if (want_n) (LANE).template box_step<COUNTS, ANYHIT, GENERIC>(sc, sbase, deep_ref, deep_key);                      \
+        if (YK_BOX_STEPS_PER_VOTE > 1 && (LANE).wants_box()) (LANE).template box_step<COUNTS, ANYHIT, GENERIC>(sc, sbase, deep_ref, deep_key); \
+        if (YK_BOX_STEPS_PER_VOTE > 2 && (LANE).wants_box()) (LANE).template box_step<COUNTS, ANYHIT, GENERIC>(sc, sbase, deep_ref, deep_key); \
     }                                                                                                             \
     while (__ballot_sync(0xffffffffu, (LANE).wants_tri())) {                                                      \
         if ((LANE).wants_tri()) {                                                                                 \
             uint32_t tri_; float ts_, det_; int al_;                                                              \
             if ((LANE).tri_step(sc, &tri_, &ts_, &det_, &al_)) { ON_HIT }                                         \
-            (LANE).leaf_done(sbase, deep);                                                                        \
+            (LANE).template leaf_done<COUNTS, ANYHIT, GENERIC>(sc, sbase, deep_ref, deep_key);                    \
         }                                                                                                         \
     }
 
 // Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
 template <bool COUNTS, bool SPHERES>
 __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_closest(DevScene sc, Wave w, int b, IterCounters* cur) {
-    __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
-    uint32_t deep[kStackDepth + 1 - kShortStack];
+    __shared__ uint2 s_stack[kShortStack][kTraceThreads];
+    uint32_t deep_ref[kDeepStack];
+    float deep_key[kDeepStack];
     const uint32_t n = cur->n_active;
     uint32_t* const cursor = &cur->work_closest;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&w.totals->closest_rays, (unsigned long long)n);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[0][tid]);
-    sts_u32(sbase, kNoNode);  // sentinel: popping it ends the ray
-    unsigned long long sum_nodes = 0, sum_tris = 0;
+    sts_entry(sbase, kNoNode, 0.0f);  // sentinel: popping it ends the ray (key 0 passes every deferred test)
+    uint32_t tests_before = 0;               // COUNTS: the lane's running test count when its current ray started
     uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
     bool exhausted = false;                  // warp-uniform: the global cursor ran past n
 
@@ -518,7 +602,8 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
                     path = mine;  // the queue slot: rays, hits and counters of a bounce are all in queue order
                     const float4 ro = w.st[b].ray_o[path];
                     const float4 rd = w.st[b].ray_d[path];
-                    tl.start(sbase, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w);
+                    if (COUNTS) tests_before = tl.n_tests;
+                    tl.template start<COUNTS, SPHERES>(sc, sbase, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w);
                     hit_tri = kMiss; hit_t = 0.0f;
                     live = true;
                 }
@@ -532,7 +617,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
         }
         // ---- trace until too few lanes are live -----------------------------------------------------------
         for (;;) {
-            YK_TRACE_PHASES(tl, live, COUNTS, {
+            YK_TRACE_PHASES(tl, live, COUNTS, false, SPHERES, {
                 if (SPHERES && det_ != det_) {  // a sphere slot (NaN vertex lanes): shapes/sphere.rs:36-77
                     float t_s;
                     /* the direction is not kept in registers: re-read it on this rare path */
@@ -546,17 +631,14 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
             })
             if (live && !tl.wants_box()) {  // retire
                 w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
-                if (COUNTS) w.bvh_counts[path] = make_uint2(tl.n_tests, tl.n_hits);
-                sum_nodes += tl.n_tests;
-                sum_tris += tl.n_tris;
+                if (COUNTS) w.bvh_counts[path] = make_uint2(tl.n_tests - tests_before, tl.n_hits);
                 live = false;
             }
             const int busy = __popc(__ballot_sync(0xffffffffu, live));
             if (busy == 0 || (!exhausted && busy < kRefillBelow)) break;
         }
     }
-    sum_nodes = warp_sum(sum_nodes);
-    sum_tris = warp_sum(sum_tris);
+    const unsigned long long sum_nodes = warp_sum((unsigned long long)tl.n_tests), sum_tris = warp_sum((unsigned long long)tl.n_tris);
     if (lane == 0 && (sum_nodes | sum_tris)) {
         atomicAdd(&w.totals->closest_nodes, sum_nodes);
         atomicAdd(&w.totals->closest_tris, sum_tris);
@@ -571,15 +653,16 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
 template <bool SPHERES>
 __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, IterCounters* cur) {
     uint32_t* const cursor = &cur->work_shadow;
-    __shared__ uint32_t s_stack[kShortStack][kTraceThreads];
-    uint32_t deep[kStackDepth + 1 - kShortStack];
+    __shared__ uint2 s_stack[kShortStack][kTraceThreads];
+    uint32_t deep_ref[kDeepStack];
+    float deep_key[kDeepStack];
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[0][tid]);
-    sts_u32(sbase, kNoNode);
+    sts_entry(sbase, kNoNode, 0.0f);
     const uint32_t n0 = cur->mat[0], n1 = cur->mat[1], n2 = cur->mat[2], n3 = cur->mat[3];
     const uint32_t n = n0 + n1 + n2 + n3;
-    unsigned long long sum_nodes = 0, sum_tris = 0, sum_rays = 0;
+    uint32_t n_rays = 0;
     uint32_t chunk_next = 0, chunk_end = 0;
     bool exhausted = false;
 
@@ -622,7 +705,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
                 path = w.sh_path[pos];
                 mask = __float_as_uint(w.pend_extra[pos].w);
                 radiance = gray(0.0f);
-                sum_rays += __popc(mask);
+                n_rays += __popc(mask);
                 if (mask) { live = true; need_ray = true; }
                 else finish_path();
             }
@@ -636,7 +719,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             const float2 rc = w.lt_c[ref];
             contribution = rgb(ro.w, rd.w, rc.x);
             target_light = __float_as_int(rc.y);
-            tl.start(sbase, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, 0.9999f);  // interaction.rs:57-58
+            tl.template start<false, SPHERES>(sc, sbase, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, 0.9999f);  // interaction.rs:57-58
             occluded = false;
             need_ray = false;
         }
@@ -645,7 +728,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             continue;
         }
         for (;;) {
-            YK_TRACE_PHASES(tl, live, false, {
+            YK_TRACE_PHASES(tl, live, false, true, SPHERES, {
                 (void)tri_; (void)ts_;
                 bool blocks = true;
                 if (SPHERES && det_ != det_) {  // sphere slot: run the real test; spheres carry no area light
@@ -658,9 +741,6 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
                 if (blocks) { occluded = true; tl.stop(sbase); }
             })
             if (live && !need_ray && !tl.wants_box()) {  // this shadow ray is done
-                sum_nodes += tl.n_tests;
-                sum_tris += tl.n_tris;
-                tl.n_tests = 0; tl.n_tris = 0;
                 if (!occluded) radiance = radiance + contribution;
                 mask &= mask - 1;
                 if (mask) need_ray = true;
@@ -673,9 +753,8 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             }
         }
     }
-    sum_nodes = warp_sum(sum_nodes);
-    sum_tris = warp_sum(sum_tris);
-    sum_rays = warp_sum(sum_rays);
+    const unsigned long long sum_nodes = warp_sum((unsigned long long)tl.n_tests), sum_tris = warp_sum((unsigned long long)tl.n_tris);
+    const unsigned long long sum_rays = warp_sum((unsigned long long)n_rays);
     if (lane == 0 && (sum_nodes | sum_tris | sum_rays)) {
         atomicAdd(&w.totals->any_nodes, sum_nodes);
         atomicAdd(&w.totals->any_tris, sum_tris);
@@ -1373,7 +1452,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         IterCounters* nxt = &p->d_ctr[(iter + 1) & 1];
         if (iter > 0) CUDA_TRY(cudaMemsetAsync(nxt, 0, sizeof(IterCounters), s));
         CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
-        const bool spheres = sc->dev.spheres != nullptr;  // scenes without spheres run instantiations without the sphere path
+        const bool spheres = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;  // the generic instantiations: sphere slots, leaf table
         if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
             if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
             else k_trace_closest<true, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
@@ -1520,21 +1599,52 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     sc->ctx = c;
     sc->device = c->device;
     int rc;
-    // Nodes: two 16-byte words so a visit is two LDG.128 (one 32-byte sector).
-    std::vector<float4> nodes((size_t)d->n_nodes * 2);
+    // Nodes: one 64-byte record per interior node with the boxes of both children (DevScene::nodes2). Interior records are
+    // numbered in the reference's pre-order, so a first child's record follows its parent's.
+    std::vector<uint32_t> rec_of(d->n_nodes, 0);  // interior: record index; leaf: index among the leaves
+    uint32_t n_interior = 0, n_leaves = 0;
+    bool packed_leaves = d->n_tris <= (1u << kLeafFirstBits);
     for (uint32_t i = 0; i < d->n_nodes; ++i) {
         const yk_bvh_node& n = d->nodes[i];
         if (!n.is_leaf && n.split_axis > 2) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: split axis out of range");
-        uint32_t meta = n.is_leaf ? (kMetaLeaf | n.shape_count) : (1u << n.split_axis);
-        if (!n.is_leaf && n.offset >= d->n_nodes) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: child index out of range");
+        if (!n.is_leaf && (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.offset <= i))
+            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: child index out of range");
         if (n.is_leaf && (uint64_t)n.offset + n.shape_count > d->n_tris)
             return yk_set_error(YK_ERR_INVALID, "yk_scene_create: leaf range out of range");
-        float fo, fm;
-        std::memcpy(&fo, &n.offset, 4);
-        std::memcpy(&fm, &meta, 4);
-        nodes[2 * i] = make_float4(n.p_min[0], n.p_min[1], n.p_min[2], fo);
-        nodes[2 * i + 1] = make_float4(n.p_max[0], n.p_max[1], n.p_max[2], fm);
+        if (n.is_leaf) {
+            if (n.shape_count < 1 || n.shape_count > 16) packed_leaves = false;
+            rec_of[i] = n_leaves++;
+        } else {
+            rec_of[i] = n_interior++;
+        }
     }
+    if (n_interior > kRefIndexMask) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 2^29 interior nodes");
+    std::vector<uint2> leaf_table;
+    if (!packed_leaves) leaf_table.resize(n_leaves);
+    auto ref_of = [&](uint32_t i) -> uint32_t {
+        const yk_bvh_node& n = d->nodes[i];
+        if (!n.is_leaf) return kRefInterior | ((uint32_t)n.split_axis << 29) | rec_of[i];
+        if (packed_leaves) return ((uint32_t)(n.shape_count - 1) << kLeafFirstBits) | n.offset;
+        leaf_table[rec_of[i]] = make_uint2(n.offset, n.shape_count);
+        return rec_of[i];
+    };
+    std::vector<float4> nodes((size_t)std::max(n_interior, 1u) * 4, make_float4(0, 0, 0, 0));
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+        const yk_bvh_node& n = d->nodes[i];
+        if (n.is_leaf) continue;
+        const uint32_t kids[2] = {i + 1, n.offset};
+        for (int k = 0; k < 2; ++k) {
+            const yk_bvh_node& ch = d->nodes[kids[k]];
+            const uint32_t ref = ref_of(kids[k]);
+            float fr;
+            std::memcpy(&fr, &ref, 4);
+            nodes[(size_t)rec_of[i] * 4 + 2 * k] = make_float4(ch.p_min[0], ch.p_min[1], ch.p_min[2], fr);
+            nodes[(size_t)rec_of[i] * 4 + 2 * k + 1] = make_float4(ch.p_max[0], ch.p_max[1], ch.p_max[2], 0.0f);
+        }
+    }
+    sc->dev.root_ref = ref_of(0);
+    std::memcpy(sc->dev.root_min, d->nodes[0].p_min, 12);
+    std::memcpy(sc->dev.root_max, d->nodes[0].p_max, 12);
     // Triangles: three 16-byte words, vertices pre-gathered in leaf order and transposed (x0 x1 x2 | y0 y1 y2 | z0 z1 z2);
     // the w lanes carry the per-triangle ids.
     std::vector<float4> tris((size_t)d->n_tris * 3);
@@ -1569,7 +1679,8 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
         tris[3 * i + 1] = make_float4(v[1], v[4], v[7], fp);
         tris[3 * i + 2] = make_float4(v[2], v[5], v[8], fi);
     }
-    if ((rc = dev_upload(sc->allocs, &sc->dev.nodes, nodes.data(), nodes.size())) != YK_OK) return rc;
+    if ((rc = dev_upload(sc->allocs, &sc->dev.nodes2, nodes.data(), nodes.size())) != YK_OK) return rc;
+    if (!packed_leaves && (rc = dev_upload(sc->allocs, &sc->dev.leaf_table, leaf_table.data(), leaf_table.size())) != YK_OK) return rc;
     if ((rc = dev_upload(sc->allocs, &sc->dev.tris, tris.data(), tris.size())) != YK_OK) return rc;
     if (d->tri_normals && (rc = dev_upload(sc->allocs, &sc->dev.normals, d->tri_normals, (size_t)d->n_tris * 9)) != YK_OK) return rc;
     if (d->tri_uvs && (rc = dev_upload(sc->allocs, &sc->dev.uvs, d->tri_uvs, (size_t)d->n_tris * 6)) != YK_OK) return rc;
