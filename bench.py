@@ -233,7 +233,7 @@ def run_ours(args):
         film_host = np.zeros((film.res[1], film.res[0], 3), np.float32)
         flat = host_scene.flat
         scene_bytes = flat.n_nodes * 32 + flat.n_tris * (36 + 4 + 4 + 4 + 1)
-        h2d = scene_bytes + len(my_tiles) * 0 + sum(int(t["x1"] - t["x0"]) * int(t["y1"] - t["y0"]) for t in my_tiles) * 8 + 2 * 64
+        h2d = scene_bytes + len(my_tiles) * (12 + 8) + 8 + 2 * 64   # scene arrays, tile list + tile-area prefix sums, camera matrices
         d2h = n_pix * 12
         e2e_steps = max(1, min(args.steps, 2))
 

@@ -65,3 +65,6 @@ if which == "ab":  # one line per scene class, for A/B builds (YUKI_GPU_LIB=...)
     probe("heightfield 1M path8 1920x1080 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=2)
     s, c = scenes.terrain_room(xf)
     probe("terrain 10M path8 3840x2160 4spp", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8), reps=2)
+if which == "terrain1":  # one short path-traced render of the 10 M-triangle scene for ncu captures
+    s, c = scenes.terrain_room(xf)
+    probe("terrain 10M path8 3840x2160 1spp", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(1, 1), D.IntegratorType.path(8), reps=1)

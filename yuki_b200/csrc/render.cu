@@ -106,10 +106,6 @@ struct Totals {
     unsigned long long closest_nodes, closest_tris, any_nodes, any_tris, hit_hash, shadow_rays, closest_rays;
 };
 
-struct JobIn {  // as uploaded by the host: one pixel's share of the batch
-    uint16_t x, y;
-    uint32_t sample_begin;
-};
 struct Job {  // + the pixel's PCG stream, (SipHash13(x, y) << 1) | 1 (uniform.rs:77-81): one hash per pixel, not per sample
     uint16_t x, y;
     uint32_t sample_begin;
@@ -236,14 +232,29 @@ __device__ __forceinline__ unsigned long long mix_hit(uint32_t x, uint32_t y, ui
     return h;
 }
 
-// ---- per-pixel sampler stream: hash_values!(pixel.x, pixel.y) (uniform.rs:77, stratified.rs:95) ----------------
-__global__ void k_jobs_prepare(const JobIn* in, Job* out, uint32_t n) {
+// ---- pixel jobs of one pixel group, expanded on the device from the tile list -----------------------------------
+// Job j of a render is pixel (j - off[t]) of tile t in row-major order (Bounds2 iteration, math/bounds.rs:102-126), tiles
+// in list order; `off` is the prefix sum of the tile areas. Also hash_values!(pixel.x, pixel.y), the pixel's sampler
+// stream (uniform.rs:77, stratified.rs:95). The host uploads 16 bytes per tile instead of 8 per pixel.
+__global__ void k_jobs_expand(const yk_tile* tiles, const unsigned long long* off, uint32_t t_lo, uint32_t t_hi, unsigned long long j0,
+                              uint32_t n, uint32_t accumulate, Job* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const JobIn j = in[i];
+    const unsigned long long j = j0 + i;
+    uint32_t lo = t_lo, hi = t_hi;  // off[lo] <= j < off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (off[mid] <= j) lo = mid;
+        else hi = mid;
+    }
+    const yk_tile tl = tiles[lo];
+    const uint32_t local = (uint32_t)(j - off[lo]), w = (uint32_t)tl.x1 - tl.x0;
+    const uint32_t row = local / w;
     Job o;
-    o.x = j.x; o.y = j.y; o.sample_begin = j.sample_begin;
-    o.rng_inc = (hash_pixel(j.x, j.y) << 1) | 1ULL;
+    o.x = (uint16_t)(tl.x0 + (local - row * w));
+    o.y = (uint16_t)(tl.y0 + row);
+    o.sample_begin = accumulate ? tl.sample : 0u;
+    o.rng_inc = (hash_pixel(o.x, o.y) << 1) | 1ULL;
     out[i] = o;
 }
 
@@ -1276,6 +1287,8 @@ struct Pipe {
     IterCounters* d_ctr = nullptr;   // two entries, alternating per bounce
     IterCounters* h_ctr = nullptr;   // pinned: read-back for the integrators whose bounce count is unbounded (Whitted)
     Totals* h_totals = nullptr;      // pinned
+    Job* d_jobs = nullptr;           // the pixel jobs of the pipe's current pixel group
+    size_t jobs_cap = 0;
     uint32_t* d_dim_hash = nullptr;  // SamplerCfg::hash_table of the pipe's current pixel group
     size_t dim_hash_cap = 0;
     size_t hash_group = (size_t)-1;
@@ -1295,9 +1308,9 @@ struct yk_context {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {};
     Pipe pipe[kMaxPipes];
-    Job* d_jobs = nullptr;
-    JobIn* d_jobs_in = nullptr;
-    size_t jobs_cap = 0;
+    yk_tile* d_tiles = nullptr;              // the tile list of the current render and the prefix sum of its tile areas
+    unsigned long long* d_tile_off = nullptr;
+    size_t tiles_cap = 0;
     float* d_accum = nullptr;
     float* d_film = nullptr;
     int32_t* d_hit_ids = nullptr;
@@ -1567,6 +1580,7 @@ void yk_context_destroy(yk_context* c) {
         free_bag(p.wave_allocs);
         cudaFree(p.d_ctr);
         cudaFree(p.d_dim_hash);
+        cudaFree(p.d_jobs);
         cudaFreeHost(p.h_ctr);
         cudaFreeHost(p.h_totals);
         for (auto& sl : p.slot) {
@@ -1575,8 +1589,8 @@ void yk_context_destroy(yk_context* c) {
         }
         if (p.owns_stream) cudaStreamDestroy(p.stream);
     }
-    cudaFree(c->d_jobs);
-    cudaFree(c->d_jobs_in);
+    cudaFree(c->d_tiles);
+    cudaFree(c->d_tile_off);
     cudaFree(c->d_accum);
     cudaFree(c->d_film);
     cudaFree(c->d_hit_ids);
@@ -1772,21 +1786,16 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     const bool on_device = (flags & YK_RENDER_FILM_ON_DEVICE) != 0;
     const bool accumulate = fs->accumulate != 0;
 
-    // Pixel jobs in tile order, row-major inside a tile (Bounds2 iteration, math/bounds.rs:102-126).
-    std::vector<JobIn> jobs;
-    size_t area = 0;
+    // Pixel jobs: tile order, row-major inside a tile. Only the tile list and the prefix sum of the tile areas go to the
+    // device; each pixel group's jobs are expanded there (k_jobs_expand).
+    std::vector<unsigned long long> tile_off((size_t)n_tiles + 1, 0ull);
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const yk_tile& tl = tiles[t];
         if (tl.x0 >= tl.x1 || tl.y0 >= tl.y1 || tl.x1 > fs->res_x || tl.y1 > fs->res_y)
             return yk_set_error(YK_ERR_INVALID, "yk_render: tile outside the film (film.rs:224-231)");
-        area += (size_t)(tl.x1 - tl.x0) * (tl.y1 - tl.y0);
+        tile_off[t + 1] = tile_off[t] + (unsigned long long)(tl.x1 - tl.x0) * (tl.y1 - tl.y0);
     }
-    jobs.reserve(area);
-    for (uint32_t t = 0; t < n_tiles; ++t) {
-        const yk_tile& tl = tiles[t];
-        for (uint32_t y = tl.y0; y < tl.y1; ++y)
-            for (uint32_t x = tl.x0; x < tl.x1; ++x) jobs.push_back(JobIn{(uint16_t)x, (uint16_t)y, accumulate ? tl.sample : 0u});
-    }
+    const unsigned long long n_jobs_total = tile_off[n_tiles], area = n_jobs_total;
     const size_t n_pixels = (size_t)fs->res_x * fs->res_y;
     const uint32_t samples_per_job = accumulate ? 1u : spp;
 
@@ -1837,29 +1846,28 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     Timers tm;
     Totals totals{};
     CUDA_TRY(cudaEventRecord(c->ev[2], s));
-    if (!jobs.empty()) {
-        if (c->jobs_cap < jobs.size()) {
-            cudaFree(c->d_jobs);
-            cudaFree(c->d_jobs_in);
-            c->d_jobs = nullptr;
-            c->d_jobs_in = nullptr;
-            c->jobs_cap = 0;
-            CUDA_TRY(cudaMalloc((void**)&c->d_jobs, jobs.size() * sizeof(Job)));
-            CUDA_TRY(cudaMalloc((void**)&c->d_jobs_in, jobs.size() * sizeof(JobIn)));
-            c->jobs_cap = jobs.size();
+    if (n_jobs_total) {
+        if (c->tiles_cap < n_tiles) {
+            cudaFree(c->d_tiles);
+            cudaFree(c->d_tile_off);
+            c->d_tiles = nullptr;
+            c->d_tile_off = nullptr;
+            c->tiles_cap = 0;
+            CUDA_TRY(cudaMalloc((void**)&c->d_tiles, (size_t)n_tiles * sizeof(yk_tile)));
+            CUDA_TRY(cudaMalloc((void**)&c->d_tile_off, ((size_t)n_tiles + 1) * sizeof(unsigned long long)));
+            c->tiles_cap = n_tiles;
         }
-        CUDA_TRY(cudaMemcpyAsync(c->d_jobs_in, jobs.data(), jobs.size() * sizeof(JobIn), cudaMemcpyHostToDevice, s));
-        k_jobs_prepare<<<(unsigned)((jobs.size() + 255) / 256), 256, 0, s>>>(c->d_jobs_in, c->d_jobs, (uint32_t)jobs.size());
-        tm.launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(c->d_tiles, tiles, (size_t)n_tiles * sizeof(yk_tile), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->d_tile_off, tile_off.data(), tile_off.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         // Wavefront capacity: paths in flight per batch.
         uint32_t cap = opts && opts->wavefront_paths ? opts->wavefront_paths : (1u << 22);
-        const uint64_t total_paths = (uint64_t)jobs.size() * samples_per_job;
+        const uint64_t total_paths = (uint64_t)n_jobs_total * samples_per_job;
         if (cap > total_paths) cap = (uint32_t)total_paths;
         cap = std::max(cap, 32u);
         // Samples of one pixel per batch: enough to amortise per-batch fixed costs, few enough that many pixels
         // (>= 64 Ki when available) share a batch.
         uint32_t m = std::min(samples_per_job, 64u);
-        while (m > 1 && (uint64_t)m * std::min<uint64_t>(jobs.size(), 65536) > cap) m >>= 1;
+        while (m > 1 && (uint64_t)m * std::min<uint64_t>(n_jobs_total, 65536) > cap) m >>= 1;
         uint32_t jobs_per_batch = std::max(1u, cap / m);
         // Pipes: pixel groups alternate between the streams, so one group's latency-bound shading overlaps the other's
         // issue-bound traversal. A pixel's samples stay on one pipe, in order (the film sum is order-dependent).
@@ -1871,18 +1879,13 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         if (opts && opts->pipes) n_pipes = (int)opts->pipes;
         n_pipes = std::max(1, std::min(kMaxPipes, n_pipes));
         if (accumulate) n_pipes = 1;
-        if (n_pipes > 1 && jobs.size() <= jobs_per_batch) {  // one group only: split it if that leaves decent batches
-            if ((uint64_t)(jobs.size() / 2) * m >= (1u << 20)) jobs_per_batch = (uint32_t)((jobs.size() + 1) / 2);
+        if (n_pipes > 1 && n_jobs_total <= jobs_per_batch) {  // one group only: split it if that leaves decent batches
+            if ((uint64_t)(n_jobs_total / 2) * m >= (1u << 20)) jobs_per_batch = (uint32_t)((n_jobs_total + 1) / 2);
             else n_pipes = 1;
         }
         const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
         const uint32_t wave_cap = (uint32_t)std::min<uint64_t>(cap, (uint64_t)jobs_per_batch * m);
         int rc = YK_OK;
-        if (!accumulate) {
-            const unsigned g = (unsigned)((jobs.size() + 255) / 256);
-            k_zero_jobs<<<g, 256, 0, s>>>(c->d_jobs, (uint32_t)jobs.size(), c->d_accum, fs->res_x);
-            tm.launches += 1;
-        }
         CUDA_TRY(cudaEventRecord(c->ev[0], s));
         for (int pi = 0; pi < n_pipes; ++pi) {
             Pipe& p = c->pipe[pi];
@@ -1895,22 +1898,25 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         // film in stream order, so a group never spans a change of `tile.sample`: within one sample index the reference's
         // tiles are disjoint, each pixel appears once per batch and the per-pixel sum runs in tile-list order exactly
         // like the reference's `*fc += c` (film.rs:260-272).
-        std::vector<std::pair<size_t, uint32_t>> groups;  // (first job, job count)
+        struct Group { unsigned long long first; uint32_t count, t_lo, t_hi; };  // jobs [first, first + count) lie in tiles [t_lo, t_hi)
+        std::vector<Group> groups;
         {
-            size_t seg_begin = 0;
-            auto flush = [&](size_t seg_end) {
-                for (size_t j = seg_begin; j < seg_end; j += jobs_per_batch)
-                    groups.emplace_back(j, (uint32_t)std::min<size_t>(jobs_per_batch, seg_end - j));
-                seg_begin = seg_end;
-            };
-            if (accumulate) {
-                size_t j = 0;
-                for (uint32_t t = 0; t < n_tiles; ++t) {
-                    if (t > 0 && tiles[t].sample != tiles[t - 1].sample) flush(j);
-                    j += (size_t)(tiles[t].x1 - tiles[t].x0) * (tiles[t].y1 - tiles[t].y0);
+            uint32_t seg_t0 = 0;
+            auto flush = [&](uint32_t seg_t1) {  // the jobs of tiles [seg_t0, seg_t1)
+                uint32_t t = seg_t0;
+                for (unsigned long long j = tile_off[seg_t0]; j < tile_off[seg_t1]; j += jobs_per_batch) {
+                    const unsigned long long end = std::min<unsigned long long>(j + jobs_per_batch, tile_off[seg_t1]);
+                    while (tile_off[t + 1] <= j) ++t;
+                    uint32_t t_hi = t + 1;
+                    while (tile_off[t_hi] < end) ++t_hi;
+                    groups.push_back(Group{j, (uint32_t)(end - j), t, t_hi});
                 }
-            }
-            flush(jobs.size());
+                seg_t0 = seg_t1;
+            };
+            if (accumulate)
+                for (uint32_t t = 1; t < n_tiles; ++t)
+                    if (tiles[t].sample != tiles[t - 1].sample) flush(t);
+            flush(n_tiles);
         }
         const size_t n_groups = groups.size();
         uint64_t done = 0;
@@ -1919,8 +1925,25 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
             for (uint32_t s0 = 0; s0 < samples_per_job && !cancelled; s0 += m) {
                 for (int pi = 0; pi < n_pipes && g0 + pi < n_groups && !cancelled; ++pi) {
                     Pipe& p = c->pipe[pi];
-                    const size_t group = g0 + pi, j0 = groups[group].first;
-                    const uint32_t nj = groups[group].second;
+                    const size_t group = g0 + pi;
+                    const uint32_t nj = groups[group].count;
+                    if (p.hash_group != group) {  // a new pixel group on this pipe: its jobs, and a zeroed accumulator
+                        if (p.jobs_cap < nj) {
+                            CUDA_TRY(cudaStreamSynchronize(p.stream));
+                            cudaFree(p.d_jobs);
+                            p.d_jobs = nullptr;
+                            p.jobs_cap = 0;
+                            CUDA_TRY(cudaMalloc((void**)&p.d_jobs, (size_t)std::max(nj, jobs_per_batch) * sizeof(Job)));
+                            p.jobs_cap = std::max(nj, jobs_per_batch);
+                        }
+                        k_jobs_expand<<<(nj + 255) / 256, 256, 0, p.stream>>>(c->d_tiles, c->d_tile_off, groups[group].t_lo, groups[group].t_hi,
+                                                                               groups[group].first, nj, accumulate ? 1u : 0u, p.d_jobs);
+                        tm.launches += 1;
+                        if (!accumulate) {
+                            k_zero_jobs<<<(nj + 255) / 256, 256, 0, p.stream>>>(p.d_jobs, nj, c->d_accum, fs->res_x);
+                            tm.launches += 1;
+                        }
+                    }
                     RenderCfg gcfg = cfg;
                     if (sm->kind == YK_SAMPLER_STRATIFIED) {
                         // tabulate the (pixel, dimension) hashes of this pixel group once for all of its samples
@@ -1940,16 +1963,16 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
                                 p.dim_hash_cap = need;
                             }
                             k_dim_hashes<<<dim3((nj + 255) / 256, (unsigned)std::min<uint64_t>(dims, 64)), 256, 0, p.stream>>>(
-                                c->d_jobs + j0, nj, (uint32_t)dims, sm->seed, p.d_dim_hash);
+                                p.d_jobs, nj, (uint32_t)dims, sm->seed, p.d_dim_hash);
                             tm.launches += 1;
-                            p.hash_group = group;
                         }
                         gcfg.sampler.hash_table = p.d_dim_hash;
                         gcfg.sampler.n_hash_dims = (uint32_t)dims;
                         gcfg.sampler.hash_stride = nj;
                     }
+                    p.hash_group = group;
                     Batch bt;
-                    bt.jobs = c->d_jobs + j0;
+                    bt.jobs = p.d_jobs;
                     bt.n_jobs = nj;
                     bt.div_jobs = FastDiv::make(nj);
                     bt.sample_off = s0;
@@ -1957,6 +1980,11 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
                     bt.n_paths = nj * bt.n_samples;
                     rc = run_batch(c, &p, sc, gcfg, bt, accumulate, d_film, &tm, &done);
                     if (rc != YK_OK) { cudaDeviceSynchronize(); return rc; }
+                    if (!accumulate && s0 + m >= samples_per_job) {
+                        // the group's last samples are queued: `color /= sample_count` + Film::update_tile for its pixels
+                        k_film_store<<<(nj + 255) / 256, 256, 0, p.stream>>>(p.d_jobs, nj, c->d_accum, d_film, fs->res_x, (float)spp);
+                        tm.launches += 1;
+                    }
                     if (opts && opts->progress && opts->progress(opts->progress_user, done, total_paths)) cancelled = true;
                 }
             }
@@ -1974,11 +2002,6 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         }
         if (cancelled) return yk_set_error(YK_ERR_CANCELLED, "yk_render: cancelled by the progress callback");
         if (opts && opts->progress) opts->progress(opts->progress_user, done, total_paths);
-        if (!accumulate) {
-            const unsigned g = (unsigned)((jobs.size() + 255) / 256);
-            k_film_store<<<g, 256, 0, s>>>(c->d_jobs, (uint32_t)jobs.size(), c->d_accum, d_film, fs->res_x, (float)spp);
-            tm.launches += 1;
-        }
         st.samples = total_paths;
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], s));
