@@ -280,6 +280,11 @@ typedef struct {
     uint32_t res_x, res_y;
 } yk_pbrt_result;
 int yk_pbrt_load(const char* path, uint32_t max_shapes_in_node, uint32_t split_method, yk_pbrt_scene** out);
+/* Mitsuba 2.1.0 XML scene file -> the same result type (read with yk_pbrt_view, freed with yk_pbrt_destroy): the
+ * elements, defaults, X-axis mirroring and error cases of scene/mitsuba/{mod,sensor,transform,emitter,material,shape}.rs
+ * — sensor, twosided / diffuse / dielectric bsdfs, constant / point / spot emitters, PLY shapes (see
+ * csrc/host_mitsuba.cpp). The camera target is moved into the scene bounds as mod.rs:185-197 does. */
+int yk_mitsuba_load(const char* path, uint32_t max_shapes_in_node, uint32_t split_method, yk_pbrt_scene** out);
 const yk_pbrt_result* yk_pbrt_view(const yk_pbrt_scene*);
 void yk_pbrt_destroy(yk_pbrt_scene*);
 

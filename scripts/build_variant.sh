@@ -10,5 +10,5 @@ SRC=yuki_b200/csrc
   --fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
   -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-pthread \
   -Iinclude -I$SRC -shared -o build/variants/libyuki_$name.so \
-  $SRC/render.cu $SRC/host_scene.cpp $SRC/host_bvh.cpp $SRC/host_ply.cpp $SRC/host_exr.cpp $SRC/host_pbrt.cpp $SRC/post.cu -lz "$@" 2>&1 | grep -v "warning\|queue_push\|\^\|^$" || true
+  $SRC/render.cu $SRC/host_scene.cpp $SRC/host_bvh.cpp $SRC/host_ply.cpp $SRC/host_exr.cpp $SRC/host_pbrt.cpp $SRC/host_mitsuba.cpp $SRC/post.cu -lz "$@" 2>&1 | grep -v "warning\|queue_push\|\^\|^$" || true
 echo "built build/variants/libyuki_$name.so"

@@ -155,8 +155,18 @@ def load_pbrt(path: str, max_shapes_in_node: int = 1, split_method: int = D.SPLI
     """scene/pbrt/mod.rs `load`: pbrt-v3 file -> (SceneDesc, CameraParameters, FilmSettings), parsed by the C++ loader
     (csrc/host_pbrt.cpp). The description is copied out of the loader's storage, so it feeds the CUDA backend and the
     test oracle exactly like the programmatic scenes."""
+    return _load_scene_file(capi.lib().yk_pbrt_load, path, max_shapes_in_node, split_method)
+
+
+def load_mitsuba(path: str, max_shapes_in_node: int = 1, split_method: int = D.SPLIT_SAH):
+    """scene/mitsuba/mod.rs `load`: Mitsuba 2.1.0 XML file -> (SceneDesc, CameraParameters, FilmSettings), parsed by the
+    C++ loader (csrc/host_mitsuba.cpp)."""
+    return _load_scene_file(capi.lib().yk_mitsuba_load, path, max_shapes_in_node, split_method)
+
+
+def _load_scene_file(loader, path, max_shapes_in_node, split_method):
     h = C.c_void_p()
-    capi.check(capi.lib().yk_pbrt_load(str(path).encode(), int(max_shapes_in_node), int(split_method), C.byref(h)))
+    capi.check(loader(str(path).encode(), int(max_shapes_in_node), int(split_method), C.byref(h)))
     try:
         r = capi.lib().yk_pbrt_view(h).contents
         hd = r.scene

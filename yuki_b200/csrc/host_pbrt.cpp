@@ -27,6 +27,7 @@
 #include <string>
 #include <vector>
 
+#include "host_loader.h"
 #include "host_math.h"
 #include "yuki_gpu.h"
 
@@ -273,26 +274,9 @@ bool decode_png(const std::string& path, uint32_t* w_out, uint32_t* h_out, std::
 }
 
 // ---- parser state --------------------------------------------------------------------------------------------------
-struct MeshStore {
-    xform o2w;
-    std::vector<float> points, normals, uvs;
-    std::vector<uint32_t> indices;
-    int32_t material;
-};
+using MeshStore = YkMeshStore;
 
 }  // namespace
-
-struct yk_pbrt_scene {
-    std::vector<MeshStore> meshes;
-    std::vector<yk_mesh_desc> mesh_descs;
-    std::vector<yk_sphere_desc> spheres;
-    std::vector<int32_t> objects;  // file order: mesh index, or -1 - sphere index
-    std::vector<yk_texture_desc> textures;
-    std::vector<std::vector<float>> texel_storage;
-    std::vector<yk_material_desc> materials;
-    std::vector<yk_light_desc> lights;
-    yk_pbrt_result result{};
-};
 
 namespace {
 
@@ -775,35 +759,7 @@ int yk_pbrt_load(const char* path, uint32_t max_shapes_in_node, uint32_t split_m
     p.out = sc.get();
     if (!p.run(path)) return yk_set_error(YK_ERR_INVALID, "pbrt-v3: " + p.error);
     for (size_t i = 0; i < p.tex_of_storage.size(); ++i) sc->textures[p.tex_of_storage[i]].texels = sc->texel_storage[i].data();
-    for (const MeshStore& m : sc->meshes) {
-        yk_mesh_desc d{};
-        std::memcpy(d.object_to_world.m, m.o2w.m.e, 64);
-        std::memcpy(d.object_to_world.m_inv, m.o2w.inv.e, 64);
-        d.n_points = (uint32_t)(m.points.size() / 3);
-        d.n_indices = (uint32_t)m.indices.size();
-        d.points = m.points.data();
-        d.normals = m.normals.size() == m.points.size() && !m.normals.empty() ? m.normals.data() : nullptr;
-        d.uvs = m.uvs.size() / 2 == m.points.size() / 3 && !m.uvs.empty() ? m.uvs.data() : nullptr;
-        d.indices = m.indices.data();
-        d.material = m.material;
-        d.area_light = -1;  // AreaLightSource is ignored by the reference's loader (mod.rs:502)
-        sc->mesh_descs.push_back(d);
-    }
-    yk_host_scene_desc& hd = sc->result.scene;
-    hd.n_meshes = (uint32_t)sc->mesh_descs.size();
-    hd.meshes = sc->mesh_descs.data();
-    hd.n_textures = (uint32_t)sc->textures.size();
-    hd.textures = sc->textures.data();
-    hd.n_materials = (uint32_t)sc->materials.size();
-    hd.materials = sc->materials.data();
-    hd.n_lights = (uint32_t)sc->lights.size();
-    hd.lights = sc->lights.data();
-    hd.max_shapes_in_node = max_shapes_in_node ? max_shapes_in_node : 1u;
-    hd.split_method = split_method;
-    hd.n_spheres = (uint32_t)sc->spheres.size();
-    hd.spheres = sc->spheres.data();
-    hd.n_objects = (uint32_t)sc->objects.size();
-    hd.objects = sc->objects.data();
+    sc->finish(max_shapes_in_node, split_method);
     *out = sc.release();
     return YK_OK;
 }
