@@ -281,8 +281,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes / launches, "avg_launch_ms": 1e3 * t_closest / launches,
                          "launches": launches, "share_of_step": agg["trace_closest_ms"] / ms_total,
                          "note": "rank 0; 32 B per node visit + 36 B per triangle test (SURVEY.md §8d); the 37-node scene is L1/L2-resident, so achieved can exceed the HBM peak"},
-            "stage_ms_per_step": {"trace_closest": agg["trace_closest_ms"] / args.steps, "trace_any": agg["trace_any_ms"] / args.steps,
-                                  "shade": agg["shade_ms"] / args.steps},
+            "stage_ms_per_step": {k: v / args.steps for k, v in (("trace_closest", agg["trace_closest_ms"]), ("trace_any", agg["trace_any_ms"]),
+                                                                 ("shade", agg["shade_ms"])) if v > 0},  # any / shade only with YK_STAGE_TIMING=2
         }
         # CPU baseline (rank 0, N == 1 only): bounded sample of the same workload on the host cores.
         if world == 1 and not args.no_cpu_baseline:

@@ -199,8 +199,8 @@ typedef struct {
     double seconds;             /* wall time of the call */
     double device_ms;           /* CUDA-event time of the device work */
     double trace_closest_ms;    /* CUDA-event time summed over trace_closest launches */
-    double trace_any_ms;
-    double shade_ms;
+    double trace_any_ms;        /* shadow-ray and shading kernels: only timed when YK_STAGE_TIMING=2 is set in the environment */
+    double shade_ms;            /* (the extra events cost ~1.5 % of a render), else 0 */
     uint64_t kernel_launches;
     uint64_t trace_closest_launches;
 } yk_stats;

@@ -1,5 +1,6 @@
 """Quick throughput probe of the wavefront renderer (not the bench contract)."""
 import sys, os, time
+os.environ.setdefault("YK_STAGE_TIMING", "2")  # per-stage times for analysis (the library default times the closest-hit kernel only)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from yuki_b200 import api, desc as D, scenes, transforms as xf
@@ -16,7 +17,7 @@ def probe(name, scene, cam, film, sampler, integ, reps=2, **kw):
     print(f"{name}: scene {t_scene:.2f}s tris {dev.host.n_tris} nodes {dev.host.n_nodes} | {st.samples/s/1e6:.1f} Msamples/s "
           f"{st.ray_count/s/1e6:.1f} Mrays/s(closest) {(st.ray_count+st.shadow_rays)/s/1e6:.1f} Mrays/s(total) | device {st.device_ms:.1f} ms "
           f"closest {st.trace_closest_ms:.1f} any {st.trace_any_ms:.1f} shade {st.shade_ms:.1f} | launches {st.kernel_launches} | "
-          f"closest roofline {bytes_closest/ (st.trace_closest_ms/1e3) /1e9:.0f} GB/s nodes/ray {st.closest_nodes/max(st.ray_count,1):.1f}", flush=True)
+          f"closest roofline {bytes_closest/ (max(st.trace_closest_ms, 1e-9)/1e3) /1e9:.0f} GB/s nodes/ray {st.closest_nodes/max(st.ray_count,1):.1f}", flush=True)
     dev.close(); ctx.close()
 
 which = sys.argv[1] if len(sys.argv) > 1 else "cornell"

@@ -830,8 +830,7 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
             hit_slot = h.y;
             uint32_t orig = 0xffffffffu;
             if (h.y != kMiss) {
-                const uint32_t m = __float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) & 0xffffffu;
-                kind = sc.materials[m].kind;
+                kind = (__float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) >> 28) & 3u;
                 if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
             } else if (first_iteration != 2) {  // (2 = debug integrators: their li() returns no background)
                 // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
@@ -876,7 +875,7 @@ __device__ __forceinline__ void make_surface(const DevScene& sc, uint32_t tri, V
     const float4 a4 = __ldg(&sc.tris[3 * tri]), b4 = __ldg(&sc.tris[3 * tri + 1]), c4 = __ldg(&sc.tris[3 * tri + 2]);
     const V3 p0 = mk(a4.x, b4.x, c4.x), p1 = mk(a4.y, b4.y, c4.y), p2 = mk(a4.z, b4.z, c4.z);  // stored transposed
     const uint32_t packed = __float_as_uint(b4.w);
-    const uint32_t flags = packed >> 24;
+    const uint32_t flags = (packed >> 24) & 0xfu;
     *material = packed & 0xffffffu;
     if (flags & YK_TRI_IS_SPHERE) {
         sphere_surface(sc.spheres[-2 - __float_as_int(a4.w)], o, d, si);
@@ -1300,6 +1299,7 @@ struct Pipe {
         bool busy = false;
     } slot[kRing];
     uint64_t n_batches = 0;
+    int timing = 2;  // the context's stage_timing when the queued batches were recorded
 };
 
 struct yk_context {
@@ -1317,6 +1317,8 @@ struct yk_context {
     size_t film_cap = 0;
     int occ_trace_closest = 0, occ_trace_any = 0;
     int n_pipes_env = 0;  // YK_PIPES override (development)
+    int stage_timing = 1;  // CUDA events per bounce: 1 = around the closest-hit kernel (the roofline figure), 2 = every stage
+                           // (costs ~1.5 % of a Cornell render), 0 = none; environment variable YK_STAGE_TIMING
 };
 
 struct yk_scene {
@@ -1408,9 +1410,11 @@ int retire_slot(Pipe* p, int k, Timers* tm, uint64_t* done_paths) {
     for (uint32_t i = 0; i < sl.n_iters; ++i) {
         cudaEvent_t* e = &sl.ev[(size_t)i * kTimedStages];
         float ms = 0;
-        cudaEventElapsedTime(&ms, e[0], e[1]); tm->closest += ms;
-        cudaEventElapsedTime(&ms, e[2], e[3]); tm->shade += ms;
-        cudaEventElapsedTime(&ms, e[3], e[4]); tm->any += ms;
+        if (p->timing > 0) { cudaEventElapsedTime(&ms, e[0], e[1]); tm->closest += ms; }
+        if (p->timing > 1) {
+            cudaEventElapsedTime(&ms, e[2], e[3]); tm->shade += ms;
+            cudaEventElapsedTime(&ms, e[3], e[4]); tm->any += ms;
+        }
     }
     *done_paths += sl.n_paths;
     sl.busy = false;
@@ -1431,6 +1435,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
     if (!sl.done) CUDA_TRY(cudaEventCreate(&sl.done));
     sl.n_iters = 0;
     sl.n_paths = bt.n_paths;
+    p->timing = c->stage_timing;
     auto stage_event = [&](uint32_t iter, int stage) -> cudaEvent_t {
         const size_t idx = (size_t)iter * kTimedStages + stage;
         while (sl.ev.size() <= idx) {
@@ -1464,7 +1469,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         IterCounters* cur = &p->d_ctr[iter & 1];
         IterCounters* nxt = &p->d_ctr[(iter + 1) & 1];
         if (iter > 0) CUDA_TRY(cudaMemsetAsync(nxt, 0, sizeof(IterCounters), s));
-        CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
+        if (c->stage_timing > 0) CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
         const bool spheres = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;  // the generic instantiations: sphere slots, leaf table
         if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
             if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
@@ -1473,7 +1478,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             if (spheres) k_trace_closest<false, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
             else k_trace_closest<false, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
         }
-        CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
+        if (c->stage_timing > 0) CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
         tm->launches += 1;
         tm->closest_launches += 1;
         uint32_t* q_next = w.q_active[flip];
@@ -1482,12 +1487,12 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             // primary-hit digest / id image for the debug integrators too
             k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, 2, q_next);
             tm->launches += 2;
-            for (int st = 2; st < kTimedStages; ++st) CUDA_TRY(cudaEventRecord(stage_event(iter, st), s));
+            for (int st = 2; st < kTimedStages; ++st) if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, st), s));
             sl.n_iters = iter + 1;
             break;
         }
         k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
-        CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
+        if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
         tm->launches += 1;
         for (uint32_t kind = 0; kind < 4; ++kind) {
             if (!(sc->material_kinds & (1u << kind))) continue;  // no triangle of the scene has this material kind
@@ -1502,10 +1507,10 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             }
             tm->launches += 1;
         }
-        CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
+        if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
         if (spheres) k_trace_shadow<true><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
         else k_trace_shadow<false><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
-        CUDA_TRY(cudaEventRecord(stage_event(iter, 4), s));
+        if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 4), s));
         tm->launches += 1;
         sl.n_iters = iter + 1;
         q_cur = q_next;
@@ -1555,6 +1560,7 @@ int yk_context_create(int device_id, yk_context** out) {
     CUDA_TRY(cudaEventCreate(&c->ev[2]));  // timing pair around the whole render
     CUDA_TRY(cudaEventCreate(&c->ev[3]));
     if (const char* np = getenv("YK_PIPES")) c->n_pipes_env = std::max(1, std::min(kMaxPipes, atoi(np)));
+    if (const char* st = getenv("YK_STAGE_TIMING")) c->stage_timing = std::max(0, std::min(2, atoi(st)));
     for (int i = 0; i < kMaxPipes; ++i) {
         Pipe& p = c->pipe[i];
         if (i == 0) p.stream = c->stream;
@@ -1667,7 +1673,8 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
         if (d->tri_material[i] >= d->n_materials) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: material index out of range");
         if (d->materials[d->tri_material[i]].kind <= YK_MAT_GLOSSY) sc->material_kinds |= 1u << d->materials[d->tri_material[i]].kind;
         if (d->tri_area_light[i] >= (int32_t)d->n_lights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: area light out of range");
-        uint32_t packed = d->tri_material[i] | ((uint32_t)d->tri_flags[i] << 24);
+        // material index | YK_TRI_* flags << 24 | material kind << 28 (so the material sort needs no material table look-up)
+        uint32_t packed = d->tri_material[i] | ((uint32_t)(d->tri_flags[i] & 0xfu) << 24) | ((d->materials[d->tri_material[i]].kind & 3u) << 28);
         if ((d->tri_flags[i] & YK_TRI_HAS_NORMALS) && !d->tri_normals) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: normals flagged but absent");
         if ((d->tri_flags[i] & YK_TRI_HAS_UVS) && !d->tri_uvs) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: uvs flagged but absent");
         const bool is_sphere = (d->tri_flags[i] & YK_TRI_IS_SPHERE) != 0;
