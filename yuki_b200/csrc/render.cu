@@ -268,7 +268,16 @@ __global__ void k_dim_hashes(const Job* jobs, uint32_t n_jobs, uint32_t n_dims, 
 }
 
 // ---- raygen: Integrator::render loop head (integrators/mod.rs:145-169) -----------------------------
-__global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, IterCounters* first) {
+// `rng.advance(sample_index * 65536)` (uniform.rs:81-83, stratified.rs:99-101) is an LCG jump: state' = M * state + inc * P
+// with M, P functions of the distance only (the jump's additive term is linear in the stream increment). The host
+// tabulates (M, P) for the batch's <= 64 consecutive sample indices, so seeking costs two multiplies instead of the
+// O(log n) loop — which was most of this kernel's instructions.
+struct SampleJumps {
+    uint32_t first_sample;  // the table covers sample indices first_sample .. first_sample + 63
+    uint32_t _pad;
+    unsigned long long mult[64], plus[64];
+};
+__global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, SampleJumps jumps, IterCounters* first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bt.n_paths) return;
     if (i == 0) first->n_active = bt.n_paths;
@@ -276,7 +285,15 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, IterCounters* first) {
     const Job job = bt.jobs[ji];
     const uint32_t sample = job.sample_begin + bt.sample_off + si;
     SamplerState s;
-    s.start(cfg.sampler, job.x, job.y, sample, job.rng_inc, ji);
+    const uint32_t slot = sample - jumps.first_sample;
+    if (slot < 64u) {  // (always, for the batches yk_render builds)
+        s.px = job.x; s.py = job.y; s.index = sample; s.dim = 0; s.job = ji;
+        s.rng.inc = job.rng_inc;
+        const unsigned long long seeded = (cfg.sampler.seed + job.rng_inc) * kPcgMult + job.rng_inc;  // Lcg64Xsh32::new
+        s.rng.state = jumps.mult[slot] * seeded + job.rng_inc * jumps.plus[slot];
+    } else {
+        s.start(cfg.sampler, job.x, job.y, sample, job.rng_inc, ji);
+    }
     const V2 j = s.get_2d(cfg.sampler);
     // Camera::ray, camera.rs:105-114
     const V3 p_cam = xf_point(cfg.r2c, mk((float)job.x + j.x, (float)job.y + j.y, 0.0f));
@@ -1424,8 +1441,8 @@ int retire_slot(Pipe* p, int k, Timers* tm, uint64_t* done_paths) {
 // One batch on one pipe: raygen, the bounce loop, and the per-batch film step, all asynchronous on the pipe's stream.
 // Path tracing runs exactly max_depth bounces (every queue length stays on the device); Whitted's tree walk has no
 // such bound, so it reads the next bounce's ray count back once per bounce.
-int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, const Batch& bt, bool accumulate_film, float* d_film,
-              Timers* tm, uint64_t* done_paths) {
+int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, const Batch& bt, uint32_t first_sample, bool accumulate_film,
+              float* d_film, Timers* tm, uint64_t* done_paths) {
     cudaStream_t s = p->stream;
     Wave& w = p->wave;
     const int k = (int)(p->n_batches % kRing);
@@ -1448,7 +1465,21 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
 
     const int T = 256;
     CUDA_TRY(cudaMemsetAsync(p->d_ctr, 0, 2 * sizeof(IterCounters), s));
-    k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt, &p->d_ctr[0]);
+    SampleJumps jumps;
+    jumps.first_sample = first_sample;
+    jumps._pad = 0;
+    for (uint32_t k = 0; k < 64; ++k) {  // Lcg64Xsh32::advance with increment 1
+        unsigned long long delta = (unsigned long long)(first_sample + k) * 65536ull, am = 1, ap = 0, cm = 6364136223846793005ull, cp = 1;
+        while (delta) {
+            if (delta & 1ull) { am *= cm; ap = ap * cm + cp; }
+            cp = (cm + 1ull) * cp;
+            cm *= cm;
+            delta >>= 1;
+        }
+        jumps.mult[k] = am;
+        jumps.plus[k] = ap;
+    }
+    k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt, jumps, &p->d_ctr[0]);
     tm->launches += 1;
     const bool debug = cfg.integrator >= YK_INTEGRATOR_BVH_INTERSECTIONS;
     const bool sync_loop = cfg.integrator == YK_INTEGRATOR_WHITTED;
@@ -1985,7 +2016,9 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
                     bt.sample_off = s0;
                     bt.n_samples = std::min(m, samples_per_job - s0);
                     bt.n_paths = nj * bt.n_samples;
-                    rc = run_batch(c, &p, sc, gcfg, bt, accumulate, d_film, &tm, &done);
+                    // the batch's first sample index: s0, or the sample of the group's tiles (accumulating films: one per group)
+                    const uint32_t first_sample = accumulate ? (uint32_t)tiles[groups[group].t_lo].sample : s0;
+                    rc = run_batch(c, &p, sc, gcfg, bt, first_sample, accumulate, d_film, &tm, &done);
                     if (rc != YK_OK) { cudaDeviceSynchronize(); return rc; }
                     if (!accumulate && s0 + m >= samples_per_job) {
                         // the group's last samples are queued: `color /= sample_count` + Film::update_tile for its pixels
