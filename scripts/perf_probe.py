@@ -29,8 +29,8 @@ if which == "c16":
     probe("cornell 1024^2 path8 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=3)
 if which == "capsweep":
     s, c = scenes.cornell(xf, light="rect", tall_box="glass")
-    for cap in (1 << 22, 1 << 21, 1 << 20, 1 << 19, 1 << 18):
-        probe(f"cornell 1024^2 path8 16spp cap {cap}", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=2, wavefront_paths=cap)
+    for cap in (1 << 25, 1 << 24, 1 << 23, 1 << 22, 1 << 21):
+        probe(f"cornell 1024^2 path8 64spp cap {cap}", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8), reps=2, wavefront_paths=cap)
 if which == "terrain":
     import time as _t
     t0 = _t.time(); s, c = scenes.terrain_room(xf); print(f"terrain scene desc {_t.time()-t0:.1f}s", flush=True)

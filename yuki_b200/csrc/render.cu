@@ -269,15 +269,27 @@ __global__ void k_dim_hashes(const Job* jobs, uint32_t n_jobs, uint32_t n_dims, 
 
 // ---- raygen: Integrator::render loop head (integrators/mod.rs:145-169) -----------------------------
 // `rng.advance(sample_index * 65536)` (uniform.rs:81-83, stratified.rs:99-101) is an LCG jump: state' = M * state + inc * P
-// with M, P functions of the distance only (the jump's additive term is linear in the stream increment). The host
-// tabulates (M, P) for the batch's <= 64 consecutive sample indices, so seeking costs two multiplies instead of the
+// with M, P functions of the distance only (the jump's additive term is linear in the stream increment). A tiny kernel
+// (k_sample_jumps) tabulates (M, P) for the batch's consecutive sample indices, so seeking costs two multiplies instead of the
 // O(log n) loop — which was most of this kernel's instructions.
-struct SampleJumps {
-    uint32_t first_sample;  // the table covers sample indices first_sample .. first_sample + 63
-    uint32_t _pad;
-    unsigned long long mult[64], plus[64];
+constexpr uint32_t kMaxBatchSamples = 256;  // consecutive sample indices of a pixel per batch (size of the jump table)
+struct SampleJump {
+    unsigned long long mult, plus;
 };
-__global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, SampleJumps jumps, IterCounters* first) {
+// jumps[k] = the (M, P) of Lcg64Xsh32::advance((first_sample + k) * 65536) for increment 1
+__global__ void k_sample_jumps(uint32_t first_sample, uint32_t n, SampleJump* jumps) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    unsigned long long delta = (unsigned long long)(first_sample + k) * 65536ull, am = 1, ap = 0, cm = kPcgMult, cp = 1;
+    while (delta) {
+        if (delta & 1ull) { am *= cm; ap = ap * cm + cp; }
+        cp = (cm + 1ull) * cp;
+        cm *= cm;
+        delta >>= 1;
+    }
+    jumps[k] = SampleJump{am, ap};
+}
+__global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, uint32_t first_sample, uint32_t n_jumps, const SampleJump* jumps, IterCounters* first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bt.n_paths) return;
     if (i == 0) first->n_active = bt.n_paths;
@@ -285,12 +297,13 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, SampleJumps jumps, Ite
     const Job job = bt.jobs[ji];
     const uint32_t sample = job.sample_begin + bt.sample_off + si;
     SamplerState s;
-    const uint32_t slot = sample - jumps.first_sample;
-    if (slot < 64u) {  // (always, for the batches yk_render builds)
+    const uint32_t slot = sample - first_sample;
+    if (slot < n_jumps) {  // (always, for the batches yk_render builds)
         s.px = job.x; s.py = job.y; s.index = sample; s.dim = 0; s.job = ji;
         s.rng.inc = job.rng_inc;
         const unsigned long long seeded = (cfg.sampler.seed + job.rng_inc) * kPcgMult + job.rng_inc;  // Lcg64Xsh32::new
-        s.rng.state = jumps.mult[slot] * seeded + job.rng_inc * jumps.plus[slot];
+        const SampleJump j = jumps[slot];
+        s.rng.state = j.mult * seeded + job.rng_inc * j.plus;
     } else {
         s.start(cfg.sampler, job.x, job.y, sample, job.rng_inc, ji);
     }
@@ -1303,6 +1316,7 @@ struct Pipe {
     IterCounters* d_ctr = nullptr;   // two entries, alternating per bounce
     IterCounters* h_ctr = nullptr;   // pinned: read-back for the integrators whose bounce count is unbounded (Whitted)
     Totals* h_totals = nullptr;      // pinned
+    SampleJump* d_jumps = nullptr;   // sampler seek table of the batch being queued (kMaxBatchSamples entries)
     Job* d_jobs = nullptr;           // the pixel jobs of the pipe's current pixel group
     size_t jobs_cap = 0;
     uint32_t* d_dim_hash = nullptr;  // SamplerCfg::hash_table of the pipe's current pixel group
@@ -1465,21 +1479,9 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
 
     const int T = 256;
     CUDA_TRY(cudaMemsetAsync(p->d_ctr, 0, 2 * sizeof(IterCounters), s));
-    SampleJumps jumps;
-    jumps.first_sample = first_sample;
-    jumps._pad = 0;
-    for (uint32_t k = 0; k < 64; ++k) {  // Lcg64Xsh32::advance with increment 1
-        unsigned long long delta = (unsigned long long)(first_sample + k) * 65536ull, am = 1, ap = 0, cm = 6364136223846793005ull, cp = 1;
-        while (delta) {
-            if (delta & 1ull) { am *= cm; ap = ap * cm + cp; }
-            cp = (cm + 1ull) * cp;
-            cm *= cm;
-            delta >>= 1;
-        }
-        jumps.mult[k] = am;
-        jumps.plus[k] = ap;
-    }
-    k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt, jumps, &p->d_ctr[0]);
+    k_sample_jumps<<<1, kMaxBatchSamples, 0, s>>>(first_sample, bt.n_samples, p->d_jumps);
+    tm->launches += 1;
+    k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt, first_sample, bt.n_samples, p->d_jumps, &p->d_ctr[0]);
     tm->launches += 1;
     const bool debug = cfg.integrator >= YK_INTEGRATOR_BVH_INTERSECTIONS;
     const bool sync_loop = cfg.integrator == YK_INTEGRATOR_WHITTED;
@@ -1600,6 +1602,7 @@ int yk_context_create(int device_id, yk_context** out) {
             p.owns_stream = true;
         }
         CUDA_TRY(cudaMalloc((void**)&p.d_ctr, 2 * sizeof(IterCounters)));
+        CUDA_TRY(cudaMalloc((void**)&p.d_jumps, kMaxBatchSamples * sizeof(SampleJump)));
         CUDA_TRY(cudaMallocHost((void**)&p.h_ctr, sizeof(IterCounters)));
         CUDA_TRY(cudaMallocHost((void**)&p.h_totals, sizeof(Totals)));
     }
@@ -1618,6 +1621,7 @@ void yk_context_destroy(yk_context* c) {
         cudaFree(p.d_ctr);
         cudaFree(p.d_dim_hash);
         cudaFree(p.d_jobs);
+        cudaFree(p.d_jumps);
         cudaFreeHost(p.h_ctr);
         cudaFreeHost(p.h_totals);
         for (auto& sl : p.slot) {
@@ -1898,13 +1902,28 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         CUDA_TRY(cudaMemcpyAsync(c->d_tiles, tiles, (size_t)n_tiles * sizeof(yk_tile), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->d_tile_off, tile_off.data(), tile_off.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
         // Wavefront capacity: paths in flight per batch.
-        uint32_t cap = opts && opts->wavefront_paths ? opts->wavefront_paths : (1u << 22);
+        // Default: as many as ~6 GB of wavefront state per pipe hold, at most 16 Mi (measured on the Cornell bench: 4 Mi -> 8 Mi ->
+        // 16 Mi -> 32 Mi paths = +8 %, +12 %, +14 %: fewer, longer launches amortise the kernels' tails and the launch gaps),
+        // and never more than a quarter of the free device memory.
+        const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
+        uint32_t cap = opts ? opts->wavefront_paths : 0u;
+        if (!cap) {
+            const uint64_t bytes_per_path = 320ull + 40ull * std::max(sc->dev.n_lights, 1u) + 52ull * stack_entries;
+            size_t free_b = 0, total_b = 0;
+            uint64_t budget = 6ull << 30;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                uint64_t held = 0;  // state already allocated for the pipes is reusable
+                for (const Pipe& p : c->pipe) held += (uint64_t)p.wave_cap * bytes_per_path;
+                budget = std::min<uint64_t>(budget, ((uint64_t)free_b + held) / 8);
+            }
+            cap = (uint32_t)std::min<uint64_t>(1u << 24, std::max<uint64_t>(1u << 20, budget / bytes_per_path));
+        }
         const uint64_t total_paths = (uint64_t)n_jobs_total * samples_per_job;
         if (cap > total_paths) cap = (uint32_t)total_paths;
         cap = std::max(cap, 32u);
         // Samples of one pixel per batch: enough to amortise per-batch fixed costs, few enough that many pixels
         // (>= 64 Ki when available) share a batch.
-        uint32_t m = std::min(samples_per_job, 64u);
+        uint32_t m = std::min(samples_per_job, kMaxBatchSamples);
         while (m > 1 && (uint64_t)m * std::min<uint64_t>(n_jobs_total, 65536) > cap) m >>= 1;
         uint32_t jobs_per_batch = std::max(1u, cap / m);
         // Pipes: pixel groups alternate between the streams, so one group's latency-bound shading overlaps the other's
@@ -1921,7 +1940,6 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
             if ((uint64_t)(n_jobs_total / 2) * m >= (1u << 20)) jobs_per_batch = (uint32_t)((n_jobs_total + 1) / 2);
             else n_pipes = 1;
         }
-        const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
         const uint32_t wave_cap = (uint32_t)std::min<uint64_t>(cap, (uint64_t)jobs_per_batch * m);
         int rc = YK_OK;
         CUDA_TRY(cudaEventRecord(c->ev[0], s));
