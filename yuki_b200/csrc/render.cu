@@ -33,7 +33,10 @@ constexpr int kMaxLights = 16;
 constexpr int kStackDepth = 64;  // bvh.rs:172
 constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTraceThreads = 128;
-constexpr int kShadeThreads = 128;
+#ifndef YK_SHADE_THREADS
+#define YK_SHADE_THREADS 128
+#endif
+constexpr int kShadeThreads = YK_SHADE_THREADS;
 #ifndef YK_TRACE_MIN_BLOCKS
 #define YK_TRACE_MIN_BLOCKS 8
 #endif
@@ -41,7 +44,7 @@ constexpr int kShadeThreads = 128;
 #define YK_SHADOW_MIN_BLOCKS 8
 #endif
 #ifndef YK_SHADE_MIN_BLOCKS
-#define YK_SHADE_MIN_BLOCKS 8
+#define YK_SHADE_MIN_BLOCKS (1024 / YK_SHADE_THREADS)
 #endif
 
 #define CUDA_TRY(expr)                                                                                          \
@@ -194,17 +197,31 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // bottleneck of classify / resolve with one atomic per warp, profiles/r01). `key` in [0, NQ) selects the queue, any
 // other value appends nothing. Must be reached by every thread of the block (blockDim.x <= 256).
 // Returns the slot the value was written to (undefined when nothing was appended).
-template <int NQ>
-__device__ __forceinline__ uint32_t block_scatter(int key, uint32_t value, uint32_t* const (&queues)[NQ], uint32_t* const (&counters)[NQ]) {
+// `K` items per thread share the block's atomics: K * blockDim.x items per global atomic and queue.
+template <int NQ, int K>
+__device__ __forceinline__ void block_scatter_multi(const int (&key)[K], const uint32_t (&value)[K], uint32_t* const (&queues)[NQ],
+                                                    uint32_t* const (&counters)[NQ], uint32_t (&pos)[K]) {
     __shared__ uint32_t s_cnt[8][NQ];
     __shared__ uint32_t s_base[NQ];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
-    uint32_t my_rank = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t run[NQ];  // warp-uniform: entries of this warp per queue so far
+    uint32_t my_rank[K];
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        const unsigned votes = __ballot_sync(0xffffffffu, key == k);
-        if (key == k) my_rank = __popc(votes & ((1u << lane) - 1u));
-        if (lane == 0) s_cnt[warp][k] = __popc(votes);
+    for (int q = 0; q < NQ; ++q) run[q] = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        my_rank[k] = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const unsigned votes = __ballot_sync(0xffffffffu, key[k] == q);
+            if (key[k] == q) my_rank[k] = run[q] + __popc(votes & lt);
+            run[q] += __popc(votes);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) s_cnt[warp][q] = run[q];
     }
     __syncthreads();
     if (threadIdx.x < NQ) {
@@ -217,13 +234,23 @@ __device__ __forceinline__ uint32_t block_scatter(int key, uint32_t value, uint3
         s_base[threadIdx.x] = total ? atomicAdd(counters[threadIdx.x], total) : 0u;
     }
     __syncthreads();
-    uint32_t pos = 0;
-    if (key >= 0 && key < NQ) {
-        pos = s_base[key] + s_cnt[warp][key] + my_rank;
-        queues[key][pos] = value;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pos[k] = 0;
+        if (key[k] >= 0 && key[k] < NQ) {
+            pos[k] = s_base[key[k]] + s_cnt[warp][key[k]] + my_rank[k];
+            queues[key[k]][pos[k]] = value[k];
+        }
     }
     __syncthreads();  // the shared arrays are reused by the next call
-    return pos;
+}
+template <int NQ>
+__device__ __forceinline__ uint32_t block_scatter(int key, uint32_t value, uint32_t* const (&queues)[NQ], uint32_t* const (&counters)[NQ]) {
+    const int keys[1] = {key};
+    const uint32_t values[1] = {value};
+    uint32_t pos[1];
+    block_scatter_multi<NQ, 1>(keys, values, queues, counters, pos);
+    return pos[0];
 }
 __device__ __forceinline__ unsigned long long mix_hit(uint32_t x, uint32_t y, uint32_t sample, uint32_t id) {
     unsigned long long h = ((unsigned long long)x << 48) ^ ((unsigned long long)y << 32) ^ ((unsigned long long)sample << 8) ^
@@ -840,58 +867,71 @@ __device__ __forceinline__ void stream_node(const Wave::Stream& st, uint32_t pos
 }
 
 // ---- classify: miss handling + compaction by material ("ray-queue sort/compaction pass") ---------------
+// K items per thread and block round (K * blockDim.x rays per global atomic): the queue counters are single addresses, and
+// same-address atomics, not bandwidth, bound this kernel. Whitted's tree walk re-queues rays here and runs with K = 1.
+#ifndef YK_CLASSIFY_ITEMS
+#define YK_CLASSIFY_ITEMS 8
+#endif
+template <int K, bool WHITTED>
 __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, int b, IterCounters* cur,
                            IterCounters* nxt, int first_iteration, uint32_t* q_next) {
     const uint32_t n = cur->n_active;
-    const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    const uint32_t per_round = gridDim.x * blockDim.x * K;
+    const uint32_t rounds = (n + per_round - 1) / per_round;
     for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
+        const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x * K;
         if (block_first >= n) break;  // block-uniform
-        const uint32_t i = block_first + threadIdx.x;
-        const bool valid = i < n;
-        uint32_t path = 0, kind = 4, hit_slot = kMiss;
-        bool requeue = false;
-        StackEntry node{};
-        uint32_t node_dim = 0;
+        uint32_t idx[K], path[K], hit_slot[K];
+        int key[K];
+        StackEntry node[WHITTED ? K : 1];
+        uint32_t node_dim[WHITTED ? K : 1];
         unsigned long long hh = 0;
-        if (valid) {
-            path = queue ? queue[i] : i;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t i = block_first + k * blockDim.x + threadIdx.x;
+            idx[k] = i;
+            path[k] = 0; hit_slot[k] = kMiss; key[k] = -1;
+            if (i >= n) continue;
+            path[k] = queue ? queue[i] : i;
             const uint2 h = w.hit[i];
-            hit_slot = h.y;
+            hit_slot[k] = h.y;
             uint32_t orig = 0xffffffffu;
             if (h.y != kMiss) {
-                kind = (__float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) >> 28) & 3u;
+                key[k] = (int)((__float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) >> 28) & 3u);
                 if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
             } else if (first_iteration != 2) {  // (2 = debug integrators: their li() returns no background)
                 // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
                 const float4 bw = w.st[b].beta[i];
-                float4 L = w.L[path];
+                float4 L = w.L[path[k]];
                 L.x = L.x + bw.x * sc.background[0];
                 L.y = L.y + bw.y * sc.background[1];
                 L.z = L.z + bw.z * sc.background[2];
-                w.L[path] = L;
-                if (cfg.integrator == YK_INTEGRATOR_WHITTED) {
-                    node_dim = __float_as_uint(bw.w) >> kDimShift;
-                    requeue = stack_pop(w, path, &node);
+                w.L[path[k]] = L;
+                if (WHITTED) {
+                    node_dim[WHITTED ? k : 0] = __float_as_uint(bw.w) >> kDimShift;
+                    if (stack_pop(w, path[k], &node[WHITTED ? k : 0])) key[k] = 4;
                 }
             }
             if (first_iteration) {
-                const uint32_t si = bt.div_jobs.div(path);
-                const Job job = bt.jobs[path - si * bt.n_jobs];
+                const uint32_t si = bt.div_jobs.div(path[k]);
+                const Job job = bt.jobs[path[k] - si * bt.n_jobs];
                 const uint32_t sample = job.sample_begin + bt.sample_off + si;
-                hh = mix_hit(job.x, job.y, sample, orig);
+                hh += mix_hit(job.x, job.y, sample, orig);
                 if (cfg.hit_ids && sample == cfg.aux_sample) cfg.hit_ids[(size_t)job.y * cfg.res_x + job.x] = (int32_t)orig;
             }
         }
         uint32_t* const queues[5] = {w.q_mat, w.q_mat + (size_t)w.cap, w.q_mat + (size_t)2 * w.cap, w.q_mat + (size_t)3 * w.cap, q_next};
         uint32_t* const counters[5] = {&cur->mat[0], &cur->mat[1], &cur->mat[2], &cur->mat[3], &nxt->n_active};
-        const int key = !valid ? -1 : (requeue ? 4 : (kind < 4 ? (int)kind : -1));
-        const uint32_t pos = block_scatter<5>(key, path, queues, counters);
-        if (key >= 0 && key < 4) {
-            w.q_mat_tri[(size_t)key * w.cap + pos] = hit_slot;
-            w.q_mat_slot[(size_t)key * w.cap + pos] = i;
-        } else if (key == 4) {
-            stream_node(w.st[b ^ 1], pos, node, node_dim, w.st[b].rng[i]);
+        uint32_t pos[K];
+        block_scatter_multi<5, K>(key, path, queues, counters, pos);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (key[k] >= 0 && key[k] < 4) {
+                w.q_mat_tri[(size_t)key[k] * w.cap + pos[k]] = hit_slot[k];
+                w.q_mat_slot[(size_t)key[k] * w.cap + pos[k]] = idx[k];
+            } else if (WHITTED && key[k] == 4) {
+                stream_node(w.st[b ^ 1], pos[k], node[WHITTED ? k : 0], node_dim[WHITTED ? k : 0], w.st[b].rng[idx[k]]);
+            }
         }
         if (first_iteration) {
             hh = warp_sum(hh);
@@ -1488,7 +1528,8 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
     const int trace_blocks_closest = c->sm_count * std::max(1, c->occ_trace_closest);
     const int trace_blocks_shadow = c->sm_count * std::max(1, c->occ_trace_any);
     const int wide_blocks = c->sm_count * 16;
-    const int classify_blocks = grid_for(bt.n_paths, T, c->sm_count * 8);
+    const int classify_items = cfg.integrator == YK_INTEGRATOR_WHITTED ? 1 : YK_CLASSIFY_ITEMS;
+    const int classify_blocks = grid_for(bt.n_paths, T * classify_items, c->sm_count * 8);
     const int shade_blocks = grid_for(bt.n_paths, kShadeThreads, wide_blocks);
     const int closest_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_closest);
     const int shadow_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_shadow);
@@ -1518,13 +1559,14 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         if (debug) {
             k_debug_shade<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt.n_paths);
             // primary-hit digest / id image for the debug integrators too
-            k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, 2, q_next);
+            k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, 2, q_next);
             tm->launches += 2;
             for (int st = 2; st < kTimedStages; ++st) if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, st), s));
             sl.n_iters = iter + 1;
             break;
         }
-        k_classify<<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
+        if (cfg.integrator == YK_INTEGRATOR_WHITTED) k_classify<1, true><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
+        else k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
         tm->launches += 1;
         for (uint32_t kind = 0; kind < 4; ++kind) {
