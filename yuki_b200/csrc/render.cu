@@ -1002,9 +1002,13 @@ __device__ __forceinline__ void make_surface(const DevScene& sc, uint32_t tri, V
 }
 
 // textures/constant.rs:23-30, textures/image_texture.rs:81-111
+__device__ __noinline__ RGB tex_image_eval(const DevTexture& t, V2 uv);
 __device__ __forceinline__ RGB tex_eval(const DevScene& sc, int32_t index, V2 uv) {
     const DevTexture& t = sc.textures[index];
     if (t.kind == YK_TEX_CONSTANT) return rgb(t.value[0], t.value[1], t.value[2]);
+    return tex_image_eval(t, uv);
+}
+__device__ __noinline__ RGB tex_image_eval(const DevTexture& t, V2 uv) {
     float sx = uv.x - truncf(uv.x), sy = uv.y - truncf(uv.y);
     if (sx < 0.0f) sx = 1.0f + sx;
     if (sy < 0.0f) sy = 1.0f + sy;
@@ -1127,7 +1131,7 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 // Radiance is not summed here: each light that needs a visibility test leaves its shadow ray and contribution in
 // lt_*, and k_trace_shadow adds the unoccluded terms in light order. Surviving paths are appended to the next
 // active queue (one atomic per block).
-template <uint32_t KIND>
+template <uint32_t KIND, bool PATH>
 __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
                                                                                const uint32_t* queue_tri, const uint32_t* queue_slot, int b,
                                                                                IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
@@ -1206,7 +1210,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             const bool add_le = depth == 0 || was_specular;
 
             uint32_t new_flags = 0;
-            if (cfg.integrator == YK_INTEGRATOR_PATH) {
+            if (PATH) {
                 // path.rs:121-129 — beta multiplies the emitted term here and again in the fold (reference quirk)
                 const RGB extra = add_le ? beta * le : gray(0.0f);
                 w.pend_extra[g] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
@@ -1569,16 +1573,29 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         else k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
         tm->launches += 1;
+        const bool is_path = cfg.integrator == YK_INTEGRATOR_PATH;
         for (uint32_t kind = 0; kind < 4; ++kind) {
             if (!(sc->material_kinds & (1u << kind))) continue;  // no triangle of the scene has this material kind
             uint32_t* q = w.q_mat + (size_t)kind * w.cap;
             uint32_t* qt = w.q_mat_tri + (size_t)kind * w.cap;
             uint32_t* qs = w.q_mat_slot + (size_t)kind * w.cap;
             switch (kind) {
-                case YK_MAT_MATTE: k_shade<YK_MAT_MATTE><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
-                case YK_MAT_GLASS: k_shade<YK_MAT_GLASS><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
-                case YK_MAT_METAL: k_shade<YK_MAT_METAL><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
-                default: k_shade<YK_MAT_GLOSSY><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); break;
+                case YK_MAT_MATTE:
+                    if (is_path) k_shade<YK_MAT_MATTE, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    else k_shade<YK_MAT_MATTE, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    break;
+                case YK_MAT_GLASS:
+                    if (is_path) k_shade<YK_MAT_GLASS, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    else k_shade<YK_MAT_GLASS, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    break;
+                case YK_MAT_METAL:
+                    if (is_path) k_shade<YK_MAT_METAL, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    else k_shade<YK_MAT_METAL, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    break;
+                default:
+                    if (is_path) k_shade<YK_MAT_GLOSSY, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    else k_shade<YK_MAT_GLOSSY, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
+                    break;
             }
             tm->launches += 1;
         }

@@ -126,7 +126,7 @@ YK_DEV uint64_t hash_pixel(uint32_t px, uint32_t py) {
     return s.finish();
 }
 // message = x:u16 y:u16 dim:u32 seed:u64 (16 bytes) -> two full words + the length block
-YK_DEV uint64_t hash_pixel_dim_seed(uint32_t px, uint32_t py, uint32_t dim, uint64_t seed) {
+static __device__ __noinline__ uint64_t hash_pixel_dim_seed(uint32_t px, uint32_t py, uint32_t dim, uint64_t seed) {  // tabulated on the hot path
     Sip s; s.init();
     s.absorb((uint64_t)(px & 0xffffu) | ((uint64_t)(py & 0xffffu) << 16) | ((uint64_t)dim << 32));
     s.absorb(seed);
@@ -342,7 +342,7 @@ YK_DEV bool sphere_test(const yk_sphere& sp, V3 o_w, V3 d_w, float t_max, float*
 // Surface interaction of a sphere hit (:79-117) moved to world space by `&object_to_world * SurfaceInteraction`
 // (interaction.rs:141-164). atan2 / acos are CUDA's, not glibc's: uv and the shading frame can differ from the CPU
 // path in the last bits (radiance tolerance); the hit itself uses only + - * / sqrt and is exact.
-YK_DEV void sphere_surface(const yk_sphere& sp, V3 o_w, V3 d_w, Surface* si) {
+static __device__ __noinline__ void sphere_surface(const yk_sphere& sp, V3 o_w, V3 d_w, Surface* si) {  // rare: out of line
     float t = 0.0f;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
     sphere_test(sp, o_w, d_w, __int_as_float(0x7f800000), &t, &o, &d);
