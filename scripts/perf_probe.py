@@ -79,3 +79,10 @@ if which == "jitter":  # run-to-run variation of one render (device time between
         t0 = time.time()
         r = rn.render(dev, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8))
         print(f"rep {i}: device {r.stats.device_ms:.1f} ms wall {1e3*(time.time()-t0):.1f} ms closest {r.stats.trace_closest_ms:.1f} any {r.stats.trace_any_ms:.1f} shade {r.stats.shade_ms:.1f}", flush=True)
+if which == "jitter_hf4":
+    s, c = scenes.heightfield(xf, 708, 708)
+    ctx = api.Context(0); dev = api.Scene(ctx, s); rn = api.Renderer(ctx)
+    for i in range(8):
+        t0 = time.time()
+        r = rn.render(dev, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8))
+        print(f"rep {i}: device {r.stats.device_ms:.1f} ms wall {1e3*(time.time()-t0):.1f} ms closest {r.stats.trace_closest_ms:.1f} any {r.stats.trace_any_ms:.1f} shade {r.stats.shade_ms:.1f} launches {r.stats.kernel_launches}", flush=True)
