@@ -14,6 +14,8 @@ def probe(name, scene, cam, film, sampler, integ, reps=2, **kw):
         r = rn.render(dev, cam, film, sampler, integ, **kw)
         if best is None or r.stats.device_ms < best.stats.device_ms:
             best = r
+        if os.environ.get("YK_PROBE_VERBOSE"):
+            print(f"    rep {i}: device {r.stats.device_ms:.2f} ms, lib wall {1e3 * r.stats.seconds:.2f} ms", flush=True)
     st = best.stats
     s = st.device_ms / 1e3
     bytes_closest = 32 * st.closest_nodes + 36 * st.closest_tris

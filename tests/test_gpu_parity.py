@@ -316,3 +316,32 @@ def test_deep_traversal_stack_spills_bit_exact(gpu_ctx, oracle, xf):
     r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, s, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.path(4))
     assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
     assert r.stats.any_nodes == o_st.any_nodes and r.stats.closest_nodes == o_st.closest_nodes
+
+
+def test_maximum_film_coordinates_and_sample_indices(gpu_ctx, oracle, xf):
+    """The limits the reference asserts (integrators/mod.rs:140-141): pixel coordinates and sample indices up to 0xFFFF.
+    A 65535-pixel-wide film rendered at its two ends, and the last sample index (65535) of a 256x256-strata sampler in
+    accumulate mode, both bit-identical to the oracle (the sampler seek distance is 65535 * 65536 there)."""
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    film = D.FilmSettings((65535, 20), 16)
+    all_tiles = api.film_tiles(film)
+    assert len(all_tiles) == 4096 * 2 and int(all_tiles["x1"].max()) == 65535
+    pick = all_tiles[(all_tiles["x0"] < 32) | (all_tiles["x1"] > 65535 - 32) | ((all_tiles["x0"] >= 32768 - 16) & (all_tiles["x0"] < 32768 + 16))]
+    smp, integ = D.SamplerType.stratified(2, 2), D.IntegratorType.path(5)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    r = rn.render(dev, cam, film, smp, integ, tiles=pick)
+    o_img, _, o_st = oracle.OracleScene(scene).render(cam, film, smp, integ, tiles=pick)
+    assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+    assert r.stats.ray_count == o_st.ray_count and r.stats.samples == sum(int(t["x1"] - t["x0"]) * int(t["y1"] - t["y0"]) for t in pick) * 4
+    # last sample index of the largest sampler the interface admits
+    film2 = D.FilmSettings((64, 48), 16, accumulate=True)
+    big = D.SamplerType.stratified(256, 256)
+    tiles = api.film_tiles(film2).copy()
+    tiles["sample"] = 65535
+    out = np.zeros((48, 64, 3), np.float32)
+    r2 = rn.render(dev, cam, film2, big, integ, tiles=tiles, film_out=out)
+    o2, _, o2_st = oracle.OracleScene(scene).render(cam, film2, big, integ, tiles=tiles)
+    dev.close()
+    assert np.array_equal(out.view(np.uint32), o2.view(np.uint32)) and float(o2.max()) > 0.0
+    assert r2.stats.ray_count == o2_st.ray_count

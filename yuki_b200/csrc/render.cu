@@ -1392,6 +1392,7 @@ struct yk_context {
     size_t film_cap = 0;
     int occ_trace_closest = 0, occ_trace_any = 0;
     int n_pipes_env = 0;  // YK_PIPES override (development)
+    uint64_t mem_budget = 0;  // bytes of wavefront state per pipe the default batch size may use (set at the first render)
     int stage_timing = 1;  // CUDA events per bounce: 1 = around the closest-hit kernel (the roofline figure), 2 = every stage
                            // (costs ~1.5 % of a Cornell render), 0 = none; environment variable YK_STAGE_TIMING
 };
@@ -1968,14 +1969,12 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         uint32_t cap = opts ? opts->wavefront_paths : 0u;
         if (!cap) {
             const uint64_t bytes_per_path = 320ull + 40ull * std::max(sc->dev.n_lights, 1u) + 52ull * stack_entries;
-            size_t free_b = 0, total_b = 0;
-            uint64_t budget = 6ull << 30;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                uint64_t held = 0;  // state already allocated for the pipes is reusable
-                for (const Pipe& p : c->pipe) held += (uint64_t)p.wave_cap * bytes_per_path;
-                budget = std::min<uint64_t>(budget, ((uint64_t)free_b + held) / 8);
+            if (!c->mem_budget) {  // asked once per context: cudaMemGetInfo can take milliseconds
+                size_t free_b = 0, total_b = 0;
+                c->mem_budget = 6ull << 30;
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->mem_budget = std::min<uint64_t>(c->mem_budget, (uint64_t)free_b / 8);
             }
-            cap = (uint32_t)std::min<uint64_t>(1u << 24, std::max<uint64_t>(1u << 20, budget / bytes_per_path));
+            cap = (uint32_t)std::min<uint64_t>(1u << 24, std::max<uint64_t>(1u << 20, c->mem_budget / bytes_per_path));
         }
         const uint64_t total_paths = (uint64_t)n_jobs_total * samples_per_job;
         if (cap > total_paths) cap = (uint32_t)total_paths;
