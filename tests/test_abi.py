@@ -73,3 +73,45 @@ def test_host_scene_validation(xf):
     scene.meshes[0].area_light = 0                                            # a point light cannot be an area light
     with pytest.raises(capi.YukiGpuError):
         api.HostScene(scene)
+
+
+C_CLIENT = r"""
+/* A plain C99 client of include/yuki_gpu.h: what a Rust `extern "C"` / bindgen crate sees. */
+#include <stdio.h>
+#include <stdlib.h>
+#include "yuki_gpu.h"
+int main(void) {
+    uint32_t n = yk_film_tiles(1024, 1024, 16, NULL, 0);
+    yk_tile* tiles = (yk_tile*)malloc(sizeof(yk_tile) * n);
+    if (yk_film_tiles(1024, 1024, 16, tiles, n) != n) return 2;
+    yk_camera_params cp = {{0.f, 0.f, -3.f}, {0.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, YK_FOV_X, 40.f};
+    yk_camera cam;
+    if (yk_camera_make(&cp, 1024, 1024, &cam) != YK_OK) return 3;
+    yk_context* ctx = NULL;
+    int rc = yk_context_create(0, &ctx);
+    printf("%u %u %u %d %d %zu %zu\n", n, (unsigned)tiles[0].x0, (unsigned)tiles[0].y0, rc, rc == YK_OK ? 0 : (int)(yk_last_error()[0] != 0),
+           sizeof(yk_bvh_node), sizeof(yk_tile));
+    if (ctx) yk_context_destroy(ctx);
+    free(tiles);
+    return 0;
+}
+"""
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 and a C program must link and call it."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "client.c"
+    src.write_text(C_CLIENT)
+    exe = tmp_path / "client"
+    libdir = os.path.join(ROOT, "yuki_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lyuki_gpu", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    n, x0, y0, rc, has_msg, node_size, tile_size = (int(v) for v in out)
+    assert n == 4096 and (x0, y0) == (496, 496)           # first spiral tile = the centre tile (film.rs:340-347)
+    assert rc in (0, -2) and (rc == 0 or has_msg == 1)     # YK_OK with a GPU, YK_ERR_CUDA + message without one
+    assert node_size == 32 and tile_size == 16
