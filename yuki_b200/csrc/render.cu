@@ -9,6 +9,7 @@
 //
 // Compiled with --fmad=false: every float op is the reference's un-fused IEEE op.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <chrono>
@@ -17,7 +18,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <future>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "yk_device.cuh"
@@ -1341,6 +1345,53 @@ __global__ void k_fill_i32(int32_t* p, size_t n, int32_t v) {
     if (i < n) p[i] = v;
 }
 
+// ---- scene packing (yk_scene_create): the reference-layout arrays are repacked on the device ---------------------------
+__global__ void k_scene_interior_flags(const yk_bvh_node* nodes, uint32_t n, uint32_t* flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = nodes[i].is_leaf ? 0u : 1u;
+}
+// rec[i] = number of interior nodes before node i: an interior node's record index; i - rec[i] = a leaf's table index.
+__global__ void k_scene_records(const yk_bvh_node* nodes, const uint32_t* rec, uint32_t n, int packed_leaves, uint2* leaf_table, float4* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const yk_bvh_node nd = nodes[i];
+    if (nd.is_leaf) return;
+    const uint32_t kids[2] = {i + 1, nd.offset};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const yk_bvh_node ch = nodes[kids[k]];
+        uint32_t ref;
+        if (!ch.is_leaf) ref = kRefInterior | ((uint32_t)ch.split_axis << 29) | rec[kids[k]];
+        else if (packed_leaves) ref = ((uint32_t)(ch.shape_count - 1) << kLeafFirstBits) | ch.offset;
+        else {
+            ref = kids[k] - rec[kids[k]];
+            leaf_table[ref] = make_uint2(ch.offset, ch.shape_count);
+        }
+        out[(size_t)rec[i] * 4 + 2 * k] = make_float4(ch.p_min[0], ch.p_min[1], ch.p_min[2], __uint_as_float(ref));
+        out[(size_t)rec[i] * 4 + 2 * k + 1] = make_float4(ch.p_max[0], ch.p_max[1], ch.p_max[2], 0.0f);
+    }
+}
+__global__ void k_scene_tris(const float* verts, const uint32_t* orig, const uint32_t* mat, const int32_t* alight, const uint8_t* flags,
+                             const int32_t* sphere, const uint8_t* mat_kind, uint32_t n, float4* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = mat[i], f = flags[i];
+    // material index | YK_TRI_* flags << 24 | material kind << 28 (so the material sort needs no material table look-up)
+    const uint32_t packed = m | ((f & 0xfu) << 24) | (((uint32_t)mat_kind[m] & 3u) << 28);
+    const float fp = __uint_as_float(packed), fi = __uint_as_float(orig[i]);
+    if (f & YK_TRI_IS_SPHERE) {  // NaN vertex lanes + (-2 - sphere index) where triangles keep their area light
+        const float qnan = __int_as_float(0x7fc00000);
+        out[3 * (size_t)i] = make_float4(qnan, qnan, qnan, __int_as_float(-2 - sphere[i]));
+        out[3 * (size_t)i + 1] = make_float4(qnan, qnan, qnan, fp);
+        out[3 * (size_t)i + 2] = make_float4(qnan, qnan, qnan, fi);
+        return;
+    }
+    const float* v = verts + (size_t)i * 9;
+    out[3 * (size_t)i] = make_float4(v[0], v[3], v[6], __int_as_float(alight[i]));
+    out[3 * (size_t)i + 1] = make_float4(v[1], v[4], v[7], fp);
+    out[3 * (size_t)i + 2] = make_float4(v[2], v[5], v[8], fi);
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1714,92 +1765,141 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     sc->ctx = c;
     sc->device = c->device;
     int rc;
-    // Nodes: one 64-byte record per interior node with the boxes of both children (DevScene::nodes2). Interior records are
-    // numbered in the reference's pre-order, so a first child's record follows its parent's.
-    std::vector<uint32_t> rec_of(d->n_nodes, 0);  // interior: record index; leaf: index among the leaves
-    uint32_t n_interior = 0, n_leaves = 0;
-    bool packed_leaves = d->n_tris <= (1u << kLeafFirstBits);
-    for (uint32_t i = 0; i < d->n_nodes; ++i) {
-        const yk_bvh_node& n = d->nodes[i];
-        if (!n.is_leaf && n.split_axis > 2) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: split axis out of range");
-        if (!n.is_leaf && (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.offset <= i))
-            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: child index out of range");
-        if (n.is_leaf && (uint64_t)n.offset + n.shape_count > d->n_tris)
-            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: leaf range out of range");
-        if (n.is_leaf) {
-            if (n.shape_count < 1 || n.shape_count > 16) packed_leaves = false;
-            rec_of[i] = n_leaves++;
-        } else {
-            rec_of[i] = n_interior++;
-        }
-    }
-    if (n_interior > kRefIndexMask) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 2^29 interior nodes");
-    std::vector<uint2> leaf_table;
-    if (!packed_leaves) leaf_table.resize(n_leaves);
-    auto ref_of = [&](uint32_t i) -> uint32_t {
-        const yk_bvh_node& n = d->nodes[i];
-        if (!n.is_leaf) return kRefInterior | ((uint32_t)n.split_axis << 29) | rec_of[i];
-        if (packed_leaves) return ((uint32_t)(n.shape_count - 1) << kLeafFirstBits) | n.offset;
-        leaf_table[rec_of[i]] = make_uint2(n.offset, n.shape_count);
-        return rec_of[i];
+    // The reference-layout arrays go to the device as they are and are repacked there (k_scene_*): no host-side copy of
+    // the scene is built. Meanwhile host threads validate the same arrays (indices, ranges, flags).
+    struct Check {
+        const char* error = nullptr;
+        uint32_t n_interior = 0, kinds = 0;
+        bool small_leaves = true;
     };
-    std::vector<float4> nodes((size_t)std::max(n_interior, 1u) * 4, make_float4(0, 0, 0, 0));
-    for (uint32_t i = 0; i < d->n_nodes; ++i) {
-        const yk_bvh_node& n = d->nodes[i];
-        if (n.is_leaf) continue;
-        const uint32_t kids[2] = {i + 1, n.offset};
-        for (int k = 0; k < 2; ++k) {
-            const yk_bvh_node& ch = d->nodes[kids[k]];
-            const uint32_t ref = ref_of(kids[k]);
-            float fr;
-            std::memcpy(&fr, &ref, 4);
-            nodes[(size_t)rec_of[i] * 4 + 2 * k] = make_float4(ch.p_min[0], ch.p_min[1], ch.p_min[2], fr);
-            nodes[(size_t)rec_of[i] * 4 + 2 * k + 1] = make_float4(ch.p_max[0], ch.p_max[1], ch.p_max[2], 0.0f);
+    const unsigned n_workers = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto validate = [d, n_workers](unsigned wi) -> Check {
+        Check ck;
+        auto fail = [&ck](const char* m) { if (!ck.error) ck.error = m; };
+        const uint64_t n0 = (uint64_t)d->n_nodes * wi / n_workers, n1 = (uint64_t)d->n_nodes * (wi + 1) / n_workers;
+        for (uint64_t i = n0; i < n1; ++i) {
+            const yk_bvh_node& n = d->nodes[i];
+            if (!n.is_leaf) {
+                ck.n_interior += 1;
+                if (n.split_axis > 2) fail("yk_scene_create: split axis out of range");
+                // children follow their parent (pre-order, bvh.rs:396-419): the walk cannot cycle
+                if (n.offset >= d->n_nodes || i + 1 >= d->n_nodes || n.offset <= i + 1) fail("yk_scene_create: child index out of range");
+            } else {
+                if ((uint64_t)n.offset + n.shape_count > d->n_tris) fail("yk_scene_create: leaf range out of range");
+                if (n.shape_count < 1 || n.shape_count > 16) ck.small_leaves = false;
+            }
         }
-    }
-    sc->dev.root_ref = ref_of(0);
-    std::memcpy(sc->dev.root_min, d->nodes[0].p_min, 12);
-    std::memcpy(sc->dev.root_max, d->nodes[0].p_max, 12);
-    // Triangles: three 16-byte words, vertices pre-gathered in leaf order and transposed (x0 x1 x2 | y0 y1 y2 | z0 z1 z2);
-    // the w lanes carry the per-triangle ids.
-    std::vector<float4> tris((size_t)d->n_tris * 3);
-    for (uint32_t i = 0; i < d->n_tris; ++i) {
-        const float* v = d->tri_vertices + (size_t)i * 9;
-        if (d->tri_material[i] >= d->n_materials) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: material index out of range");
-        if (d->materials[d->tri_material[i]].kind <= YK_MAT_GLOSSY) sc->material_kinds |= 1u << d->materials[d->tri_material[i]].kind;
-        if (d->tri_area_light[i] >= (int32_t)d->n_lights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: area light out of range");
-        // material index | YK_TRI_* flags << 24 | material kind << 28 (so the material sort needs no material table look-up)
-        uint32_t packed = d->tri_material[i] | ((uint32_t)(d->tri_flags[i] & 0xfu) << 24) | ((d->materials[d->tri_material[i]].kind & 3u) << 28);
-        if ((d->tri_flags[i] & YK_TRI_HAS_NORMALS) && !d->tri_normals) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: normals flagged but absent");
-        if ((d->tri_flags[i] & YK_TRI_HAS_UVS) && !d->tri_uvs) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: uvs flagged but absent");
-        const bool is_sphere = (d->tri_flags[i] & YK_TRI_IS_SPHERE) != 0;
-        if (is_sphere && (!d->tri_sphere || !d->spheres || d->tri_sphere[i] < 0 || (uint32_t)d->tri_sphere[i] >= d->n_spheres))
-            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: sphere slot without a valid sphere index");
-        if (is_sphere) {  // NaN vertex lanes + (-2 - sphere index) where triangles keep their area light
-            const float qnan = std::nanf("");
-            const int32_t tag = -2 - d->tri_sphere[i];
-            float ft, fp2, fi2;
-            std::memcpy(&ft, &tag, 4);
-            std::memcpy(&fp2, &packed, 4);
-            std::memcpy(&fi2, &d->tri_orig_id[i], 4);
-            tris[3 * i] = make_float4(qnan, qnan, qnan, ft);
-            tris[3 * i + 1] = make_float4(qnan, qnan, qnan, fp2);
-            tris[3 * i + 2] = make_float4(qnan, qnan, qnan, fi2);
-            continue;
+        const uint64_t t0 = (uint64_t)d->n_tris * wi / n_workers, t1 = (uint64_t)d->n_tris * (wi + 1) / n_workers;
+        for (uint64_t i = t0; i < t1; ++i) {
+            const uint32_t m = d->tri_material[i];
+            if (m >= d->n_materials) { fail("yk_scene_create: material index out of range"); continue; }
+            if (d->materials[m].kind <= YK_MAT_GLOSSY) ck.kinds |= 1u << d->materials[m].kind;
+            const int32_t al = d->tri_area_light[i];
+            if (al >= (int32_t)d->n_lights) fail("yk_scene_create: area light out of range");
+            else if (al >= 0 && d->lights[al].kind != YK_LIGHT_RECT) fail("yk_scene_create: area light must be rectangular");
+            const uint8_t f = d->tri_flags[i];
+            if ((f & YK_TRI_HAS_NORMALS) && !d->tri_normals) fail("yk_scene_create: normals flagged but absent");
+            if ((f & YK_TRI_HAS_UVS) && !d->tri_uvs) fail("yk_scene_create: uvs flagged but absent");
+            if ((f & YK_TRI_IS_SPHERE) && (!d->tri_sphere || !d->spheres || d->tri_sphere[i] < 0 || (uint32_t)d->tri_sphere[i] >= d->n_spheres))
+                fail("yk_scene_create: sphere slot without a valid sphere index");
         }
-        float fa, fp, fi;
-        std::memcpy(&fa, &d->tri_area_light[i], 4);
-        std::memcpy(&fp, &packed, 4);
-        std::memcpy(&fi, &d->tri_orig_id[i], 4);
-        tris[3 * i] = make_float4(v[0], v[3], v[6], fa);
-        tris[3 * i + 1] = make_float4(v[1], v[4], v[7], fp);
-        tris[3 * i + 2] = make_float4(v[2], v[5], v[8], fi);
-    }
-    if ((rc = dev_upload(sc->allocs, &sc->dev.nodes2, nodes.data(), nodes.size())) != YK_OK) return rc;
-    if (!packed_leaves && (rc = dev_upload(sc->allocs, &sc->dev.leaf_table, leaf_table.data(), leaf_table.size())) != YK_OK) return rc;
-    if ((rc = dev_upload(sc->allocs, &sc->dev.tris, tris.data(), tris.size())) != YK_OK) return rc;
+        return ck;
+    };
+    for (uint32_t i = 0; i < d->n_materials; ++i)
+        if (d->materials[i].kind > YK_MAT_GLOSSY) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: unknown material kind");
+    for (uint32_t i = 0; i < d->n_lights; ++i)
+        if (d->lights[i].kind > YK_LIGHT_DISTANT) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: unknown light kind");
+    std::vector<std::future<Check>> checks;
+    for (unsigned wi = 0; wi < n_workers; ++wi) checks.push_back(std::async(std::launch::async, validate, wi));
+    auto join_checks = [&](Check* total) {
+        for (auto& f : checks) {
+            const Check ck = f.get();
+            if (ck.error && !total->error) total->error = ck.error;
+            total->n_interior += ck.n_interior;
+            total->kinds |= ck.kinds;
+            total->small_leaves = total->small_leaves && ck.small_leaves;
+        }
+        checks.clear();
+    };
+    struct Cleanup {  // on an error return: wait for the validators, release what was uploaded
+        std::function<void()> fn;
+        bool armed = true;
+        ~Cleanup() { if (armed) fn(); }
+    };
+    std::vector<void*> temps;
+    Cleanup cleanup{[&] {
+        Check ignore;
+        join_checks(&ignore);
+        cudaDeviceSynchronize();
+        free_bag(temps);
+        free_bag(sc->allocs);
+    }};
+    const yk_bvh_node* r_nodes = nullptr;
+    const float* r_verts = nullptr;
+    const uint32_t *r_orig = nullptr, *r_mat = nullptr;
+    const int32_t *r_alight = nullptr, *r_sphere = nullptr;
+    const uint8_t *r_flags = nullptr, *r_kinds = nullptr;
+    std::vector<uint8_t> kinds(std::max(d->n_materials, 1u), 0);
+    for (uint32_t i = 0; i < d->n_materials; ++i) kinds[i] = (uint8_t)d->materials[i].kind;
+    if ((rc = dev_upload(temps, &r_nodes, d->nodes, d->n_nodes)) != YK_OK) return rc;
+    if ((rc = dev_upload(temps, &r_verts, d->tri_vertices, (size_t)d->n_tris * 9)) != YK_OK) return rc;
+    if ((rc = dev_upload(temps, &r_orig, d->tri_orig_id, d->n_tris)) != YK_OK) return rc;
+    if ((rc = dev_upload(temps, &r_mat, d->tri_material, d->n_tris)) != YK_OK) return rc;
+    if ((rc = dev_upload(temps, &r_alight, d->tri_area_light, d->n_tris)) != YK_OK) return rc;
+    if ((rc = dev_upload(temps, &r_flags, d->tri_flags, d->n_tris)) != YK_OK) return rc;
+    if (d->tri_sphere && (rc = dev_upload(temps, &r_sphere, d->tri_sphere, d->n_tris)) != YK_OK) return rc;
+    if ((rc = dev_upload(temps, &r_kinds, kinds.data(), kinds.size())) != YK_OK) return rc;
     if (d->tri_normals && (rc = dev_upload(sc->allocs, &sc->dev.normals, d->tri_normals, (size_t)d->n_tris * 9)) != YK_OK) return rc;
     if (d->tri_uvs && (rc = dev_upload(sc->allocs, &sc->dev.uvs, d->tri_uvs, (size_t)d->n_tris * 6)) != YK_OK) return rc;
+    Check total;
+    join_checks(&total);
+    if (total.error) return yk_set_error(YK_ERR_INVALID, total.error);
+    if (total.n_interior > kRefIndexMask) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 2^29 interior nodes");
+    sc->material_kinds = total.kinds;
+    const uint32_t n_interior = total.n_interior, n_leaves = d->n_nodes - n_interior;
+    const bool packed_leaves = total.small_leaves && d->n_tris <= (1u << kLeafFirstBits);
+
+    // Nodes: one 64-byte record per interior node with the boxes of both children (DevScene::nodes2). Interior records are
+    // numbered in the reference's pre-order (an exclusive scan of the interior flags), so a first child's record follows
+    // its parent's; leaves are numbered the same way for the leaf table.
+    {
+        cudaStream_t st = c->stream;
+        const uint32_t n = d->n_nodes;
+        uint32_t *d_flag = nullptr, *d_rec = nullptr;
+        float4* d_rec_out = nullptr;
+        uint2* d_leaf = nullptr;
+        if ((rc = dev_alloc(temps, &d_flag, n)) != YK_OK || (rc = dev_alloc(temps, &d_rec, n)) != YK_OK) return rc;
+        if ((rc = dev_alloc(sc->allocs, &d_rec_out, (size_t)std::max(n_interior, 1u) * 4)) != YK_OK) return rc;
+        if (!packed_leaves && (rc = dev_alloc(sc->allocs, &d_leaf, n_leaves)) != YK_OK) return rc;
+        k_scene_interior_flags<<<(n + 255) / 256, 256, 0, st>>>(r_nodes, n, d_flag);
+        size_t scan_bytes = 0;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag, d_rec, (int)n, st));
+        unsigned char* d_scan = nullptr;
+        if ((rc = dev_alloc(temps, &d_scan, scan_bytes)) != YK_OK) return rc;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_flag, d_rec, (int)n, st));
+        k_scene_records<<<(n + 255) / 256, 256, 0, st>>>(r_nodes, d_rec, n, packed_leaves ? 1 : 0, d_leaf, d_rec_out);
+        sc->dev.nodes2 = d_rec_out;
+        sc->dev.leaf_table = d_leaf;
+        const yk_bvh_node& root = d->nodes[0];
+        if (!root.is_leaf) sc->dev.root_ref = kRefInterior | ((uint32_t)root.split_axis << 29);  // record 0
+        else if (packed_leaves) sc->dev.root_ref = ((uint32_t)(root.shape_count - 1) << kLeafFirstBits) | root.offset;
+        else {
+            sc->dev.root_ref = 0;  // leaf 0 of the table; nobody's child, so it is written here
+            const uint2 entry = make_uint2(root.offset, root.shape_count);
+            CUDA_TRY(cudaMemcpyAsync(d_leaf, &entry, sizeof entry, cudaMemcpyHostToDevice, st));
+        }
+        std::memcpy(sc->dev.root_min, root.p_min, 12);
+        std::memcpy(sc->dev.root_max, root.p_max, 12);
+        // Triangles: three 16-byte words, vertices pre-gathered in leaf order and transposed (x0 x1 x2 | y0 y1 y2 | z0 z1 z2);
+        // the w lanes carry the per-triangle ids.
+        float4* d_tris = nullptr;
+        if ((rc = dev_alloc(sc->allocs, &d_tris, (size_t)d->n_tris * 3)) != YK_OK) return rc;
+        k_scene_tris<<<(d->n_tris + 255) / 256, 256, 0, st>>>(r_verts, r_orig, r_mat, r_alight, r_flags, r_sphere, r_kinds, d->n_tris, d_tris);
+        sc->dev.tris = d_tris;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(st));
+        free_bag(temps);
+    }
 
     std::vector<DevTexture> tex(d->n_textures);
     for (uint32_t i = 0; i < d->n_textures; ++i) {
@@ -1841,11 +1941,6 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
         }
         mats[i] = dm;
     }
-    for (uint32_t i = 0; i < d->n_lights; ++i)
-        if (d->lights[i].kind > YK_LIGHT_DISTANT) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: unknown light kind");
-    for (uint32_t i = 0; i < d->n_tris; ++i)
-        if (d->tri_area_light[i] >= 0 && d->lights[d->tri_area_light[i]].kind != YK_LIGHT_RECT)
-            return yk_set_error(YK_ERR_INVALID, "yk_scene_create: area light must be rectangular");
     if ((rc = dev_upload(sc->allocs, &sc->dev.textures, tex.data(), tex.size())) != YK_OK) return rc;
     if ((rc = dev_upload(sc->allocs, &sc->dev.materials, mats.data(), mats.size())) != YK_OK) return rc;
     if ((rc = dev_upload(sc->allocs, &sc->dev.lights, d->lights, d->n_lights)) != YK_OK) return rc;
@@ -1854,6 +1949,7 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     sc->dev.n_tris = d->n_tris;
     sc->dev.n_nodes = d->n_nodes;
     std::memcpy(sc->dev.background, d->background, 12);
+    cleanup.armed = false;
     *out = sc.release();
     return YK_OK;
 }
