@@ -1,0 +1,238 @@
+// Types shared by the wavefront kernels and the host driver of render.cu: the device-resident scene, the per-bounce
+// counters, the SoA path state, and the block-aggregated queue append.
+// Part of the single translation unit render.cu (compiled --fmad=false: every float op is the reference's un-fused IEEE op).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "yk_device.cuh"
+#include "yuki_gpu.h"
+
+int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
+
+using namespace ykd;
+
+namespace {
+
+
+constexpr int kMaxLights = 16;
+constexpr int kStackDepth = 64;  // bvh.rs:172
+constexpr uint32_t kMiss = 0xffffffffu;
+constexpr int kTraceThreads = 128;
+#ifndef YK_SHADE_THREADS
+#define YK_SHADE_THREADS 128
+#endif
+constexpr int kShadeThreads = YK_SHADE_THREADS;
+#ifndef YK_TRACE_MIN_BLOCKS
+#define YK_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef YK_SHADOW_MIN_BLOCKS
+#define YK_SHADOW_MIN_BLOCKS 8
+#endif
+#ifndef YK_SHADE_MIN_BLOCKS
+#define YK_SHADE_MIN_BLOCKS (1024 / YK_SHADE_THREADS)
+#endif
+
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return yk_set_error(YK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+// ---- device-resident scene ------------------------------------------------------------------------
+struct DevTexture {
+    uint32_t kind, width, height, _pad;
+    float value[3];
+    float _pad2;
+    const float* texels;
+};
+struct DevMaterial {
+    uint32_t kind;
+    int32_t tex[3];
+    float eta;
+    uint32_t remap;
+    float const_alpha;  // >= 0: roughness texture is constant, alpha fully evaluated on the host
+    uint32_t _pad;
+};
+struct DevScene {
+    // One 64-byte record per *interior* node holding the boxes of its two children:
+    //   (p_min child0, ref0) (p_max child0, -) (p_min child1, ref1) (p_max child1, -)
+    // child0 = the node after its parent in the reference's pre-order array, child1 = second_child_index (bvh.rs:396-419).
+    // A visit loads both boxes with one request; leaves have no record of their own (their shape range is in the ref).
+    const float4* nodes2;
+    const uint2* leaf_table;  // null: leaf refs are packed (count - 1) << 27 | first; else ref = index of (first, count)
+    const float4* tris;    // 3 x float4 per triangle: (x0 x1 x2, area_light) (y0 y1 y2, material | flags<<24) (z0 z1 z2, orig_id)
+    const float* normals;  // 9 per triangle or null
+    const float* uvs;      // 6 per triangle or null
+    const DevTexture* textures;
+    const DevMaterial* materials;
+    const yk_light* lights;
+    const yk_sphere* spheres;  // sphere slots of `tris`: vertex lanes are NaN (so the triangle test "accepts" them and the
+                               // rare hit path takes over), row 0's w = -2 - sphere index
+    uint32_t n_lights, n_tris, n_nodes;
+    float background[3];
+    float root_min[3], root_max[3];  // the root's own box (tested once per ray)
+    uint32_t root_ref;
+};
+// Child refs: interior = kRefInterior | split_axis << 29 | record index (the axis picks the near child before the record is
+// loaded); leaf = bit 31 clear, see leaf_table. kNoNode (all ones) is the stack sentinel / "no node".
+constexpr uint32_t kRefInterior = 0x80000000u;
+constexpr uint32_t kRefIndexMask = 0x1fffffffu;
+constexpr uint32_t kLeafFirstBits = 27;
+
+// ---- per-iteration device counters ----------------------------------------------------------------
+// Queue lengths never leave the device: every kernel of a bounce reads its element count from `cur` and appends to
+// `nxt`, so a batch is one asynchronous launch sequence (no host round trip per bounce).
+struct IterCounters {
+    uint32_t n_active;      // rays of this bounce (length of the active queue)
+    uint32_t mat[4];        // material queue lengths
+    uint32_t work_closest;  // dynamic ray fetch cursors
+    uint32_t work_shadow;
+    uint32_t _pad;
+};
+struct Totals {
+    unsigned long long closest_nodes, closest_tris, any_nodes, any_tris, hit_hash, shadow_rays, closest_rays;
+};
+
+struct Job {  // + the pixel's PCG stream, (SipHash13(x, y) << 1) | 1 (uniform.rs:77-81): one hash per pixel, not per sample
+    uint16_t x, y;
+    uint32_t sample_begin;
+    unsigned long long rng_inc;
+};
+// Path i of a batch is sample (sample_begin + sample_off + i / n_jobs) of pixel jobs[i % n_jobs]: a warp holds
+// 32 neighbouring pixels of one tile row at the same sample index.
+struct Batch {
+    const Job* jobs;
+    uint32_t n_jobs, sample_off, n_samples, n_paths;
+    FastDiv div_jobs;  // by n_jobs
+};
+
+// ---- wavefront state (SoA, capacity `cap` paths) --------------------------------------------------
+// Per bounce a path touches: ray (32 B) + hit (8 B) in the traversal; ray, hit, rng state (8 B), beta (16 B) in
+// shading, which writes the next ray / beta / rng state, the pending radiance terms (32 B) and 40 B per light that
+// needs a shadow ray; the shadow kernel reads those back and does the one read-modify-write of L.
+struct Wave {
+    uint32_t cap, n_lights, stack_entries;
+    // Per-bounce path state, streamed: bounce b reads st[b & 1] at the ray's queue slot and the shading kernels write the
+    // survivors' state to st[(b + 1) & 1] at their position in the next queue. Every kernel therefore reads and writes
+    // dense, (near-)coalesced arrays; nothing is gathered through a path index except L and the Whitted stack.
+    struct Stream {
+        float4* ray_o;   // o.xyz, t_max
+        float4* ray_d;   // d.xyz, -
+        float4* beta;    // throughput (path) / node weight (whitted); w = flags | sampler dimension << kDimShift
+        unsigned long long* rng;
+    } st[2];
+    uint2* hit;         // per queue slot: t bits, shape slot (kMiss = none)
+    uint2* bvh_counts;  // BVHIntersections: tests, hits
+    float4* L;       // accumulated radiance
+    // The five arrays below are the shading kernels' hand-over to the shadow kernel. They are indexed by the *shading
+    // position* g (position in the concatenation of this bounce's four material queues), not by path: the shading
+    // kernels write them fully coalesced and the shadow kernel streams them with no dependent gather.
+    uint32_t* sh_path;   // path of shading position g
+    float4* pend_beta;   // weight to apply to this bounce's radiance; w = clamp flag
+    float4* pend_extra;  // emitted term of this bounce; w = bit mask of the lights whose shadow ray must be traced
+    float4* lt_o;        // cap * n_lights: shadow ray o.xyz | contribution.r   (contribution = f * li * cos / pdf)
+    float4* lt_d;        //                 shadow ray d.xyz | contribution.g
+    float2* lt_c;        //                 contribution.b   | area light id of the sampled light (int bits, -1 = none)
+    float4* stack;       // whitted: stack_entries * cap * 3 float4
+    uint32_t* stack_top; // whitted
+    uint32_t* q_active[2];
+    uint32_t* q_mat;     // 4 * cap: paths per material kind
+    uint32_t* q_mat_tri; // 4 * cap: the hit shape slot of each entry
+    uint32_t* q_mat_slot; // 4 * cap: the entry's slot in this bounce's active queue (index of st[] / hit[])
+    Totals* totals;
+};
+// beta.w flag word
+constexpr uint32_t kFlagSpecular = 0x100u;   // path: specular_bounce / whitted: is_specular
+constexpr uint32_t kFlagAlive = 0x200u;
+constexpr uint32_t kDepthMask = 0xffu;       // path: bounces / whitted: depth
+constexpr uint32_t kDimShift = 10;           // sampler dimension (stratified.rs:40) in the upper 22 bits
+constexpr uint32_t kFlagMask = (1u << kDimShift) - 1u;
+
+struct RenderCfg {
+    SamplerCfg sampler;
+    uint32_t integrator, max_depth, has_clamp;
+    float clamp;
+    float c2w[16], r2c[16];
+    uint32_t res_x, res_y;
+    uint32_t aux_sample;
+    int32_t* hit_ids;  // device, or null
+};
+
+// ---- helpers --------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 f4v(float4 a) { return {a.x, a.y, a.z}; }
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// Block-aggregated append to one of NQ queues: one global atomic per queue per block (same-address atomics were the
+// bottleneck of classify / resolve with one atomic per warp, profiles/r01). `key` in [0, NQ) selects the queue, any
+// other value appends nothing. Must be reached by every thread of the block (blockDim.x <= 256).
+// Returns the slot the value was written to (undefined when nothing was appended).
+// `K` items per thread share the block's atomics: K * blockDim.x items per global atomic and queue.
+template <int NQ, int K>
+__device__ __forceinline__ void block_scatter_multi(const int (&key)[K], const uint32_t (&value)[K], uint32_t* const (&queues)[NQ],
+                                                    uint32_t* const (&counters)[NQ], uint32_t (&pos)[K]) {
+    __shared__ uint32_t s_cnt[8][NQ];
+    __shared__ uint32_t s_base[NQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t run[NQ];  // warp-uniform: entries of this warp per queue so far
+    uint32_t my_rank[K];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) run[q] = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        my_rank[k] = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const unsigned votes = __ballot_sync(0xffffffffu, key[k] == q);
+            if (key[k] == q) my_rank[k] = run[q] + __popc(votes & lt);
+            run[q] += __popc(votes);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) s_cnt[warp][q] = run[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        uint32_t total = 0;
+        for (int wi = 0; wi < n_warps; ++wi) {
+            const uint32_t c = s_cnt[wi][threadIdx.x];
+            s_cnt[wi][threadIdx.x] = total;  // exclusive prefix over the block's warps
+            total += c;
+        }
+        s_base[threadIdx.x] = total ? atomicAdd(counters[threadIdx.x], total) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pos[k] = 0;
+        if (key[k] >= 0 && key[k] < NQ) {
+            pos[k] = s_base[key[k]] + s_cnt[warp][key[k]] + my_rank[k];
+            queues[key[k]][pos[k]] = value[k];
+        }
+    }
+    __syncthreads();  // the shared arrays are reused by the next call
+}
+template <int NQ>
+__device__ __forceinline__ uint32_t block_scatter(int key, uint32_t value, uint32_t* const (&queues)[NQ], uint32_t* const (&counters)[NQ]) {
+    const int keys[1] = {key};
+    const uint32_t values[1] = {value};
+    uint32_t pos[1];
+    block_scatter_multi<NQ, 1>(keys, values, queues, counters, pos);
+    return pos[0];
+}
+__device__ __forceinline__ unsigned long long mix_hit(uint32_t x, uint32_t y, uint32_t sample, uint32_t id) {
+    unsigned long long h = ((unsigned long long)x << 48) ^ ((unsigned long long)y << 32) ^ ((unsigned long long)sample << 8) ^
+                           (unsigned long long)id * 0x9E3779B97F4A7C15ULL;
+    h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 29;
+    return h;
+}
+
+}  // namespace

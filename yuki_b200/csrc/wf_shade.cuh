@@ -1,0 +1,478 @@
+// The material sort (classify) and the per-material shading kernels: surface set-up, BSDFs, light sampling, the Path and
+// Whitted integrator bodies (integrators/path.rs, whitted.rs), and the debug integrators.
+// Part of the single translation unit render.cu (compiled --fmad=false: every float op is the reference's un-fused IEEE op).
+#pragma once
+#include "wf_common.cuh"
+#include "wf_trace.cuh"
+
+namespace {
+
+// ---- whitted stack ------------------------------------------------------------------------------------
+struct StackEntry {
+    V3 o, d;
+    RGB weight;
+    uint32_t flags;  // depth | specular
+};
+__device__ __forceinline__ void stack_push(const Wave& w, uint32_t path, const StackEntry& e) {
+    const uint32_t top = w.stack_top[path];
+    float4* base = w.stack + ((size_t)top * w.cap + path) * 3;
+    base[0] = make_float4(e.o.x, e.o.y, e.o.z, e.d.x);
+    base[1] = make_float4(e.d.y, e.d.z, e.weight.r, e.weight.g);
+    base[2] = make_float4(e.weight.b, __uint_as_float(e.flags), 0.0f, 0.0f);
+    w.stack_top[path] = top + 1;
+}
+// Pops the next pending node of the path's tree. Returns false when the tree is done.
+__device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path, StackEntry* e) {
+    const uint32_t top = w.stack_top[path];
+    if (top == 0) return false;
+    const float4* base = w.stack + ((size_t)(top - 1) * w.cap + path) * 3;
+    const float4 a = base[0], b = base[1], c = base[2];
+    w.stack_top[path] = top - 1;
+    e->o = mk(a.x, a.y, a.z);
+    e->d = mk(a.w, b.x, b.y);
+    e->weight = rgb(b.z, b.w, c.x);
+    e->flags = __float_as_uint(c.y);
+    return true;
+}
+// Writes a tree node as the path's next ray (the sampler dimension `dim` carries on: the reference shares one sampler
+// through the recursion).
+__device__ __forceinline__ void stream_node(const Wave::Stream& st, uint32_t pos, const StackEntry& e, uint32_t dim, unsigned long long rng) {
+    st.ray_o[pos] = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+    st.ray_d[pos] = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+    st.beta[pos] = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (dim << kDimShift)));
+    st.rng[pos] = rng;
+}
+
+// ---- classify: miss handling + compaction by material ("ray-queue sort/compaction pass") ---------------
+// K items per thread and block round (K * blockDim.x rays per global atomic): the queue counters are single addresses, and
+// same-address atomics, not bandwidth, bound this kernel. Whitted's tree walk re-queues rays here and runs with K = 1.
+#ifndef YK_CLASSIFY_ITEMS
+#define YK_CLASSIFY_ITEMS 8
+#endif
+template <int K, bool WHITTED>
+__global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, int b, IterCounters* cur,
+                           IterCounters* nxt, int first_iteration, uint32_t* q_next) {
+    const uint32_t n = cur->n_active;
+    const uint32_t per_round = gridDim.x * blockDim.x * K;
+    const uint32_t rounds = (n + per_round - 1) / per_round;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x * K;
+        if (block_first >= n) break;  // block-uniform
+        uint32_t idx[K], path[K], hit_slot[K];
+        int key[K];
+        StackEntry node[WHITTED ? K : 1];
+        uint32_t node_dim[WHITTED ? K : 1];
+        unsigned long long hh = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t i = block_first + k * blockDim.x + threadIdx.x;
+            idx[k] = i;
+            path[k] = 0; hit_slot[k] = kMiss; key[k] = -1;
+            if (i >= n) continue;
+            path[k] = queue ? queue[i] : i;
+            const uint2 h = w.hit[i];
+            hit_slot[k] = h.y;
+            uint32_t orig = 0xffffffffu;
+            if (h.y != kMiss) {
+                key[k] = (int)((__float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) >> 28) & 3u);
+                if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
+            } else if (first_iteration != 2) {  // (2 = debug integrators: their li() returns no background)
+                // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
+                const float4 bw = w.st[b].beta[i];
+                float4 L = w.L[path[k]];
+                L.x = L.x + bw.x * sc.background[0];
+                L.y = L.y + bw.y * sc.background[1];
+                L.z = L.z + bw.z * sc.background[2];
+                w.L[path[k]] = L;
+                if (WHITTED) {
+                    node_dim[WHITTED ? k : 0] = __float_as_uint(bw.w) >> kDimShift;
+                    if (stack_pop(w, path[k], &node[WHITTED ? k : 0])) key[k] = 4;
+                }
+            }
+            if (first_iteration) {
+                const uint32_t si = bt.div_jobs.div(path[k]);
+                const Job job = bt.jobs[path[k] - si * bt.n_jobs];
+                const uint32_t sample = job.sample_begin + bt.sample_off + si;
+                hh += mix_hit(job.x, job.y, sample, orig);
+                if (cfg.hit_ids && sample == cfg.aux_sample) cfg.hit_ids[(size_t)job.y * cfg.res_x + job.x] = (int32_t)orig;
+            }
+        }
+        uint32_t* const queues[5] = {w.q_mat, w.q_mat + (size_t)w.cap, w.q_mat + (size_t)2 * w.cap, w.q_mat + (size_t)3 * w.cap, q_next};
+        uint32_t* const counters[5] = {&cur->mat[0], &cur->mat[1], &cur->mat[2], &cur->mat[3], &nxt->n_active};
+        uint32_t pos[K];
+        block_scatter_multi<5, K>(key, path, queues, counters, pos);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (key[k] >= 0 && key[k] < 4) {
+                w.q_mat_tri[(size_t)key[k] * w.cap + pos[k]] = hit_slot[k];
+                w.q_mat_slot[(size_t)key[k] * w.cap + pos[k]] = idx[k];
+            } else if (WHITTED && key[k] == 4) {
+                stream_node(w.st[b ^ 1], pos[k], node[WHITTED ? k : 0], node_dim[WHITTED ? k : 0], w.st[b].rng[idx[k]]);
+            }
+        }
+        if (first_iteration) {
+            hh = warp_sum(hh);
+            if ((threadIdx.x & 31) == 0 && hh) atomicAdd(&w.totals->hit_hash, hh);
+        }
+    }
+}
+
+// ---- surface set-up: Triangle::intersect's SurfaceInteraction part (triangle.rs:141-226) ----------------
+__device__ __forceinline__ void make_surface(const DevScene& sc, uint32_t tri, V3 o, V3 d, Surface* si, uint32_t* material) {
+    const float4 a4 = __ldg(&sc.tris[3 * tri]), b4 = __ldg(&sc.tris[3 * tri + 1]), c4 = __ldg(&sc.tris[3 * tri + 2]);
+    const V3 p0 = mk(a4.x, b4.x, c4.x), p1 = mk(a4.y, b4.y, c4.y), p2 = mk(a4.z, b4.z, c4.z);  // stored transposed
+    const uint32_t packed = __float_as_uint(b4.w);
+    const uint32_t flags = (packed >> 24) & 0xfu;
+    *material = packed & 0xffffffu;
+    if (flags & YK_TRI_IS_SPHERE) {
+        sphere_surface(sc.spheres[-2 - __float_as_int(a4.w)], o, d, si);
+        return;
+    }
+    // Barycentrics: re-run the (deterministic) triangle test that the traversal accepted.
+    TriRay tr;
+    tr.setup(d);
+    TriHit h{0, 0, 0, 0};
+    tri_test(tr, o, __int_as_float(0x7f800000), p0, p1, p2, &h);
+    V2 uv0{0.0f, 0.0f}, uv1{1.0f, 0.0f}, uv2{1.0f, 1.0f};  // triangle.rs:143-155
+    if (flags & YK_TRI_HAS_UVS) {
+        const float* u = sc.uvs + (size_t)tri * 6;
+        uv0 = {u[0], u[1]}; uv1 = {u[2], u[3]}; uv2 = {u[4], u[5]};
+    }
+    const float du02 = uv0.x - uv2.x, dv02 = uv0.y - uv2.y, du12 = uv1.x - uv2.x, dv12 = uv1.y - uv2.y;
+    const V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    const float uv_det = du02 * dv12 - dv02 * du12;
+    V3 dpdu;
+    if (uv_det == 0.0f) {
+        V3 unused;
+        frame_from(unit(cross64(p2 - p0, p1 - p0)), &dpdu, &unused);
+    } else {
+        const float inv = 1.0f / uv_det;
+        dpdu = (dp02 * dv12 - dp12 * dv02) * inv;
+    }
+    si->p = p0 * h.b0 + p1 * h.b1 + p2 * h.b2;
+    si->uv = {uv0.x * h.b0 + uv1.x * h.b1 + uv2.x * h.b2, uv0.y * h.b0 + uv1.y * h.b1 + uv2.y * h.b2};
+    si->wo = -d;
+    si->area_light = __float_as_int(a4.w);
+    V3 n = unit(cross64(dp02, dp12));
+    if (flags & YK_TRI_SWAPS_HANDEDNESS) n = -n;
+    si->n = n;
+    si->sh_n = n;
+    si->sh_dpdu = dpdu;
+    if (flags & YK_TRI_HAS_NORMALS) {  // triangle.rs:197-224 + set_shading_geometry, interaction.rs:126-132
+        const float* nn = sc.normals + (size_t)tri * 9;
+        const V3 n0 = mk(nn[0], nn[1], nn[2]), n1 = mk(nn[3], nn[4], nn[5]), n2 = mk(nn[6], nn[7], nn[8]);
+        V3 ns = unit(n0 * h.b0 + n1 * h.b1 + n2 * h.b2);
+        if (dot0(ns, ns) > 0.0f) ns = unit(ns);
+        else ns = si->n;
+        V3 ss = unit(dpdu);
+        V3 ts = cross64(ss, ns);
+        if (dot0(ts, ts) > 0.0f) {
+            ts = unit(ts);
+            ss = cross64(ts, ns);
+        } else {
+            frame_from(ns, &ss, &ts);
+        }
+        si->sh_n = unit(cross64(ss, ts));
+        si->n = flip_toward_n(si->n, si->sh_n);
+        si->sh_dpdu = ss;
+    }
+}
+
+// textures/constant.rs:23-30, textures/image_texture.rs:81-111
+__device__ __noinline__ RGB tex_image_eval(const DevTexture& t, V2 uv);
+__device__ __forceinline__ RGB tex_eval(const DevScene& sc, int32_t index, V2 uv) {
+    const DevTexture& t = sc.textures[index];
+    if (t.kind == YK_TEX_CONSTANT) return rgb(t.value[0], t.value[1], t.value[2]);
+    return tex_image_eval(t, uv);
+}
+__device__ __noinline__ RGB tex_image_eval(const DevTexture& t, V2 uv) {
+    float sx = uv.x - truncf(uv.x), sy = uv.y - truncf(uv.y);
+    if (sx < 0.0f) sx = 1.0f + sx;
+    if (sy < 0.0f) sy = 1.0f + sy;
+    sy = 1.0f - sy;
+    sx = sx * (float)t.width - 0.5f;
+    sy = sy * (float)t.height - 0.5f;
+    const uint32_t ix = sx > 0.0f ? (uint32_t)sx : 0u, iy = sy > 0.0f ? (uint32_t)sy : 0u;
+    const float* px = t.texels + ((size_t)iy * t.width + ix) * 3;
+    return rgb(__ldg(px), __ldg(px + 1), __ldg(px + 2));
+}
+
+__device__ __forceinline__ float roughness_to_alpha(float r) {  // trowbridge_reitz.rs:22-30
+    const float x = (float)log((double)fmaxf(r, 0.001f));
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+template <uint32_t KIND>
+__device__ __forceinline__ void make_bsdf(const DevScene& sc, const DevMaterial& m, const Surface& si, Bsdf* b) {
+    b->kind = KIND;
+    b->empty = false;
+    b->ng = si.n;
+    b->ns = si.sh_n;
+    b->ss = unit(si.sh_dpdu);
+    b->ts = cross64(b->ns, b->ss);
+    b->c1 = gray(0.0f);
+    b->p0 = 0.0f;
+    b->p1 = -1.0f;
+    if (KIND == YK_MAT_MATTE) {  // matte.rs:22-40, oren_nayar.rs:18-25
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        const float sigma = tex_eval(sc, m.tex[1], si.uv).r;
+        b->empty = black(b->c0);
+        if (sigma != 0.0f) {
+            const float s2 = sigma * sigma;
+            b->p0 = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+            b->p1 = 0.45f * s2 / (s2 + 0.09f);
+            if (b->p1 < 0.0f) b->p1 = 0.0f;  // cannot happen for real sigma; keeps the Lambertian tag (p1 < 0) unambiguous
+        }
+    } else if (KIND == YK_MAT_GLASS) {  // glass.rs:27-45
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        b->c1 = tex_eval(sc, m.tex[1], si.uv);
+        b->p0 = m.eta;
+    } else if (KIND == YK_MAT_METAL) {  // metal.rs:34-61, trowbridge_reitz.rs:16-20
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        b->c1 = tex_eval(sc, m.tex[1], si.uv);
+        if (m.const_alpha >= 0.0f) b->p0 = m.const_alpha;
+        else {
+            float r = tex_eval(sc, m.tex[2], si.uv).r;
+            if (m.remap) r = roughness_to_alpha(r);
+            b->p0 = fmaxf(r, 0.001f);
+        }
+    } else {  // glossy.rs:32-58 (alpha = roughness^2)
+        b->c0 = tex_eval(sc, m.tex[0], si.uv);
+        if (m.const_alpha >= 0.0f) b->p0 = m.const_alpha;
+        else {
+            float r = tex_eval(sc, m.tex[1], si.uv).r;
+            if (m.remap) r = roughness_to_alpha(r);
+            b->p0 = fmaxf(r * r, 0.001f);
+        }
+    }
+}
+
+// Light::sample_li for the four light kinds (lights/*.rs). Returns false when no visibility test exists.
+struct LightSample {
+    V3 l;
+    RGB li;
+    float pdf;
+    bool has_vis;
+    Ray vis;
+    int vis_light;
+};
+__device__ __forceinline__ void sample_light(const yk_light& L, int index, const Surface& si, V2 u, LightSample* s) {
+    s->vis_light = -1;
+    s->pdf = 1.0f;
+    s->has_vis = true;
+    const RGB I = rgb(L.i[0], L.i[1], L.i[2]);
+    const V3 lp = mk(L.p[0], L.p[1], L.p[2]);
+    if (L.kind == YK_LIGHT_POINT) {  // point_light.rs:27-49
+        const V3 to = lp - si.p;
+        const float d2 = dot0(to, to);
+        s->li = I / d2;
+        s->l = to / sqrtf(d2);
+        s->vis = spawn_ray_to(si.p, si.n, lp);
+    } else if (L.kind == YK_LIGHT_SPOT) {  // spot_light.rs:38-80
+        const V3 to = lp - si.p;
+        const float d2 = dot0(to, to);
+        s->l = to / sqrtf(d2);
+        const float ct = unit(xf_vec(L.world_to_light, -s->l)).z;
+        float fall;
+        if (ct < L.cos_total_width) fall = 0.0f;
+        else if (ct > L.cos_falloff_start) fall = 1.0f;
+        else {
+            const float dl = (ct - L.cos_total_width) / (L.cos_falloff_start - L.cos_total_width);
+            fall = (dl * dl) * (dl * dl);
+        }
+        s->li = I * fall / d2;
+        s->has_vis = !black(s->li);
+        s->vis = spawn_ray_to(si.p, si.n, lp);
+    } else if (L.kind == YK_LIGHT_RECT) {  // rectangular_light.rs:46-72
+        const V3 p = xf_point(L.sample_to_world, mk(u.x, 0.0f, u.y));
+        const V3 n = xf_normal(L.sample_to_world_inv, mk(0.0f, -1.0f, 0.0f));
+        const V3 wi = unit(p - si.p);
+        const float c = dotn(n, -wi);
+        s->li = c > 0.0f ? I : gray(0.0f);
+        s->l = wi;
+        s->vis = spawn_ray_to(si.p, si.n, p);
+        s->vis_light = index;
+        const V3 dp = si.p - p;
+        s->pdf = dot0(dp, dp) / (fabsf(c) * L.area);
+    } else {  // distant_light.rs:24-43
+        s->li = I;
+        s->l = lp;
+        s->vis = spawn_ray_to(si.p, si.n, si.p + lp * 10000.0f);
+    }
+}
+
+// ---- shading: one kernel instance per material kind ----------------------------------------------------
+// Covers Material::compute_scattering_functions, the light fold (path.rs:102-119 / whitted.rs:109-126), the
+// emitted term, BSDF sampling + throughput update + Russian roulette (path.rs:121-171), and the specular
+// recursion of whitted.rs:132-170 flattened onto a per-sample DFS stack (children inherit weight * f * |cos|).
+// Radiance is not summed here: each light that needs a visibility test leaves its shadow ray and contribution in
+// lt_*, and k_trace_shadow adds the unoccluded terms in light order. Surviving paths are appended to the next
+// active queue (one atomic per block).
+template <uint32_t KIND, bool PATH>
+__global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
+                                                                               const uint32_t* queue_tri, const uint32_t* queue_slot, int b,
+                                                                               IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
+    const uint32_t n = cur->mat[KIND];
+    uint32_t g_base = 0;  // shading position of this kind's first queue entry (classify has finished: the counts are final)
+    if (KIND > 0) g_base += cur->mat[0];
+    if (KIND > 1) g_base += cur->mat[1];
+    if (KIND > 2) g_base += cur->mat[2];
+    const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
+        if (block_first >= n) break;  // block-uniform
+        const uint32_t i = block_first + threadIdx.x;
+        bool alive = false;
+        uint32_t path = 0;
+        // the survivor's state for the next bounce, written after the compaction assigns its position
+        float4 nx_o = make_float4(0, 0, 0, 0), nx_d = make_float4(0, 0, 0, 0), nx_beta = make_float4(0, 0, 0, 0);
+        unsigned long long nx_rng = 0;
+        if (i < n) {
+            path = queue[i];
+            const uint32_t g = g_base + i;
+            w.sh_path[g] = path;
+            const uint32_t hit_slot = queue_tri[i], slot = queue_slot[i];
+            const float4 ro = w.st[b].ray_o[slot], rd = w.st[b].ray_d[slot];
+            const V3 o = f4v(ro), d = f4v(rd);
+            Surface si;
+            uint32_t mat_index;
+            make_surface(sc, hit_slot, o, d, &si, &mat_index);
+            Bsdf bsdf;
+            make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
+
+            const float4 beta4 = w.st[b].beta[slot];
+            RGB beta = rgb(beta4.x, beta4.y, beta4.z);
+            const uint32_t flags = __float_as_uint(beta4.w) & kFlagMask;
+            const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
+            const bool was_specular = (flags & kFlagSpecular) != 0;
+
+            const uint32_t sample_i = bt.div_jobs.div(path), job_i = path - sample_i * bt.n_jobs;
+            const Job job = bt.jobs[job_i];
+            SamplerState smp;
+            smp.rng.state = w.st[b].rng[slot];
+            smp.rng.inc = job.rng_inc;
+            smp.dim = __float_as_uint(beta4.w) >> kDimShift;
+            smp.px = job.x;
+            smp.py = job.y;
+            smp.index = job.sample_begin + bt.sample_off + sample_i;
+            smp.job = job_i;
+
+            // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
+            uint32_t shadow_mask = 0;
+            for (uint32_t k = 0; k < sc.n_lights; ++k) {
+                const V2 u = smp.get_2d(cfg.sampler);
+                LightSample ls;
+                sample_light(sc.lights[k], (int)k, si, u, &ls);
+                if (!black(ls.li)) {
+                    const RGB f = bsdf.f(si.wo, ls.l);
+                    if (ls.has_vis && !black(f)) {
+                        const RGB c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
+                        const size_t ref = (size_t)k * w.cap + g;
+                        w.lt_o[ref] = make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, c.r);
+                        w.lt_d[ref] = make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, c.g);
+                        w.lt_c[ref] = make_float2(c.b, __int_as_float(ls.vis_light));
+                        shadow_mask |= 1u << k;
+                    }
+                }
+            }
+
+            // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
+            RGB le = gray(0.0f);
+            // The integrators pass -ray.d here and (Path) to sample_f, but si.wo to Bsdf::f; the two differ for spheres, whose
+            // si.wo went through object_to_world once more (sphere.rs:116, interaction.rs:155).
+            const V3 wo_ray = -d;
+            if (si.area_light >= 0 && dotn(si.n, wo_ray) > 0.0f) {
+                const yk_light& al = sc.lights[si.area_light];
+                le = rgb(al.i[0], al.i[1], al.i[2]);
+            }
+            const bool add_le = depth == 0 || was_specular;
+
+            uint32_t new_flags = 0;
+            if (PATH) {
+                // path.rs:121-129 — beta multiplies the emitted term here and again in the fold (reference quirk)
+                const RGB extra = add_le ? beta * le : gray(0.0f);
+                w.pend_extra[g] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
+                w.pend_beta[g] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
+                const Bsdf::Sample s = bsdf.sample_f(wo_ray, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137 (wo = -ray.d)
+                if (!(black(s.f) || s.pdf == 0.0f)) {
+                    alive = true;
+                    const bool spec = (s.type & BX_SPECULAR) != 0;
+                    beta = beta * (s.f * fabsf(dotn(s.wi, si.sh_n)) / s.pdf);
+                    const Ray nr = spawn_ray(si.p, si.n, s.wi);
+                    if (depth > 3) {  // Russian roulette, path.rs:163-169
+                        const float q = fmaxf(1.0f - beta.g, 0.05f);
+                        if (smp.get_1d(cfg.sampler) < q) alive = false;
+                        else beta = beta * (gray(1.0f) / (1.0f - q));
+                    }
+                    const uint32_t bounces = depth + 1;
+                    if (bounces >= cfg.max_depth) alive = false;
+                    new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u);
+                    nx_o = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
+                    nx_d = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+                    nx_beta = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
+                }
+            } else {
+                // whitted.rs:128-170
+                const RGB extra = add_le ? le : gray(0.0f);
+                w.pend_extra[g] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
+                w.pend_beta[g] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+                StackEntry child[2];
+                int n_child = 0;
+                if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
+                    const uint32_t wants[2] = {BX_SPECULAR | BX_REFLECTION, BX_SPECULAR | BX_TRANSMISSION};
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const Bsdf::Sample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, wants[c]);
+                        if (s.type == 0u) continue;  // BxdfType::NONE: no ray, no radiance
+                        const Ray nr = spawn_ray(si.p, si.n, s.wi);
+                        StackEntry e;
+                        e.o = nr.o;
+                        e.d = nr.d;
+                        e.weight = beta * s.f * fabsf(dotn(s.wi, si.sh_n));
+                        e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u);
+                        child[n_child++] = e;
+                    }
+                }
+                if (n_child == 2) stack_push(w, path, child[1]);  // transmission waits until the reflection subtree is done
+                StackEntry e = child[0];
+                alive = n_child >= 1 || stack_pop(w, path, &e);
+                nx_o = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+                nx_d = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+                nx_beta = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
+            }
+            nx_rng = smp.rng.state;
+        }
+        uint32_t* const queues[1] = {q_next};
+        uint32_t* const counters[1] = {&nxt->n_active};
+        const uint32_t npos = block_scatter<1>(alive ? 0 : -1, path, queues, counters);
+        if (alive) {  // a finished path's ray / throughput / sampler state is never read again
+            const Wave::Stream& out = w.st[b ^ 1];
+            out.ray_o[npos] = nx_o;
+            out.ray_d[npos] = nx_d;
+            out.beta[npos] = nx_beta;
+            out.rng[npos] = nx_rng;
+        }
+    }
+}
+
+// ---- debug integrators (bvh_heatmap.rs, geometry_normals.rs, shading_normals.rs, shading_uvs.rs) --------
+__global__ void k_debug_shade(DevScene sc, Wave w, RenderCfg cfg, uint32_t n) {
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= n) return;
+    const uint2 h = w.hit[path];
+    RGB c = gray(0.0f);
+    if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
+        const uint2 cnt = w.bvh_counts[path];
+        c = rgb((float)cnt.x, (float)cnt.y, h.y != kMiss ? (float)cnt.y : 0.0f);
+    } else if (h.y != kMiss) {
+        Surface si;
+        uint32_t m;
+        make_surface(sc, h.y, f4v(w.st[0].ray_o[path]), f4v(w.st[0].ray_d[path]), &si, &m);  // first bounce: slot == path
+        if (cfg.integrator == YK_INTEGRATOR_GEOMETRY_NORMALS) c = rgb(si.n.x, si.n.y, si.n.z) / 2.0f + gray(0.5f);
+        else if (cfg.integrator == YK_INTEGRATOR_SHADING_NORMALS) c = rgb(si.sh_n.x, si.sh_n.y, si.sh_n.z) / 2.0f + gray(0.5f);
+        else c = rgb(si.uv.x, si.uv.y, 0.0f);
+    }
+    w.L[path] = make_float4(c.r, c.g, c.b, 0.0f);
+}
+
+}  // namespace
