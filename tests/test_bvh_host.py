@@ -65,6 +65,18 @@ def test_parallel_build_equals_serial_reference(oracle, xf):
     assert np.array_equal(host.order(), osc.order())
 
 
+@pytest.mark.parametrize("split,max_shapes", [(D.SPLIT_SAH, 1), (D.SPLIT_MIDDLE, 4)])
+def test_wide_node_passes_equal_serial_reference(oracle, xf, split, max_shapes):
+    """More than 2^19 primitives: the product builder runs the top nodes' bounds / bucket / partition passes on several
+    threads. The parallel partition must reproduce itertools::partition's permutation (leaf order, multi-shape leaves)."""
+    scene, _ = scenes.heightfield(xf, 560, 560, seed=11, split_method=split, max_shapes_in_node=max_shapes)
+    assert scene.n_triangles() > (1 << 19)
+    host = api.HostScene(scene)
+    osc = oracle.OracleScene(scene)
+    assert host.nodes().tobytes() == osc.nodes().tobytes()
+    assert np.array_equal(host.order(), osc.order())
+
+
 def test_max_shapes_in_node(oracle, xf):
     scene, _ = scenes.heightfield(xf, 32, 32, seed=5, split_method=D.SPLIT_EQUAL_COUNTS)
     scene.max_shapes_in_node = 4

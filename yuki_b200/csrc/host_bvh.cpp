@@ -4,8 +4,9 @@
 // exactly the nodes the reference visits (its intersection_test_count, bvh.rs:177, is a parity gate).
 //
 // Not a port of the reference's two-phase build (arena tree + flatten): subtrees are emitted straight
-// into a flat vector, and large subtrees are built concurrently and spliced (their leaf ranges are
-// disjoint slices of the primitive array, so the result does not depend on the schedule).
+// into a flat vector, large subtrees are built concurrently and spliced (their leaf ranges are
+// disjoint slices of the primitive array, so the result does not depend on the schedule), and the
+// passes over the biggest nodes (bounds, SAH buckets, the partition) run on several threads.
 #include <algorithm>
 #include <atomic>
 #include <future>
@@ -67,6 +68,90 @@ struct Builder {
         return kept;
     }
 
+    // ---- the top of the tree: one node's passes over millions of primitives, spread over threads -------------------
+    // (below kWideNode the concurrently built subtrees provide the parallelism). Every pass is order-independent — min /
+    // max unions and counts — except the partition, whose parallel form reproduces the sequential permutation exactly.
+    static constexpr size_t kWideNode = 1u << 19;
+    unsigned workers = 1;
+
+    template <class F>
+    void for_chunks(size_t n, F&& f) const {  // f(chunk, begin, end) on `workers` threads; chunk < workers
+        const unsigned w = (unsigned)std::min<size_t>(workers, std::max<size_t>(1, n / 65536));
+        std::vector<std::future<void>> futs;
+        for (unsigned c = 1; c < w; ++c) futs.push_back(std::async(std::launch::async, [&f, c, w, n] { f(c, n * c / w, n * (c + 1) / w); }));
+        f(0u, (size_t)0, n / w);
+        for (auto& x : futs) x.get();
+    }
+    // itertools::partition's result, computed in parallel: the sequential two-ended scan swaps the k-th failing element
+    // met from the front with the k-th passing element met from the back, and the two scans meet at K = the number of
+    // passing elements; so the failing positions below K pair, in order, with the passing positions at or above K taken
+    // from the back. Elements outside those two sets never move.
+    template <class Keep>
+    size_t wide_front_partition(Prim* a, size_t n, Keep keep) const {
+        std::vector<uint8_t> pass(n);
+        std::vector<size_t> cnt(workers + 1, 0);
+        for_chunks(n, [&](unsigned c, size_t b, size_t e) {
+            size_t k = 0;
+            for (size_t i = b; i < e; ++i) k += (pass[i] = keep(a[i]) ? 1 : 0);
+            cnt[c + 1] = k;
+        });
+        size_t K = 0;
+        for (size_t c : cnt) K += c;
+        std::vector<size_t> fail_front, pass_back;  // increasing positions
+        {
+            std::vector<std::vector<size_t>> ff(workers), pb(workers);
+            for_chunks(n, [&](unsigned c, size_t b, size_t e) {
+                for (size_t i = b; i < e; ++i) {
+                    if (i < K && !pass[i]) ff[c].push_back(i);
+                    else if (i >= K && pass[i]) pb[c].push_back(i);
+                }
+            });
+            for (auto& v : ff) fail_front.insert(fail_front.end(), v.begin(), v.end());
+            for (auto& v : pb) pass_back.insert(pass_back.end(), v.begin(), v.end());
+        }
+        const size_t m = fail_front.size();  // == pass_back.size()
+        for_chunks(m, [&](unsigned, size_t b, size_t e) {
+            for (size_t k = b; k < e; ++k) std::swap(a[fail_front[k]], a[pass_back[m - 1 - k]]);
+        });
+        return K;
+    }
+    template <class Keep>
+    size_t front_partition(Prim* a, size_t n, Keep keep) const {
+        return (workers > 1 && n >= kWideNode) ? wide_front_partition(a, n, keep) : stable_front_partition(a, n, keep);
+    }
+    box3 prim_bounds(size_t lo, size_t hi) const {
+        if (workers > 1 && hi - lo >= kWideNode) {
+            std::vector<box3> part(workers, empty_box());
+            for_chunks(hi - lo, [&](unsigned c, size_t b, size_t e) {
+                box3 x = empty_box();
+                for (size_t i = lo + b; i < lo + e; ++i) x = merge(x, prims[i].box);
+                part[c] = x;
+            });
+            box3 x = empty_box();
+            for (const box3& p : part) x = merge(x, p);
+            return x;
+        }
+        box3 x = empty_box();
+        for (size_t i = lo; i < hi; ++i) x = merge(x, prims[i].box);
+        return x;
+    }
+    box3 key_bounds(size_t lo, size_t hi) const {
+        if (workers > 1 && hi - lo >= kWideNode) {
+            std::vector<box3> part(workers, empty_box());
+            for_chunks(hi - lo, [&](unsigned c, size_t b, size_t e) {
+                box3 x = empty_box();
+                for (size_t i = lo + b; i < lo + e; ++i) x = grow(x, prims[i].key);
+                part[c] = x;
+            });
+            box3 x = empty_box();
+            for (const box3& p : part) x = merge(x, p);
+            return x;
+        }
+        box3 x = empty_box();
+        for (size_t i = lo; i < hi; ++i) x = grow(x, prims[i].key);
+        return x;
+    }
+
     size_t median_split(size_t lo, size_t hi, int axis) {  // split_equal_counts, bvh.rs:422-436
         const size_t mid = (lo + hi) / 2;
         std::nth_element(prims + lo, prims + mid, prims + hi,
@@ -81,16 +166,33 @@ struct Builder {
         if (method == YK_SPLIT_EQUAL_COUNTS) return median_split(lo, hi, axis);
         if (method == YK_SPLIT_MIDDLE) {  // split_middle, bvh.rs:438-450
             const float pivot = (kb.lo.get(axis) + kb.hi.get(axis)) / 2.0f;
-            return lo + stable_front_partition(prims + lo, n, [=](const Prim& p) { return p.key.get(axis) < pivot; });
+            return lo + front_partition(prims + lo, n, [=](const Prim& p) { return p.key.get(axis) < pivot; });
         }
         if (n <= 2) return lo;  // bvh.rs:461-462
         size_t count[kBuckets] = {};
         box3 bbox[kBuckets];
         for (auto& b : bbox) b = empty_box();
-        for (size_t i = lo; i < hi; ++i) {
-            const int b = bucket_index(kb, prims[i], axis);
-            count[b] += 1;
-            bbox[b] = merge(bbox[b], prims[i].box);
+        if (workers > 1 && n >= kWideNode) {
+            struct Part { size_t count[kBuckets]; box3 bbox[kBuckets]; };
+            std::vector<Part> part(workers);
+            for (Part& p : part)
+                for (int b = 0; b < kBuckets; ++b) { p.count[b] = 0; p.bbox[b] = empty_box(); }
+            for_chunks(n, [&](unsigned c, size_t b0, size_t e0) {
+                Part& p = part[c];
+                for (size_t i = lo + b0; i < lo + e0; ++i) {
+                    const int b = bucket_index(kb, prims[i], axis);
+                    p.count[b] += 1;
+                    p.bbox[b] = merge(p.bbox[b], prims[i].box);
+                }
+            });
+            for (const Part& p : part)
+                for (int b = 0; b < kBuckets; ++b) { count[b] += p.count[b]; bbox[b] = merge(bbox[b], p.bbox[b]); }
+        } else {
+            for (size_t i = lo; i < hi; ++i) {
+                const int b = bucket_index(kb, prims[i], axis);
+                count[b] += 1;
+                bbox[b] = merge(bbox[b], prims[i].box);
+            }
         }
         // Suffix boxes/counts once instead of the reference's O(buckets^2) folds; min/max unions are exact
         // and association-free, so each side's box and count are identical.
@@ -120,7 +222,7 @@ struct Builder {
             }
         }
         if (!(best_cost < (float)n)) return SIZE_MAX;
-        return lo + stable_front_partition(prims + lo, n, [&](const Prim& p) { return bucket_index(kb, p, axis) <= best; });
+        return lo + front_partition(prims + lo, n, [&](const Prim& p) { return bucket_index(kb, p, axis) <= best; });
     }
 
     static void emit_leaf(std::vector<yk_bvh_node>& out, const box3& box, size_t lo, size_t hi) {
@@ -136,15 +238,13 @@ struct Builder {
     // Appends the subtree over prims[lo, hi) to `out` in pre-order; returns its bounds. Node indices
     // written into `offset` are relative to out[0]; `depth` bounds how far down subtrees run as tasks.
     box3 emit(std::vector<yk_bvh_node>& out, size_t lo, size_t hi, int task_depth) {
-        box3 box = empty_box();
-        for (size_t i = lo; i < hi; ++i) box = merge(box, prims[i].box);
+        const box3 box = prim_bounds(lo, hi);
         const size_t n = hi - lo;
         if (n <= leaf_max) {
             emit_leaf(out, box, lo, hi);
             return box;
         }
-        box3 kb = empty_box();
-        for (size_t i = lo; i < hi; ++i) kb = grow(kb, prims[i].key);
+        const box3 kb = key_bounds(lo, hi);
         const int axis = widest_axis(kb);
         if (kb.hi.get(axis) == kb.lo.get(axis)) {  // bvh.rs:343
             emit_leaf(out, box, lo, hi);
@@ -260,6 +360,7 @@ int bvh_build_boxes(const float* boxes6, uint32_t n_tris, uint32_t max_shapes_in
     unsigned hw = std::thread::hardware_concurrency();
     int task_depth = 0;
     while ((1u << task_depth) < hw && task_depth < 6) ++task_depth;
+    bld.workers = std::max(1u, std::min(hw, 32u));
     bld.emit(*nodes, 0, n_tris, task_depth);
     if (bld.failed) {
         *why = "BVH: Split failed (bvh.rs:368)";
