@@ -176,6 +176,38 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def large_scene_leg(api, xf, ctx, peak):
+    """Supplementary measurement (N == 1 only, not the contract's `value`): the geometry of BASELINE.json configs[4] — the
+    10 M-triangle terrain at 3840x2160, Path max_depth 8 — at 4 spp on one pipe, so that the line also carries the
+    closest-hit kernel's roofline on a scene whose BVH (554 MB of records + 480 MB of triangles) cannot live in the caches.
+    Same accounting as `roofline`: (32 B x node visits + 36 B x shape tests) / CUDA-event time of the k_trace_closest launches."""
+    from yuki_b200 import scenes
+    t0 = time.perf_counter()
+    scene, cam = scenes.terrain_room(xf)
+    dev = api.Scene(ctx, scene)
+    t_build = time.perf_counter() - t0
+    rn = api.Renderer(ctx)
+    film = D.FilmSettings((3840, 2160), 16)
+    sampler, integ = D.SamplerType.stratified(2, 2, jitter=True), D.IntegratorType.path(MAX_DEPTH)
+    rn.render(dev, cam, film, sampler, integ, pipes=1)  # warm-up
+    steps, ms, cms, nodes, tris, rays, shadow, samples, launches = 2, 0.0, 0.0, 0, 0, 0, 0, 0, 0
+    for _ in range(steps):
+        st = rn.render(dev, cam, film, sampler, integ, pipes=1).stats
+        ms += st.device_ms; cms += st.trace_closest_ms; nodes += st.closest_nodes; tris += st.closest_tris
+        rays += st.ray_count; shadow += st.shadow_rays; samples += st.samples; launches += st.trace_closest_launches
+    n_tris, n_nodes = dev.host.n_tris, dev.host.n_nodes
+    dev.close()
+    alg = 32 * nodes + 36 * tris
+    achieved = alg / (max(cms, 1e-9) / 1e3) / 1e9
+    return {"workload": "configs[4] geometry: 10M-triangle terrain + material objects 3840x2160, Path max_depth 8, 4 spp stratified 2x2, one pipe",
+            "triangles": n_tris, "bvh_nodes": n_nodes, "host_build_and_upload_s": t_build, "steps": steps,
+            "msamples_per_s": samples / (ms / 1e3) / 1e6, "mrays_per_s": rays / (ms / 1e3) / 1e6,
+            "mrays_per_s_total": (rays + shadow) / (ms / 1e3) / 1e6,
+            "roofline": {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_launch": alg / max(launches, 1), "avg_launch_ms": cms / max(launches, 1), "launches": launches,
+                         "share_of_step": cms / ms, "nodes_per_ray": nodes / max(rays, 1), "shape_tests_per_ray": tris / max(rays, 1)}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -252,9 +284,18 @@ def run_ours(args):
         d2h = n_pix * 12
         e2e_steps = max(1, min(args.steps, 2))
 
+        film_pinned = torch.empty(n_pix * 3, dtype=torch.float32).pin_memory() if world > 1 and rank == 0 else None
+
         def e2e_step():
             d2 = api.Scene(ctx, scene, host=host_scene)       # yk_scene_create: host arrays -> HBM
-            rn.render(d2, cam, film, sampler, integ, tiles=my_tiles, film_out=film_host)   # jobs H2D, film D2H
+            if world == 1:
+                rn.render(d2, cam, film, sampler, integ, tiles=my_tiles, film_out=film_host)   # jobs H2D, film D2H
+            else:  # every rank renders its tiles, the film is assembled on rank 0 over NVLink and read back there
+                d_film.zero_()
+                rn.render(d2, cam, film, sampler, integ, tiles=my_tiles, device_film_ptr=d_film.data_ptr())
+                dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    film_pinned.copy_(d_film)
             d2.close()
 
         e2e_step()
@@ -269,6 +310,10 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_value = total_samples * e2e_steps / float(e2e_s.item()) / 1e6
+
+    large = None
+    if rank == 0 and world == 1 and not args.no_large_scene and SCENE == "cornell":
+        large = large_scene_leg(api, xf, ctx, peaks()[0])
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -289,7 +334,8 @@ def run_ours(args):
             "gpu_launches": int(counts[2].item()),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "includes": "yk_scene_create + yk_render with host film (pinned staging inside the library)"},
+                    "steps": e2e_steps, "includes": "yk_scene_create + yk_render with host film (pinned staging inside the library)" if world == 1 else
+                    "per rank yk_scene_create + yk_render of its tiles, NCCL sum-reduce of the film to rank 0, read-back to pinned host memory there"},
             "roofline": {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                          "peak_source": peak_src,
@@ -305,6 +351,8 @@ def run_ours(args):
             sample = f"{CPU_SAMPLE_SPP} of the {spp} samples of every pixel ({st.samples} samples), same scene/sampler/integrator"
             line["cpu_baseline"] = {"value": st.samples / st.seconds / 1e6, "unit": "Msamples/s", "cores": st.threads, "kind": "port",
                                     "sample": sample, "seconds": st.seconds}
+        if large is not None:
+            line["large_scene"] = large
         print(json.dumps(line), flush=True)
     dev.close()
     ctx.close()
@@ -319,6 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-scene", action="store_true", help="skip the supplementary 10 M-triangle roofline leg (N == 1 only)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = BASELINE.json configs[1] (default, the contract's line); c5 = configs[4]")
     ap.add_argument("--spp-side", type=int, default=0, help="override the stratified grid side (spp = side^2); the line's config says so")
     args = ap.parse_args()
