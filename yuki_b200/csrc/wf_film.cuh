@@ -14,7 +14,7 @@ __global__ void k_film_accumulate(Wave w, Batch bt, float* accum, uint32_t res_x
     float* a = accum + ((size_t)job.y * res_x + job.x) * 3;
     float r = a[0], g = a[1], b = a[2];
     for (uint32_t s = 0; s < bt.n_samples; ++s) {
-        const float4 L = w.L[(size_t)s * bt.n_jobs + j];
+        const float4 L = ld_once(&w.L[(size_t)s * bt.n_jobs + j]);
         r = r + L.x; g = g + L.y; b = b + L.z;
     }
     a[0] = r; a[1] = g; a[2] = b;
@@ -34,7 +34,7 @@ __global__ void k_film_add(Wave w, Batch bt, float* film, uint32_t res_x) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= bt.n_paths) return;
     const Job job = bt.jobs[bt.div_jobs.mod(i)];
-    const float4 L = w.L[i];
+    const float4 L = ld_once(&w.L[i]);
     float* f = film + ((size_t)job.y * res_x + job.x) * 3;
     atomicAdd(f, L.x); atomicAdd(f + 1, L.y); atomicAdd(f + 2, L.z);
 }

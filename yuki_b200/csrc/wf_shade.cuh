@@ -70,7 +70,7 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
             path[k] = 0; hit_slot[k] = kMiss; key[k] = -1;
             if (i >= n) continue;
             path[k] = queue ? queue[i] : i;
-            const uint2 h = w.hit[i];
+            const uint2 h = ld_once(&w.hit[i]);
             hit_slot[k] = h.y;
             uint32_t orig = 0xffffffffu;
             if (h.y != kMiss) {
@@ -104,8 +104,8 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (key[k] >= 0 && key[k] < 4) {
-                w.q_mat_tri[(size_t)key[k] * w.cap + pos[k]] = hit_slot[k];
-                w.q_mat_slot[(size_t)key[k] * w.cap + pos[k]] = idx[k];
+                st_once(&w.q_mat_tri[(size_t)key[k] * w.cap + pos[k]], hit_slot[k]);
+                st_once(&w.q_mat_slot[(size_t)key[k] * w.cap + pos[k]], idx[k]);
             } else if (WHITTED && key[k] == 4) {
                 stream_node(w.st[b ^ 1], pos[k], node[WHITTED ? k : 0], node_dim[WHITTED ? k : 0], w.st[b].rng[idx[k]]);
             }
@@ -308,6 +308,13 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 // Radiance is not summed here: each light that needs a visibility test leaves its shadow ray and contribution in
 // lt_*, and k_trace_shadow adds the unoccluded terms in light order. Surviving paths are appended to the next
 // active queue (one atomic per block).
+// Measured: prefetching a block's queue lines two rounds ahead takes 5 % off the shading kernels (+1.6 % Cornell render);
+// prefetching the state those entries point to (next round's, or this round's late-used beta / rng / job) adds nothing.
+#ifndef YK_SHADE_PREFETCH
+#define YK_SHADE_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <uint32_t KIND, bool PATH>
 __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
                                                                                const uint32_t* queue_tri, const uint32_t* queue_slot, int b,
@@ -324,15 +331,22 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         const uint32_t i = block_first + threadIdx.x;
         bool alive = false;
         uint32_t path = 0;
+#if YK_SHADE_PREFETCH
+        // the block's queue entries two rounds ahead: pull them into the L2 now (one 128-byte line per warp and queue)
+        if ((threadIdx.x & 31) == 0) {
+            const uint32_t i_ahead = i + 2 * gridDim.x * blockDim.x;
+            if (i_ahead < n) { prefetch_l2(queue + i_ahead); prefetch_l2(queue_tri + i_ahead); prefetch_l2(queue_slot + i_ahead); }
+        }
+#endif
         // the survivor's state for the next bounce, written after the compaction assigns its position
         float4 nx_o = make_float4(0, 0, 0, 0), nx_d = make_float4(0, 0, 0, 0), nx_beta = make_float4(0, 0, 0, 0);
         unsigned long long nx_rng = 0;
         if (i < n) {
-            path = queue[i];
+            path = ld_once(&queue[i]);
             const uint32_t g = g_base + i;
-            w.sh_path[g] = path;
-            const uint32_t hit_slot = queue_tri[i], slot = queue_slot[i];
-            const float4 ro = w.st[b].ray_o[slot], rd = w.st[b].ray_d[slot];
+            st_once(&w.sh_path[g], path);
+            const uint32_t hit_slot = ld_once(&queue_tri[i]), slot = ld_once(&queue_slot[i]);
+            const float4 ro = ld_once(&w.st[b].ray_o[slot]), rd = ld_once(&w.st[b].ray_d[slot]);
             const V3 o = f4v(ro), d = f4v(rd);
             Surface si;
             uint32_t mat_index;
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             Bsdf bsdf;
             make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
 
-            const float4 beta4 = w.st[b].beta[slot];
+            const float4 beta4 = ld_once(&w.st[b].beta[slot]);
             RGB beta = rgb(beta4.x, beta4.y, beta4.z);
             const uint32_t flags = __float_as_uint(beta4.w) & kFlagMask;
             const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
@@ -349,7 +363,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             const uint32_t sample_i = bt.div_jobs.div(path), job_i = path - sample_i * bt.n_jobs;
             const Job job = bt.jobs[job_i];
             SamplerState smp;
-            smp.rng.state = w.st[b].rng[slot];
+            smp.rng.state = ld_once(&w.st[b].rng[slot]);
             smp.rng.inc = job.rng_inc;
             smp.dim = __float_as_uint(beta4.w) >> kDimShift;
             smp.px = job.x;
@@ -368,9 +382,9 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     if (ls.has_vis && !black(f)) {
                         const RGB c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
                         const size_t ref = (size_t)k * w.cap + g;
-                        w.lt_o[ref] = make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, c.r);
-                        w.lt_d[ref] = make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, c.g);
-                        w.lt_c[ref] = make_float2(c.b, __int_as_float(ls.vis_light));
+                        st_once(&w.lt_o[ref], make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, c.r));
+                        st_once(&w.lt_d[ref], make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, c.g));
+                        st_once(&w.lt_c[ref], make_float2(c.b, __int_as_float(ls.vis_light)));
                         shadow_mask |= 1u << k;
                     }
                 }
@@ -391,8 +405,8 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             if (PATH) {
                 // path.rs:121-129 — beta multiplies the emitted term here and again in the fold (reference quirk)
                 const RGB extra = add_le ? beta * le : gray(0.0f);
-                w.pend_extra[g] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
-                w.pend_beta[g] = make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f);
+                st_once(&w.pend_extra[g], make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask)));
+                st_once(&w.pend_beta[g], make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f));
                 const Bsdf::Sample s = bsdf.sample_f(wo_ray, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137 (wo = -ray.d)
                 if (!(black(s.f) || s.pdf == 0.0f)) {
                     alive = true;
@@ -414,8 +428,8 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             } else {
                 // whitted.rs:128-170
                 const RGB extra = add_le ? le : gray(0.0f);
-                w.pend_extra[g] = make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask));
-                w.pend_beta[g] = make_float4(beta.r, beta.g, beta.b, 0.0f);
+                st_once(&w.pend_extra[g], make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask)));
+                st_once(&w.pend_beta[g], make_float4(beta.r, beta.g, beta.b, 0.0f));
                 StackEntry child[2];
                 int n_child = 0;
                 if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
@@ -447,10 +461,10 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         const uint32_t npos = block_scatter<1>(alive ? 0 : -1, path, queues, counters);
         if (alive) {  // a finished path's ray / throughput / sampler state is never read again
             const Wave::Stream& out = w.st[b ^ 1];
-            out.ray_o[npos] = nx_o;
-            out.ray_d[npos] = nx_d;
-            out.beta[npos] = nx_beta;
-            out.rng[npos] = nx_rng;
+            st_once(&out.ray_o[npos], nx_o);
+            st_once(&out.ray_d[npos], nx_d);
+            st_once(&out.beta[npos], nx_beta);
+            st_once(&out.rng[npos], nx_rng);
         }
     }
 }

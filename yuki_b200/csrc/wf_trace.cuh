@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
                 const uint32_t mine = chunk_next + __popc(idle & lt_mask);
                 if (!live && mine < chunk_end) {
                     path = mine;  // the queue slot: rays, hits and counters of a bounce are all in queue order
-                    const float4 ro = w.st[b].ray_o[path];
-                    const float4 rd = w.st[b].ray_d[path];
+                    const float4 ro = ld_once(&w.st[b].ray_o[path]);
+                    const float4 rd = ld_once(&w.st[b].ray_d[path]);
                     if (COUNTS) tests_before = tl.n_tests;
                     tl.template start<COUNTS, SPHERES>(sc, sbase, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w);
                     hit_tri = kMiss; hit_t = 0.0f;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
                 }
             })
             if (live && !tl.wants_box()) {  // retire
-                w.hit[path] = make_uint2(__float_as_uint(hit_t), hit_tri);
+                st_once(&w.hit[path], make_uint2(__float_as_uint(hit_t), hit_tri));
                 if (COUNTS) w.bvh_counts[path] = make_uint2(tl.n_tests - tests_before, tl.n_hits);
                 live = false;
             }
