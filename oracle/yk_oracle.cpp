@@ -163,6 +163,37 @@ int yko_render(const yko_scene* sc, const yko_camera_params* cp, const yko_film_
     return 0;
 }
 
+int yko_debug_ray_path(const yko_scene* sc, const yko_camera_params* cp, const yko_film_settings* fs, const yko_sampler_desc* sd,
+                       const yko_integrator_desc* id, uint32_t px, uint32_t py, yko_debug_ray* out, uint32_t cap, float* li_rgb,
+                       uint64_t* ray_count) {
+    Camera cam;
+    if (!make_camera(cp, fs->res_x, fs->res_y, &cam)) return -1;
+    // `sampler.instantiate(false).as_ref().clone()` (window.rs:884): never started on a pixel sample
+    Sampler sampler{};
+    sampler.kind = (SamplerKind)sd->kind;
+    sampler.nx = sd->nx;
+    sampler.ny = sd->kind == SAMPLER_UNIFORM ? 1 : sd->ny;
+    sampler.jitter = sd->jitter != 0;
+    sampler.seed = sd->seed;
+    sampler.rng = Pcg32::make(sd->seed, 0);
+    Integrator integ{(IntegratorKind)id->kind, id->max_depth, id->has_clamp != 0, id->indirect_clamp};
+    ThreadStats st;
+    RenderCtx ctx{sc->s, integ, &st};
+    const V2 jitter = sampler.get_2d();
+    const Ray ray = camera_ray(cam, V2{(float)px + jitter.x, (float)py + jitter.y});  // window.rs:886-888
+    RayLog rays;
+    const RadianceResult r = integrator_li_debug(ctx, ray, sampler, &rays);
+    for (size_t i = 0; i < rays.size() && i < cap; ++i) {
+        out[i].o[0] = rays[i].ray.o.x; out[i].o[1] = rays[i].ray.o.y; out[i].o[2] = rays[i].ray.o.z;
+        out[i].d[0] = rays[i].ray.d.x; out[i].d[1] = rays[i].ray.d.y; out[i].d[2] = rays[i].ray.d.z;
+        out[i].t_max = rays[i].ray.t_max;
+        out[i].ray_type = rays[i].ray_type;
+    }
+    if (li_rgb) { li_rgb[0] = r.li.r; li_rgb[1] = r.li.g; li_rgb[2] = r.li.b; }
+    if (ray_count) *ray_count = r.rays;
+    return (int)rays.size();
+}
+
 uint32_t yko_film_tiles(uint32_t rx, uint32_t ry, uint32_t dim, yko_tile* out, uint32_t cap) {
     std::vector<FilmTile> t = film_tiles(rx, ry, dim);
     for (size_t i = 0; i < t.size() && i < cap; ++i) out[i] = {t[i].x0, t[i].y0, t[i].x1, t[i].y1, t[i].sample, 0, t[i].index};

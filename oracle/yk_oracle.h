@@ -102,6 +102,15 @@ int yko_render(const yko_scene*, const yko_camera_params*, const yko_film_settin
                const yko_integrator_desc*, const yko_tile* tiles, uint32_t n_tiles, uint32_t n_threads,
                float* film_rgb, int32_t* hit_ids, uint32_t aux_sample, yko_stats* stats);
 
+/* launch_debug_ray (app/window.rs:812-905) + Integrator::li_debug (integrators/mod.rs:103-118): the rays of one path through
+   film pixel (px, py), traced with a freshly cloned sampler (pixel (0,0), sample 0, PCG stream 0, no seek). ray_type:
+   0 direct, 1 reflection, 2 refraction, 3 normal, 4 shadow (integrators/mod.rs:82-89). Returns the number of rays the
+   integrator collected (at most `cap` are written), or -1 on a degenerate camera. */
+typedef struct { float o[3]; float d[3]; float t_max; uint32_t ray_type; } yko_debug_ray;
+int yko_debug_ray_path(const yko_scene*, const yko_camera_params*, const yko_film_settings*, const yko_sampler_desc*,
+                       const yko_integrator_desc*, uint32_t px, uint32_t py, yko_debug_ray* out, uint32_t cap,
+                       float* li_rgb, uint64_t* ray_count);
+
 /* host helpers restated from film.rs / camera.rs / math/transforms.rs */
 uint32_t yko_film_tiles(uint32_t res_x, uint32_t res_y, uint32_t tile_dim, yko_tile* out, uint32_t cap);
 int yko_camera_make(const yko_camera_params*, uint32_t res_x, uint32_t res_y, float* camera_to_world16,

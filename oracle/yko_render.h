@@ -53,14 +53,43 @@ struct RenderCtx {
     ThreadStats* st;
 };
 
-// Direct lighting fold shared by Whitted (whitted.rs:109-126) and Path (path.rs:102-119).
-inline Spec light_fold(const RenderCtx& c, const SurfaceInteraction& si, const Bsdf& bsdf, Sampler& sampler) {
+// integrators/mod.rs:76-89: the rays li_debug() collects for the ray visualisation.
+enum RayType : uint32_t { RAY_DIRECT = 0, RAY_REFLECTION = 1, RAY_REFRACTION = 2, RAY_NORMAL = 3, RAY_SHADOW = 4 };
+struct IntegratorRay {
+    Ray ray;
+    uint32_t ray_type;
+};
+using RayLog = std::vector<IntegratorRay>;
+
+// whitted.rs:84-88 / path.rs:58-62
+inline float min_debug_ray_length(const Scene& scene) {
+    Bounds3 b = scene.bounds();
+    int i = maximum_extent(b);
+    const float hi = i == 0 ? b.p_max.x : (i == 1 ? b.p_max.y : b.p_max.z), lo = i == 0 ? b.p_min.x : (i == 1 ? b.p_min.y : b.p_min.z);
+    return (hi - lo) / 10.0f;
+}
+// Bounds3::intersections, math/bounds.rs:196-205: the far slab distance, if the ray meets the box at all.
+inline bool bounds_intersections_tmax(const Bounds3& b, const Ray& ray, float* t_max) {
+    V3 inv_dir = {1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z};
+    V3 a0 = b.p_min - ray.o, a1 = b.p_max - ray.o;
+    V3 t0 = {a0.x * inv_dir.x, a0.y * inv_dir.y, a0.z * inv_dir.z};
+    V3 t1 = {a1.x * inv_dir.x, a1.y * inv_dir.y, a1.z * inv_dir.z};
+    float tmin = fmax_(max_comp(vmin(t0, t1)), 0.0f);
+    float tmax = fmin_(min_comp(vmax(t0, t1)), ray.t_max);
+    *t_max = tmax;
+    return tmin <= tmax;
+}
+
+// Direct lighting fold shared by Whitted (whitted.rs:109-126) and Path (path.rs:102-119). `rays` (li_debug only) receives
+// the shadow ray of every light sample that carries a visibility test, occluded or not, black f or not.
+inline Spec light_fold(const RenderCtx& c, const SurfaceInteraction& si, const Bsdf& bsdf, Sampler& sampler, RayLog* rays = nullptr) {
     Spec acc = spec1(0.0f);
     for (int32_t li = 0; li < (int32_t)c.scene.lights.size(); ++li) {
         LightSample ls = sample_li(c.scene, li, si, sampler.get_2d());  // every light consumes a get_2d
         if (!is_black(ls.li)) {
             Spec f = bsdf.f(si.wo, ls.l, BXDF_ALL);
             if (ls.has_vis) {
+                if (rays) rays->push_back({ls.vis_ray, RAY_SHADOW});
                 if (!is_black(f)) {
                     c.st->shadow_rays += 1;
                     if (!c.scene.any_intersect(ls.vis_ray, ls.vis_area_light, &c.st->ts))
@@ -74,9 +103,16 @@ inline Spec light_fold(const RenderCtx& c, const SurfaceInteraction& si, const B
 
 // whitted.rs:74-182 (+ specular_contribution :38-70)
 inline RadianceResult whitted_li(const RenderCtx& c, Ray ray, uint32_t depth, Sampler& sampler, bool is_specular,
-                                 int32_t* primary_id) {
+                                 int32_t* primary_id, RayLog* rays = nullptr) {
     IntersectionResult ir = c.scene.intersect(ray, &c.st->ts);
     if (primary_id) *primary_id = ir.has_hit ? (int32_t)c.scene.shapes[ir.hit.shape].orig_id : -1;
+    if (rays) {  // :89-105
+        rays->push_back({ray, RAY_DIRECT});
+        if (ir.has_hit) {
+            rays->back().ray.t_max = ir.hit.t;
+            rays->push_back({Ray{ir.hit.si.p, ir.hit.si.n, min_debug_ray_length(c.scene)}, RAY_NORMAL});
+        }
+    }
     RadianceResult out;
     if (!ir.has_hit) {
         out.li = c.scene.background;
@@ -87,7 +123,7 @@ inline RadianceResult whitted_li(const RenderCtx& c, Ray ray, uint32_t depth, Sa
     const Triangle& tri = c.scene.shapes[ir.hit.shape];
     Bsdf bsdf = compute_scattering_functions(c.scene, c.scene.materials[tri.material], si);
     uint64_t ray_count = 1;
-    Spec sum_li = light_fold(c, si, bsdf, sampler);
+    Spec sum_li = light_fold(c, si, bsdf, sampler, rays);
     if (depth == 0 || is_specular) sum_li += emitted_radiance(c.scene, si, -ray.d);
     if (depth + 1 < c.integ.max_depth) {
         const uint8_t kinds[2] = {BXDF_REFLECTION, BXDF_TRANSMISSION};
@@ -95,8 +131,11 @@ inline RadianceResult whitted_li(const RenderCtx& c, Ray ray, uint32_t depth, Sa
             BxdfSample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, (uint8_t)(BXDF_SPECULAR | kinds[k]));
             if (s.sample_type == BXDF_NONE) continue;  // zero radiance, zero rays
             Ray refl = spawn_ray(si.p, si.n, s.wi);
+            const size_t first_child_ray = rays ? rays->size() : 0;
             RadianceResult child =
-                whitted_li(c, refl, depth + 1, sampler, (s.sample_type & BXDF_SPECULAR) != 0, nullptr);
+                whitted_li(c, refl, depth + 1, sampler, (s.sample_type & BXDF_SPECULAR) != 0, nullptr, rays);
+            // :136-160: the subtree's rays are appended with its first ray re-typed
+            if (rays && rays->size() > first_child_ray) (*rays)[first_child_ray].ray_type = k == 0 ? RAY_REFLECTION : RAY_REFRACTION;
             sum_li += s.f * child.li * std::fabs(dot_nv(s.wi, si.sh_n));
             ray_count += child.rays;
         }
@@ -107,21 +146,31 @@ inline RadianceResult whitted_li(const RenderCtx& c, Ray ray, uint32_t depth, Sa
 }
 
 // path.rs:49-178
-inline RadianceResult path_li(const RenderCtx& c, Ray ray, Sampler& sampler, int32_t* primary_id) {
+inline RadianceResult path_li(const RenderCtx& c, Ray ray, Sampler& sampler, int32_t* primary_id, RayLog* rays = nullptr) {
     Spec L = spec1(0.0f), beta = spec1(1.0f);
     uint32_t bounces = 0;
     bool specular_bounce = false;
     uint64_t ray_count = 0;
     if (primary_id) *primary_id = -1;
+    uint32_t ray_type = RAY_DIRECT;  // only used when collecting into `rays`
     while (bounces < c.integ.max_depth) {
+        if (rays) {  // :71-86: bounce rays are drawn up to the scene bounds until a hit shortens them
+            float t_max = ray.t_max;
+            if (ray_type != RAY_DIRECT && !bounds_intersections_tmax(c.scene.bounds(), ray, &t_max)) t_max = min_debug_ray_length(c.scene);
+            rays->push_back({Ray{ray.o, ray.d, t_max}, ray_type});
+        }
         ray_count += 1;
         IntersectionResult ir = c.scene.intersect(ray, &c.st->ts);
         if (bounces == 0 && primary_id && ir.has_hit) *primary_id = (int32_t)c.scene.shapes[ir.hit.shape].orig_id;
         if (ir.has_hit) {
             const SurfaceInteraction& si = ir.hit.si;
             const Triangle& tri = c.scene.shapes[ir.hit.shape];
+            if (rays) {  // :91-98
+                rays->back().ray.t_max = ir.hit.t;
+                rays->push_back({Ray{si.p, si.n, min_debug_ray_length(c.scene)}, RAY_NORMAL});
+            }
             Bsdf bsdf = compute_scattering_functions(c.scene, c.scene.materials[tri.material], si);
-            Spec radiance = light_fold(c, si, bsdf, sampler);
+            Spec radiance = light_fold(c, si, bsdf, sampler, rays);
             // :121-123 — beta is applied here AND again below (reference quirk, reproduced)
             if (bounces == 0 || specular_bounce) radiance += beta * emitted_radiance(c.scene, si, -ray.d);
             if (bounces > 0 && c.integ.has_clamp) radiance = smin(radiance, spec1(1.0f) * c.integ.indirect_clamp);
@@ -132,6 +181,7 @@ inline RadianceResult path_li(const RenderCtx& c, Ray ray, Sampler& sampler, int
             specular_bounce = (s.sample_type & BXDF_SPECULAR) != 0;
             beta *= s.f * std::fabs(dot_nv(s.wi, si.sh_n)) / s.pdf;
             ray = spawn_ray(si.p, si.n, s.wi);
+            ray_type = (s.sample_type & BXDF_REFLECTION) ? RAY_REFLECTION : RAY_REFRACTION;  // :146-153 (anything else panics there)
         } else {
             L += beta * c.scene.background;
             break;
@@ -144,6 +194,16 @@ inline RadianceResult path_li(const RenderCtx& c, Ray ray, Sampler& sampler, int
         bounces += 1;
     }
     return {L, ray_count};
+}
+
+// Integrator::li_debug (integrators/mod.rs:103-118): Whitted and Path collect rays, the debug integrators keep the trait's
+// default (zero radiance, no rays, zero ray count).
+inline RadianceResult integrator_li_debug(const RenderCtx& c, Ray ray, Sampler& sampler, RayLog* rays) {
+    switch (c.integ.kind) {
+        case INTEGRATOR_WHITTED: return whitted_li(c, ray, 0, sampler, false, nullptr, rays);
+        case INTEGRATOR_PATH: return path_li(c, ray, sampler, nullptr, rays);
+        default: return RadianceResult{};
+    }
 }
 
 inline RadianceResult integrator_li(const RenderCtx& c, Ray ray, Sampler& sampler, int32_t* primary_id) {

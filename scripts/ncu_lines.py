@@ -1,8 +1,10 @@
-"""Per-source-line instruction counts from `ncu --page source --csv --print-source cuda,sass` (first kernel in the file).
-usage: ncu_lines.py file.csv [min_share_pct]"""
+"""Per-source-line instruction counts from `ncu --page source --csv --print-source cuda,sass` (k-th kernel in the file).
+usage: ncu_lines.py file.csv [min_share_pct] [kernel_index=0]"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+want = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+seen = -1
 hdr = None
 lines = []
 n_fn = 0
@@ -11,8 +13,11 @@ for r in rows:
     if r and r[0] == "File Path":
         cur_file = r[1].split("/")[-1]
     if r and r[0] == "Function Name":
-        if hdr is not None and not r[1].startswith(fn):
-            break
+        if seen < 0 or not r[1].startswith(fn):
+            seen += 1
+            if seen > want:
+                break
+            hdr, lines = None, []
         fn = r[1]
     if r and r[0] == "Line No":
         hdr = r
