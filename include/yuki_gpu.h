@@ -173,6 +173,14 @@ typedef struct {
     const int32_t* tri_sphere;      /* NULL, or per leaf slot: index into `spheres`, -1 for triangles */
 } yk_scene_desc;
 
+/* integrators/mod.rs:76-89 */
+typedef enum { YK_RAY_DIRECT = 0, YK_RAY_REFLECTION = 1, YK_RAY_REFRACTION = 2, YK_RAY_NORMAL = 3, YK_RAY_SHADOW = 4 } yk_ray_type;
+typedef struct {
+    float o[3], d[3];
+    float t_max;
+    uint32_t ray_type;             /* yk_ray_type */
+} yk_integrator_ray;
+
 /* ---- render options / statistics ------------------------------------------------------------ */
 #define YK_RENDER_FILM_ON_DEVICE 1u  /* film_rgb (and opts.hit_ids) are device pointers on the context's GPU */
 #define YK_RENDER_KEEP_FILM 2u       /* non-accumulating render: pixels outside `tiles` are left untouched (default) */
@@ -224,6 +232,15 @@ void yk_scene_destroy(yk_scene*);
 int yk_render(yk_context*, const yk_scene*, const yk_camera*, const yk_film_settings*, const yk_sampler*,
               const yk_integrator*, const yk_tile* tiles, uint32_t n_tiles, const yk_render_opts* opts,
               float* film_rgb, yk_stats* stats);
+/* launch_debug_ray (app/window.rs:812-905) -> Integrator::li_debug (integrators/mod.rs:103-118): traces ONE path through
+ * film pixel (film_px_x, film_px_y) with a freshly cloned sampler (pixel (0,0), sample index 0, PCG stream 0, never seeked:
+ * window.rs:884) and returns the rays the integrator collects for the ray visualisation (path.rs:71-153,
+ * whitted.rs:89-170), in the reference's order. Writes at most `cap` rays; *n_rays is the number collected. `li_rgb`
+ * (3 floats) and `ray_count` are li_debug's RadianceResult. The debug integrators keep the trait's default: no rays, zero
+ * radiance, zero ray count. */
+int yk_debug_ray(yk_context*, const yk_scene*, const yk_camera*, const yk_sampler*, const yk_integrator*,
+                 uint32_t film_px_x, uint32_t film_px_y, yk_integrator_ray* rays, uint32_t cap, uint32_t* n_rays,
+                 float* li_rgb, uint64_t* ray_count);
 /* Device synchronisation helpers for callers that time with their own CUDA events. */
 void* yk_context_stream(yk_context*);   /* cudaStream_t the renderer launches on */
 

@@ -58,6 +58,8 @@ def lib():
     L.yko_scene_copy_order.restype = None
     L.yko_render.argtypes = [vp, C.POINTER(capi.CameraParams), C.POINTER(capi.FilmSettings), C.POINTER(capi.Sampler),
                              C.POINTER(capi.Integrator), vp, u32, u32, vp, vp, u32, C.POINTER(OStats)]
+    L.yko_debug_ray_path.argtypes = [vp, C.POINTER(capi.CameraParams), C.POINTER(capi.FilmSettings), C.POINTER(capi.Sampler),
+                                     C.POINTER(capi.Integrator), u32, u32, vp, u32, fp, C.POINTER(C.c_uint64)]
     L.yko_film_tiles.argtypes = [u32, u32, u32, vp, u32]
     L.yko_film_tiles.restype = u32
     L.yko_camera_make.argtypes = [C.POINTER(capi.CameraParams), u32, u32, fp, fp]
@@ -244,6 +246,20 @@ class OracleScene:
         if rc != 0:
             raise RuntimeError("oracle render failed")
         return out, ids, st
+
+    def debug_ray(self, camera_params, film, sampler, integrator, film_px, max_rays=4096):
+        """launch_debug_ray + li_debug (app/window.rs:812-905): (rays as capi.DEBUG_RAY_DTYPE, li, ray count)."""
+        cp, fs, sm, ig = capi.camera_params(camera_params), capi.film_settings(film), capi.sampler(sampler), capi.integrator(integrator)
+        rays = np.zeros(max_rays, dtype=capi.DEBUG_RAY_DTYPE)
+        li = np.zeros(3, np.float32)
+        count = C.c_uint64(0)
+        n = lib().yko_debug_ray_path(self._h, C.byref(cp), C.byref(fs), C.byref(sm), C.byref(ig), int(film_px[0]), int(film_px[1]),
+                                     rays.ctypes.data, max_rays, capi.fptr(li), C.byref(count))
+        if n < 0:
+            raise RuntimeError("oracle debug ray failed")
+        if n > max_rays:
+            return self.debug_ray(camera_params, film, sampler, integrator, film_px, max_rays=n)
+        return rays[:n].copy(), li, int(count.value)
 
     def trace(self, o, d, t_max=None, brute_force=False):
         o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)

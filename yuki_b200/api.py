@@ -381,6 +381,26 @@ class Renderer:
             self._messages = []
         self._in_progress = False
 
+    def debug_ray(self, scene: Scene, camera_params: D.CameraParameters, film: D.FilmSettings, sampler: D.SamplerType,
+                  integrator: D.IntegratorType, film_px, max_rays: int = 4096):
+        """`launch_debug_ray` (app/window.rs:812-905): the rays `Integrator::li_debug` collects for one path through film pixel
+        `film_px`, as a DEBUG_RAY_DTYPE array in the reference's order, plus li_debug's (li, ray_scene_intersections). None
+        when the pixel lies outside the film (window.rs:866-869, 898-901)."""
+        x, y = int(film_px[0]), int(film_px[1])
+        if x < 0 or y < 0 or x >= int(film.res[0]) or y >= int(film.res[1]):
+            return None
+        cam = make_camera(camera_params, film)
+        sm, ig = capi.sampler(sampler), capi.integrator(integrator)
+        rays = np.zeros(max_rays, dtype=capi.DEBUG_RAY_DTYPE)
+        n = C.c_uint32(0)
+        li = np.zeros(3, np.float32)
+        count = C.c_uint64(0)
+        capi.check(capi.lib().yk_debug_ray(self.ctx._h, scene._h, C.byref(cam), C.byref(sm), C.byref(ig), x, y,
+                                           C.c_void_p(rays.ctypes.data), max_rays, C.byref(n), capi.fptr(li), C.byref(count)))
+        if n.value > max_rays:
+            return self.debug_ray(scene, camera_params, film, sampler, integrator, film_px, max_rays=n.value)
+        return rays[:n.value].copy(), li, int(count.value)
+
     def render(self, scene: Scene, camera_params: D.CameraParameters, film: D.FilmSettings, sampler: D.SamplerType,
                integrator: D.IntegratorType, tiles: Optional[np.ndarray] = None, want_hit_ids: bool = False,
                aux_sample: int = 0, wavefront_paths: int = 0, film_out: Optional[np.ndarray] = None,

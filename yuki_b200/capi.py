@@ -57,6 +57,8 @@ class Tile(C.Structure):
                 ("sample", C.c_uint16), ("_pad", C.c_uint16), ("index", C.c_uint32)]
 
 
+# yk_integrator_ray (integrators/mod.rs:76-89): ray_type 0 direct, 1 reflection, 2 refraction, 3 normal, 4 shadow
+DEBUG_RAY_DTYPE = np.dtype([("o", "<f4", (3,)), ("d", "<f4", (3,)), ("t_max", "<f4"), ("ray_type", "<u4")])
 TILE_DTYPE = np.dtype([("x0", "<u2"), ("y0", "<u2"), ("x1", "<u2"), ("y1", "<u2"), ("sample", "<u2"), ("_pad", "<u2"),
                        ("index", "<u4")])
 
@@ -161,6 +163,7 @@ EXPORTS = [
     "yk_context_stream", "yk_bvh_build", "yk_host_scene_build", "yk_host_scene_destroy", "yk_host_scene_flat", "yk_camera_make",
     "yk_film_tiles", "yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_new", "yk_xf_look_at",
     "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy", "yk_write_exr", "yk_tonemap_filmic", "yk_heatmap", "yk_pbrt_load", "yk_pbrt_view", "yk_pbrt_destroy", "yk_mitsuba_load",
+    "yk_debug_ray",
 ]
 
 _lib = None
@@ -186,6 +189,8 @@ def lib():
     L.yk_scene_destroy.restype = None
     L.yk_render.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(FilmSettings), C.POINTER(Sampler), C.POINTER(Integrator),
                             vp, u32, C.POINTER(RenderOpts), vp, C.POINTER(Stats)]
+    L.yk_debug_ray.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(Sampler), C.POINTER(Integrator), u32, u32, vp, u32,
+                               C.POINTER(u32), fp, C.POINTER(C.c_uint64)]
     L.yk_bvh_build.argtypes = [fp, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u32)]
     L.yk_host_scene_build.argtypes = [C.POINTER(HostSceneDesc), C.POINTER(vp)]
     L.yk_host_scene_destroy.argtypes = [vp]

@@ -250,6 +250,10 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         if (c->stage_timing > 0) CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
         tm->launches += 1;
         tm->closest_launches += 1;
+        if (cfg.debug_log) {  // yk_debug_ray: log this bounce of the single path before it is shaded
+            k_debug_log<<<1, 32, 0, s>>>(sc->dev, w, cfg, bt, b, cur);
+            tm->launches += 1;
+        }
         uint32_t* q_next = w.q_active[flip];
         if (debug) {
             k_debug_shade<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt.n_paths);
@@ -600,9 +604,12 @@ void yk_scene_destroy(yk_scene* s) {
     delete s;
 }
 
-int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_film_settings* fs, const yk_sampler* sm,
-              const yk_integrator* in, const yk_tile* tiles, uint32_t n_tiles, const yk_render_opts* opts, float* film_rgb,
-              yk_stats* stats) {
+}  // extern "C"
+
+// yk_render, and yk_debug_ray's single path (`debug_log` = device ray list, `debug_px` = the film pixel of its camera sample).
+static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_film_settings* fs, const yk_sampler* sm,
+                       const yk_integrator* in, const yk_tile* tiles, uint32_t n_tiles, const yk_render_opts* opts, float* film_rgb,
+                       yk_stats* stats, DebugLog* debug_log, const float* debug_px) {
     const auto wall0 = std::chrono::steady_clock::now();
     if (!c || !sc || !cam || !fs || !sm || !in || !film_rgb) return yk_set_error(YK_ERR_INVALID, "yk_render: null argument");
     if (sc->ctx != c) return yk_set_error(YK_ERR_INVALID, "yk_render: scene belongs to another context");
@@ -655,6 +662,8 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
     cfg.res_x = fs->res_x;
     cfg.res_y = fs->res_y;
     cfg.aux_sample = opts ? opts->aux_sample : 0u;
+    cfg.debug_log = debug_log;
+    if (debug_log) { cfg.debug_px[0] = debug_px[0]; cfg.debug_px[1] = debug_px[1]; }
 
     // Device film / accumulators.
     if (c->film_cap < n_pixels) {
@@ -792,6 +801,10 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
                             k_zero_jobs<<<(nj + 255) / 256, 256, 0, p.stream>>>(p.d_jobs, nj, c->d_accum, fs->res_x);
                             tm.launches += 1;
                         }
+                        if (debug_log) {
+                            k_debug_job<<<1, 1, 0, p.stream>>>(p.d_jobs);
+                            tm.launches += 1;
+                        }
                     }
                     RenderCfg gcfg = cfg;
                     if (sm->kind == YK_SAMPLER_STRATIFIED) {
@@ -882,6 +895,74 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
         st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
         *stats = st;
     }
+    return YK_OK;
+}
+
+extern "C" {
+
+int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_film_settings* fs, const yk_sampler* sm,
+              const yk_integrator* in, const yk_tile* tiles, uint32_t n_tiles, const yk_render_opts* opts, float* film_rgb,
+              yk_stats* stats) {
+    return render_impl(c, sc, cam, fs, sm, in, tiles, n_tiles, opts, film_rgb, stats, nullptr, nullptr);
+}
+
+// launch_debug_ray (app/window.rs:812-905): one path, its rays collected by k_debug_log between the wavefront stages. The
+// path is "sample 0 of pixel (0, 0)" of a 1x1 accumulating film — the state of a freshly cloned sampler — except that it
+// draws from PCG stream 0 (k_debug_job) and that its camera sample lands on the requested film pixel (k_raygen).
+int yk_debug_ray(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_sampler* sm, const yk_integrator* in,
+                 uint32_t film_px_x, uint32_t film_px_y, yk_integrator_ray* rays, uint32_t cap, uint32_t* n_rays, float* li_rgb,
+                 uint64_t* ray_count) {
+    if (!c || !sc || !cam || !sm || !in || !n_rays || (cap && !rays)) return yk_set_error(YK_ERR_INVALID, "yk_debug_ray: null argument");
+    if (film_px_x > 0xffffu || film_px_y > 0xffffu) return yk_set_error(YK_ERR_INVALID, "yk_debug_ray: film pixel must fit u16");
+    *n_rays = 0;
+    if (li_rgb) li_rgb[0] = li_rgb[1] = li_rgb[2] = 0.0f;
+    if (ray_count) *ray_count = 0;
+    if (in->kind > YK_INTEGRATOR_SHADING_UVS) return yk_set_error(YK_ERR_INVALID, "yk_debug_ray: unknown integrator");
+    if (in->kind != YK_INTEGRATOR_WHITTED && in->kind != YK_INTEGRATOR_PATH) return YK_OK;  // default li_debug, integrators/mod.rs:103-118
+    if (sc->ctx != c) return yk_set_error(YK_ERR_INVALID, "yk_debug_ray: scene belongs to another context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    // min_debug_ray_length (path.rs:58-62): Bounds3::maximum_extent (math/bounds.rs:147-156) of the BVH's bounds
+    const float* lo = sc->dev.root_min;
+    const float* hi = sc->dev.root_max;
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    const int axis = (dx > dy && dx > dz) ? 0 : (dy > dz ? 1 : 2);
+    DebugLog head{};
+    head.cap = cap;
+    head.min_len = (hi[axis] - lo[axis]) / 10.0f;
+    DebugLog* d_log = nullptr;
+    yk_integrator_ray* d_rays = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_log, sizeof(DebugLog)));
+    if (cudaMalloc((void**)&d_rays, std::max<size_t>(cap, 1) * sizeof(yk_integrator_ray)) != cudaSuccess) {
+        cudaFree(d_log);
+        return yk_set_error(YK_ERR_CUDA, "yk_debug_ray: out of device memory");
+    }
+    head.rays = d_rays;
+    int rc = YK_OK;
+    auto release = [&]() { cudaFree(d_log); cudaFree(d_rays); };
+    if (cudaMemcpy(d_log, &head, sizeof(DebugLog), cudaMemcpyHostToDevice) != cudaSuccess) {
+        release();
+        return yk_set_error(YK_ERR_CUDA, "yk_debug_ray: upload failed");
+    }
+    yk_film_settings fs{};
+    fs.res_x = 1; fs.res_y = 1; fs.tile_dim = 16; fs.accumulate = 1;  // accumulate: render sample index `tile.sample` = 0 only
+    yk_tile tile{};
+    tile.x0 = 0; tile.y0 = 0; tile.x1 = 1; tile.y1 = 1; tile.sample = 0; tile.index = 0;
+    yk_render_opts opts{};
+    opts.pipes = 1;
+    float li[3] = {0.0f, 0.0f, 0.0f};
+    yk_stats st{};
+    const float px[2] = {(float)film_px_x, (float)film_px_y};
+    rc = render_impl(c, sc, cam, &fs, sm, in, &tile, 1, &opts, li, &st, d_log, px);
+    if (rc == YK_OK) {
+        if (cudaMemcpy(&head, d_log, sizeof(DebugLog), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(rays, d_rays, (size_t)std::min(head.count, cap) * sizeof(yk_integrator_ray), cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = yk_set_error(YK_ERR_CUDA, "yk_debug_ray: read-back failed");
+    }
+    release();
+    if (rc != YK_OK) return rc;
+    *n_rays = head.count;
+    if (li_rgb) { li_rgb[0] = li[0]; li_rgb[1] = li[1]; li_rgb[2] = li[2]; }
+    if (ray_count) *ray_count = st.ray_count;
     return YK_OK;
 }
 

@@ -175,9 +175,18 @@ struct Wave {
 // beta.w flag word
 constexpr uint32_t kFlagSpecular = 0x100u;   // path: specular_bounce / whitted: is_specular
 constexpr uint32_t kFlagAlive = 0x200u;
+constexpr uint32_t kFlagTransmission = 0x400u;  // the ray left a TRANSMISSION lobe (ray type of li_debug, path.rs:146-153)
 constexpr uint32_t kDepthMask = 0xffu;       // path: bounces / whitted: depth
-constexpr uint32_t kDimShift = 10;           // sampler dimension (stratified.rs:40) in the upper 22 bits
+constexpr uint32_t kDimShift = 11;           // sampler dimension (stratified.rs:40) in the upper 21 bits
 constexpr uint32_t kFlagMask = (1u << kDimShift) - 1u;
+
+// Ray list of Integrator::li_debug (integrators/mod.rs:76-118), filled by k_debug_log for the one path of yk_debug_ray.
+struct DebugLog {
+    uint32_t count, cap;
+    float min_len;  // min_debug_ray_length: a tenth of the scene bounds' largest extent (path.rs:58-62, whitted.rs:84-88)
+    uint32_t _pad;
+    yk_integrator_ray* rays;
+};
 
 struct RenderCfg {
     SamplerCfg sampler;
@@ -187,6 +196,8 @@ struct RenderCfg {
     uint32_t res_x, res_y;
     uint32_t aux_sample;
     int32_t* hit_ids;  // device, or null
+    DebugLog* debug_log;  // yk_debug_ray only: the single path's rays; the camera sample lands on film pixel debug_px
+    float debug_px[2];
 };
 
 // ---- helpers --------------------------------------------------------------------------------------

@@ -32,6 +32,10 @@ __global__ void k_jobs_expand(const yk_tile* tiles, const unsigned long long* of
     out[i] = o;
 }
 
+// yk_debug_ray: the freshly cloned sampler of launch_debug_ray draws from PCG stream 0 (`Pcg32::new(seed, 0)`, stratified.rs:73,
+// uniform.rs:57), not from the pixel's stream
+__global__ void k_debug_job(Job* jobs) { jobs[0].rng_inc = 1ULL; }
+
 // hash_values!(pixel.x, pixel.y, dimension, seed) for every (dimension, pixel) of a pixel group (SamplerCfg::hash_table)
 __global__ void k_dim_hashes(const Job* jobs, uint32_t n_jobs, uint32_t n_dims, unsigned long long seed, uint32_t* out) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,7 +87,9 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, uint32_t first_sample,
     }
     const V2 j = s.get_2d(cfg.sampler);
     // Camera::ray, camera.rs:105-114
-    const V3 p_cam = xf_point(cfg.r2c, mk((float)job.x + j.x, (float)job.y + j.y, 0.0f));
+    // (yk_debug_ray: the sampler belongs to pixel (0, 0) — a fresh clone, window.rs:884 — but the ray leaves through debug_px)
+    const float fx = cfg.debug_log ? cfg.debug_px[0] : (float)job.x, fy = cfg.debug_log ? cfg.debug_px[1] : (float)job.y;
+    const V3 p_cam = xf_point(cfg.r2c, mk(fx + j.x, fy + j.y, 0.0f));
     const V3 d_cam = unit(p_cam);
     const V3 o = xf_point(cfg.c2w, mk(0.0f, 0.0f, 0.0f));
     const V3 d = xf_vec(cfg.c2w, d_cam);

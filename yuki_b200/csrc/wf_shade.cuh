@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     }
                     const uint32_t bounces = depth + 1;
                     if (bounces >= cfg.max_depth) alive = false;
-                    new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u);
+                    new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u) | ((s.type & BX_TRANSMISSION) ? kFlagTransmission : 0u);
                     nx_o = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
                     nx_d = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
                     nx_beta = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                         e.o = nr.o;
                         e.d = nr.d;
                         e.weight = beta * s.f * fabsf(dotn(s.wi, si.sh_n));
-                        e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u);
+                        e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u) | (c == 1 ? kFlagTransmission : 0u);
                         child[n_child++] = e;
                     }
                 }
@@ -466,6 +466,64 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             st_once(&out.beta[npos], nx_beta);
             st_once(&out.rng[npos], nx_rng);
         }
+    }
+}
+
+// ---- Integrator::li_debug (integrators/mod.rs:103-118): the ray list of one path ------------------------
+// yk_debug_ray renders a single path through the ordinary wavefront kernels; this one-thread kernel runs after each bounce's
+// closest-hit kernel and appends what Path / Whitted::li_internal collect (path.rs:71-113, whitted.rs:89-121): the bounce ray
+// (cut at the hit, else at the scene bounds for Path's secondary rays), the geometric normal at the hit, and the shadow ray
+// of every light sample that carries a visibility test. It re-draws the light samples from a copy of the path's sampler
+// state, exactly as the shading kernel that follows does.
+__global__ void k_debug_log(DevScene sc, Wave w, RenderCfg cfg, Batch bt, int b, const IterCounters* cur) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || cur->n_active == 0) return;
+    DebugLog* log = cfg.debug_log;
+    auto push = [&](V3 o, V3 d, float t_max, uint32_t type) {
+        const uint32_t k = log->count++;
+        if (k >= log->cap) return;
+        yk_integrator_ray r;
+        r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z;
+        r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
+        r.t_max = t_max;
+        r.ray_type = type;
+        log->rays[k] = r;
+    };
+    const float4 ro = w.st[b].ray_o[0], rd = w.st[b].ray_d[0], beta4 = w.st[b].beta[0];
+    const V3 o = f4v(ro), d = f4v(rd);
+    const uint2 h = w.hit[0];
+    const uint32_t word = __float_as_uint(beta4.w), depth = word & kDepthMask;
+    const uint32_t type = depth == 0 ? YK_RAY_DIRECT : ((word & kFlagTransmission) ? YK_RAY_REFRACTION : YK_RAY_REFLECTION);
+    float t_log = ro.w;  // ray.t_max
+    if (h.y != kMiss) {
+        t_log = __uint_as_float(h.x);
+    } else if (cfg.integrator == YK_INTEGRATOR_PATH && type != YK_RAY_DIRECT) {  // Bounds3::intersections, math/bounds.rs:176-205
+        const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+        const float t0x = (sc.root_min[0] - o.x) * ix, t0y = (sc.root_min[1] - o.y) * iy, t0z = (sc.root_min[2] - o.z) * iz;
+        const float t1x = (sc.root_max[0] - o.x) * ix, t1y = (sc.root_max[1] - o.y) * iy, t1z = (sc.root_max[2] - o.z) * iz;
+        const float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fmaxf(fminf(t0y, t1y), fminf(t0z, t1z))), 0.0f);
+        const float tmax = fminf(fminf(fmaxf(t0x, t1x), fminf(fmaxf(t0y, t1y), fmaxf(t0z, t1z))), ro.w);
+        t_log = tmin <= tmax ? tmax : log->min_len;
+    }
+    push(o, d, t_log, type);
+    if (h.y == kMiss) return;
+    Surface si;
+    uint32_t mat_index;
+    make_surface(sc, h.y, o, d, &si, &mat_index);
+    push(si.p, si.n, log->min_len, YK_RAY_NORMAL);
+    const Job job = bt.jobs[0];
+    SamplerState smp;
+    smp.rng.state = w.st[b].rng[0];
+    smp.rng.inc = job.rng_inc;
+    smp.dim = word >> kDimShift;
+    smp.px = job.x;
+    smp.py = job.y;
+    smp.index = job.sample_begin + bt.sample_off;
+    smp.job = 0;
+    for (uint32_t k = 0; k < sc.n_lights; ++k) {
+        const V2 u = smp.get_2d(cfg.sampler);
+        LightSample ls;
+        sample_light(sc.lights[k], (int)k, si, u, &ls);
+        if (!black(ls.li) && ls.has_vis) push(ls.vis.o, ls.vis.d, ls.vis.t_max, YK_RAY_SHADOW);
     }
 }
 
