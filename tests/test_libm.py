@@ -1,4 +1,5 @@
-"""yk_libm.h restates glibc's sinf/cosf; on this host it must be bit-identical to the libm the oracle calls."""
+"""yk_libm.h restates glibc's sinf / cosf / atanf / atan2f / acosf; on this host it must be bit-identical to the libm the
+oracle calls."""
 import os
 import subprocess
 import sys
@@ -35,3 +36,52 @@ def test_sinf_cosf_bit_identical_to_host_libm(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     n, bad = out.stdout.split()
     assert out.returncode == 0 and int(bad) == 0 and int(n) > 10_000_000, out.stdout
+
+
+SRC_INV = r'''
+#include <cstdio>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include "yk_libm.h"
+static uint32_t rng = 12345;
+static uint32_t nx() { rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5; return rng; }
+static bool differ(float a, float b) { return memcmp(&a, &b, 4) != 0 && !(a != a && b != b); }
+int main() {
+    unsigned long long n = 0, bad = 0;
+    for (uint32_t u = 0; u <= 0x7f800000u; u += 37) for (int sg = 0; sg < 2; ++sg) {  // every binade, both signs, infinities
+        uint32_t b = u | (sg ? 0x80000000u : 0u); float x; memcpy(&x, &b, 4);
+        bad += differ(atanf(x), yklibm::atanf_glibc(x)); ++n;
+    }
+    for (uint32_t u = 0; u <= 0x3f800010u; u += 11) for (int sg = 0; sg < 2; ++sg) {  // [-1, 1] and just outside (NaN)
+        uint32_t b = u | (sg ? 0x80000000u : 0u); float x; memcpy(&x, &b, 4);
+        bad += differ(acosf(x), yklibm::acosf_glibc(x)); ++n;
+    }
+    for (long i = 0; i < 40000000L; ++i) {
+        uint32_t a = nx(), b = nx();
+        if (i & 1) {  // magnitudes a sphere's hit point has; the other half sweeps every exponent pair
+            a = (a & 0x807fffffu) | ((100 + (a >> 23) % 56) << 23);
+            b = (b & 0x807fffffu) | ((100 + (b >> 23) % 56) << 23);
+        }
+        float y, x; memcpy(&y, &a, 4); memcpy(&x, &b, 4);
+        bad += differ(atan2f(y, x), yklibm::atan2f_glibc(y, x)); ++n;
+    }
+    const float sp[] = {0.0f, -0.0f, 1.0f, -1.0f, INFINITY, -INFINITY, 1e-30f, -1e-30f, 1e30f, NAN, 0.5f, -0.5f};
+    for (float y : sp) for (float x : sp) {
+        bad += differ(atan2f(y, x), yklibm::atan2f_glibc(y, x));
+        bad += differ(acosf(x), yklibm::acosf_glibc(x)); bad += differ(atanf(x), yklibm::atanf_glibc(x)); n += 3;
+    }
+    printf("%llu %llu\n", n, bad);
+    return bad != 0;
+}
+'''
+
+
+def test_atanf_atan2f_acosf_bit_identical_to_host_libm(tmp_path):
+    src = tmp_path / "t.cpp"
+    src.write_text(SRC_INV)
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "yuki_b200", "csrc"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    n, bad = out.stdout.split()
+    assert out.returncode == 0 and int(bad) == 0 and int(n) > 100_000_000, out.stdout

@@ -147,8 +147,8 @@ int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries
     WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap) WAVE_ALLOC(q_mat_tri, (size_t)4 * cap) WAVE_ALLOC(q_mat_slot, (size_t)4 * cap)
     WAVE_ALLOC(totals, 1)
     if (stack_entries) {
-        WAVE_ALLOC(stack, (size_t)stack_entries * cap * 3)
-        WAVE_ALLOC(stack_top, cap)
+        WAVE_ALLOC(stack, (size_t)stack_entries * cap * 5)
+        WAVE_ALLOC(tree_rng, cap)
     }
 #undef WAVE_ALLOC
     p->wave = w;
@@ -299,6 +299,10 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         else k_trace_shadow<false><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 4), s));
         tm->launches += 1;
+        if (cfg.integrator == YK_INTEGRATOR_WHITTED) {
+            k_tree_return<<<shade_blocks, kShadeThreads, 0, s>>>(w, b, cur, nxt, q_next);
+            tm->launches += 1;
+        }
         sl.n_iters = iter + 1;
         q_cur = q_next;
         flip ^= 1;
@@ -712,7 +716,7 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
         const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
         uint32_t cap = opts ? opts->wavefront_paths : 0u;
         if (!cap) {
-            const uint64_t bytes_per_path = 320ull + 40ull * std::max(sc->dev.n_lights, 1u) + 52ull * stack_entries;
+            const uint64_t bytes_per_path = 320ull + 40ull * std::max(sc->dev.n_lights, 1u) + (80ull * stack_entries + (stack_entries ? 8ull : 0ull));
             if (!c->mem_budget) {  // asked once per context: cudaMemGetInfo can take milliseconds
                 size_t free_b = 0, total_b = 0;
                 c->mem_budget = 6ull << 30;

@@ -149,7 +149,7 @@ struct Wave {
     struct Stream {
         float4* ray_o;   // o.xyz, t_max
         float4* ray_d;   // d.xyz, -
-        float4* beta;    // throughput (path) / node weight (whitted); w = flags | sampler dimension << kDimShift
+        float4* beta;    // throughput (path; 1 for whitted); w = flags | sampler dimension << kDimShift
         unsigned long long* rng;
     } st[2];
     uint2* hit;         // per queue slot: t bits, shape slot (kMiss = none)
@@ -159,13 +159,13 @@ struct Wave {
     // position* g (position in the concatenation of this bounce's four material queues), not by path: the shading
     // kernels write them fully coalesced and the shadow kernel streams them with no dependent gather.
     uint32_t* sh_path;   // path of shading position g
-    float4* pend_beta;   // weight to apply to this bounce's radiance; w = clamp flag
+    float4* pend_beta;   // path: weight to apply to this bounce's radiance; w = clamp flag. whitted: node depth | has-children << 8, sampler dimension, -, -1
     float4* pend_extra;  // emitted term of this bounce; w = bit mask of the lights whose shadow ray must be traced
     float4* lt_o;        // cap * n_lights: shadow ray o.xyz | contribution.r   (contribution = f * li * cos / pdf)
     float4* lt_d;        //                 shadow ray d.xyz | contribution.g
     float2* lt_c;        //                 contribution.b   | area light id of the sampled light (int bits, -1 = none)
-    float4* stack;       // whitted: stack_entries * cap * 3 float4
-    uint32_t* stack_top; // whitted
+    float4* stack;       // whitted: recursion frames, stack_entries * cap * 5 float4 (wf_shade.cuh)
+    unsigned long long* tree_rng;  // whitted: sampler state after shading position g (nodes without children)
     uint32_t* q_active[2];
     uint32_t* q_mat;     // 4 * cap: paths per material kind
     uint32_t* q_mat_tri; // 4 * cap: the hit shape slot of each entry

@@ -98,7 +98,6 @@ __global__ void k_raygen(Wave w, RenderCfg cfg, Batch bt, uint32_t first_sample,
     st_once(&w.st[0].rng[i], (unsigned long long)s.rng.state);
     st_once(&w.st[0].beta[i], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(kFlagAlive | (s.dim << kDimShift))));
     st_once(&w.L[i], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-    if (w.stack_top) w.stack_top[i] = 0;
 }
 
 }  // namespace

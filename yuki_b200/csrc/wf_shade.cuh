@@ -7,39 +7,54 @@
 
 namespace {
 
-// ---- whitted stack ------------------------------------------------------------------------------------
-struct StackEntry {
+// ---- whitted recursion frames ----------------------------------------------------------------------------
+// Whitted::li_internal recurses (whitted.rs:132-170): a node's radiance is `lights (+ Le)`, then
+// `+= f * li(child) * |cos|` for the reflection child, then for the transmission child. The wavefront walks that tree
+// depth first, one node per path and bounce, and evaluates it bottom-up like the recursion does, so every float
+// operation has the reference's operands: frame d of a path holds the partial sum of its depth-d node, the factor of the
+// child being evaluated and, while the reflection subtree runs, the waiting transmission child.
+//   frame[0] = sum_li.rgb | -          frame[1] = f.rgb | |cos| of the running child
+//   frame[2] = waiting child: o.xyz | d.x   frame[3] = d.yz | f.rg   frame[4] = f.b | |cos| | flags (0 = none) | -
+constexpr int kFrameWords = 5;
+constexpr uint32_t kFramePending = 0x80000000u;
+struct TreeRay {
     V3 o, d;
-    RGB weight;
-    uint32_t flags;  // depth | specular
+    uint32_t flags;  // depth | specular | transmission
 };
-__device__ __forceinline__ void stack_push(const Wave& w, uint32_t path, const StackEntry& e) {
-    const uint32_t top = w.stack_top[path];
-    float4* base = w.stack + ((size_t)top * w.cap + path) * 3;
-    base[0] = make_float4(e.o.x, e.o.y, e.o.z, e.d.x);
-    base[1] = make_float4(e.d.y, e.d.z, e.weight.r, e.weight.g);
-    base[2] = make_float4(e.weight.b, __uint_as_float(e.flags), 0.0f, 0.0f);
-    w.stack_top[path] = top + 1;
+__device__ __forceinline__ float4* frame_of(const Wave& w, uint32_t depth, uint32_t path) {
+    return w.stack + ((size_t)depth * w.cap + path) * kFrameWords;
 }
-// Pops the next pending node of the path's tree. Returns false when the tree is done.
-__device__ __forceinline__ bool stack_pop(const Wave& w, uint32_t path, StackEntry* e) {
-    const uint32_t top = w.stack_top[path];
-    if (top == 0) return false;
-    const float4* base = w.stack + ((size_t)(top - 1) * w.cap + path) * 3;
-    const float4 a = base[0], b = base[1], c = base[2];
-    w.stack_top[path] = top - 1;
-    e->o = mk(a.x, a.y, a.z);
-    e->d = mk(a.w, b.x, b.y);
-    e->weight = rgb(b.z, b.w, c.x);
-    e->flags = __float_as_uint(c.y);
-    return true;
+// The depth-`depth` node of `path` finished with radiance `li`: hand it to the parent (`sum_li += s.f * child.li * |cos|`,
+// whitted.rs:160-166) and climb while the parents finish too. Returns true with the next ray of the tree when a parent
+// still has its transmission child waiting; false once the root is done (its radiance is then the path's L).
+__device__ __forceinline__ bool tree_return(const Wave& w, uint32_t path, uint32_t depth, RGB li, TreeRay* next) {
+    while (depth > 0) {
+        float4* fr = frame_of(w, depth - 1, path);
+        const float4 a = fr[0], cf = fr[1], p4 = fr[4];
+        const RGB sum = rgb(a.x, a.y, a.z) + rgb(cf.x, cf.y, cf.z) * li * cf.w;
+        const uint32_t pflags = __float_as_uint(p4.z);
+        if (pflags & kFramePending) {
+            const float4 p2 = fr[2], p3 = fr[3];
+            fr[0] = make_float4(sum.r, sum.g, sum.b, 0.0f);
+            fr[1] = make_float4(p3.z, p3.w, p4.x, p4.y);
+            fr[4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            next->o = mk(p2.x, p2.y, p2.z);
+            next->d = mk(p2.w, p3.x, p3.y);
+            next->flags = pflags & ~kFramePending;
+            return true;
+        }
+        li = sum;
+        depth -= 1;
+    }
+    w.L[path] = make_float4(li.r, li.g, li.b, 0.0f);
+    return false;
 }
-// Writes a tree node as the path's next ray (the sampler dimension `dim` carries on: the reference shares one sampler
-// through the recursion).
-__device__ __forceinline__ void stream_node(const Wave::Stream& st, uint32_t pos, const StackEntry& e, uint32_t dim, unsigned long long rng) {
+// Writes a tree node as the path's next ray (the sampler state carries on: the reference shares one sampler through
+// the recursion).
+__device__ __forceinline__ void stream_node(const Wave::Stream& st, uint32_t pos, const TreeRay& e, uint32_t dim, unsigned long long rng) {
     st.ray_o[pos] = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
     st.ray_d[pos] = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
-    st.beta[pos] = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (dim << kDimShift)));
+    st.beta[pos] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(e.flags | kFlagAlive | (dim << kDimShift)));
     st.rng[pos] = rng;
 }
 
@@ -60,7 +75,7 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
         if (block_first >= n) break;  // block-uniform
         uint32_t idx[K], path[K], hit_slot[K];
         int key[K];
-        StackEntry node[WHITTED ? K : 1];
+        TreeRay node[WHITTED ? K : 1];
         uint32_t node_dim[WHITTED ? K : 1];
         unsigned long long hh = 0;
 #pragma unroll
@@ -77,16 +92,17 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
                 key[k] = (int)((__float_as_uint(__ldg(&sc.tris[3 * h.y + 1]).w) >> 28) & 3u);
                 if (first_iteration) orig = __float_as_uint(__ldg(&sc.tris[3 * h.y + 2]).w);
             } else if (first_iteration != 2) {  // (2 = debug integrators: their li() returns no background)
-                // path.rs:155-160 / whitted.rs:174: background weighted by the throughput / node weight
                 const float4 bw = w.st[b].beta[i];
-                float4 L = w.L[path[k]];
-                L.x = L.x + bw.x * sc.background[0];
-                L.y = L.y + bw.y * sc.background[1];
-                L.z = L.z + bw.z * sc.background[2];
-                w.L[path[k]] = L;
-                if (WHITTED) {
+                if (WHITTED) {  // whitted.rs:174: this node's radiance is the background
                     node_dim[WHITTED ? k : 0] = __float_as_uint(bw.w) >> kDimShift;
-                    if (stack_pop(w, path[k], &node[WHITTED ? k : 0])) key[k] = 4;
+                    const uint32_t depth = __float_as_uint(bw.w) & kDepthMask;
+                    if (tree_return(w, path[k], depth, rgb(sc.background[0], sc.background[1], sc.background[2]), &node[WHITTED ? k : 0])) key[k] = 4;
+                } else {  // path.rs:155-160: background weighted by the throughput
+                    float4 L = w.L[path[k]];
+                    L.x = L.x + bw.x * sc.background[0];
+                    L.y = L.y + bw.y * sc.background[1];
+                    L.z = L.z + bw.z * sc.background[2];
+                    w.L[path[k]] = L;
                 }
             }
             if (first_iteration) {
@@ -426,11 +442,13 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     nx_beta = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
                 }
             } else {
-                // whitted.rs:128-170
+                // whitted.rs:128-170: this node's own terms go to the shadow / fold kernel; k_tree_return then either parks
+                // their sum in the node's frame (children pending) or hands it to the parent
                 const RGB extra = add_le ? le : gray(0.0f);
                 st_once(&w.pend_extra[g], make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask)));
-                st_once(&w.pend_beta[g], make_float4(beta.r, beta.g, beta.b, 0.0f));
-                StackEntry child[2];
+                TreeRay child[2];
+                RGB child_f[2];
+                float child_cos[2];
                 int n_child = 0;
                 if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
                     const uint32_t wants[2] = {BX_SPECULAR | BX_REFLECTION, BX_SPECULAR | BX_TRANSMISSION};
@@ -439,20 +457,34 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                         const Bsdf::Sample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, wants[c]);
                         if (s.type == 0u) continue;  // BxdfType::NONE: no ray, no radiance
                         const Ray nr = spawn_ray(si.p, si.n, s.wi);
-                        StackEntry e;
+                        TreeRay e;
                         e.o = nr.o;
                         e.d = nr.d;
-                        e.weight = beta * s.f * fabsf(dotn(s.wi, si.sh_n));
                         e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u) | (c == 1 ? kFlagTransmission : 0u);
+                        child_f[n_child] = s.f;
+                        child_cos[n_child] = fabsf(dotn(s.wi, si.sh_n));
                         child[n_child++] = e;
                     }
                 }
-                if (n_child == 2) stack_push(w, path, child[1]);  // transmission waits until the reflection subtree is done
-                StackEntry e = child[0];
-                alive = n_child >= 1 || stack_pop(w, path, &e);
-                nx_o = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
-                nx_d = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
-                nx_beta = make_float4(e.weight.r, e.weight.g, e.weight.b, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
+                alive = n_child >= 1;
+                st_once(&w.pend_beta[g], make_float4(__uint_as_float(depth | (alive ? 0x100u : 0u)), __uint_as_float(smp.dim), 0.0f, -1.0f));
+                if (alive) {
+                    float4* fr = frame_of(w, depth, path);
+                    fr[1] = make_float4(child_f[0].r, child_f[0].g, child_f[0].b, child_cos[0]);
+                    if (n_child == 2) {  // transmission waits until the reflection subtree is done
+                        fr[2] = make_float4(child[1].o.x, child[1].o.y, child[1].o.z, child[1].d.x);
+                        fr[3] = make_float4(child[1].d.y, child[1].d.z, child_f[1].r, child_f[1].g);
+                        fr[4] = make_float4(child_f[1].b, child_cos[1], __uint_as_float(child[1].flags | kFramePending), 0.0f);
+                    } else {
+                        fr[4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                    const TreeRay& e = child[0];
+                    nx_o = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+                    nx_d = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+                    nx_beta = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
+                } else {
+                    w.tree_rng[g] = smp.rng.state;  // the sampler goes on with whichever node the tree visits next
+                }
             }
             nx_rng = smp.rng.state;
         }
@@ -466,6 +498,35 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             st_once(&out.beta[npos], nx_beta);
             st_once(&out.rng[npos], nx_rng);
         }
+    }
+}
+
+// ---- Whitted: nodes shaded this bounce return their radiance ---------------------------------------------
+// Runs after the shadow / fold kernel, which left `lights (+ Le)` of every node shaded this bounce in pend_extra. A node
+// with children parks it in its frame; a finished node hands it up the tree (tree_return), which may release a waiting
+// transmission ray into the next bounce's queue.
+__global__ void k_tree_return(Wave w, int b, IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
+    const uint32_t n = cur->mat[0] + cur->mat[1] + cur->mat[2] + cur->mat[3];
+    const uint32_t rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
+        if (block_first >= n) break;  // block-uniform
+        const uint32_t g = block_first + threadIdx.x;
+        bool alive = false;
+        uint32_t path = 0, dim = 0;
+        TreeRay next;
+        if (g < n) {
+            path = w.sh_path[g];
+            const float4 info = w.pend_beta[g], li4 = w.pend_extra[g];
+            const uint32_t word = __float_as_uint(info.x), depth = word & kDepthMask;
+            dim = __float_as_uint(info.y);
+            if (word & 0x100u) frame_of(w, depth, path)[0] = make_float4(li4.x, li4.y, li4.z, 0.0f);
+            else alive = tree_return(w, path, depth, rgb(li4.x, li4.y, li4.z), &next);
+        }
+        uint32_t* const queues[1] = {q_next};
+        uint32_t* const counters[1] = {&nxt->n_active};
+        const uint32_t npos = block_scatter<1>(alive ? 0 : -1, path, queues, counters);
+        if (alive) stream_node(w.st[b ^ 1], npos, next, dim, w.tree_rng[g]);
     }
 }
 

@@ -414,7 +414,11 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
     auto finish_path = [&]() {  // path.rs:121-129
         const float4 pe = w.pend_extra[pos], pb = w.pend_beta[pos];
         RGB r = radiance + rgb(pe.x, pe.y, pe.z);
-        if (pb.w != 0.0f) r = rgb(fminf(r.r, cfg.clamp), fminf(r.g, cfg.clamp), fminf(r.b, cfg.clamp));
+        if (pb.w > 0.0f) r = rgb(fminf(r.r, cfg.clamp), fminf(r.g, cfg.clamp), fminf(r.b, cfg.clamp));
+        if (pb.w < 0.0f) {  // whitted.rs:109-130 (w = -1): the node's own radiance, summed up the tree by k_tree_return
+            w.pend_extra[pos] = make_float4(r.r, r.g, r.b, pe.w);
+            return;
+        }
         float4 L = w.L[path];
         L.x = L.x + pb.x * r.r;
         L.y = L.y + pb.y * r.g;

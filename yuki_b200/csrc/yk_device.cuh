@@ -340,8 +340,8 @@ YK_DEV bool sphere_test(const yk_sphere& sp, V3 o_w, V3 d_w, float t_max, float*
     return true;
 }
 // Surface interaction of a sphere hit (:79-117) moved to world space by `&object_to_world * SurfaceInteraction`
-// (interaction.rs:141-164). atan2 / acos are CUDA's, not glibc's: uv and the shading frame can differ from the CPU
-// path in the last bits (radiance tolerance); the hit itself uses only + - * / sqrt and is exact.
+// (interaction.rs:141-164). atan2 / acos restate glibc's routines (yk_libm.h) like sin / cos, so uv and the shading
+// frame carry the bits the CPU path computes; the hit itself uses only + - * / sqrt.
 static __device__ __noinline__ void sphere_surface(const yk_sphere& sp, V3 o_w, V3 d_w, Surface* si) {  // rare: out of line
     float t = 0.0f;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
@@ -349,11 +349,11 @@ static __device__ __noinline__ void sphere_surface(const yk_sphere& sp, V3 o_w, 
     V3 p = o + d * t;
     p = p * (sp.radius / length(p - mk(0.0f, 0.0f, 0.0f)));
     if (p.x == 0.0f && p.y == 0.0f) p.x = 1e-5f * sp.radius;
-    float phi = atan2f(p.y, p.x);
+    float phi = yklibm::atan2f_glibc(p.y, p.x);
     if (phi < 0.0f) phi += 2.0f * kPi;
     const float phi_max = 2.0f * kPi, theta_min = kPi, theta_max = 0.0f;
     const float u = phi / phi_max;
-    const float theta = acosf(clamp01ish(p.z / sp.radius, -1.0f, 1.0f));
+    const float theta = yklibm::acosf_glibc(clamp01ish(p.z / sp.radius, -1.0f, 1.0f));
     const float v = (theta - theta_min) / (theta_max - theta_min);
     const float z_radius = sqrtf(p.x * p.x + p.y * p.y);
     const float inv_z_radius = 1.0f / z_radius;

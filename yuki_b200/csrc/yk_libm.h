@@ -120,4 +120,156 @@ YK_HD float cosf_glibc(float y) {
     return (float)cos((double)y);
 }
 
+// ---- atanf / atan2f / acosf ------------------------------------------------------------------------
+// glibc 2.39 still ships the fdlibm single-precision routines for these (sysdeps/ieee754/flt-32/
+// s_atanf.c, e_atan2f.c, e_acosf.c; compiled without contraction): argument reduction to one of four
+// intervals plus an odd/even split polynomial for atan, a rational approximation (with a split square
+// root above 0.5) for acos. Only + - * / sqrt in f32, so the device evaluates them exactly when compiled
+// --fmad=false -prec-div=true -prec-sqrt=true. Used by Sphere::intersect's (phi, theta)
+// (shapes/sphere.rs:86-93); tests/test_libm.py compares with the host libm.
+YK_HD float from_bits_(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+#endif
+}
+YK_HD float sqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+    return __fsqrt_rn(x);
+#else
+    return __builtin_sqrtf(x);
+#endif
+}
+YK_HD float div_(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+YK_HD float atanf_glibc(float x) {
+    const float a0 = 3.3333334327e-01f, a1 = -2.0000000298e-01f, a2 = 1.4285714924e-01f, a3 = -1.1111110449e-01f,
+                a4 = 9.0908870101e-02f, a5 = -7.6918758452e-02f, a6 = 6.6610731184e-02f, a7 = -5.8335702866e-02f,
+                a8 = 4.9768779427e-02f, a9 = -3.6531571299e-02f, a10 = 1.6285819933e-02f;
+    const uint32_t hx = bits_(x), ix = hx & 0x7fffffffu;
+    const bool neg = (hx >> 31) != 0;
+    float hi = 0.0f, lo = 0.0f;  // atan of the interval's centre (0.5, 1, 1.5, inf), split in two floats
+    bool reduced = true;
+    if (ix >= 0x4c000000u) {  // |x| >= 2^25
+        if (ix > 0x7f800000u) return x + x;
+        return neg ? -1.5707962513e+00f - 7.5497894159e-08f : 1.5707962513e+00f + 7.5497894159e-08f;
+    }
+    if (ix < 0x3ee00000u) {  // |x| < 7/16
+        if (ix < 0x31000000u) return x;  // |x| < 2^-29
+        reduced = false;
+    } else {
+        x = from_bits_(ix);
+        if (ix < 0x3f980000u) {
+            if (ix < 0x3f300000u) {
+                hi = 4.6364760399e-01f; lo = 5.0121582440e-09f;
+                x = div_(2.0f * x - 1.0f, 2.0f + x);
+            } else {
+                hi = 7.8539812565e-01f; lo = 3.7748947079e-08f;
+                x = div_(x - 1.0f, x + 1.0f);
+            }
+        } else if (ix < 0x401c0000u) {
+            hi = 9.8279368877e-01f; lo = 3.4473217170e-08f;
+            x = div_(x - 1.5f, 1.0f + 1.5f * x);
+        } else {
+            hi = 1.5707962513e+00f; lo = 7.5497894159e-08f;
+            x = div_(-1.0f, x);
+        }
+    }
+    const float z = x * x;
+    const float w = z * z;
+    const float s1 = z * (a0 + w * (a2 + w * (a4 + w * (a6 + w * (a8 + w * a10)))));
+    const float s2 = w * (a1 + w * (a3 + w * (a5 + w * (a7 + w * a9))));
+    if (!reduced) return x - x * (s1 + s2);
+    const float r = hi - ((x * (s1 + s2) - lo) - x);
+    return neg ? -r : r;
+}
+
+YK_HD float atan2f_glibc(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+                pi_lo = -8.7422776573e-08f;
+    const uint32_t hx = bits_(x), hy = bits_(y), ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+    if (ix > 0x7f800000u || iy > 0x7f800000u) return x + y;
+    if (hx == 0x3f800000u) return atanf_glibc(y);
+    const uint32_t m = (hy >> 31) | ((hx >> 30) & 2u);  // 2*sign(x) + sign(y)
+    if (iy == 0) {
+        if (m < 2) return y;
+        return m == 2 ? pi + tiny : -pi - tiny;
+    }
+    if (ix == 0) return (hy >> 31) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    if (ix == 0x7f800000u) {
+        if (iy == 0x7f800000u) {
+            switch (m) {
+                case 0: return pi_o_4 + tiny;
+                case 1: return -pi_o_4 - tiny;
+                case 2: return 3.0f * pi_o_4 + tiny;
+                default: return -3.0f * pi_o_4 - tiny;
+            }
+        }
+        switch (m) {
+            case 0: return 0.0f;
+            case 1: return -0.0f;
+            case 2: return pi + tiny;
+            default: return -pi - tiny;
+        }
+    }
+    if (iy == 0x7f800000u) return (hy >> 31) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int32_t k = ((int32_t)iy - (int32_t)ix) >> 23;
+    float z;
+    if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+    else if ((hx >> 31) && k < -60) z = 0.0f;
+    else z = atanf_glibc(from_bits_(bits_(div_(y, x)) & 0x7fffffffu));
+    switch (m) {
+        case 0: return z;
+        case 1: return from_bits_(bits_(z) ^ 0x80000000u);
+        case 2: return pi - (z - pi_lo);
+        default: return (z - pi_lo) - pi;
+    }
+}
+
+YK_HD float acosf_glibc(float x) {
+    const float pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f,
+                pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f, pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f,
+                pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f, qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f,
+                qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+    const uint32_t hx = bits_(x), ix = hx & 0x7fffffffu;
+    const bool neg = (hx >> 31) != 0;
+    if (ix == 0x3f800000u) return neg ? pi + 2.0f * pio2_lo : 0.0f;
+    if (ix > 0x3f800000u) return div_(x - x, x - x);
+    if (ix < 0x3f000000u) {  // |x| < 0.5
+        if (ix <= 0x32800000u) return pio2_hi + pio2_lo;
+        const float z = x * x;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float r = div_(p, q);
+        return pio2_hi - (x - (pio2_lo - r * x));
+    }
+    if (neg) {  // x < -0.5
+        const float z = (1.0f + x) * 0.5f;
+        const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        const float s = sqrt_(z);
+        const float r = div_(p, q);
+        const float w = r * s - pio2_lo;
+        return pi - 2.0f * (s + w);
+    }
+    const float z = (1.0f - x) * 0.5f;
+    const float s = sqrt_(z);
+    const float df = from_bits_(bits_(s) & 0xfffff000u);
+    const float c = div_(z - df * df, s + df);
+    const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const float q = 1.0f + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const float r = div_(p, q);
+    const float w = r * s + c;
+    return 2.0f * (df + w);
+}
+
 }  // namespace yklibm
