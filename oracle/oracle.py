@@ -80,6 +80,8 @@ def lib():
         getattr(L, n).restype = None
     L.yko_cross.argtypes = [fp, fp, fp]
     L.yko_cross.restype = None
+    L.yko_math_kat.argtypes = [u32, fp, fp]
+    L.yko_math_kat.restype = C.c_int
     L.yko_siphash13.argtypes = [C.c_char_p, C.c_uint64]
     L.yko_siphash13.restype = C.c_uint64
     L.yko_pcg32_sequence.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u32, vp]
@@ -154,6 +156,16 @@ class _Xf:
 
 
 transforms = _Xf()
+
+
+def math_kat(op, values, n_out):
+    """yko_math.h helper `op` (see yko_math_kat) on a flat list of floats; returns n_out floats."""
+    vals = np.zeros(max(len(values), 16), np.float32)
+    vals[:len(values)] = values
+    out = np.zeros(8, np.float32)
+    if lib().yko_math_kat(op, _f(vals, len(vals)), out.ctypes.data_as(C.POINTER(C.c_float))) != 0:
+        raise ValueError("yko_math_kat failed")
+    return out[:n_out].copy()
 
 
 def cross(a, b):

@@ -241,6 +241,46 @@ void yko_xf_vec(const yko_transform* t, const float* p, float* o) { st3(xf_vec(t
 void yko_xf_normal(const yko_transform* t, const float* p, float* o) { st3(xf_normal(to_xf(*t), ld3(p)), o); }
 void yko_cross(const float* a, const float* b, float* o) { st3(cross(ld3(a), ld3(b)), o); }
 
+// One entry point over the vector / bounds / transform helpers of yko_math.h the hot path is built from, so that the
+// reference's own unit tests (tests/src/{vector,normal,point,ray,bounds,transform}.rs) can be replayed against them
+// (tests/test_oracle_math.py). `in` / `out` are flat float arrays whose meaning depends on `op`.
+int yko_math_kat(uint32_t op, const float* in, float* out) {
+    const V3 a = ld3(in), b = ld3(in + 3);
+    switch (op) {
+        case 0: out[0] = dot(a, b); return 0;                 // Vec3::dot
+        case 1: out[0] = dot_nv(a, b); return 0;              // Vec3::dot_n / Normal::dot_v
+        case 2: out[0] = len_sqr(a); return 0;
+        case 3: out[0] = len(a); return 0;
+        case 4: st3(normalized(a), out); return 0;
+        case 5: st3(vmin(a, b), out); return 0;
+        case 6: st3(vmax(a, b), out); return 0;
+        case 7: out[0] = min_comp(a); return 0;
+        case 8: out[0] = max_comp(a); return 0;
+        case 9: out[0] = (float)max_dimension(a); return 0;
+        case 10: st3(permuted(a, (int)in[3], (int)in[4], (int)in[5]), out); return 0;
+        case 11: { Bounds3 r = union_p(bounds_new(a, b), ld3(in + 6)); st3(r.p_min, out); st3(r.p_max, out + 3); return 0; }
+        case 12: { Bounds3 r = union_b(bounds_new(a, b), bounds_new(ld3(in + 6), ld3(in + 9))); st3(r.p_min, out); st3(r.p_max, out + 3); return 0; }
+        case 13: st3(diagonal(bounds_new(a, b)), out); return 0;
+        case 14: st3(offset(bounds_new(a, b), ld3(in + 6)), out); return 0;
+        case 15: out[0] = surface_area(bounds_new(a, b)); return 0;
+        case 16: out[0] = (float)maximum_extent(bounds_new(a, b)); return 0;
+        case 17: { Bounds3 r = bounds_default(); st3(r.p_min, out); st3(r.p_max, out + 3); return 0; }
+        case 18: {  // Transform::new(m).swaps_handedness()
+            M44 m;
+            for (int i = 0; i < 16; ++i) m.m[i / 4][i % 4] = in[i];
+            Transform t;
+            if (!xf_new(m, &t)) return -1;
+            out[0] = xf_swaps_handedness(t) ? 1.0f : 0.0f;
+            return 0;
+        }
+        case 19: { Ray r{a, b, in[6]}; st3(r.o + r.d * in[7], out); return 0; }  // Ray::point(t)
+        case 20: out[0] = len(b - a); return 0;               // Point3::dist
+        case 21: out[0] = len_sqr(b - a); return 0;           // Point3::dist_sqr
+        case 22: st3(faceforward(a, b), out); return 0;
+        default: return -2;
+    }
+}
+
 uint64_t yko_siphash13(const uint8_t* msg, uint64_t n) { return siphash13(msg, (size_t)n); }
 void yko_pcg32_sequence(uint64_t state, uint64_t stream, uint64_t adv, uint32_t n, uint32_t* out) {
     Pcg32 p = Pcg32::make(state, stream);

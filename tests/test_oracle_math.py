@@ -1,4 +1,5 @@
-"""Math KATs taken from the reference's own unit tests (tests/src/{matrix,transform,vector,bounds}.rs), replayed against
+"""Math KATs taken from the reference's own unit tests (tests/src/{matrix,transform,vector,normal,point,ray,bounds}.rs —
+every test there that touches a helper the hot path uses), replayed against
 both the oracle and the product's host helpers, plus product == oracle bit-for-bit on random inputs."""
 import numpy as np
 import pytest
@@ -108,3 +109,78 @@ def test_product_and_oracle_transforms_are_bit_identical(oracle, xf):
         la_p = xf.look_at(d, d + v, (0.0, 1.0, 0.0))
         la_o = ox.look_at(d, d + v, (0.0, 1.0, 0.0))
         assert np.array_equal(la_p.m.view(np.uint32), la_o.m.view(np.uint32))
+
+
+# ---- the rest of the reference's unit tests that touch helpers the hot path is built from ------------------------
+# (vector / normal / point / ray / bounds / transform; the Vec2 / Vec4 / integer variants exercise the same derive-generated
+# bodies and have no counterpart here.) Opcodes: oracle/yk_oracle.cpp:yko_math_kat.
+def _k(oracle, op, values, n_out=1):
+    out = oracle.math_kat(op, [float(v) for v in values], n_out)
+    return float(out[0]) if n_out == 1 else [float(v) for v in out]
+
+
+def test_vector_kats(oracle):
+    """tests/src/vector.rs:81-211, normal.rs:42-73"""
+    f32 = np.float32
+    assert _k(oracle, 0, (2, 3, 4, 5, 6, 7)) == 2 * 5 + 3 * 6 + 4 * 7                   # Vec3::dot
+    assert _k(oracle, 1, (2, 3, 4, 5, 6, 7)) == 2.0 * 5.0 + 3.0 * 6.0 + 4.0 * 7.0         # dot_n / Normal::dot / dot_v
+    assert _k(oracle, 2, (2, 3, 4)) == 2 * 2 + 3 * 3 + 4 * 4                              # len_sqr
+    assert abs(_k(oracle, 3, (2, 3, 4)) - float(np.sqrt(f32(29.0)))) <= 1.1920929e-07     # len (assert_abs_diff_eq, f32 epsilon)
+    n = _k(oracle, 4, (1, 1, 1), 3)
+    assert abs(_k(oracle, 3, n) - 1.0) <= 1.1920929e-07                                   # normalized().len() == 1
+    assert _k(oracle, 5, (0, 2, 4, 3, 1, 5), 3) == [0, 1, 4] == _k(oracle, 5, (3, 1, 5, 0, 2, 4), 3)   # min, commutes
+    assert _k(oracle, 6, (0, 2, 4, 3, 1, 5), 3) == [3, 2, 5] == _k(oracle, 6, (3, 1, 5, 0, 2, 4), 3)   # max
+    assert _k(oracle, 7, (0, 1, 2)) == 0.0 and _k(oracle, 8, (0, 1, 2)) == 2.0            # min_comp / max_comp
+    assert _k(oracle, 9, (0, 1, 2)) == 2                                                  # max_dimension
+    assert _k(oracle, 10, (3, 4, 5, 1, 2, 0), 3) == [4, 5, 3]                             # permuted(1, 2, 0)
+
+
+def test_point_and_ray_kats(oracle):
+    """tests/src/point.rs:42-62, ray.rs:49-56"""
+    p0 = np.array([1, 2, 3], np.float32)
+    p1 = p0 + np.array(_k(oracle, 4, (4, 5, 6), 3), np.float32) * np.float32(3.0)
+    assert abs(_k(oracle, 20, (*p0, *p1)) - 3.0) <= 1.1920929e-07 * 4                     # dist (the sum is rounded twice more)
+    assert abs(_k(oracle, 21, (*p0, *p1)) - 9.0) <= 1e-5                                  # dist_sqr
+    assert _k(oracle, 19, (1, 2, 3, 4, 5, 6, 1.0, 1.0), 3) == [5, 7, 9]                    # r.point(1) == o + d
+    assert _k(oracle, 19, (1, 2, 3, 4, 5, 6, 1.0, 2.0), 3) == [9, 12, 15]                  # r.point(2) == o + d * 2
+
+
+def test_bounds_kats(oracle):
+    """tests/src/bounds.rs:25-35, 65-119, 272-381 (the Bounds3<f32> cases; the Bounds2 loops run on xy with z = 0)"""
+    fmax = float(np.finfo(np.float32).max)
+    assert _k(oracle, 17, (), 6) == [fmax] * 3 + [-fmax] * 3                              # default(): p_min = MAX, p_max = MIN
+    bb = (0, 0, 0, 2, 2, 2)
+    assert _k(oracle, 11, (*bb, 1, 1, 1), 6) == list(bb)                                  # union_p inside
+    assert _k(oracle, 11, (0, 0, 0, 2, 2, 0, 3, 1, 0), 6) == [0, 0, 0, 3, 2, 0]
+    assert _k(oracle, 11, (0, 0, 0, 2, 2, 0, 3, 4, 0), 6) == [0, 0, 0, 3, 4, 0]
+    assert _k(oracle, 11, (0, 0, 0, 2, 2, 0, -3, -4, 0), 6) == [-3, -4, 0, 2, 2, 0]
+    pts = [(0, 0, 0), (1, 1, 0), (2, 2, 0), (3, 3, 0)]
+    import itertools
+    for l, k, j, i in itertools.permutations(range(4)):                                   # union_b of any two disjoint pairs
+        assert _k(oracle, 12, (*pts[l], *pts[k], *pts[j], *pts[i]), 6) == [0, 0, 0, 3, 3, 0]
+    assert _k(oracle, 12, (*pts[1], *pts[2], *pts[0], *pts[3]), 6) == [0, 0, 0, 3, 3, 0]
+    assert _k(oracle, 12, (*pts[0], *pts[3], *pts[1], *pts[2]), 6) == [0, 0, 0, 3, 3, 0]
+    assert _k(oracle, 12, (*bb, 1, 1, 1, 1, 1, 1), 6) == list(bb) == _k(oracle, 12, (1, 1, 1, 1, 1, 1, *bb), 6)
+    assert _k(oracle, 13, (1, 2, 3, 5, 8, 11), 3) == [4, 6, 8]                            # diagonal
+    assert _k(oracle, 14, (1, 2, 3, 4, 5, 6, 2.5, 3.5, 4.5), 3) == [0.5, 0.5, 0.5]        # offset
+    p0 = (1.0, 2.0, 0.0)
+    for axis in range(2):                                                                 # the Bounds2 offset walk, on xy
+        for step, want in ((0.0, 0.0), (1.0, 0.5), (2.0, 1.0), (4.0, 2.0), (-2.0, -1.0)):
+            pp = list(p0)
+            pp[axis] += step
+            got = _k(oracle, 14, (1, 2, 0, 3, 4, 1, *pp), 3)
+            assert got[axis] == want and got[1 - axis] == 0.0
+    assert _k(oracle, 15, (1, 2, 3, 3, 5, 7)) == 52 == _k(oracle, 15, (-1, -2, -3, -3, -5, -7))   # surface_area
+    assert _k(oracle, 16, (1, 2, 3, 4, 5, 7)) == 2                                        # maximum_extent
+    assert _k(oracle, 16, (1, 2, 3, 4, 6, 5)) == 1
+    assert _k(oracle, 16, (1, 2, 3, 7, 5, 6)) == 0
+
+
+def test_swaps_handedness_kats(oracle):
+    """tests/src/transform.rs:80-100"""
+    ident = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+    swap_yz = [1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1]
+    flip_z = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1]
+    assert _k(oracle, 18, ident) == 0.0
+    assert _k(oracle, 18, swap_yz) == 1.0
+    assert _k(oracle, 18, flip_z) == 1.0
