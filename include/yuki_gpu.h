@@ -241,6 +241,16 @@ int yk_render(yk_context*, const yk_scene*, const yk_camera*, const yk_film_sett
 int yk_debug_ray(yk_context*, const yk_scene*, const yk_camera*, const yk_sampler*, const yk_integrator*,
                  uint32_t film_px_x, uint32_t film_px_y, yk_integrator_ray* rays, uint32_t cap, uint32_t* n_rays,
                  float* li_rgb, uint64_t* ray_count);
+/* BoundingVolumeHierarchy::intersect (bvh.rs:160-232) for n caller rays (xyz triples; t_max NULL = infinity): closest
+ * hit distance (inf on a miss), the hit shape's original id (-1 on a miss) and, when counts_out (2 per ray) is given, the
+ * traversal's (intersection_test_count, intersection_count) of bvh.rs:177-179. Replaces the reference's direct
+ * Scene::intersect callers outside the integrators. */
+int yk_trace(yk_context*, const yk_scene*, const float* o_xyz, const float* d_xyz, const float* t_max, uint32_t n,
+             float* t_out, int32_t* orig_id_out, uint32_t* counts_out);
+/* VisibilityTester::unoccluded's traversal (visibility.rs:6-23 -> any_intersect, bvh.rs:235-302) for n segments
+ * o -> o + d (d unnormalised, cut at t_max = 0.9999 as interaction.rs:57-58 spawns every shadow ray):
+ * occluded_out[i] = 1 when anything lies in between. */
+int yk_occluded(yk_context*, const yk_scene*, const float* o_xyz, const float* d_xyz, uint32_t n, uint8_t* occluded_out);
 /* Device synchronisation helpers for callers that time with their own CUDA events. */
 void* yk_context_stream(yk_context*);   /* cudaStream_t the renderer launches on */
 

@@ -89,6 +89,35 @@ class Scene:
         self._h = C.c_void_p()
         capi.check(capi.lib().yk_scene_create(ctx._h, C.byref(self.host.flat), C.byref(self._h)))
 
+    def intersect(self, o, d, t_max=None, counts: bool = True):
+        """`BoundingVolumeHierarchy::intersect` (bvh.rs:160-232) for a batch of rays: (t, original shape id, (tests, hits)
+        node counters); t = inf and id = -1 on a miss."""
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        assert d.shape[0] == n
+        t = np.zeros(n, np.float32)
+        ids = np.zeros(n, np.int32)
+        cnt = np.zeros((n, 2), np.uint32)
+        tm = None
+        if t_max is not None:
+            tm_arr = np.ascontiguousarray(t_max, np.float32).reshape(-1)
+            assert tm_arr.shape[0] == n
+            tm = capi.fptr(tm_arr)
+        capi.check(capi.lib().yk_trace(self.ctx._h, self._h, capi.fptr(o), capi.fptr(d), tm, n, capi.fptr(t), ids.ctypes.data,
+                                       cnt.ctypes.data if counts else None))
+        return t, ids, cnt
+
+    def occluded(self, o, d):
+        """`VisibilityTester::unoccluded` negated (visibility.rs:6-23) for a batch of segments o -> o + d."""
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        assert d.shape[0] == n
+        out = np.zeros(n, np.uint8)
+        capi.check(capi.lib().yk_occluded(self.ctx._h, self._h, capi.fptr(o), capi.fptr(d), n, out.ctypes.data))
+        return out
+
     def close(self):
         if self._h:
             capi.lib().yk_scene_destroy(self._h)

@@ -31,6 +31,7 @@
 #include "wf_trace.cuh"
 #include "wf_shade.cuh"
 #include "wf_film.cuh"
+#include "wf_query.cuh"
 #include "wf_scene_pack.cuh"
 
 // =====================================================================================================
@@ -967,6 +968,109 @@ int yk_debug_ray(yk_context* c, const yk_scene* sc, const yk_camera* cam, const 
     *n_rays = head.count;
     if (li_rgb) { li_rgb[0] = li[0]; li_rgb[1] = li[1]; li_rgb[2] = li[2]; }
     if (ray_count) *ray_count = st.ray_count;
+    return YK_OK;
+}
+
+
+// ---- ray-batch queries ------------------------------------------------------------------------------------
+namespace {
+struct QueryBuffers {
+    std::vector<void*> bag;
+    ~QueryBuffers() { free_bag(bag); }
+};
+int query_prepare(yk_context* c, const yk_scene* sc, uint32_t n, const char* who, uint32_t* chunk) {
+    if (sc->ctx != c) return yk_set_error(YK_ERR_INVALID, std::string(who) + ": scene belongs to another context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    (void)cudaGetLastError();
+    *chunk = std::min<uint32_t>(std::max<uint32_t>(n, 32u), 1u << 22);
+    Pipe& p = c->pipe[0];
+    if (p.wave_cap >= *chunk && p.wave_lights == sc->dev.n_lights) return YK_OK;  // a render's (larger) wavefront state is reused
+    return ensure_wave(&p, *chunk, sc->dev.n_lights, 0);
+}
+}  // namespace
+
+// BoundingVolumeHierarchy::intersect (bvh.rs:160-232) for n caller rays.
+int yk_trace(yk_context* c, const yk_scene* sc, const float* o_xyz, const float* d_xyz, const float* t_max, uint32_t n, float* t_out,
+             int32_t* orig_id_out, uint32_t* counts_out) {
+    if (!c || !sc || (n && (!o_xyz || !d_xyz || !t_out || !orig_id_out))) return yk_set_error(YK_ERR_INVALID, "yk_trace: null argument");
+    if (n == 0) return YK_OK;
+    for (size_t i = 0; t_max && i < n; ++i)
+        if (t_max[i] != t_max[i]) return yk_set_error(YK_ERR_INVALID, "yk_trace: NaN t_max (Ray::new, math/ray.rs)");
+    uint32_t chunk = 0;
+    int rc = query_prepare(c, sc, n, "yk_trace", &chunk);
+    if (rc != YK_OK) return rc;
+    Pipe& p = c->pipe[0];
+    cudaStream_t s = p.stream;
+    QueryBuffers q;
+    float *d_o = nullptr, *d_d = nullptr, *d_tm = nullptr, *d_t = nullptr;
+    int32_t* d_id = nullptr;
+    uint32_t* d_cnt = nullptr;
+    if ((rc = dev_alloc(q.bag, &d_o, (size_t)3 * chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_d, (size_t)3 * chunk)) != YK_OK ||
+        (rc = dev_alloc(q.bag, &d_tm, chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_t, chunk)) != YK_OK ||
+        (rc = dev_alloc(q.bag, &d_id, chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_cnt, (size_t)2 * chunk)) != YK_OK)
+        return rc;
+    const bool generic = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;
+    const int T = 256;
+    for (size_t first = 0; first < n; first += chunk) {
+        const uint32_t m = (uint32_t)std::min<size_t>(chunk, n - first);
+        CUDA_TRY(cudaMemcpyAsync(d_o, o_xyz + 3 * first, (size_t)3 * m * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_d, d_xyz + 3 * first, (size_t)3 * m * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (t_max) CUDA_TRY(cudaMemcpyAsync(d_tm, t_max + first, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, s));
+        IterCounters ctr{};
+        ctr.n_active = m;
+        CUDA_TRY(cudaMemcpyAsync(&p.d_ctr[0], &ctr, sizeof(ctr), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), s));
+        k_query_pack<<<(m + T - 1) / T, T, 0, s>>>(p.wave, d_o, d_d, t_max ? d_tm : nullptr, m);
+        const int blocks = grid_for(m, kTraceThreads, c->sm_count * std::max(1, c->occ_trace_closest));
+        if (generic) k_trace_closest<true, true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 0, &p.d_ctr[0]);
+        else k_trace_closest<true, false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 0, &p.d_ctr[0]);
+        k_query_unpack<<<(m + T - 1) / T, T, 0, s>>>(sc->dev, p.wave, m, d_t, d_id, counts_out ? d_cnt : nullptr);
+        CUDA_TRY(cudaMemcpyAsync(t_out + first, d_t, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(orig_id_out + first, d_id, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (counts_out) CUDA_TRY(cudaMemcpyAsync(counts_out + 2 * first, d_cnt, (size_t)2 * m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return YK_OK;
+}
+
+// VisibilityTester::unoccluded's traversal (visibility.rs:6-23 -> any_intersect, bvh.rs:235-302) for n caller segments
+// o -> o + d, cut at t_max = 0.9999 like every shadow ray of the reference (interaction.rs:57-58).
+int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const float* d_xyz, uint32_t n, uint8_t* occluded_out) {
+    if (!c || !sc || (n && (!o_xyz || !d_xyz || !occluded_out))) return yk_set_error(YK_ERR_INVALID, "yk_occluded: null argument");
+    if (n == 0) return YK_OK;
+    uint32_t chunk = 0;
+    int rc = query_prepare(c, sc, n, "yk_occluded", &chunk);
+    if (rc != YK_OK) return rc;
+    Pipe& p = c->pipe[0];
+    cudaStream_t s = p.stream;
+    QueryBuffers q;
+    float *d_o = nullptr, *d_d = nullptr;
+    uint8_t* d_out = nullptr;
+    if ((rc = dev_alloc(q.bag, &d_o, (size_t)3 * chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_d, (size_t)3 * chunk)) != YK_OK ||
+        (rc = dev_alloc(q.bag, &d_out, chunk)) != YK_OK)
+        return rc;
+    const bool generic = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;
+    RenderCfg cfg{};
+    cfg.integrator = YK_INTEGRATOR_PATH;
+    const int T = 256;
+    for (size_t first = 0; first < n; first += chunk) {
+        const uint32_t m = (uint32_t)std::min<size_t>(chunk, n - first);
+        CUDA_TRY(cudaMemcpyAsync(d_o, o_xyz + 3 * first, (size_t)3 * m * sizeof(float), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_d, d_xyz + 3 * first, (size_t)3 * m * sizeof(float), cudaMemcpyHostToDevice, s));
+        IterCounters ctr{};
+        ctr.mat[0] = m;  // all segments in the first material queue's range of shading positions
+        CUDA_TRY(cudaMemcpyAsync(&p.d_ctr[0], &ctr, sizeof(ctr), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), s));
+        k_query_pack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, d_o, d_d, m);
+        const int blocks = grid_for(m, kTraceThreads, c->sm_count * std::max(1, c->occ_trace_any));
+        if (generic) k_trace_shadow<true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
+        else k_trace_shadow<false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
+        k_query_unpack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, m, d_out);
+        CUDA_TRY(cudaMemcpyAsync(occluded_out + first, d_out, m, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    CUDA_TRY(cudaGetLastError());
     return YK_OK;
 }
 

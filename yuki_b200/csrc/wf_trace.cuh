@@ -20,6 +20,7 @@ namespace {
 //  * Triangles are stored transposed (x0 x1 x2 | y0 y1 y2 | z0 z1 z2), so the watertight test's axis permutation is
 //    three index offsets instead of 18 selects.
 constexpr uint32_t kNoNode = 0xffffffffu;
+constexpr uint32_t kKeyNever = 0xffffffffu;  // stack key of a child whose slab entry lies beyond its exit
 constexpr uint32_t kChunk = 64;
 #ifndef YK_REFILL_BELOW
 #define YK_REFILL_BELOW 22
@@ -69,10 +70,10 @@ __device__ __noinline__ bool sphere_slot_test(const yk_sphere* spheres, int tag,
 //    not depend on t_max except through the final `min(.., t_max)`, so the far child's clamped entry distance is kept
 //    as the stack entry's `key` and the deferred test is `key <= t_max` at pop time: no memory access for a popped
 //    node that misses, and only nodes whose box test passes are ever loaded (half the dependent loads of a one-node-
-//    per-visit walk). A far child that can never pass (entry beyond its own exit) gets a NaN key.
+//    per-visit walk). A far child that can never pass (entry beyond its own exit) gets the key kKeyNever.
 //  * counters: the closest-hit walk always drains its stack, so both tests of a record are counted when it is loaded
 //    and never-passing far children are not pushed; the any-hit walk ends early, so it counts a far child's test when
-//    it is popped (or tested on the spot) and pushes NaN-key entries too.
+//    it is popped (or tested on the spot) and pushes kKeyNever entries too.
 struct TraceLane {
     float ox, oy, oz, ix, iy, iz, t_max;
     float okx, oky, okz, sx, sy, sz;  // watertight test: permuted origin, shear
@@ -143,6 +144,16 @@ struct TraceLane {
             enter<GENERIC>(sc, sc.root_ref);
         }
     }
+    // The deferred box test of a stacked child: the reference's `lo <= min(hi, t_max)` (f32::min ignores a NaN) with
+    // `lo <= hi` already folded into the key. Compared as unsigned bit patterns: lo >= +0 and t_max >= +0 are ordered like
+    // their bits; a NaN t_max (a hit whose t is NaN: zero-length direction, inf * 0 in the edge functions) is 0x7fffffff
+    // and, as in the reference, stops constraining the boxes; kKeyNever fails against every t_max; the sentinel's key 0
+    // passes against every t_max, so a pop can never run below the stack.
+#ifdef YK_KEY_FLOAT_COMPARE  // A/B only: the float compare this replaced (runs below the stack when t_max becomes NaN)
+    __device__ __forceinline__ bool key_fails(float key) const { return !(key <= t_max); }
+#else
+    __device__ __forceinline__ bool key_fails(float key) const { return __float_as_uint(key) > __float_as_uint(t_max); }
+#endif
     __device__ __forceinline__ bool wants_box() const { return cur != kNoNode; }
     __device__ __forceinline__ bool wants_tri() const { return leaf_pos < leaf_end; }
     __device__ __forceinline__ void push(uint32_t sbase, uint32_t* deep_ref, float* deep_key, uint32_t ref, float key) {
@@ -171,13 +182,13 @@ struct TraceLane {
                     key = deep_key[depth];
                 }
                 if (ANYHIT) n_tests += ref != kNoNode ? 1u : 0u;
-            } while (!(key <= t_max));
+            } while (key_fails(key));
         } else {
             do {
                 sp -= kStackStride;
                 lds_entry(sp, &ref, &key);
                 if (ANYHIT) n_tests += ref != kNoNode ? 1u : 0u;
-            } while (!(key <= t_max));
+            } while (key_fails(key));
         }
         if (COUNTS) n_hits += ref != kNoNode ? 1u : 0u;
         return ref;
@@ -204,9 +215,9 @@ struct TraceLane {
         const uint32_t ref_n = __float_as_uint(n0.w), ref_f = __float_as_uint(f0.w);
         const bool hit_n = lo_n <= fminf(hi_n, t_max);
         const bool ok_f = !(lo_f > hi_f);  // can the far child pass at all? (a NaN hi is ignored by the reference's min)
-        const float key_f = ok_f ? lo_f : __int_as_float(0x7fc00000);
+        const float key_f = ok_f ? lo_f : __uint_as_float(kKeyNever);
         // near missed: nothing happens before the far child's test, t_max is what the pop would see
-        const bool hit_f = !hit_n && key_f <= t_max;
+        const bool hit_f = !hit_n && !key_fails(key_f);
         n_tests += (ANYHIT && hit_n) ? 1u : 2u;
         if (COUNTS) n_hits += (hit_n || hit_f) ? 1u : 0u;
         const bool do_push = hit_n && (ANYHIT || ok_f);
@@ -223,7 +234,7 @@ struct TraceLane {
                     sp -= kStackStride;
                     lds_entry(sp, &take, &key);
                     if (ANYHIT) n_tests += take != kNoNode ? 1u : 0u;
-                } while (!(key <= t_max));
+                } while (key_fails(key));
                 if (COUNTS) n_hits += take != kNoNode ? 1u : 0u;
             }
         }
