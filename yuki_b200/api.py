@@ -8,6 +8,7 @@ only marshals descriptors. It fails loudly when the CUDA library or a GPU is mis
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 import time
 from dataclasses import dataclass
@@ -281,12 +282,62 @@ class Film:
         n_tiles = ((w + settings.tile_dim - 1) // settings.tile_dim) * ((h + settings.tile_dim - 1) // settings.tile_dim)
         self.samples = np.zeros(n_tiles, np.uint16) if settings.accumulate else None
         self.dirty = False
+        self.meta = None   # what was rendered into it (set by render_progressive / Film.load)
 
     def clear(self):
         self.pixels[...] = 0.0
         if self.samples is not None:
             self.samples[...] = 0
         self.dirty = True
+
+    # ---- checkpoint / resume of an accumulating film -------------------------------------------
+    # The reference keeps the film's running sum and `samples[tile.index]` (film.rs:74, 260-272) but never writes them
+    # out. With seekable samplers a (pixel, sample index) evaluation does not depend on what was rendered before, so
+    # the pair (sum, counts) is a complete checkpoint: rendering the missing sample indices into a restored film gives
+    # the bits of an uninterrupted render (the film adds samples in ascending index order either way).
+    def save(self, path: str, meta: Optional[dict] = None):
+        """Writes pixels (+ per-tile sample counts and a small `meta` dict naming the render) to `path` (.npz) atomically:
+        the file is complete or absent, never torn, so a render killed mid-checkpoint resumes from the previous one."""
+        import json
+        tmp = f"{path}.tmp.{os.getpid()}"
+        arrays = {"pixels": self.pixels, "res": np.array(self.settings.res, np.int64), "tile_dim": np.array(self.settings.tile_dim, np.int64),
+                  "accumulate": np.array(1 if self.settings.accumulate else 0, np.int64),
+                  "meta": np.frombuffer(json.dumps(meta or {}, sort_keys=True).encode(), dtype=np.uint8)}
+        if self.samples is not None:
+            arrays["samples"] = self.samples
+        with open(tmp, "wb") as f:
+            np.savez(f, **arrays)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, path)
+
+    @staticmethod
+    def load(path: str, expect_meta: Optional[dict] = None) -> "Film":
+        """Restores a film written by `save`. `expect_meta`, when given, must equal the stored dict (a checkpoint of another
+        scene / sampler / integrator must not be continued)."""
+        import json
+        with np.load(path) as z:
+            fs = D.FilmSettings((int(z["res"][0]), int(z["res"][1])), int(z["tile_dim"]), accumulate=bool(int(z["accumulate"])))
+            film = Film(fs)
+            if z["pixels"].shape != film.pixels.shape or z["pixels"].dtype != np.float32:
+                raise ValueError(f"{path}: pixel array does not match the stored film settings")
+            film.pixels[...] = z["pixels"]
+            if film.samples is not None:
+                if "samples" not in z or z["samples"].shape != film.samples.shape:
+                    raise ValueError(f"{path}: per-tile sample counts missing or of the wrong size")
+                film.samples[...] = z["samples"]
+            meta = json.loads(bytes(z["meta"]).decode() or "{}")
+        if expect_meta is not None and json.loads(json.dumps(expect_meta, sort_keys=True)) != meta:
+            raise ValueError(f"{path}: checkpoint belongs to another render ({meta} != {expect_meta})")
+        film.meta = meta
+        film.dirty = True
+        return film
+
+
+def json_roundtrip(obj):
+    """`obj` as it comes back from a JSON file (tuples become lists), for comparing in-memory and stored metadata."""
+    import json
+    return json.loads(json.dumps(obj, sort_keys=True))
 
 
 @dataclass
@@ -386,6 +437,46 @@ class Renderer:
 
         self._thread = threading.Thread(target=work, daemon=True)
         self._thread.start()
+
+    def render_progressive(self, scene: Scene, camera_params: D.CameraParameters, film: Film, sampler: D.SamplerType,
+                           integrator: D.IntegratorType, samples_per_pass: int = 16, checkpoint_path: Optional[str] = None,
+                           max_passes: Optional[int] = None, render_fn=None, **render_kw):
+        """Accumulating render that can stop and continue (`render_manager.rs:135-143` renders one tile list per sample index
+        into a summing film; this drives it in passes of `samples_per_pass` indices). Starts at the film's first missing
+        sample index — 0 for a fresh film, k for one restored with `Film.load` — and, after every pass, updates
+        `film.samples` and (optionally) rewrites the checkpoint. Returns the number of sample indices the film now holds.
+        `render_fn(tiles, film_out)` defaults to this renderer's `render`; tests on CPU pass the oracle's."""
+        fs = film.settings
+        if not fs.accumulate or film.samples is None:
+            raise ValueError("render_progressive needs an accumulating film (FilmSettings.accumulate)")
+        spp = sampler.samples_per_pixel()
+        done = int(film.samples.min()) if film.samples.size else spp
+        if film.samples.size and int(film.samples.max()) != done:
+            raise ValueError("film tiles hold different sample counts: not a checkpoint of complete passes")
+        if done > spp:
+            raise ValueError(f"film already holds {done} samples per pixel, the sampler has {spp}")
+        meta = {"spp": spp, "sampler": [sampler.kind, sampler.nx, sampler.ny, bool(sampler.jitter), int(sampler.seed)],
+                "integrator": [integrator.kind, integrator.max_depth]}
+        if film.meta and film.meta != json_roundtrip(meta):
+            raise ValueError(f"film was rendered with other settings: {film.meta}")
+        film.meta = json_roundtrip(meta)
+        base = film_tiles(fs)
+        if render_fn is None:
+            def render_fn(tiles, film_out):
+                return self.render(scene, camera_params, fs, sampler, integrator, tiles=tiles, film_out=film_out, **render_kw)
+        passes = 0
+        while done < spp and (max_passes is None or passes < max_passes):
+            hi = min(spp, done + max(1, int(samples_per_pass)))
+            tiles = np.concatenate([base] * (hi - done))
+            tiles["sample"] = np.repeat(np.arange(done, hi, dtype=np.uint16), len(base))
+            render_fn(tiles, film.pixels)
+            np.add.at(film.samples, tiles["index"], 1)   # samples[tile.index] += 1, film.rs:270
+            film.dirty = True
+            done = hi
+            passes += 1
+            if checkpoint_path:
+                film.save(checkpoint_path, meta=film.meta)
+        return done
 
     def check_status(self):
         """Latest `RenderProgress`, or `RenderFinished` once the task is done; None when nothing new (renderer/mod.rs:61-120)."""
