@@ -221,7 +221,8 @@ typedef struct yk_host_scene yk_host_scene;
 const char* yk_last_error(void);
 int yk_context_create(int device_id, yk_context** out);
 void yk_context_destroy(yk_context*);
-/* Copies the flattened scene to device SoA buffers. Host arrays may be freed on return. */
+/* Copies the flattened scene to device SoA buffers. Host arrays may be freed on return. At most 32 lights (one bit each in
+ * the shading kernels' shadow-ray mask); more -> YK_ERR_INVALID. */
 int yk_scene_create(yk_context*, const yk_scene_desc*, yk_scene** out);
 void yk_scene_destroy(yk_scene*);
 /* Renders `tiles` (normally yk_film_tiles' spiral list, or this GPU's share of it) and writes the film.

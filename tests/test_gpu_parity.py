@@ -224,6 +224,30 @@ def test_distant_light_and_background_in_an_open_scene(gpu_ctx, oracle, xf, inte
     assert r.stats.ray_count == o_st.ray_count and r.stats.shadow_rays == o_st.shadow_rays
 
 
+def test_many_lights_and_the_light_limit(gpu_ctx, oracle, xf):
+    """32 lights (the shadow-ray mask's width) of every kind, folded in light order; a 33rd is refused at scene creation."""
+    scene, cam = scenes.material_room(xf)
+    rng = np.random.default_rng(4)
+    while len(scene.lights) < 32:
+        k = len(scene.lights)
+        pos = tuple(float(v) for v in rng.uniform((-1.0, 0.3, -1.0), (1.0, 1.1, 1.0)))
+        if k % 3 == 0:
+            scene.lights.append(D.Light(D.LIGHT_DISTANT, xf.identity(), (0.05, 0.05, 0.06), direction=tuple(float(v) for v in rng.uniform(-1, 1, 3))))
+        elif k % 3 == 1:
+            scene.lights.append(D.Light(D.LIGHT_POINT, xf.translation(pos), tuple(float(v) for v in rng.uniform(0.02, 0.1, 3))))
+        else:
+            spot = xf.mul(xf.translation(pos), xf.rotation(float(rng.uniform(0.5, 2.5)), (1.0, 0.2, 0.0)))
+            scene.lights.append(D.Light(D.LIGHT_SPOT, spot, (0.4, 0.4, 0.3), total_width_deg=40.0, falloff_start_deg=25.0))
+    film = D.FilmSettings((64, 36), 16)
+    for integ in (D.IntegratorType.path(4), D.IntegratorType.whitted(3)):
+        r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(2, 2), integ)
+        assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+        assert r.stats.shadow_rays == o_st.shadow_rays and r.stats.any_nodes == o_st.any_nodes
+    scene.lights.append(D.Light(D.LIGHT_POINT, xf.translation((0.0, 1.0, 0.0)), (0.1, 0.1, 0.1)))
+    with pytest.raises(RuntimeError, match="32 lights"):
+        api.Scene(gpu_ctx, scene)
+
+
 def test_round_trip_properties_at_full_size(gpu_ctx, xf):
     """Size-independent properties on the benchmark-size film (the oracle would take minutes here): rendering the two
     interleaved halves of the tile list separately and summing equals rendering all tiles; re-rendering is idempotent;

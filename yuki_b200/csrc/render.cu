@@ -406,7 +406,7 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     if (!d->n_nodes || !d->nodes || !d->n_tris || !d->tri_vertices || !d->tri_orig_id || !d->tri_material || !d->tri_area_light ||
         !d->tri_flags)
         return yk_set_error(YK_ERR_INVALID, "yk_scene_create: missing node / triangle arrays");
-    if (d->n_lights > (uint32_t)kMaxLights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 16 lights");
+    if (d->n_lights > (uint32_t)kMaxLights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 32 lights");
     if (d->n_materials > 0xffffffu) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: too many materials");
     CUDA_TRY(cudaSetDevice(c->device));
     auto sc = std::make_unique<yk_scene>();

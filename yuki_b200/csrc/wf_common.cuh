@@ -17,7 +17,7 @@ using namespace ykd;
 namespace {
 
 
-constexpr int kMaxLights = 16;
+constexpr int kMaxLights = 32;  // one bit per light in the shading kernels' shadow-ray mask
 constexpr int kStackDepth = 64;  // bvh.rs:172
 constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTraceThreads = 128;
