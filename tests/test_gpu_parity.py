@@ -248,6 +248,21 @@ def test_many_lights_and_the_light_limit(gpu_ctx, oracle, xf):
         api.Scene(gpu_ctx, scene)
 
 
+@pytest.mark.parametrize("integ", [D.IntegratorType.path(0), D.IntegratorType.path(1), D.IntegratorType.whitted(0), D.IntegratorType.whitted(1),
+                                   D.IntegratorType.bvh_intersections()])
+def test_degenerate_settings(gpu_ctx, oracle, xf, integ):
+    """max_depth 0 / 1 (path.rs:66: the loop body never / once runs), a 1x1 film, a tile larger than the film, one sample."""
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass")
+    for film, smp in ((D.FilmSettings((1, 1), 16), D.SamplerType.uniform(1)),
+                      (D.FilmSettings((23, 9), 64), D.SamplerType.stratified(1, 1)),
+                      (D.FilmSettings((17, 31), 7), D.SamplerType.stratified(2, 3, jitter=False))):
+        r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, smp, integ)
+        assert np.array_equal(r.hit_ids, o_ids)
+        assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+        assert r.stats.ray_count == o_st.ray_count and r.stats.shadow_rays == o_st.shadow_rays
+        assert r.stats.samples == film.res[0] * film.res[1] * smp.samples_per_pixel()
+
+
 def test_round_trip_properties_at_full_size(gpu_ctx, xf):
     """Size-independent properties on the benchmark-size film (the oracle would take minutes here): rendering the two
     interleaved halves of the tile list separately and summing equals rendering all tiles; re-rendering is idempotent;
