@@ -88,3 +88,16 @@ if which == "jitter_hf4":
         t0 = time.time()
         r = rn.render(dev, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8))
         print(f"rep {i}: device {r.stats.device_ms:.1f} ms wall {1e3*(time.time()-t0):.1f} ms closest {r.stats.trace_closest_ms:.1f} any {r.stats.trace_any_ms:.1f} shade {r.stats.shade_ms:.1f} launches {r.stats.kernel_launches}", flush=True)
+if which == "query":  # yk_trace / yk_occluded through the ABI with host arrays (copies included): incoherent rays on the 1 M-triangle mesh
+    s, c = scenes.heightfield(xf, 708, 708)
+    ctx = api.Context(0); dev = api.Scene(ctx, s)
+    rng = np.random.default_rng(1)
+    n = 1 << 23
+    o = rng.uniform((-0.7, -0.4, -0.7), (0.7, 0.6, 0.7), (n, 3)).astype(np.float32)
+    d = (rng.uniform((-0.7, -0.4, -0.7), (0.7, 0.6, 0.7), (n, 3)).astype(np.float32) - o)
+    for name, fn in (("yk_trace", lambda: dev.intersect(o, d)), ("yk_trace (no counters)", lambda: dev.intersect(o, d, counts=False)), ("yk_occluded", lambda: dev.occluded(o, d))):
+        best = 1e9
+        for i in range(4):
+            t0 = time.perf_counter(); r = fn(); best = min(best, time.perf_counter() - t0)
+        print(f"{name}: {n / best / 1e6:.1f} Mrays/s end to end ({n} incoherent rays, host arrays in and out)", flush=True)
+    dev.close(); ctx.close()

@@ -84,6 +84,12 @@ struct yk_context {
     int occ_trace_closest = 0, occ_trace_any = 0;
     int n_pipes_env = 0;  // YK_PIPES override (development)
     uint64_t mem_budget = 0;  // bytes of wavefront state per pipe the default batch size may use (set at the first render)
+    std::vector<void*> query_allocs;  // yk_trace / yk_occluded staging (rays in, results out), kept between calls
+    uint32_t query_cap = 0;
+    float *q_o = nullptr, *q_d = nullptr, *q_tm = nullptr, *q_t = nullptr;
+    int32_t* q_id = nullptr;
+    uint32_t* q_cnt = nullptr;
+    uint8_t* q_occ = nullptr;
     int stage_timing = 1;  // CUDA events per bounce: 1 = around the closest-hit kernel (the roofline figure), 2 = every stage
                            // (costs ~1.5 % of a Cornell render), 0 = none; environment variable YK_STAGE_TIMING
 };
@@ -389,6 +395,7 @@ void yk_context_destroy(yk_context* c) {
         }
         if (p.owns_stream) cudaStreamDestroy(p.stream);
     }
+    free_bag(c->query_allocs);
     cudaFree(c->d_tiles);
     cudaFree(c->d_tile_off);
     cudaFree(c->d_accum);
@@ -974,15 +981,25 @@ int yk_debug_ray(yk_context* c, const yk_scene* sc, const yk_camera* cam, const 
 
 // ---- ray-batch queries ------------------------------------------------------------------------------------
 namespace {
-struct QueryBuffers {
-    std::vector<void*> bag;
-    ~QueryBuffers() { free_bag(bag); }
-};
 int query_prepare(yk_context* c, const yk_scene* sc, uint32_t n, const char* who, uint32_t* chunk) {
     if (sc->ctx != c) return yk_set_error(YK_ERR_INVALID, std::string(who) + ": scene belongs to another context");
     CUDA_TRY(cudaSetDevice(c->device));
     (void)cudaGetLastError();
     *chunk = std::min<uint32_t>(std::max<uint32_t>(n, 32u), 1u << 22);
+    if (c->query_cap < *chunk) {  // staging grows to the largest chunk asked for and stays
+        free_bag(c->query_allocs);
+        c->query_cap = 0;
+        std::vector<void*>& bag = c->query_allocs;
+        int rc = YK_OK;
+        if ((rc = dev_alloc(bag, &c->q_o, (size_t)3 * *chunk)) != YK_OK || (rc = dev_alloc(bag, &c->q_d, (size_t)3 * *chunk)) != YK_OK ||
+            (rc = dev_alloc(bag, &c->q_tm, *chunk)) != YK_OK || (rc = dev_alloc(bag, &c->q_t, *chunk)) != YK_OK ||
+            (rc = dev_alloc(bag, &c->q_id, *chunk)) != YK_OK || (rc = dev_alloc(bag, &c->q_cnt, (size_t)2 * *chunk)) != YK_OK ||
+            (rc = dev_alloc(bag, &c->q_occ, *chunk)) != YK_OK) {
+            free_bag(bag);
+            return rc;
+        }
+        c->query_cap = *chunk;
+    }
     Pipe& p = c->pipe[0];
     if (p.wave_cap >= *chunk && p.wave_lights == sc->dev.n_lights) return YK_OK;  // a render's (larger) wavefront state is reused
     return ensure_wave(&p, *chunk, sc->dev.n_lights, 0);
@@ -1001,14 +1018,9 @@ int yk_trace(yk_context* c, const yk_scene* sc, const float* o_xyz, const float*
     if (rc != YK_OK) return rc;
     Pipe& p = c->pipe[0];
     cudaStream_t s = p.stream;
-    QueryBuffers q;
-    float *d_o = nullptr, *d_d = nullptr, *d_tm = nullptr, *d_t = nullptr;
-    int32_t* d_id = nullptr;
-    uint32_t* d_cnt = nullptr;
-    if ((rc = dev_alloc(q.bag, &d_o, (size_t)3 * chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_d, (size_t)3 * chunk)) != YK_OK ||
-        (rc = dev_alloc(q.bag, &d_tm, chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_t, chunk)) != YK_OK ||
-        (rc = dev_alloc(q.bag, &d_id, chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_cnt, (size_t)2 * chunk)) != YK_OK)
-        return rc;
+    float *d_o = c->q_o, *d_d = c->q_d, *d_tm = c->q_tm, *d_t = c->q_t;
+    int32_t* d_id = c->q_id;
+    uint32_t* d_cnt = c->q_cnt;
     const bool generic = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;
     const int T = 256;
     for (size_t first = 0; first < n; first += chunk) {
@@ -1044,12 +1056,8 @@ int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const flo
     if (rc != YK_OK) return rc;
     Pipe& p = c->pipe[0];
     cudaStream_t s = p.stream;
-    QueryBuffers q;
-    float *d_o = nullptr, *d_d = nullptr;
-    uint8_t* d_out = nullptr;
-    if ((rc = dev_alloc(q.bag, &d_o, (size_t)3 * chunk)) != YK_OK || (rc = dev_alloc(q.bag, &d_d, (size_t)3 * chunk)) != YK_OK ||
-        (rc = dev_alloc(q.bag, &d_out, chunk)) != YK_OK)
-        return rc;
+    float *d_o = c->q_o, *d_d = c->q_d;
+    uint8_t* d_out = c->q_occ;
     const bool generic = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;
     RenderCfg cfg{};
     cfg.integrator = YK_INTEGRATOR_PATH;
