@@ -101,3 +101,8 @@ if which == "query":  # yk_trace / yk_occluded through the ABI with host arrays 
             t0 = time.perf_counter(); r = fn(); best = min(best, time.perf_counter() - t0)
         print(f"{name}: {n / best / 1e6:.1f} Mrays/s end to end ({n} incoherent rays, host arrays in and out)", flush=True)
     dev.close(); ctx.close()
+if which == "whitted":  # config 1 (Cornell 512^2, Whitted depth 3, 16 spp) and a deeper tree
+    s, c = scenes.cornell(xf, light="point", tall_box="glass")
+    probe("cornell 512^2 whitted3 16spp", s, c, D.FilmSettings((512, 512), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(3), reps=4)
+    probe("cornell 1024^2 whitted3 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.whitted(3), reps=3)
+    probe("cornell 1024^2 whitted6 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(6), reps=3)
