@@ -44,7 +44,7 @@ def test_resume_equals_uninterrupted_render_with_the_oracle_as_renderer(tmp_path
     osc = oracle.OracleScene(scene)
 
     def render_fn_for(film):
-        return lambda tiles, film_out: osc.render(cam, fs, smp, integ, tiles=tiles, film_out=film_out, threads=2)
+        return lambda tiles, film_out: osc.render(cam, fs, smp, integ, tiles=tiles, film_out=film_out, threads=1)
 
     rn = api.Renderer.__new__(api.Renderer)   # the host logic only: no GPU context on this path
     whole, ck = _check_resume(tmp_path, rn, render_fn_for, fs, smp, integ, (None, cam))
@@ -91,6 +91,8 @@ def test_gpu_resume_equals_uninterrupted_render(tmp_path, gpu_ctx, oracle, xf):
     whole, _ = _check_resume(tmp_path, rn, lambda film: None, fs, smp, integ, (dev, cam))
     tiles = np.concatenate([api.film_tiles(fs)] * 9)
     tiles["sample"] = np.repeat(np.arange(9, dtype=np.uint16), len(tiles) // 9)
-    o_img, _, _ = oracle.OracleScene(scene).render(cam, fs, smp, integ, tiles=tiles)
+    # one worker: with several, the reference (and the oracle) add the samples of a pixel in whatever order the workers
+    # finish; the GPU adds them in tile-list order, which is the single-thread order (use_single_render_thread)
+    o_img, _, _ = oracle.OracleScene(scene).render(cam, fs, smp, integ, tiles=tiles, threads=1)
     assert np.array_equal(whole.pixels.view(np.uint32), o_img.view(np.uint32))
     dev.close()

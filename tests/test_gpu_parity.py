@@ -263,6 +263,30 @@ def test_degenerate_settings(gpu_ctx, oracle, xf, integ):
         assert r.stats.samples == film.res[0] * film.res[1] * smp.samples_per_pixel()
 
 
+def test_image_textured_roughness_is_remapped_with_glibc_logf(gpu_ctx, oracle, xf):
+    """Metal / Glossy roughness from an image texture with remap_roughness: roughness_to_alpha (trowbridge_reitz.rs:22-30)
+    runs per hit on the device, through the restated glibc logf (constant roughness is converted on the host)."""
+    scene, cam = scenes.material_room(xf)
+    rng = np.random.default_rng(8)
+    rough = np.repeat(rng.uniform(0.0, 0.95, (32, 32, 1)).astype(np.float32), 3, axis=2)   # includes values below the 1e-3 floor
+    rough[0, :4] = 0.0
+    t = scene.add_texture(D.Texture.from_image(rough))
+    n_mapped = 0
+    for i, m in enumerate(scene.materials):
+        if m.kind == D.MAT_METAL:
+            scene.materials[i] = D.Material(D.MAT_METAL, (m.tex[0], m.tex[1], t), remap_roughness=True)
+            n_mapped += 1
+        elif m.kind == D.MAT_GLOSSY:
+            scene.materials[i] = D.Material(D.MAT_GLOSSY, (m.tex[0], t), remap_roughness=True)
+            n_mapped += 1
+    assert n_mapped == 2
+    film = D.FilmSettings((160, 90), 16)
+    for integ in (D.IntegratorType.path(6), D.IntegratorType.whitted(3)):
+        r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(3, 3), integ)
+        assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
+        assert r.stats.ray_count == o_st.ray_count and r.stats.shadow_rays == o_st.shadow_rays
+
+
 def test_round_trip_properties_at_full_size(gpu_ctx, xf):
     """Size-independent properties on the benchmark-size film (the oracle would take minutes here): rendering the two
     interleaved halves of the tile list separately and summing equals rendering all tiles; re-rendering is idempotent;

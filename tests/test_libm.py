@@ -1,4 +1,4 @@
-"""yk_libm.h restates glibc's sinf / cosf / atanf / atan2f / acosf; on this host it must be bit-identical to the libm the
+"""yk_libm.h restates glibc's sinf / cosf / atanf / atan2f / acosf / logf; on this host it must be bit-identical to the libm the
 oracle calls."""
 import os
 import subprocess
@@ -85,3 +85,39 @@ def test_atanf_atan2f_acosf_bit_identical_to_host_libm(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     n, bad = out.stdout.split()
     assert out.returncode == 0 and int(bad) == 0 and int(n) > 100_000_000, out.stdout
+
+
+SRC_LOG = r'''
+#include <cstdio>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include "yk_libm.h"
+int main() {
+    unsigned long long n = 0, bad = 0;
+    for (uint64_t u = 0; u <= 0x7f800000ull; u += 3) {   // zero, subnormals, every binade, infinity
+        uint32_t b = (uint32_t)u; float x; memcpy(&x, &b, 4);
+        float a = logf(x), c = yklibm::logf_glibc(x);
+        bad += memcmp(&a, &c, 4) != 0; ++n;
+    }
+    for (uint32_t b = 0x3a000000u; b < 0x3f800000u; ++b) {   // every float of roughness_to_alpha's domain [1e-3, 1)
+        float x; memcpy(&x, &b, 4);
+        float a = logf(x), c = yklibm::logf_glibc(x);
+        bad += memcmp(&a, &c, 4) != 0; ++n;
+    }
+    float neg = yklibm::logf_glibc(-1.0f), nan_in = yklibm::logf_glibc(NAN);
+    bad += !(neg != neg) + !(nan_in != nan_in);
+    printf("%llu %llu\n", n, bad);
+    return bad != 0;
+}
+'''
+
+
+def test_logf_bit_identical_to_host_libm(tmp_path):
+    src = tmp_path / "t.cpp"
+    src.write_text(SRC_LOG)
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "yuki_b200", "csrc"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    n, bad = out.stdout.split()
+    assert out.returncode == 0 and int(bad) == 0 and int(n) > 700_000_000, out.stdout

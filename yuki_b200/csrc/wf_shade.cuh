@@ -213,8 +213,8 @@ __device__ __noinline__ RGB tex_image_eval(const DevTexture& t, V2 uv) {
     return rgb(__ldg(px), __ldg(px + 1), __ldg(px + 2));
 }
 
-__device__ __forceinline__ float roughness_to_alpha(float r) {  // trowbridge_reitz.rs:22-30
-    const float x = (float)log((double)fmaxf(r, 0.001f));
+static __device__ __noinline__ float roughness_to_alpha(float r) {  // trowbridge_reitz.rs:22-30 (rare: image-textured roughness)
+    const float x = yklibm::logf_glibc(fmaxf(r, 0.001f));  // f32::ln = glibc's logf, restated (yk_libm.h)
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 

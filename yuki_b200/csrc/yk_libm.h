@@ -272,4 +272,49 @@ YK_HD float acosf_glibc(float x) {
     return 2.0f * (df + w);
 }
 
+// ---- logf -------------------------------------------------------------------------------------------
+// glibc 2.39's logf is the Arm Optimized Routines one: k = exponent, a 16-entry table of (1/c, log c) by the top four
+// mantissa bits, r = z/c - 1 and a cubic in r, all in f64, rounded once. Used by roughness_to_alpha
+// (trowbridge_reitz.rs:22-30) when a Metal / Glossy roughness comes from an image texture (constant textures are
+// converted on the host). tests/test_libm.py compares every positive float with the host libm.
+#if defined(__CUDACC__)  // the table lives in device memory there (a local copy would cost every caller 256 B of stack)
+#define YK_LOGF_FN __device__ inline
+#define YK_LOGF_TABLE static __device__ const
+#else
+#define YK_LOGF_FN inline
+#define YK_LOGF_TABLE static const
+#endif
+YK_LOGF_TABLE double kLogfTable[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2},
+};
+YK_LOGF_FN float logf_glibc(float x) {
+    const double ln2 = 0x1.62e42fefa39efp-1, a0 = -0x1.00ea348b88334p-2, a1 = 0x1.5575b0be00b6ap-2, a2 = -0x1.ffffef20a4123p-2;
+    uint32_t ix = bits_(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {  // zero, subnormal, negative, inf, NaN
+        if (ix * 2u == 0u) return -from_bits_(0x7f800000u);
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) return from_bits_(0x7fc00000u);
+        ix = bits_(x * 0x1p23f) - (23u << 23);
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int32_t)tmp >> 23;
+    const double z = (double)from_bits_(ix - (tmp & 0xff800000u));
+    const double r = mul_(z, kLogfTable[i][0]) - 1.0;
+    const double y0 = kLogfTable[i][1] + mul_((double)k, ln2);
+    const double r2 = mul_(r, r);
+    double y = mul_(a1, r) + a2;
+    y = mul_(a0, r2) + y;
+    y = mul_(y, r2) + (y0 + r);
+    return (float)y;
+}
+
 }  // namespace yklibm
