@@ -27,6 +27,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries the one JSON line and nothing else: whatever libraries write to file descriptor 1 while the bench runs
+# (NCCL's version banner under NCCL_DEBUG=VERSION, NCCL_DEBUG=INFO output) is sent to stderr; emit() writes the line to
+# the real stdout.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_REAL_STDOUT = None  # main() moves file descriptor 1 aside
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 from yuki_b200 import desc as D  # noqa: E402
 
@@ -173,7 +186,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def large_scene_leg(api, xf, ctx, peak):
@@ -353,7 +366,7 @@ def run_ours(args):
                                     "sample": sample, "seconds": st.seconds}
         if large is not None:
             line["large_scene"] = large
-        print(json.dumps(line), flush=True)
+        emit(line)
     dev.close()
     ctx.close()
     if world > 1:
@@ -371,6 +384,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = BASELINE.json configs[1] (default, the contract's line); c5 = configs[4]")
     ap.add_argument("--spp-side", type=int, default=0, help="override the stratified grid side (spp = side^2); the line's config says so")
     args = ap.parse_args()
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     select_workload(args.workload, args.spp_side)
     if args.impl == "reference":
         run_reference(args)
