@@ -167,3 +167,45 @@ def test_batches_above_one_chunk_equal_small_batches(gpu_ctx, oracle, xf):
     o_img, _, _ = osc.render(cam, film, D.SamplerType.uniform(1), D.IntegratorType.bvh_intersections())
     assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
     dev.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_callers_on_one_context_are_serialised(gpu_ctx, xf):
+    """several caller threads may use one context; the library serialises the calls that share its pipes.
+    (ctypes drops the GIL during a call, so these really overlap.)"""
+    import threading
+    scene, cam = scenes.heightfield(xf, 48, 48, seed=2)
+    dev = api.Scene(gpu_ctx, scene)
+    rng = np.random.default_rng(6)
+    o, d = _random_rays(rng, 400000, (-0.7, -0.4, -0.7), (0.7, 0.6, 0.7))
+    film = D.FilmSettings((256, 192), 16)
+    smp, integ = D.SamplerType.stratified(2, 2), D.IntegratorType.path(4)
+    want_t, want_ids, want_cnt = dev.intersect(o, d)
+    want_occ = dev.occluded(o, d)
+    want_film = api.Renderer(gpu_ctx).render(dev, cam, film, smp, integ).film
+    errors = []
+
+    def queries():
+        try:
+            for _ in range(6):
+                t, ids, cnt = dev.intersect(o, d)
+                assert np.array_equal(t.view(np.uint32), want_t.view(np.uint32)) and np.array_equal(ids, want_ids) and np.array_equal(cnt, want_cnt)
+                assert np.array_equal(dev.occluded(o, d), want_occ)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def renders():
+        try:
+            rn = api.Renderer(gpu_ctx)
+            for _ in range(6):
+                assert np.array_equal(rn.render(dev, cam, film, smp, integ).film.view(np.uint32), want_film.view(np.uint32))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=queries), threading.Thread(target=renders), threading.Thread(target=queries)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    dev.close()

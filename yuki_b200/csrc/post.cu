@@ -14,6 +14,7 @@
 #include "yuki_gpu.h"
 
 int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
+int yk_context_activate(yk_context* c);                 // render.cu: cudaSetDevice(the context's device)
 
 namespace {
 
@@ -107,6 +108,7 @@ int yk_tonemap_filmic(yk_context* c, const float* film_rgb, uint32_t res_x, uint
                       uint32_t tile_dim, float exposure, float* out_rgb) {
     if (!c || !film_rgb || !out_rgb || !res_x || !res_y) return yk_set_error(YK_ERR_INVALID, "yk_tonemap_filmic: null / empty argument");
     if (tile_samples && !tile_dim) return yk_set_error(YK_ERR_INVALID, "yk_tonemap_filmic: tile_dim is zero");
+    if (int rc = yk_context_activate(c)) return rc;
     cudaStream_t s = (cudaStream_t)yk_context_stream(c);
     const size_t n = (size_t)res_x * res_y, bytes = n * 3 * sizeof(float);
     float *d_in = nullptr, *d_out = nullptr, *d_aux = nullptr;
@@ -130,6 +132,7 @@ int yk_heatmap(yk_context* c, const float* film_rgb, uint32_t res_x, uint32_t re
     if (!c || !film_rgb || !out_rgb || !res_x || !res_y || !min_val || !max_val)
         return yk_set_error(YK_ERR_INVALID, "yk_heatmap: null / empty argument");
     if (channel > 3) return yk_set_error(YK_ERR_INVALID, "yk_heatmap: channel must be 0..3 (R, G, B, luminance)");
+    if (int rc = yk_context_activate(c)) return rc;
     cudaStream_t s = (cudaStream_t)yk_context_stream(c);
     const size_t n = (size_t)res_x * res_y, bytes = n * 3 * sizeof(float);
     float *d_in = nullptr, *d_out = nullptr, *d_aux = nullptr;

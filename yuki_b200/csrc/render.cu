@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
@@ -69,6 +70,7 @@ struct Pipe {
 };
 
 struct yk_context {
+    std::recursive_mutex mu;  // calls that use the context's pipes are serialised (one context, many caller threads)
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -334,6 +336,12 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
 }
 
 }  // namespace
+
+// Makes the context's device current on the calling thread (post.cu: the display passes may be called from any thread).
+int yk_context_activate(yk_context* c) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    return YK_OK;
+}
 
 extern "C" {
 
@@ -635,6 +643,7 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
     if (in->kind == YK_INTEGRATOR_WHITTED && in->max_depth > 24)
         return yk_set_error(YK_ERR_INVALID, "yk_render: whitted max_depth above 24 is not supported");
     if (n_tiles && !tiles) return yk_set_error(YK_ERR_INVALID, "yk_render: null tile list");
+    std::lock_guard<std::recursive_mutex> guard(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
     (void)cudaGetLastError();  // do not inherit a stale error from an unrelated earlier call
     cudaStream_t s = c->stream;
@@ -1013,6 +1022,7 @@ int yk_trace(yk_context* c, const yk_scene* sc, const float* o_xyz, const float*
     if (n == 0) return YK_OK;
     for (size_t i = 0; t_max && i < n; ++i)
         if (t_max[i] != t_max[i]) return yk_set_error(YK_ERR_INVALID, "yk_trace: NaN t_max (Ray::new, math/ray.rs)");
+    std::lock_guard<std::recursive_mutex> guard(c->mu);
     uint32_t chunk = 0;
     int rc = query_prepare(c, sc, n, "yk_trace", &chunk);
     if (rc != YK_OK) return rc;
@@ -1051,6 +1061,7 @@ int yk_trace(yk_context* c, const yk_scene* sc, const float* o_xyz, const float*
 int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const float* d_xyz, uint32_t n, uint8_t* occluded_out) {
     if (!c || !sc || (n && (!o_xyz || !d_xyz || !occluded_out))) return yk_set_error(YK_ERR_INVALID, "yk_occluded: null argument");
     if (n == 0) return YK_OK;
+    std::lock_guard<std::recursive_mutex> guard(c->mu);
     uint32_t chunk = 0;
     int rc = query_prepare(c, sc, n, "yk_occluded", &chunk);
     if (rc != YK_OK) return rc;
