@@ -1,6 +1,6 @@
 """Diagnostic: per-pixel comparison of the CUDA path and the oracle on a small scene."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from yuki_b200 import api, desc as D, scenes, transforms as xf
 from oracle import oracle as O
