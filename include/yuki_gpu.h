@@ -252,6 +252,12 @@ int yk_trace(yk_context*, const yk_scene*, const float* o_xyz, const float* d_xy
  * o -> o + d (d unnormalised, cut at t_max = 0.9999 as interaction.rs:57-58 spawns every shadow ray):
  * occluded_out[i] = 1 when anything lies in between. */
 int yk_occluded(yk_context*, const yk_scene*, const float* o_xyz, const float* d_xyz, uint32_t n, uint8_t* occluded_out);
+/* Sampler::{start_pixel_sample(p, index, 0), get_1d, get_2d} (sampling/mod.rs:46-57, uniform.rs:72-94, stratified.rs:90-143)
+ * on the device, for n (pixel x, pixel y, sample index) triples: every triple starts a sampler the way Integrator::render
+ * does (integrators/mod.rs:163) and performs the draws of `pattern` (1 = get_1d: one float, 2 = get_2d: two floats);
+ * `out` receives sum(pattern) floats per triple. The component-level view of what the kernels draw per path. */
+int yk_sampler_draws(yk_context*, const yk_sampler*, const uint32_t* pixel_index_xyi, uint32_t n, const uint8_t* pattern,
+                     uint32_t n_pattern, float* out);
 /* Device synchronisation helpers for callers that time with their own CUDA events. */
 void* yk_context_stream(yk_context*);   /* cudaStream_t the renderer launches on */
 

@@ -131,6 +131,17 @@ class Scene:
             pass
 
 
+def sampler_draws(ctx: Context, sampler: D.SamplerType, pixel_index, pattern) -> np.ndarray:
+    """`Sampler::{start_pixel_sample, get_1d, get_2d}` on the device: for every (x, y, sample index) row of `pixel_index`
+    the draws of `pattern` (1 = get_1d, 2 = get_2d) after `start_pixel_sample(p, index, 0)`; returns (n, sum(pattern))."""
+    pi = np.ascontiguousarray(pixel_index, np.uint32).reshape(-1, 3)
+    pat = bytes(pattern)
+    out = np.zeros((pi.shape[0], sum(pattern)), np.float32)
+    sm = capi.sampler(sampler)
+    capi.check(capi.lib().yk_sampler_draws(ctx._h, C.byref(sm), pi.ctypes.data, pi.shape[0], pat, len(pat), capi.fptr(out)))
+    return out
+
+
 def make_camera(params: D.CameraParameters, film: D.FilmSettings) -> capi.Camera:
     """Camera::new (camera.rs:52-102)."""
     cam = capi.Camera()

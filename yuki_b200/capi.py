@@ -163,7 +163,7 @@ EXPORTS = [
     "yk_context_stream", "yk_bvh_build", "yk_host_scene_build", "yk_host_scene_destroy", "yk_host_scene_flat", "yk_camera_make",
     "yk_film_tiles", "yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_new", "yk_xf_look_at",
     "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy", "yk_write_exr", "yk_tonemap_filmic", "yk_heatmap", "yk_pbrt_load", "yk_pbrt_view", "yk_pbrt_destroy", "yk_mitsuba_load",
-    "yk_debug_ray", "yk_trace", "yk_occluded",
+    "yk_debug_ray", "yk_trace", "yk_occluded", "yk_sampler_draws",
 ]
 
 _lib = None
@@ -193,6 +193,7 @@ def lib():
                                C.POINTER(u32), fp, C.POINTER(C.c_uint64)]
     L.yk_trace.argtypes = [vp, vp, fp, fp, fp, u32, fp, vp, vp]
     L.yk_occluded.argtypes = [vp, vp, fp, fp, u32, vp]
+    L.yk_sampler_draws.argtypes = [vp, C.POINTER(Sampler), vp, u32, C.c_char_p, u32, fp]
     L.yk_bvh_build.argtypes = [fp, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u32)]
     L.yk_host_scene_build.argtypes = [C.POINTER(HostSceneDesc), C.POINTER(vp)]
     L.yk_host_scene_destroy.argtypes = [vp]

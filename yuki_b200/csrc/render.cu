@@ -1093,4 +1093,56 @@ int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const flo
     return YK_OK;
 }
 
+
+// Sampler::{start_pixel_sample, get_1d, get_2d} evaluated on the device for n (pixel x, pixel y, sample index) triples.
+int yk_sampler_draws(yk_context* c, const yk_sampler* sm, const uint32_t* pixel_index_xyi, uint32_t n, const uint8_t* pattern,
+                     uint32_t n_pattern, float* out) {
+    if (!c || !sm || (n && (!pixel_index_xyi || !out)) || (n_pattern && !pattern)) return yk_set_error(YK_ERR_INVALID, "yk_sampler_draws: null argument");
+    if (sm->kind > YK_SAMPLER_STRATIFIED) return yk_set_error(YK_ERR_INVALID, "yk_sampler_draws: unknown sampler");
+    const uint32_t spp = sm->kind == YK_SAMPLER_UNIFORM ? sm->nx : sm->nx * sm->ny;
+    if (spp == 0 || spp > 0x10000u) return yk_set_error(YK_ERR_INVALID, "yk_sampler_draws: samples per pixel must be in 1..65536");
+    uint32_t floats = 0;
+    for (uint32_t k = 0; k < n_pattern; ++k) {
+        if (pattern[k] != 1 && pattern[k] != 2) return yk_set_error(YK_ERR_INVALID, "yk_sampler_draws: pattern entries are 1 (get_1d) or 2 (get_2d)");
+        floats += pattern[k];
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (pixel_index_xyi[3 * i] > 0xffffu || pixel_index_xyi[3 * i + 1] > 0xffffu || pixel_index_xyi[3 * i + 2] > 0xffffu)
+            return yk_set_error(YK_ERR_INVALID, "yk_sampler_draws: pixel coordinates and sample index must fit u16 (integrators/mod.rs:140-141)");
+    if (n == 0 || floats == 0) return YK_OK;
+    std::lock_guard<std::recursive_mutex> guard(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    SamplerCfg cfg{};
+    cfg.kind = sm->kind;
+    cfg.nx = sm->nx;
+    cfg.ny = sm->kind == YK_SAMPLER_UNIFORM ? 1u : sm->ny;
+    cfg.jitter = sm->jitter;
+    cfg.seed = sm->seed;
+    cfg.div_nx = FastDiv::make(cfg.nx);
+    cfg.div_ny = FastDiv::make(cfg.ny);
+    cfg.div_n = FastDiv::make(cfg.nx * cfg.ny);
+    std::vector<void*> bag;
+    uint32_t* d_in = nullptr;
+    uint8_t* d_pat = nullptr;
+    float* d_out = nullptr;
+    int rc = YK_OK;
+    if ((rc = dev_alloc(bag, &d_in, (size_t)3 * n)) != YK_OK || (rc = dev_alloc(bag, &d_pat, n_pattern)) != YK_OK ||
+        (rc = dev_alloc(bag, &d_out, (size_t)n * floats)) != YK_OK) {
+        free_bag(bag);
+        return rc;
+    }
+    cudaStream_t s = c->stream;
+    cudaError_t e = cudaMemcpyAsync(d_in, pixel_index_xyi, (size_t)3 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pat, pattern, n_pattern, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        k_sampler_draws<<<(n + 127) / 128, 128, 0, s>>>(cfg, d_in, n, d_pat, n_pattern, floats, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * floats * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    free_bag(bag);
+    if (e != cudaSuccess) return yk_set_error(YK_ERR_CUDA, std::string("yk_sampler_draws: ") + cudaGetErrorString(e));
+    return YK_OK;
+}
+
 }  // extern "C"

@@ -47,4 +47,26 @@ __global__ void k_query_unpack_segments(Wave w, uint32_t n, uint8_t* __restrict_
     out[i] = w.L[i].x == 0.0f ? 1 : 0;
 }
 
+// Sampler::{start_pixel_sample(p, index, 0), get_1d, get_2d} (sampling/mod.rs:46-57, uniform.rs:72-94, stratified.rs:90-143)
+// for n (pixel, sample index) pairs: each thread starts a sampler the way Integrator::render does (integrators/mod.rs:163)
+// and performs the same sequence of draws (pattern[k] = 1: get_1d, 2: get_2d); out holds sum(pattern) floats per pair.
+__global__ void k_sampler_draws(SamplerCfg cfg, const uint32_t* __restrict__ pixel_index, uint32_t n, const uint8_t* __restrict__ pattern,
+                                uint32_t n_pattern, uint32_t floats_per_pair, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t px = pixel_index[3 * i], py = pixel_index[3 * i + 1], index = pixel_index[3 * i + 2];
+    SamplerState s;
+    s.start(cfg, px, py, index, (hash_pixel(px, py) << 1) | 1ULL, 0);
+    float* o = out + (size_t)i * floats_per_pair;
+    for (uint32_t k = 0; k < n_pattern; ++k) {
+        if (pattern[k] == 1) {
+            *o++ = s.get_1d(cfg);
+        } else {
+            const V2 u = s.get_2d(cfg);
+            *o++ = u.x;
+            *o++ = u.y;
+        }
+    }
+}
+
 }  // namespace
