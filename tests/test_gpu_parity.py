@@ -198,24 +198,9 @@ def test_whitted_is_bit_identical_to_the_oracle(gpu_ctx, oracle, xf):
         assert r.stats.ray_count == o_st.ray_count and r.stats.shadow_rays == o_st.shadow_rays
 
 
-def _open_scene(xf):
-    """Objects of every material on a floor under a sky: rays leave the scene at every depth (background term), lit by a
-    DistantLight (distant_light.rs:17-43) and a point light."""
-    s = D.SceneDesc(background=(0.2, 0.25, 0.3))
-    zero = s.add_texture(D.Texture.constant(0.0))
-    floor = s.add_material(D.Material(D.MAT_MATTE, (s.add_texture(D.Texture.constant(0.6, 0.6, 0.55)), zero)))
-    p, i = scenes._quad([(-2, 0, -2), (-2, 0, 2), (2, 0, 2), (2, 0, -2)])
-    s.meshes.append(D.Mesh(xf.identity(), p, i, floor))
-    scenes.add_material_objects(xf, s)
-    s.lights.append(D.Light(D.LIGHT_DISTANT, xf.identity(), (2.0, 1.9, 1.7), direction=(0.3, 1.0, 0.2)))
-    s.lights.append(D.Light(D.LIGHT_POINT, xf.translation((-0.8, 1.5, 1.0)), (1.5, 1.5, 1.8)))
-    cam = D.CameraParameters((0.0, 0.9, 2.6), (0.0, 0.2, 0.0), fov_axis=D.FOV_X, fov_deg=40.0)
-    return s, cam
-
-
 @pytest.mark.parametrize("integ", [D.IntegratorType.path(6), D.IntegratorType.whitted(4)])
 def test_distant_light_and_background_in_an_open_scene(gpu_ctx, oracle, xf, integ):
-    scene, cam = _open_scene(xf)
+    scene, cam = scenes.open_scene(xf)
     film = D.FilmSettings((120, 80), 16)
     r, o_img, o_ids, o_st = _both(gpu_ctx, oracle, xf, scene, cam, film, D.SamplerType.stratified(3, 3), integ)
     assert np.array_equal(r.hit_ids, o_ids)

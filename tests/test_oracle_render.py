@@ -18,7 +18,13 @@ def golden_cases(xf):
     room, rcam = scenes.material_room(xf)
     hf, hcam = scenes.heightfield(xf, 48, 48, seed=3)
     film = D.FilmSettings((48, 48), 16)
+    c_sphere, _ = scenes.cornell(xf, light="rect", tall_box="glass", sphere=True, split_method=D.SPLIT_MIDDLE)
+    sky, scam = scenes.open_scene(xf)
     return {
+        "cornell_sphere_path6_s2x2": (c_sphere, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.path(6)),
+        "cornell_sphere_whitted4_s2x2": (c_sphere, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(4)),
+        "open_scene_distant_path6_s3x3": (sky, scam, D.FilmSettings((60, 40), 16), D.SamplerType.stratified(3, 3), D.IntegratorType.path(6)),
+        "room_whitted5_s2x2": (room, rcam, D.FilmSettings((64, 36), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(5)),
         "cornell_point_whitted3_s2x2": (c_point, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(3)),
         "cornell_rect_path8_s2x2": (c_rect, cam, film, D.SamplerType.stratified(2, 2), D.IntegratorType.path(8)),
         "cornell_rect_path8_uniform3": (c_rect, cam, film, D.SamplerType.uniform(3), D.IntegratorType.path(8)),

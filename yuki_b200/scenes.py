@@ -313,6 +313,21 @@ def material_room(xf, split_method=D.SPLIT_SAH):
     return s, cam
 
 
+def open_scene(xf):
+    """Objects of every material on a floor under a sky: rays leave the scene at every depth (background term), lit by a
+    DistantLight (distant_light.rs:17-43) and a point light."""
+    s = D.SceneDesc(background=(0.2, 0.25, 0.3))
+    zero = s.add_texture(D.Texture.constant(0.0))
+    floor = s.add_material(D.Material(D.MAT_MATTE, (s.add_texture(D.Texture.constant(0.6, 0.6, 0.55)), zero)))
+    p, i = _quad([(-2, 0, -2), (-2, 0, 2), (2, 0, 2), (2, 0, -2)])
+    s.meshes.append(D.Mesh(xf.identity(), p, i, floor))
+    add_material_objects(xf, s)
+    s.lights.append(D.Light(D.LIGHT_DISTANT, xf.identity(), (2.0, 1.9, 1.7), direction=(0.3, 1.0, 0.2)))
+    s.lights.append(D.Light(D.LIGHT_POINT, xf.translation((-0.8, 1.5, 1.0)), (1.5, 1.5, 1.8)))
+    cam = D.CameraParameters((0.0, 0.9, 2.6), (0.0, 0.2, 0.0), fov_axis=D.FOV_X, fov_deg=40.0)
+    return s, cam
+
+
 def terrain_room(xf, nx=3163, nz=1581, seed=5, split_method=D.SPLIT_SAH):
     """Config 5: jittered terrain (3163 x 1581 quads = 10 001 406 triangles) with the config-4 objects floating above,
     lit by the same point / spot / rect lights; open sky (grey background)."""
