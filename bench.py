@@ -49,13 +49,17 @@ SPP_NX = SPP_NY = 32
 MAX_DEPTH = 8
 CPU_SAMPLE_SPP = 32  # bounded CPU sample: sample indices 0..31 of every pixel (accumulate-mode tiles), ~10 s on 15 host threads
 SCENE = "cornell"
+# The device-resident leg (`value`, `roofline`) runs on one pipe so that the CUDA-event time of a kernel launch is the kernel's
+# own; the end-to-end leg (`e2e`) makes the call a user makes, with the library's default of two overlapping pipes.
+VALUE_PIPES = 1
 
 
 def select_workload(name, spp_side):
     """The default (and the driver's) workload is BASELINE.json configs[1]. `--workload c5` switches to configs[4] (the
     10 M-triangle scene at 3840x2160, Path 8, 64x64 = 4096 spp) for scaling studies; `--spp-side` shortens either."""
-    global WORKLOAD, RES, SPP_NX, SPP_NY, SCENE, CPU_SAMPLE_SPP
+    global WORKLOAD, RES, SPP_NX, SPP_NY, SCENE, CPU_SAMPLE_SPP, VALUE_PIPES
     if name == "c5":
+        VALUE_PIPES = 0  # scaling studies: the library's default (two pipes) on every leg
         SCENE, RES, SPP_NX, SPP_NY = "terrain", (3840, 2160), 64, 64
         CPU_SAMPLE_SPP = 1  # one sample index of every pixel: 8.3 M samples
         WORKLOAD = "10M-triangle terrain + material objects 3840x2160, Path max_depth 8, 4096 spp stratified 64x64"
@@ -254,7 +258,7 @@ def run_ours(args):
         def step():
             flush.zero_()
             d_film.zero_()
-            r = rn.render(dev, cam, film, sampler, integ, tiles=my_tiles, device_film_ptr=d_film.data_ptr())
+            r = rn.render(dev, cam, film, sampler, integ, tiles=my_tiles, device_film_ptr=d_film.data_ptr(), pipes=VALUE_PIPES)
             if world > 1:
                 dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)  # tiles are disjoint: sum == gather, bit-exact
             return r.stats
@@ -341,7 +345,10 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tile_dim": 16, "partition": f"spiral tiles interleaved over {world} rank(s)",
                        "l2": "256 MB L2 flush between steps; wavefront state (several GB per batch) exceeds the 126 MB L2" + ("; the 37-node scene is cache-resident by nature" if SCENE == "cornell" else ""),
-                       "wavefront": "up to 16 Mi paths per batch, queue lengths on the device (no host sync per bounce)"},
+                       "wavefront": "up to 16 Mi paths per batch, queue lengths on the device (no host sync per bounce)",
+                       "pipes": ("value / roofline: one pipe, so that a kernel's event-bracketed time is its own; e2e: the library default, "
+                                 "two pipes overlapping one batch's shading with the other's traversal") if VALUE_PIPES == 1
+                       else "library default (two pipes) on every leg"},
             "mrays_per_s": float(counts[0].item()) / (ms_total / 1e3) / 1e6,
             "mrays_per_s_total": float((counts[0] + counts[1]).item()) / (ms_total / 1e3) / 1e6,
             "gpu_launches": int(counts[2].item()),

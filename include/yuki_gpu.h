@@ -192,7 +192,7 @@ typedef struct {
     uint32_t wavefront_paths;   /* paths in flight per batch; 0 = default */
     int32_t* hit_ids;           /* optional res_x*res_y out: original triangle id of the primary hit of sample `aux_sample` (-1 miss) */
     uint32_t aux_sample;
-    uint32_t pipes;             /* wavefront batches in flight on separate CUDA streams: 1 or 2; 0 = chosen from the scene */
+    uint32_t pipes;             /* wavefront batches in flight on separate CUDA streams: 1 or 2; 0 = default (2; 1 for Whitted) */
     yk_progress_fn progress;
     void* progress_user;
 } yk_render_opts;

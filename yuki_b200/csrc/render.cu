@@ -752,10 +752,11 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
         // Pipes: pixel groups alternate between the streams, so one group's latency-bound shading overlaps the other's
         // issue-bound traversal. A pixel's samples stay on one pipe, in order (the film sum is order-dependent).
         // The accumulating film adds with atomics across tiles, so it keeps to one stream.
-        // Default: a second pipe only where a bounce is many small launches (several material kinds / lights), measured
-        // +17 % on the config-4 room and +5 % on the Cornell box (profiles/r01); YK_PIPES / opts->pipes override.
-        int n_pipes = c->n_pipes_env > 0 ? c->n_pipes_env
-                                         : ((__builtin_popcount(sc->material_kinds) + (int)sc->dev.n_lights >= 5) ? 2 : 1);
+        // Default: two pipes. Measured on one box with the current kernels (profiles/r01/README.md): Cornell +5 %, config-4
+        // room +6 %, 1 M-triangle heightfield +10 %, 10 M-triangle terrain +12 %. Whitted's bounce loop waits for the host
+        // once per bounce, which would serialise the pipes, so it keeps one. YK_PIPES / opts->pipes override (bench.py
+        // times its device-resident leg on one pipe so that the event-bracketed kernel times stay exclusive).
+        int n_pipes = c->n_pipes_env > 0 ? c->n_pipes_env : (in->kind == YK_INTEGRATOR_WHITTED ? 1 : 2);
         if (opts && opts->pipes) n_pipes = (int)opts->pipes;
         n_pipes = std::max(1, std::min(kMaxPipes, n_pipes));
         if (accumulate) n_pipes = 1;
