@@ -151,8 +151,9 @@ int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries
         WAVE_ALLOC(st[k].ray_o, cap) WAVE_ALLOC(st[k].ray_d, cap) WAVE_ALLOC(st[k].beta, cap) WAVE_ALLOC(st[k].rng, cap)
     }
     WAVE_ALLOC(hit, cap) WAVE_ALLOC(bvh_counts, cap) WAVE_ALLOC(L, cap)
-    WAVE_ALLOC(sh_path, cap) WAVE_ALLOC(pend_beta, cap) WAVE_ALLOC(pend_extra, cap)
-    WAVE_ALLOC(lt_o, cap * nl) WAVE_ALLOC(lt_d, cap * nl) WAVE_ALLOC(lt_c, cap * nl)
+    // (+ one chunk of slack: the shadow kernel prefetches whole 64-path chunks of these arrays without per-line bounds tests)
+    WAVE_ALLOC(sh_path, (size_t)cap + 64) WAVE_ALLOC(pend_beta, (size_t)cap + 64) WAVE_ALLOC(pend_extra, (size_t)cap + 64)
+    WAVE_ALLOC(lt_o, cap * nl + 64) WAVE_ALLOC(lt_d, cap * nl + 64) WAVE_ALLOC(lt_c, cap * nl + 64)
     WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap) WAVE_ALLOC(q_mat_tri, (size_t)4 * cap) WAVE_ALLOC(q_mat_slot, (size_t)4 * cap)
     WAVE_ALLOC(totals, 1)
     if (stack_entries) {

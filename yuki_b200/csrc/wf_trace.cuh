@@ -397,6 +397,9 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
 // `radiance += beta * Le`, the indirect clamp and `L += beta * radiance` (path.rs:113-129, whitted.rs:120-130).
 // One *path* per queue entry (the four material queues, concatenated); a lane traces its path's shadow rays one after
 // the other in light order, so the float sums associate exactly like the reference's fold.
+#ifndef YK_SHADOW_PREFETCH
+#define YK_SHADOW_PREFETCH 1  // measured: shadow / fold kernel -2.6 %, Cornell render +0.7 %; reserving one chunk ahead (2) loses it to spills
+#endif
 template <bool SPHERES>
 __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_shadow(DevScene sc, Wave w, RenderCfg cfg, IterCounters* cur) {
     uint32_t* const cursor = &cur->work_shadow;
@@ -422,6 +425,31 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
     int target_light = -1;
     RGB radiance = gray(0.0f), contribution = gray(0.0f);
 
+    // The kernel's inputs are streamed once, 16 - 40 B per array and path, and a lane needs them the moment it picks a path up:
+    // ncu shows the kernel waiting on exactly these loads (long-scoreboard ~6 warps per issue, issue-active 60 %,
+    // profiles/r01/ncu_shadow_cornell.txt). So a warp pulls a chunk's lines (the hand-over arrays of light 0 and the pending
+    // terms: 38 lines of 128 B for 64 paths) into the L2 when it reserves the chunk.
+    auto prefetch_chunk = [&](uint32_t base) {
+        if (base >= n) return;
+        const int a = lane >> 3;  // 0 pend_extra, 1 lt_o, 2 lt_d, 3 pend_beta: 8 lines each
+        const char* p = a == 0 ? (const char*)(w.pend_extra + base) : a == 1 ? (const char*)(w.lt_o + base)
+                      : a == 2 ? (const char*)(w.lt_d + base) : (const char*)(w.pend_beta + base);
+        // (no per-line bounds test: the arrays are allocated with a chunk of slack, ensure_wave)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (lane & 7) * 128));
+        if (lane < 6) {
+            const char* q = lane < 4 ? (const char*)(w.lt_c + base) + lane * 128 : (const char*)(w.sh_path + base) + (lane - 4) * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+    };
+#if YK_SHADOW_PREFETCH == 2
+    uint32_t ahead = 0;
+    {
+        uint32_t b0 = 0;
+        if (lane == 0) b0 = atomicAdd(cursor, kChunk);
+        ahead = __shfl_sync(0xffffffffu, b0, 0);
+        prefetch_chunk(ahead);
+    }
+#endif
     auto finish_path = [&]() {  // path.rs:121-129
         const float4 pe = w.pend_extra[pos], pb = w.pend_beta[pos];
         RGB r = radiance + rgb(pe.x, pe.y, pe.z);
@@ -443,9 +471,20 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             const unsigned idle = __ballot_sync(0xffffffffu, !live);
             if (!idle || exhausted) break;
             if (chunk_next >= chunk_end) {
+#if YK_SHADOW_PREFETCH == 2
+                uint32_t base = ahead;  // reserved (and prefetched) while the previous chunk was being consumed
+                uint32_t nxt_base = 0;
+                if (lane == 0) nxt_base = atomicAdd(cursor, kChunk);
+                ahead = __shfl_sync(0xffffffffu, nxt_base, 0);
+                prefetch_chunk(ahead);
+#else
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(cursor, kChunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
+#if YK_SHADOW_PREFETCH == 1
+                prefetch_chunk(base);
+#endif
+#endif
                 chunk_next = base;
                 chunk_end = base + kChunk < n ? base + kChunk : n;
                 if (base >= n) { exhausted = true; chunk_next = chunk_end = 0; break; }
