@@ -82,6 +82,8 @@ def lib():
     L.yko_cross.restype = None
     L.yko_math_kat.argtypes = [u32, fp, fp]
     L.yko_math_kat.restype = C.c_int
+    L.yko_lobe_eval.argtypes = [u32, fp, u32, fp, u32, fp]
+    L.yko_lobe_eval.restype = C.c_int
     L.yko_siphash13.argtypes = [C.c_char_p, C.c_uint64]
     L.yko_siphash13.restype = C.c_uint64
     L.yko_pcg32_sequence.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u32, vp]
@@ -166,6 +168,32 @@ def math_kat(op, values, n_out):
     if lib().yko_math_kat(op, _f(vals, len(vals)), out.ctypes.data_as(C.POINTER(C.c_float))) != 0:
         raise ValueError("yko_math_kat failed")
     return out[:n_out].copy()
+
+
+LOBE_LAMBERT, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_GGX_CONDUCTOR, LOBE_GGX_SCHLICK = range(6)
+
+
+def lobe_f_pdf(kind, params, wo, wi):
+    """f(wo, wi) (n, 3) and pdf(wo, wi) (n,) of one BxDF in its local frame (z = normal)."""
+    wo = np.ascontiguousarray(np.broadcast_to(np.asarray(wo, np.float32), np.asarray(wi).shape), np.float32)
+    x = np.ascontiguousarray(np.concatenate([wo, np.asarray(wi, np.float32)], axis=1), np.float32)
+    prm = np.zeros(16, np.float32)
+    prm[:len(params)] = params
+    out = np.zeros((x.shape[0], 4), np.float32)
+    assert lib().yko_lobe_eval(kind, capi.fptr(prm), 0, capi.fptr(x), x.shape[0], capi.fptr(out)) == 0
+    return out[:, :3], out[:, 3]
+
+
+def lobe_sample(kind, params, wo, u):
+    """sample_f(wo, u): (wi (n, 3), f (n, 3), pdf (n,), sample type (n,)) — type 0 = no sample."""
+    u = np.asarray(u, np.float32)
+    wo = np.ascontiguousarray(np.broadcast_to(np.asarray(wo, np.float32), (u.shape[0], 3)), np.float32)
+    x = np.ascontiguousarray(np.concatenate([wo, u, np.zeros((u.shape[0], 1), np.float32)], axis=1), np.float32)
+    prm = np.zeros(16, np.float32)
+    prm[:len(params)] = params
+    out = np.zeros((x.shape[0], 8), np.float32)
+    assert lib().yko_lobe_eval(kind, capi.fptr(prm), 1, capi.fptr(x), x.shape[0], capi.fptr(out)) == 0
+    return out[:, :3], out[:, 3:6], out[:, 6], out[:, 7].astype(np.int32)
 
 
 def cross(a, b):

@@ -281,6 +281,53 @@ int yko_math_kat(uint32_t op, const float* in, float* out) {
     }
 }
 
+// The BxDFs of materials/bsdfs/*.rs in their local frame (z = normal), for analytic property tests of the restatement
+// (tests/test_oracle_bsdf.py: pdf normalisation, sample / eval consistency, energy bounds, Fresnel closed forms).
+// kind: 0 Lambertian(r), 1 Oren-Nayar(r, sigma rad), 2 specular reflection(r, eta), 3 specular transmission(r, eta),
+// 4 Torrance-Sparrow / GGX with conductor Fresnel(eta_t rgb, k rgb, alpha), 5 the same with Schlick Fresnel(rs rgb, alpha).
+// mode 0: in = n x (wo, wi) -> out = n x (f rgb, pdf); mode 1: in = n x (wo, u0, u1, 0) -> out = n x (wi, f rgb, pdf, type).
+int yko_lobe_eval(uint32_t kind, const float* params, uint32_t mode, const float* in, uint32_t n, float* out) {
+    Lobe l{};
+    l.r = spec(params[0], params[1], params[2]);
+    switch (kind) {
+        case 0: l.kind = LOBE_LAMBERT; break;
+        case 1: {  // oren_nayar.rs:18-25
+            l.kind = LOBE_OREN_NAYAR;
+            const float s2 = params[3] * params[3];
+            l.a = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+            l.b = 0.45f * s2 / (s2 + 0.09f);
+        } break;
+        case 2: l.kind = LOBE_SPEC_REFL; l.fresnel = FRESNEL_DIELECTRIC; l.eta_i = 1.0f; l.eta_t = params[3]; break;
+        case 3: l.kind = LOBE_SPEC_TRANS; l.eta_i = 1.0f; l.eta_t = params[3]; break;
+        case 4:
+            l.kind = LOBE_MICROFACET; l.fresnel = FRESNEL_CONDUCTOR; l.c_eta_i = spec1(1.0f);
+            l.c_eta_t = spec(params[3], params[4], params[5]); l.c_k = spec(params[6], params[7], params[8]);
+            l.alpha = fmax_(params[9], 0.001f);
+            break;
+        case 5:
+            l.kind = LOBE_MICROFACET; l.fresnel = FRESNEL_SCHLICK; l.rs = spec(params[3], params[4], params[5]);
+            l.alpha = fmax_(params[6], 0.001f);
+            break;
+        default: return -1;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 6 * (size_t)i;
+        const V3 wo = ld3(a);
+        if (mode == 0) {
+            const V3 wi = ld3(a + 3);
+            const Spec f = l.f(wo, wi);
+            float* o = out + 4 * (size_t)i;
+            o[0] = f.r; o[1] = f.g; o[2] = f.b; o[3] = l.pdf(wo, wi);
+        } else {
+            const BxdfSample sm = l.sample_f(wo, V2{a[3], a[4]});
+            float* o = out + 8 * (size_t)i;
+            st3(sm.wi, o);
+            o[3] = sm.f.r; o[4] = sm.f.g; o[5] = sm.f.b; o[6] = sm.pdf; o[7] = (float)sm.sample_type;
+        }
+    }
+    return 0;
+}
+
 uint64_t yko_siphash13(const uint8_t* msg, uint64_t n) { return siphash13(msg, (size_t)n); }
 void yko_pcg32_sequence(uint64_t state, uint64_t stream, uint64_t adv, uint32_t n, uint32_t* out) {
     Pcg32 p = Pcg32::make(state, stream);
