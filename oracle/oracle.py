@@ -84,6 +84,8 @@ def lib():
     L.yko_math_kat.restype = C.c_int
     L.yko_lobe_eval.argtypes = [u32, fp, u32, fp, u32, fp]
     L.yko_lobe_eval.restype = C.c_int
+    L.yko_light_sample.argtypes = [vp, u32, fp, u32, fp]
+    L.yko_light_sample.restype = C.c_int
     L.yko_siphash13.argtypes = [C.c_char_p, C.c_uint64]
     L.yko_siphash13.restype = C.c_uint64
     L.yko_pcg32_sequence.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u32, vp]
@@ -300,6 +302,16 @@ class OracleScene:
         if n > max_rays:
             return self.debug_ray(camera_params, film, sampler, integrator, film_px, max_rays=n)
         return rays[:n].copy(), li, int(count.value)
+
+    def light_sample(self, light, p, n, u):
+        """`Light::sample_li` for shading points p with normals n and samples u: dict of l, li, pdf, has_vis, vis_o, vis_d."""
+        u = np.asarray(u, np.float32).reshape(-1, 2)
+        m = u.shape[0]
+        x = np.ascontiguousarray(np.concatenate([np.broadcast_to(np.asarray(p, np.float32), (m, 3)),
+                                                 np.broadcast_to(np.asarray(n, np.float32), (m, 3)), u], axis=1), np.float32)
+        out = np.zeros((m, 14), np.float32)
+        assert lib().yko_light_sample(self._h, int(light), capi.fptr(x), m, capi.fptr(out)) == 0
+        return {"l": out[:, 0:3], "li": out[:, 3:6], "pdf": out[:, 6], "has_vis": out[:, 7] != 0, "vis_o": out[:, 8:11], "vis_d": out[:, 11:14]}
 
     def trace(self, o, d, t_max=None, brute_force=False):
         o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)

@@ -328,6 +328,30 @@ int yko_lobe_eval(uint32_t kind, const float* params, uint32_t mode, const float
     return 0;
 }
 
+// Light::sample_li (lights/*.rs) of light `light` for n shading points: in = n x (p xyz, n xyz, u0, u1),
+// out = n x (l xyz, li rgb, pdf, has_vis, vis ray o xyz, vis ray d xyz) = 14 floats. For tests/test_oracle_lights.py.
+int yko_light_sample(const yko_scene* sc, uint32_t light, const float* in, uint32_t n, float* out) {
+    const Scene& s = sc->s;
+    if (light >= s.lights.size()) return -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + 8 * (size_t)i;
+        SurfaceInteraction si{};
+        si.p = ld3(a);
+        si.n = ld3(a + 3);
+        si.sh_n = si.n;
+        si.area_light = -1;
+        const LightSample ls = sample_li(s, (int32_t)light, si, V2{a[6], a[7]});
+        float* o = out + 14 * (size_t)i;
+        st3(ls.l, o);
+        o[3] = ls.li.r; o[4] = ls.li.g; o[5] = ls.li.b;
+        o[6] = ls.pdf;
+        o[7] = ls.has_vis ? 1.0f : 0.0f;
+        st3(ls.has_vis ? ls.vis_ray.o : v3(0, 0, 0), o + 8);
+        st3(ls.has_vis ? ls.vis_ray.d : v3(0, 0, 0), o + 11);
+    }
+    return 0;
+}
+
 uint64_t yko_siphash13(const uint8_t* msg, uint64_t n) { return siphash13(msg, (size_t)n); }
 void yko_pcg32_sequence(uint64_t state, uint64_t stream, uint64_t adv, uint32_t n, uint32_t* out) {
     Pcg32 p = Pcg32::make(state, stream);

@@ -131,7 +131,9 @@ void yko_xf_normal(const yko_transform*, const float* n3, float* out3);
 void yko_cross(const float* a3, const float* b3, float* out3);
 int yko_math_kat(uint32_t op, const float* in, float* out);
 /* one BxDF of materials/bsdfs in its local frame: f / pdf (mode 0) or sample_f (mode 1) for n inputs, see yk_oracle.cpp */
-int yko_lobe_eval(uint32_t kind, const float* params, uint32_t mode, const float* in, uint32_t n, float* out);       /* yko_math.h helpers by opcode, for the reference's unit-test KATs */
+int yko_lobe_eval(uint32_t kind, const float* params, uint32_t mode, const float* in, uint32_t n, float* out);
+/* Light::sample_li of one light of the scene for n shading points, see yk_oracle.cpp */
+int yko_light_sample(const yko_scene*, uint32_t light, const float* in, uint32_t n, float* out);       /* yko_math.h helpers by opcode, for the reference's unit-test KATs */
 
 /* KAT / self-check helpers */
 uint64_t yko_siphash13(const uint8_t* msg, uint64_t n);
