@@ -91,3 +91,39 @@ def test_image_texture_is_nearest_texel_with_flipped_v(oracle):
     safe &= (np.abs(fx - np.round(fx)) > 1e-3) & (np.abs(fy - np.round(fy)) > 1e-3)
     assert safe.sum() > 800
     assert np.allclose(out[safe], img[iy[safe], ix[safe]], rtol=1e-5)
+
+
+def test_direct_lighting_and_shadow_of_a_point_light_are_analytic(oracle):
+    """Whitted depth 1 (= Path depth 1) on a Lambertian plane: L = kd / pi * I / d^2 * cos(theta), and zero inside the
+    shadow an occluding square casts from the light (its outline projected onto the plane)."""
+    scene, cam = _quad_scene()
+    light = np.array([0.4, 0.3, 2.0])
+    scene.lights.append(D.Light(D.LIGHT_POINT, xf.translation(tuple(light)), (3.0, 2.0, 1.0)))
+    # occluder: the square |x - 0.2|, |y + 0.1| < 0.25 at height z = 1, facing away from the camera's view of the plane below
+    oc = np.array([(-0.05, -0.35, 1), (0.45, -0.35, 1), (0.45, 0.15, 1), (-0.05, 0.15, 1)], np.float32)
+    zero = scene.add_texture(D.Texture.constant(0.0))
+    black = scene.add_material(D.Material(D.MAT_MATTE, (zero, zero)))
+    scene.meshes.append(D.Mesh(xf.identity(), oc, np.array([0, 1, 2, 0, 2, 3], np.uint32), black))
+    film = D.FilmSettings((96, 72), 16)
+    smp = D.SamplerType.stratified(1, 1, jitter=False)
+    osc = oracle.OracleScene(scene)
+    img_w, ids, _ = osc.render(cam, film, smp, D.IntegratorType.whitted(1), want_hit_ids=True)
+    img_p, _, _ = osc.render(cam, film, smp, D.IntegratorType.path(1))
+    assert np.array_equal(img_w.view(np.uint32), img_p.view(np.uint32))
+    _, _, _, p, inside = _pixel_centre_hits(oracle, cam, film)
+    on_plane = inside & (ids >= 0) & (ids < 2)               # pixels that see the plane (not the occluder in front of it)
+    # shadow: the segment p -> light crosses z = 1 inside the occluder
+    s = (1.0 - p[..., 2]) / (light[2] - p[..., 2])
+    q = p + s[..., None] * (light - p)
+    dx, dy = np.abs(q[..., 0] - 0.2), np.abs(q[..., 1] + 0.1)
+    shadowed = (dx < 0.25 - 2e-3) & (dy < 0.25 - 2e-3)
+    lit = (dx > 0.25 + 2e-3) | (dy > 0.25 + 2e-3)
+    edge = (np.abs(np.abs(p[..., 0]) - 1) > 1e-2) & (np.abs(np.abs(p[..., 1]) - 1) > 1e-2)
+    assert (on_plane & shadowed).sum() > 30 and (on_plane & lit & edge).sum() > 500
+    assert (img_w[on_plane & shadowed & edge] == 0).all()
+    to = light - p
+    d2 = (to ** 2).sum(axis=-1)
+    cos = to[..., 2] / np.sqrt(d2)
+    want = (0.5 / np.pi) * np.array([3.0, 2.0, 1.0]) * (cos / d2)[..., None]
+    sel = on_plane & lit & edge
+    assert np.allclose(img_w[sel], want[sel], rtol=2e-5)
