@@ -20,3 +20,18 @@ for name, (scene, cam, film, smp, integ) in T.golden_cases(xf).items():
     out[name] = T.digest(img, ids, st)
     print(name, out[name]["film_mean"], out[name]["ray_count"])
 json.dump(out, open(T.GOLDEN, "w"), indent=1, sort_keys=True)
+
+# sampler draws (Sampler::start_pixel_sample + get_1d / get_2d): a few (pixel, index) triples per sampler configuration
+import numpy as np  # noqa: E402
+import test_sampler_gpu as TS  # noqa: E402
+
+draws = {}
+for smp in TS.SAMPLERS:
+    key = f"k{smp.kind}_{smp.nx}x{smp.ny}_j{int(smp.jitter)}_s{smp.seed}"
+    rows = []
+    for (px, py, idx) in TS.golden_triples(smp):
+        rows.append({"pixel": [px, py], "index": idx,
+                     "bits": [int(b) for b in O.sampler_draws(smp, px, py, idx, TS.GOLDEN_PATTERN).view(np.uint32)]})
+    draws[key] = rows
+json.dump({"pattern": TS.GOLDEN_PATTERN, "draws": draws}, open(TS.GOLDEN_DRAWS, "w"), indent=None, sort_keys=True)
+print("sampler draws:", sum(len(v) for v in draws.values()), "rows")
