@@ -127,3 +127,30 @@ def test_direct_lighting_and_shadow_of_a_point_light_are_analytic(oracle):
     want = (0.5 / np.pi) * np.array([3.0, 2.0, 1.0]) * (cos / d2)[..., None]
     sel = on_plane & lit & edge
     assert np.allclose(img_w[sel], want[sel], rtol=2e-5)
+
+
+def test_deeper_paths_add_nothing_over_a_single_plane_and_the_background_is_weighted_by_the_throughput(oracle):
+    """Every bounce ray off a lone plane escapes. With a black sky Path depth 8 is Path depth 1 bit for bit; with a sky of
+    radiance B each path gains beta * B = kd * B exactly once (cosine sampling of a Lambertian: f cos / pdf = kd), and camera
+    rays that miss return B (path.rs:155-160)."""
+    scene, cam = _quad_scene()
+    scene.lights.append(D.Light(D.LIGHT_POINT, xf.translation((0.4, 0.3, 2.0)), (3.0, 2.0, 1.0)))
+    film = D.FilmSettings((64, 48), 16)
+    smp = D.SamplerType.stratified(2, 2)
+    osc = oracle.OracleScene(scene)
+    p1, ids, st1 = osc.render(cam, film, smp, D.IntegratorType.path(1), want_hit_ids=True)
+    p8, _, st8 = osc.render(cam, film, smp, D.IntegratorType.path(8))
+    assert np.array_equal(p1.view(np.uint32), p8.view(np.uint32))
+    n_samples = 64 * 48 * 4
+    assert st1.ray_count == n_samples and n_samples < st8.ray_count < 2 * n_samples     # camera rays + one escaping bounce ray per hit
+    assert st8.ray_count - n_samples > 0.2 * n_samples and st8.shadow_rays == st1.shadow_rays
+    sky = (0.2, 0.4, 0.8)
+    scene.background = sky
+    osc2 = oracle.OracleScene(scene)
+    b1, ids1, _ = osc2.render(cam, film, smp, D.IntegratorType.path(1), want_hit_ids=True)
+    b8, _, _ = osc2.render(cam, film, smp, D.IntegratorType.path(8))
+    _, _, _, p, inside = _pixel_centre_hits(oracle, cam, film)
+    well_inside = (np.abs(p[..., 0]) < 0.9) & (np.abs(p[..., 1]) < 0.9)
+    well_outside = (np.abs(p[..., 0]) > 1.1) | (np.abs(p[..., 1]) > 1.1)
+    assert np.allclose(b8[well_outside], sky, rtol=1e-6) and np.allclose(b1[well_outside], sky, rtol=1e-6)
+    assert np.allclose(b8[well_inside] - b1[well_inside], 0.5 * np.float32(sky), rtol=2e-4, atol=1e-6)
