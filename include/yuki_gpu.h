@@ -184,6 +184,8 @@ typedef struct {
 /* ---- render options / statistics ------------------------------------------------------------ */
 #define YK_RENDER_FILM_ON_DEVICE 1u  /* film_rgb (and opts.hit_ids) are device pointers on the context's GPU */
 #define YK_RENDER_KEEP_FILM 2u       /* non-accumulating render: pixels outside `tiles` are left untouched (default) */
+#define YK_RAY_SORT_TRACE_ONLY 16u   /* yk_render_opts.ray_sort flag: only the closest-hit kernel walks the sorted order (default: the
+                                        material sort does too, so shading and shadow rays run in the same order) */
 
 typedef int (*yk_progress_fn)(void* user, uint64_t samples_done, uint64_t samples_total); /* return !=0 to cancel */
 
@@ -195,6 +197,11 @@ typedef struct {
     uint32_t pipes;             /* wavefront batches in flight on separate CUDA streams: 1 or 2; 0 = default (2; 1 for Whitted) */
     yk_progress_fn progress;
     void* progress_user;
+    uint32_t ray_sort;          /* path tracing: order bounce rays for coherence before they are traced (a counting sort over the ray
+                                   queue, csrc/wf_sort.cuh). 0 = default (by scene size), 1 = off, 2 = key = leaf slot of the shape the ray
+                                   leaves + direction octant, 3 = key = Morton cell of the ray origin + direction octant. The film does
+                                   not depend on it (bit-identical either way). */
+    uint32_t _reserved;
 } yk_render_opts;
 
 typedef struct {
@@ -258,6 +265,32 @@ int yk_occluded(yk_context*, const yk_scene*, const float* o_xyz, const float* d
  * `out` receives sum(pattern) floats per triple. The component-level view of what the kernels draw per path. */
 int yk_sampler_draws(yk_context*, const yk_sampler*, const uint32_t* pixel_index_xyi, uint32_t n, const uint8_t* pattern,
                      uint32_t n_pattern, float* out);
+/* ---- several GPUs of one process (csrc/multi.inl) ------------------------------------------------------------------
+ * The reference drives all of its workers from one RenderManager and one shared tile queue
+ * (renderer/render_manager.rs:78-97,197-236; render_worker.rs:172-198). yk_multi is that for G devices: one context and
+ * one host worker thread per device, the scene replicated, the tile list consumed through one shared cursor in list
+ * (spiral) order, and the film assembled on the first device by direct peer (NVLink) stores from the other devices'
+ * film kernels — no gather step (devices without a peer mapping are gathered with peer copies at the end). */
+typedef struct yk_multi yk_multi;
+typedef struct yk_multi_scene yk_multi_scene;
+int yk_multi_create(const int* device_ids, int n_devices, yk_multi** out);
+void yk_multi_destroy(yk_multi*);
+int yk_multi_device_count(const yk_multi*);
+yk_context* yk_multi_context(yk_multi*, int i);      /* the i-th device's context (owned by the group) */
+int yk_multi_peer_stores(const yk_multi*, int i);    /* 1: device i stores into the first device's film directly */
+/* yk_scene_create on every device: validated once, uploaded in parallel from the caller's host arrays. */
+int yk_multi_scene_create(yk_multi*, const yk_scene_desc*, yk_multi_scene** out);
+void yk_multi_scene_destroy(yk_multi_scene*);
+/* yk_render over all devices of the group. Same arguments and film semantics; `film_rgb` / opts->hit_ids are host
+ * buffers, or (YK_RENDER_FILM_ON_DEVICE) buffers on the FIRST device. Non-accumulating renders hand out runs of tiles
+ * dynamically; accumulating renders send a tile to device `tile.index mod G`, so that a pixel's per-sample adds keep the
+ * tile-list order (film.rs:260-272) and the film equals the single-device one bit for bit. `stats` = sums over the
+ * devices with device_ms = the busiest device's; `per_device` (NULL or G entries) = each device's own sums, device_ms
+ * being its busy time. */
+int yk_multi_render(yk_multi*, const yk_multi_scene*, const yk_camera*, const yk_film_settings*, const yk_sampler*,
+                    const yk_integrator*, const yk_tile* tiles, uint32_t n_tiles, const yk_render_opts* opts, float* film_rgb,
+                    yk_stats* stats, yk_stats* per_device);
+
 /* Device synchronisation helpers for callers that time with their own CUDA events. */
 void* yk_context_stream(yk_context*);   /* cudaStream_t the renderer launches on */
 

@@ -106,3 +106,41 @@ if which == "whitted":  # config 1 (Cornell 512^2, Whitted depth 3, 16 spp) and 
     probe("cornell 512^2 whitted3 16spp", s, c, D.FilmSettings((512, 512), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(3), reps=4)
     probe("cornell 1024^2 whitted3 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.whitted(3), reps=3)
     probe("cornell 1024^2 whitted6 16spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.whitted(6), reps=3)
+if which == "sortab":  # ray-queue sort A/B (yk_render_opts.ray_sort): every scene class, sort off / leaf-slot key / Morton key, both orders
+    names = {1: "off", 2: "slot", 3: "morton", 2 | 16: "slot/trace-only", 3 | 16: "morton/trace-only"}
+    only = sys.argv[2].split(",") if len(sys.argv) > 2 else ["cornell", "room", "hf", "terrain"]
+    def sweep(name, s, c, film, smp, integ):
+        ctx = api.Context(0); dev = api.Scene(ctx, s); rn = api.Renderer(ctx)
+        ref = None
+        for pipes in (1, 2):
+            for mode in (1, 2, 3, 2 | 16, 3 | 16):
+                best = None
+                for i in range(4):
+                    r = rn.render(dev, c, film, smp, integ, ray_sort=mode, pipes=pipes)
+                    if best is None or r.stats.device_ms < best.stats.device_ms:
+                        best = r
+                st = best.stats
+                if ref is None:
+                    ref = best.film.copy()
+                same = bool(np.array_equal(ref.view(np.uint32), best.film.view(np.uint32)))
+                print(f"{name} pipes {pipes} sort {names[mode]:18s}: {st.samples / st.device_ms / 1e3:8.1f} Msamples/s device {st.device_ms:7.2f} ms closest {st.trace_closest_ms:6.2f} "
+                      f"any {st.trace_any_ms:6.2f} shade {st.shade_ms:6.2f} launches {st.kernel_launches} film==unsorted {same}", flush=True)
+        dev.close(); ctx.close()
+    if "cornell" in only:
+        s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+        sweep("cornell 1024^2 path8 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8))
+    if "room" in only:
+        s, c = scenes.material_room(xf)
+        sweep("room 1080p path8 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
+    if "hf" in only:
+        s, c = scenes.heightfield(xf, 708, 708)
+        sweep("heightfield 1M path8 1080p 16spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8))
+    if "terrain" in only:
+        s, c = scenes.terrain_room(xf)
+        sweep("terrain 10M path8 4K 4spp", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8))
+if which == "room4":  # one batch of the material room for ncu captures
+    s, c = scenes.material_room(xf)
+    probe("room 1080p path8 4spp", s, c, D.FilmSettings((1920, 1080), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.path(8), reps=0, pipes=1)
+if which == "whitted1":
+    s, c = scenes.cornell(xf, light="point", tall_box="glass")
+    probe("cornell 1024^2 whitted4 4spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(4), reps=0)

@@ -430,3 +430,30 @@ def test_maximum_film_coordinates_and_sample_indices(gpu_ctx, oracle, xf):
     dev.close()
     assert np.array_equal(out.view(np.uint32), o2.view(np.uint32)) and float(o2.max()) > 0.0
     assert r2.stats.ray_count == o2_st.ray_count
+
+
+@pytest.mark.parametrize("scene_name", ["room", "heightfield", "sphere_room"])
+def test_ray_sort_is_invisible_in_the_results(gpu_ctx, oracle, xf, scene_name):
+    """The ray-queue sort between bounces (csrc/wf_sort.cuh) only changes the order rays are processed in: film bits,
+    ray counts and traversal counters equal the unsorted render's (and the oracle's) for both keys and both orders."""
+    if scene_name == "room":
+        scene, cam = scenes.material_room(xf)
+    elif scene_name == "heightfield":
+        scene, cam = scenes.heightfield(xf, 64, 64, seed=5)
+    else:
+        scene, cam = scenes.cornell(xf, light="rect", tall_box="glass", sphere=True)
+    film = D.FilmSettings((96, 64), 16)
+    smp, integ = D.SamplerType.stratified(3, 2), D.IntegratorType.path(8)
+    dev = api.Scene(gpu_ctx, scene)
+    rn = api.Renderer(gpu_ctx)
+    base = rn.render(dev, cam, film, smp, integ, ray_sort=1)
+    o_img, _, o_st = oracle.OracleScene(scene).render(cam, film, smp, integ)
+    assert np.array_equal(base.film.view(np.uint32), o_img.view(np.uint32))
+    for mode in (2, 3, 2 | 16, 3 | 16):
+        for kw in ({}, {"wavefront_paths": 2048}, {"pipes": 1}):
+            r = rn.render(dev, cam, film, smp, integ, ray_sort=mode, **kw)
+            assert np.array_equal(r.film.view(np.uint32), base.film.view(np.uint32)), (mode, kw)
+            for k in ("ray_count", "shadow_rays", "closest_nodes", "closest_tris", "any_nodes", "any_tris", "primary_hit_hash"):
+                assert getattr(r.stats, k) == getattr(base.stats, k), (mode, kw, k)
+    assert base.stats.ray_count == o_st.ray_count and base.stats.closest_nodes == o_st.closest_nodes
+    dev.close()

@@ -73,6 +73,11 @@ def test_non_float_coordinates_are_ignored_like_the_reference(tmp_path):
      "element face 0\nproperty list uchar int vertex_indices\nend_header\n0 0 0 0 1 0\n", "panics"),
     ("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n"
      "0 0 0\n1 0 0\n", "truncated"),
+    # element counts the payload cannot hold: a parse error, never a length_error / bad_alloc unwinding through the C ABI
+    ("ply\nformat ascii 1.0\nelement vertex 9000000000000000000\nproperty float x\nproperty float y\nproperty float z\nelement face 1\n"
+     "property list uchar int vertex_indices\nend_header\n0 0 0\n", "truncated"),
+    ("ply\nformat binary_little_endian 1.0\nelement vertex 18446744073709551615\nproperty float x\nproperty float y\nproperty float z\nelement face 0\n"
+     "property list uchar int vertex_indices\nend_header\n", "truncated"),
 ])
 def test_rejected_files(tmp_path, body, needle):
     f = tmp_path / "bad.ply"

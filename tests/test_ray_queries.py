@@ -146,6 +146,32 @@ def test_corner_case_rays(gpu_ctx, oracle, xf):
 
 
 @pytest.mark.gpu
+def test_degenerate_directions_on_sphere_scenes_and_leaf_tables(gpu_ctx, oracle, xf):
+    """A zero-length or NaN direction gives every triangle a NaN determinant, which the triangle test accepts
+    (triangle.rs:109-130: every comparison is false) — the same signature the NaN vertex lanes of a sphere slot produce. The
+    generic kernels (sphere slots and / or a leaf table, i.e. leaves of more than 16 shapes) must still tell the two apart:
+    a triangle stays a triangle hit with t = NaN, as in the reference; only tagged slots reach the sphere test."""
+    cases = [scenes.cornell(xf, light="rect", tall_box="glass", sphere=True)[0],
+             scenes.cornell(xf, light="rect", tall_box="glass", sphere=True, max_shapes_in_node=40)[0],   # root leaf, spheres, leaf table
+             scenes.heightfield(xf, 24, 24, seed=4, max_shapes_in_node=40)[0]]                            # leaf table, no spheres
+    nan = np.nan
+    for scene in cases:
+        dev, osc = api.Scene(gpu_ctx, scene), oracle.OracleScene(scene)
+        rng = np.random.default_rng(8)
+        o, d = _random_rays(rng, 4000, (-0.6, -0.4, -0.6), (0.6, 0.6, 0.6))
+        d[0::8] = 0.0                       # zero-length directions
+        d[1::8, 0] = nan                    # one NaN component
+        d[2::8] = (nan, nan, nan)
+        d[3::8] = (0.0, -0.0, 0.0)
+        o[4::8] = (0.3, 0.3, -0.3)          # inside the Cornell box (and on the heightfield's side)
+        t, ids = _same(dev, osc, o, d)
+        _same_occluded(dev, osc, o, d)
+        # the renderer still works on this context afterwards (no poisoned CUDA context)
+        assert dev.intersect(o[5:6], d[5:6])[0].shape == (1,)
+        dev.close()
+
+
+@pytest.mark.gpu
 def test_batches_above_one_chunk_equal_small_batches(gpu_ctx, oracle, xf):
     """More rays than one internal chunk (2^22): the result is independent of how the batch is cut, and the renderer
     still works afterwards (the query reuses / replaces the wavefront state of pipe 0)."""

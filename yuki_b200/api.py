@@ -131,6 +131,93 @@ class Scene:
             pass
 
 
+class MultiContext:
+    """G devices of this process behind one handle (`yk_multi`): the counterpart of the reference's RenderManager with its
+    workers and one shared tile queue (renderer/render_manager.rs:78-97, 197-236)."""
+
+    def __init__(self, device_ids):
+        ids = [int(d) for d in device_ids]
+        arr = (C.c_int * len(ids))(*ids)
+        self._h = C.c_void_p()
+        capi.check(capi.lib().yk_multi_create(arr, len(ids), C.byref(self._h)))
+        self.device_ids = ids
+
+    @property
+    def n_devices(self):
+        return len(self.device_ids)
+
+    def peer_stores(self):
+        """Per device: does it store finished pixels straight into the first device's film (NVLink peer mapping)?"""
+        return [bool(capi.lib().yk_multi_peer_stores(self._h, i)) for i in range(self.n_devices)]
+
+    def close(self):
+        if self._h:
+            capi.lib().yk_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiScene:
+    """The scene replicated on every device of a MultiContext (validated once, uploaded in parallel)."""
+
+    def __init__(self, mctx: MultiContext, scene: D.SceneDesc, host: Optional[HostScene] = None):
+        self.mctx = mctx
+        self.host = host or HostScene(scene)
+        self._h = C.c_void_p()
+        capi.check(capi.lib().yk_multi_scene_create(mctx._h, C.byref(self.host.flat), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            capi.lib().yk_multi_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def multi_render(mctx: MultiContext, scene: MultiScene, camera_params: D.CameraParameters, film: D.FilmSettings, sampler: D.SamplerType,
+                 integrator: D.IntegratorType, tiles: Optional[np.ndarray] = None, want_hit_ids: bool = False, aux_sample: int = 0,
+                 film_out: Optional[np.ndarray] = None, device_film_ptr: Optional[int] = None, pipes: int = 0, ray_sort: int = 0,
+                 wavefront_paths: int = 0):
+    """`yk_multi_render`: the tile list rendered by all devices of the group, popped from one shared cursor; the film is
+    assembled on the first device by peer stores. Returns (RenderResult with the summed stats, per-device stats list)."""
+    cam = make_camera(camera_params, film)
+    if tiles is None:
+        tiles = film_tiles(film)
+    tiles = np.ascontiguousarray(tiles, dtype=capi.TILE_DTYPE)
+    res_x, res_y = int(film.res[0]), int(film.res[1])
+    opts = capi.RenderOpts()
+    opts.aux_sample = aux_sample
+    opts.pipes = pipes
+    opts.ray_sort = ray_sort
+    opts.wavefront_paths = wavefront_paths
+    hit_ids = None
+    if device_film_ptr is not None:
+        opts.flags |= capi.RENDER_FILM_ON_DEVICE
+        film_arr, film_ptr = None, C.c_void_p(device_film_ptr)
+    else:
+        film_arr = film_out if film_out is not None else np.zeros((res_y, res_x, 3), dtype=np.float32)
+        assert film_arr.dtype == np.float32 and film_arr.flags["C_CONTIGUOUS"] and film_arr.size == res_x * res_y * 3
+        film_ptr = C.c_void_p(film_arr.ctypes.data)
+        if want_hit_ids:
+            hit_ids = np.full((res_y, res_x), -1, dtype=np.int32)
+            opts.hit_ids = hit_ids.ctypes.data
+    fs, sm, ig = capi.film_settings(film), capi.sampler(sampler), capi.integrator(integrator)
+    stats = capi.Stats()
+    per = (capi.Stats * mctx.n_devices)()
+    capi.check(capi.lib().yk_multi_render(mctx._h, scene._h, C.byref(cam), C.byref(fs), C.byref(sm), C.byref(ig),
+                                          C.c_void_p(tiles.ctypes.data), len(tiles), C.byref(opts), film_ptr, C.byref(stats), per))
+    return RenderResult(film_arr, hit_ids, stats), list(per)
+
+
 def sampler_draws(ctx: Context, sampler: D.SamplerType, pixel_index, pattern) -> np.ndarray:
     """`Sampler::{start_pixel_sample, get_1d, get_2d}` on the device: for every (x, y, sample index) row of `pixel_index`
     the draws of `pattern` (1 = get_1d, 2 = get_2d) after `start_pixel_sample(p, index, 0)`; returns (n, sum(pattern))."""
@@ -535,7 +622,7 @@ class Renderer:
     def render(self, scene: Scene, camera_params: D.CameraParameters, film: D.FilmSettings, sampler: D.SamplerType,
                integrator: D.IntegratorType, tiles: Optional[np.ndarray] = None, want_hit_ids: bool = False,
                aux_sample: int = 0, wavefront_paths: int = 0, film_out: Optional[np.ndarray] = None,
-               device_film_ptr: Optional[int] = None, progress=None, pipes: int = 0) -> RenderResult:
+               device_film_ptr: Optional[int] = None, progress=None, pipes: int = 0, ray_sort: int = 0) -> RenderResult:
         cam = make_camera(camera_params, film)
         if tiles is None:
             tiles = film_tiles(film)
@@ -545,6 +632,7 @@ class Renderer:
         opts.wavefront_paths = wavefront_paths
         opts.aux_sample = aux_sample
         opts.pipes = pipes
+        opts.ray_sort = ray_sort   # 0 default, 1 off, 2 leaf-slot key, 3 Morton key (yk_render_opts.ray_sort)
         hit_ids = None
         if device_film_ptr is not None:
             opts.flags |= capi.RENDER_FILM_ON_DEVICE

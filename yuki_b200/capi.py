@@ -141,7 +141,8 @@ class PlyData(C.Structure):
 
 class RenderOpts(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("wavefront_paths", C.c_uint32), ("hit_ids", C.c_void_p), ("aux_sample", C.c_uint32),
-                ("pipes", C.c_uint32), ("progress", PROGRESS_FN), ("progress_user", C.c_void_p)]
+                ("pipes", C.c_uint32), ("progress", PROGRESS_FN), ("progress_user", C.c_void_p), ("ray_sort", C.c_uint32),
+                ("_reserved", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -164,6 +165,8 @@ EXPORTS = [
     "yk_film_tiles", "yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_new", "yk_xf_look_at",
     "yk_xf_mul", "yk_xf_inverted", "yk_xf_point", "yk_xf_vec", "yk_xf_normal", "yk_light_make", "yk_selftest_fastdiv", "yk_ply_load", "yk_ply_view", "yk_ply_destroy", "yk_write_exr", "yk_tonemap_filmic", "yk_heatmap", "yk_pbrt_load", "yk_pbrt_view", "yk_pbrt_destroy", "yk_mitsuba_load",
     "yk_debug_ray", "yk_trace", "yk_occluded", "yk_sampler_draws",
+    "yk_multi_create", "yk_multi_destroy", "yk_multi_device_count", "yk_multi_context", "yk_multi_peer_stores",
+    "yk_multi_scene_create", "yk_multi_scene_destroy", "yk_multi_render",
 ]
 
 _lib = None
@@ -234,6 +237,18 @@ def lib():
     for n in ("yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_mul", "yk_xf_inverted"):
         getattr(L, n).restype = None
     L.yk_light_make.argtypes = [C.POINTER(LightDesc), C.POINTER(LightDev)]
+    L.yk_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.yk_multi_destroy.argtypes = [vp]
+    L.yk_multi_destroy.restype = None
+    L.yk_multi_device_count.argtypes = [vp]
+    L.yk_multi_context.argtypes = [vp, C.c_int]
+    L.yk_multi_context.restype = vp
+    L.yk_multi_peer_stores.argtypes = [vp, C.c_int]
+    L.yk_multi_scene_create.argtypes = [vp, C.POINTER(SceneDescFlat), C.POINTER(vp)]
+    L.yk_multi_scene_destroy.argtypes = [vp]
+    L.yk_multi_scene_destroy.restype = None
+    L.yk_multi_render.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(FilmSettings), C.POINTER(Sampler), C.POINTER(Integrator),
+                                  vp, u32, C.POINTER(RenderOpts), vp, C.POINTER(Stats), C.POINTER(Stats)]
     _lib = L
     return L
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "yuki_gpu.h"
+#include "yk_guard.h"
 
 int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
 
@@ -30,6 +31,7 @@ void attr(std::vector<uint8_t>& b, const char* name, const char* type, const std
 }  // namespace
 
 extern "C" int yk_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgb) {
+    return yk_guard("yk_write_exr", [&]() -> int {
     if (!path || !rgb || !width || !height) return yk_set_error(YK_ERR_INVALID, "yk_write_exr: null / empty argument");
     std::vector<uint8_t> head;
     put_u32(head, 20000630u);  // magic
@@ -83,4 +85,5 @@ extern "C" int yk_write_exr(const char* path, uint32_t width, uint32_t height, c
     ok = (std::fclose(f) == 0) && ok;
     if (!ok) return yk_set_error(YK_ERR_INVALID, std::string("Error writing EXR to '") + path + "'");
     return YK_OK;
+    });
 }

@@ -31,6 +31,7 @@
 #include "host_loader.h"
 #include "host_math.h"
 #include "yuki_gpu.h"
+#include "yk_guard.h"
 
 int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
 extern "C" int yk_ply_load(const char* path, yk_ply** out);
@@ -757,6 +758,7 @@ struct Loader {
 }  // namespace
 
 extern "C" int yk_mitsuba_load(const char* path, uint32_t max_shapes_in_node, uint32_t split_method, yk_pbrt_scene** out) {
+    return yk_guard("yk_mitsuba_load", [&]() -> int {
     if (!path || !out) return yk_set_error(YK_ERR_INVALID, "yk_mitsuba_load: null argument");
     std::ifstream f(path, std::ios::binary);
     if (!f) return yk_set_error(YK_ERR_INVALID, std::string("mitsuba: cannot open '") + path + "'");
@@ -785,4 +787,5 @@ extern "C" int yk_mitsuba_load(const char* path, uint32_t max_shapes_in_node, ui
     sc->finish(max_shapes_in_node, split_method);
     *out = sc.release();
     return YK_OK;
+    });
 }

@@ -30,6 +30,7 @@
 #include "host_loader.h"
 #include "host_math.h"
 #include "yuki_gpu.h"
+#include "yk_guard.h"
 
 int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
 extern "C" int yk_ply_load(const char* path, yk_ply** out);
@@ -753,6 +754,7 @@ struct Parser {
 extern "C" {
 
 int yk_pbrt_load(const char* path, uint32_t max_shapes_in_node, uint32_t split_method, yk_pbrt_scene** out) {
+    return yk_guard("yk_pbrt_load", [&]() -> int {
     if (!path || !out) return yk_set_error(YK_ERR_INVALID, "yk_pbrt_load: null argument");
     auto sc = std::make_unique<yk_pbrt_scene>();
     Parser p;
@@ -762,6 +764,7 @@ int yk_pbrt_load(const char* path, uint32_t max_shapes_in_node, uint32_t split_m
     sc->finish(max_shapes_in_node, split_method);
     *out = sc.release();
     return YK_OK;
+    });
 }
 
 const yk_pbrt_result* yk_pbrt_view(const yk_pbrt_scene* s) { return s ? &s->result : nullptr; }

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <fstream>
 #include <memory>
 #include <sstream>
@@ -18,6 +19,7 @@
 #include <vector>
 
 #include "yuki_gpu.h"
+#include "yk_guard.h"
 
 int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
 
@@ -108,6 +110,7 @@ struct Reader {
 extern "C" {
 
 int yk_ply_load(const char* path, yk_ply** out) {
+    return yk_guard("yk_ply_load", [&]() -> int {
     if (!path || !out) return yk_set_error(YK_ERR_INVALID, "yk_ply_load: null argument");
     std::ifstream in(path, std::ios::binary);
     if (!in) return yk_set_error(YK_ERR_INVALID, std::string("Could not open '") + path + "'");  // ply.rs:27-30
@@ -193,6 +196,17 @@ int yk_ply_load(const char* path, yk_ply** out) {
             return yk_set_error(YK_ERR_INVALID, "PLY: ny/nz before nx or v before u (the reference panics on this layout)");
     }
 
+    // Element counts come straight from the header: bound what is reserved up front by what the payload can hold (a row
+    // takes at least one byte per property in every format), so that a hostile `element vertex 9e18` is a parse error
+    // ("truncated payload") and not a length_error / bad_alloc.
+    uint64_t payload_bytes = 0;
+    {
+        const std::streampos here = in.tellg();
+        in.seekg(0, std::ios::end);
+        const std::streampos end = in.tellg();
+        in.seekg(here);
+        if (here >= 0 && end >= here) payload_bytes = (uint64_t)(end - here);
+    }
     auto ply = std::make_unique<yk_ply>();
     Reader rd{in, fmt};
     for (const Element& e : elements) {
@@ -203,9 +217,10 @@ int yk_ply_load(const char* path, yk_ply** out) {
                 if (!p.is_list && p.type == PlyType::F32 && p.name == "nx") e_has_normal = true;
                 if (!p.is_list && p.type == PlyType::F32 && p.name == "u") e_has_uv = true;
             }
-            ply->points.reserve((size_t)e.count * 3);
-            if (e_has_normal) ply->normals.reserve((size_t)e.count * 3);
-            if (e_has_uv) ply->uvs.reserve((size_t)e.count * 2);
+            const uint64_t rows = std::min<uint64_t>(e.count, payload_bytes / std::max<size_t>(e.props.size(), 1));
+            ply->points.reserve((size_t)rows * 3);
+            if (e_has_normal) ply->normals.reserve((size_t)rows * 3);
+            if (e_has_uv) ply->uvs.reserve((size_t)rows * 2);
         }
         std::vector<uint32_t> poly;
         for (uint64_t row = 0; row < e.count; ++row) {
@@ -258,6 +273,7 @@ int yk_ply_load(const char* path, yk_ply** out) {
         if (i >= n_points) return yk_set_error(YK_ERR_INVALID, "PLY: face index past the vertex list");
     *out = ply.release();
     return YK_OK;
+    });
 }
 
 void yk_ply_view(const yk_ply* p, yk_ply_data* out) {

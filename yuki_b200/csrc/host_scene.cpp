@@ -10,6 +10,7 @@
 #include "host_math.h"
 #include "yk_fastdiv.h"
 #include "yuki_gpu.h"
+#include "yk_guard.h"
 
 namespace ykh {
 int bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
@@ -57,6 +58,7 @@ struct yk_host_scene {
 extern "C" {
 
 int yk_light_make(const yk_light_desc* d, yk_light* out) {
+    return yk_guard("yk_light_make", [&]() -> int {
     if (!d || !out) return yk_set_error(YK_ERR_INVALID, "yk_light_make: null argument");
     std::memset(out, 0, sizeof(*out));
     out->kind = d->kind;
@@ -86,10 +88,12 @@ int yk_light_make(const yk_light_desc* d, yk_light* out) {
             return yk_set_error(YK_ERR_INVALID, "yk_light_make: unknown light kind");
     }
     return YK_OK;
+    });
 }
 
 int yk_bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes_in_node, uint32_t split_method,
                  yk_bvh_node* nodes, uint32_t* n_nodes, uint32_t* order) {
+    return yk_guard("yk_bvh_build", [&]() -> int {
     if (!nodes || !n_nodes || !order) return yk_set_error(YK_ERR_INVALID, "yk_bvh_build: null output");
     std::vector<yk_bvh_node> nv;
     std::vector<uint32_t> ov;
@@ -100,9 +104,11 @@ int yk_bvh_build(const float* tri_vertices, uint32_t n_tris, uint32_t max_shapes
     std::memcpy(order, ov.data(), ov.size() * sizeof(uint32_t));
     *n_nodes = (uint32_t)nv.size();
     return YK_OK;
+    });
 }
 
 int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
+    return yk_guard("yk_host_scene_build", [&]() -> int {
     if (!d || !out) return yk_set_error(YK_ERR_INVALID, "yk_host_scene_build: null argument");
     auto hs = std::make_unique<yk_host_scene>();
 
@@ -262,6 +268,7 @@ int yk_host_scene_build(const yk_host_scene_desc* d, yk_host_scene** out) {
     std::memcpy(hs->background, d->background, 12);
     *out = hs.release();
     return YK_OK;
+    });
 }
 
 void yk_host_scene_destroy(yk_host_scene* hs) { delete hs; }
@@ -292,6 +299,7 @@ void yk_host_scene_flat(const yk_host_scene* hs, yk_scene_desc* o) {
 
 // Camera::new, camera.rs:52-102
 int yk_camera_make(const yk_camera_params* p, uint32_t res_x, uint32_t res_y, yk_camera* out) {
+    return yk_guard("yk_camera_make", [&]() -> int {
     if (!p || !out || !res_x || !res_y) return yk_set_error(YK_ERR_INVALID, "yk_camera_make: bad argument");
     xform w2c;
     if (!xf_look_at(load3(p->position), load3(p->target), load3(p->up), &w2c))
@@ -327,6 +335,7 @@ int yk_camera_make(const yk_camera_params* p, uint32_t res_x, uint32_t res_y, yk
     std::memcpy(out->camera_to_world, c2w.m.e, 64);
     std::memcpy(out->raster_to_camera, raster_to_cam.m.e, 64);
     return YK_OK;
+    });
 }
 
 // generate_tiles + outward_spiral, film.rs:299-376. Walks the square spiral around the centre tile and
@@ -372,18 +381,22 @@ void yk_xf_translation(const float* d, yk_transform* o) { from_xform(xf_translat
 void yk_xf_scale(float x, float y, float z, yk_transform* o) { from_xform(xf_scaling(x, y, z), o); }
 void yk_xf_rotation(float theta, const float* axis, yk_transform* o) { from_xform(xf_rotate(theta, load3(axis)), o); }
 int yk_xf_new(const float* m16, yk_transform* o) {
+    return yk_guard("yk_xf_new", [&]() -> int {
     mat4 m;
     std::memcpy(m.e, m16, 64);
     xform t;
     if (!xf_from_matrix(m, &t)) return yk_set_error(YK_ERR_SINGULAR, "Can't invert, singular matrix");
     from_xform(t, o);
     return YK_OK;
+    });
 }
 int yk_xf_look_at(const float* pos, const float* target, const float* up, yk_transform* o) {
+    return yk_guard("yk_xf_look_at", [&]() -> int {
     xform t;
     if (!xf_look_at(load3(pos), load3(target), load3(up), &t)) return yk_set_error(YK_ERR_SINGULAR, "Can't invert, singular matrix");
     from_xform(t, o);
     return YK_OK;
+    });
 }
 void yk_xf_mul(const yk_transform* a, const yk_transform* b, yk_transform* o) { from_xform(xf_compose(to_xform(*a), to_xform(*b)), o); }
 void yk_xf_inverted(const yk_transform* a, yk_transform* o) { from_xform(xf_flip(to_xform(*a)), o); }

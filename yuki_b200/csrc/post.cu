@@ -12,6 +12,7 @@
 #include <string>
 
 #include "yuki_gpu.h"
+#include "yk_guard.h"
 
 int yk_set_error(int code, const std::string& msg);  // host_scene.cpp
 int yk_context_activate(yk_context* c);                 // render.cu: cudaSetDevice(the context's device)
@@ -106,6 +107,7 @@ extern "C" {
 
 int yk_tonemap_filmic(yk_context* c, const float* film_rgb, uint32_t res_x, uint32_t res_y, const float* tile_samples, uint32_t n_tiles,
                       uint32_t tile_dim, float exposure, float* out_rgb) {
+    return yk_guard("yk_tonemap_filmic", [&]() -> int {
     if (!c || !film_rgb || !out_rgb || !res_x || !res_y) return yk_set_error(YK_ERR_INVALID, "yk_tonemap_filmic: null / empty argument");
     if (tile_samples && !tile_dim) return yk_set_error(YK_ERR_INVALID, "yk_tonemap_filmic: tile_dim is zero");
     if (int rc = yk_context_activate(c)) return rc;
@@ -125,10 +127,12 @@ int yk_tonemap_filmic(yk_context* c, const float* film_rgb, uint32_t res_x, uint
     POST_TRY(cudaStreamSynchronize(s));
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_aux);
     return YK_OK;
+    });
 }
 
 int yk_heatmap(yk_context* c, const float* film_rgb, uint32_t res_x, uint32_t res_y, uint32_t channel, int auto_range, float* min_val,
                float* max_val, float* out_rgb) {
+    return yk_guard("yk_heatmap", [&]() -> int {
     if (!c || !film_rgb || !out_rgb || !res_x || !res_y || !min_val || !max_val)
         return yk_set_error(YK_ERR_INVALID, "yk_heatmap: null / empty argument");
     if (channel > 3) return yk_set_error(YK_ERR_INVALID, "yk_heatmap: channel must be 0..3 (R, G, B, luminance)");
@@ -158,6 +162,7 @@ int yk_heatmap(yk_context* c, const float* film_rgb, uint32_t res_x, uint32_t re
     }
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_aux);
     return YK_OK;
+    });
 }
 
 }  // extern "C"

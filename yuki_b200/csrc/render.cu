@@ -14,6 +14,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -35,6 +36,9 @@
 #include "wf_query.cuh"
 #include "wf_scene_pack.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+#include "yk_guard.h"
+
 // =====================================================================================================
 // Host side: context, scene upload, wavefront driver.
 // =====================================================================================================
@@ -49,6 +53,9 @@ struct Pipe {
     Wave wave{};
     std::vector<void*> wave_allocs;
     uint32_t wave_cap = 0, wave_lights = 0, wave_stack = 0;
+    bool wave_sort = false;          // the ray-sort arrays are allocated
+    void* sort_scan_tmp = nullptr;   // cub scan workspace for the sort's bins
+    size_t sort_scan_bytes = 0;
     IterCounters* d_ctr = nullptr;   // two entries, alternating per bounce
     IterCounters* h_ctr = nullptr;   // pinned: read-back for the integrators whose bounce count is unbounded (Whitted)
     Totals* h_totals = nullptr;      // pinned
@@ -83,7 +90,7 @@ struct yk_context {
     float* d_film = nullptr;
     int32_t* d_hit_ids = nullptr;
     size_t film_cap = 0;
-    int occ_trace_closest = 0, occ_trace_any = 0;
+    int occ_trace_closest = 0, occ_trace_any = 0, occ_trace_rays = 0;
     int n_pipes_env = 0;  // YK_PIPES override (development)
     uint64_t mem_budget = 0;  // bytes of wavefront state per pipe the default batch size may use (set at the first render)
     std::vector<void*> query_allocs;  // yk_trace / yk_occluded staging (rays in, results out), kept between calls
@@ -92,6 +99,13 @@ struct yk_context {
     int32_t* q_id = nullptr;
     uint32_t* q_cnt = nullptr;
     uint8_t* q_occ = nullptr;
+    // Ray sort between bounces (wf_sort.cuh). key: 0 = off, 1 = leaf slot of the shape the ray leaves + octant, 2 = Morton cell of
+    // the origin + octant, -1 = by scene size (render_impl). order: 1 = closest-hit kernel only, 2 = material sort too.
+    // Environment: YK_SORT_KEY, YK_SORT_ORDER; yk_render_opts.ray_sort overrides the key per render.
+    int sort_key = -1, sort_order = 2;
+    // Shadow rays: 1 = one ray per lane (k_trace_shadow_rays + k_shadow_fold), 0 = one path per lane with the fold fused
+    // (k_trace_shadow). Environment: YK_SHADOW_MODE.
+    int shadow_mode = 1;
     int stage_timing = 1;  // CUDA events per bounce: 1 = around the closest-hit kernel (the roofline figure), 2 = every stage
                            // (costs ~1.5 % of a Cornell render), 0 = none; environment variable YK_STAGE_TIMING
 };
@@ -134,10 +148,12 @@ float host_roughness_to_alpha(float r) {
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
-int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries) {
-    if (p->wave_cap == cap && p->wave_lights == n_lights && p->wave_stack == stack_entries) return YK_OK;
+int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries, bool sort = false) {
+    if (p->wave_cap == cap && p->wave_lights == n_lights && p->wave_stack == stack_entries && (p->wave_sort || !sort)) return YK_OK;
     free_bag(p->wave_allocs);
     p->wave_cap = 0;
+    p->wave_sort = false;
+    p->sort_scan_tmp = nullptr;
     Wave w{};
     w.cap = cap;
     w.n_lights = n_lights;
@@ -152,7 +168,7 @@ int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries
     }
     WAVE_ALLOC(hit, cap) WAVE_ALLOC(bvh_counts, cap) WAVE_ALLOC(L, cap)
     // (+ one chunk of slack: the shadow kernel prefetches whole 64-path chunks of these arrays without per-line bounds tests)
-    WAVE_ALLOC(sh_path, (size_t)cap + 64) WAVE_ALLOC(pend_beta, (size_t)cap + 64) WAVE_ALLOC(pend_extra, (size_t)cap + 64)
+    WAVE_ALLOC(sh_path, (size_t)cap + 64) WAVE_ALLOC(sh_mask, (size_t)cap + 64) WAVE_ALLOC(pend_beta, (size_t)cap + 64) WAVE_ALLOC(pend_extra, (size_t)cap + 64)
     WAVE_ALLOC(lt_o, cap * nl + 64) WAVE_ALLOC(lt_d, cap * nl + 64) WAVE_ALLOC(lt_c, cap * nl + 64)
     WAVE_ALLOC(q_active[0], cap) WAVE_ALLOC(q_active[1], cap) WAVE_ALLOC(q_mat, (size_t)4 * cap) WAVE_ALLOC(q_mat_tri, (size_t)4 * cap) WAVE_ALLOC(q_mat_slot, (size_t)4 * cap)
     WAVE_ALLOC(totals, 1)
@@ -160,11 +176,24 @@ int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries
         WAVE_ALLOC(stack, (size_t)stack_entries * cap * 5)
         WAVE_ALLOC(tree_rng, cap)
     }
+    if (sort) {
+        WAVE_ALLOC(sort_key, cap) WAVE_ALLOC(perm, cap) WAVE_ALLOC(sort_bins, (size_t)kSortBins + 1)
+        size_t bytes = 0;
+        if (cub::DeviceScan::ExclusiveSum(nullptr, bytes, w.sort_bins, w.sort_bins, (int)kSortBins) != cudaSuccess) {
+            free_bag(bag);
+            return yk_set_error(YK_ERR_CUDA, "ensure_wave: cub scan workspace query failed");
+        }
+        unsigned char* tmp = nullptr;
+        if ((rc = dev_alloc(bag, &tmp, bytes)) != YK_OK) { free_bag(bag); return rc; }
+        p->sort_scan_tmp = tmp;
+        p->sort_scan_bytes = bytes;
+    }
 #undef WAVE_ALLOC
     p->wave = w;
     p->wave_cap = cap;
     p->wave_lights = n_lights;
     p->wave_stack = stack_entries;
+    p->wave_sort = sort;
     return YK_OK;
 }
 
@@ -238,11 +267,20 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
     const int shade_blocks = grid_for(bt.n_paths, kShadeThreads, wide_blocks);
     const int closest_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_closest);
     const int shadow_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_shadow);
+    const int shadow_rays_blocks = grid_for((uint32_t)std::min<uint64_t>((uint64_t)bt.n_paths * std::max(sc->dev.n_lights, 1u), 0xffffffffu), kTraceThreads,
+                                            c->sm_count * std::max(1, c->occ_trace_rays));
+    const int fold_blocks = grid_for(bt.n_paths, 256, c->sm_count * 8);
     uint32_t max_iters = 1;
     if (cfg.integrator == YK_INTEGRATOR_PATH) max_iters = cfg.max_depth;
     else if (sync_loop) max_iters = 0xffffffffu;
     uint32_t* q_cur = nullptr;
     int flip = 0;
+    // Ray sort (wf_sort.cuh): bounce rays are fetched through `perm`, built after the previous bounce's shading. sort_order
+    // 1 = the closest-hit kernel only, 2 = the material sort too (shading and shadow rays then run in sorted order).
+    const bool sorting = cfg.integrator == YK_INTEGRATOR_PATH && cfg.sort_key_mode != 0 && p->wave_sort && cfg.max_depth > 1;
+    const int sort_blocks = grid_for(bt.n_paths, 256, c->sm_count * 8);
+    const uint32_t* perm_trace = nullptr;
+    const uint32_t* perm_classify = nullptr;
     for (uint32_t iter = 0; iter < max_iters; ++iter) {
         const int b = (int)(iter & 1);  // this bounce reads stream b and writes stream b ^ 1
         IterCounters* cur = &p->d_ctr[iter & 1];
@@ -251,11 +289,11 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         if (c->stage_timing > 0) CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
         const bool spheres = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;  // the generic instantiations: sphere slots, leaf table
         if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
-            if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
-            else k_trace_closest<true, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
+            if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
+            else k_trace_closest<true, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
         } else {
-            if (spheres) k_trace_closest<false, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
-            else k_trace_closest<false, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur);
+            if (spheres) k_trace_closest<false, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
+            else k_trace_closest<false, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
         }
         if (c->stage_timing > 0) CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
         tm->launches += 1;
@@ -268,14 +306,14 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         if (debug) {
             k_debug_shade<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(sc->dev, w, cfg, bt.n_paths);
             // primary-hit digest / id image for the debug integrators too
-            k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, 2, q_next);
+            k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, 2, q_next, nullptr);
             tm->launches += 2;
             for (int st = 2; st < kTimedStages; ++st) if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, st), s));
             sl.n_iters = iter + 1;
             break;
         }
-        if (cfg.integrator == YK_INTEGRATOR_WHITTED) k_classify<1, true><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
-        else k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next);
+        if (cfg.integrator == YK_INTEGRATOR_WHITTED) k_classify<1, true><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next, nullptr);
+        else k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next, perm_classify);
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
         tm->launches += 1;
         const bool is_path = cfg.integrator == YK_INTEGRATOR_PATH;
@@ -305,13 +343,33 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             tm->launches += 1;
         }
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
-        if (spheres) k_trace_shadow<true><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
-        else k_trace_shadow<false><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
+        nvtxRangePushA("yk shadow rays + fold");
+        if (c->shadow_mode == 1 && sc->dev.n_lights > 0) {  // one shadow ray per lane, then the fold (wf_trace.cuh)
+            if (spheres) k_trace_shadow_rays<true><<<shadow_rays_blocks, kTraceThreads, 0, s>>>(sc->dev, w, sc->dev.n_lights, cur);
+            else k_trace_shadow_rays<false><<<shadow_rays_blocks, kTraceThreads, 0, s>>>(sc->dev, w, sc->dev.n_lights, cur);
+            k_shadow_fold<<<fold_blocks, 256, 0, s>>>(w, cfg, cur);
+            tm->launches += 1;
+        } else {  // one path per lane, its lights in order, fold fused
+            if (spheres) k_trace_shadow<true><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
+            else k_trace_shadow<false><<<shadow_blocks, kTraceThreads, 0, s>>>(sc->dev, w, cfg, cur);
+        }
+        nvtxRangePop();
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 4), s));
         tm->launches += 1;
         if (cfg.integrator == YK_INTEGRATOR_WHITTED) {
             k_tree_return<<<shade_blocks, kShadeThreads, 0, s>>>(w, b, cur, nxt, q_next);
             tm->launches += 1;
+        }
+        if (sorting && iter + 1 < max_iters) {  // order the next bounce's rays
+            nvtxRangePushA("yk ray sort");
+            CUDA_TRY(cudaMemsetAsync(w.sort_bins, 0, ((size_t)kSortBins + 1) * sizeof(uint32_t), s));
+            k_sort_hist<<<sort_blocks, 256, 0, s>>>(w, nxt);
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(p->sort_scan_tmp, p->sort_scan_bytes, w.sort_bins, w.sort_bins, (int)kSortBins, s));
+            k_sort_scatter<<<sort_blocks, 256, 0, s>>>(w, nxt);
+            nvtxRangePop();
+            tm->launches += 3;
+            perm_trace = w.perm;
+            perm_classify = cfg.sort_order >= 2 ? w.perm : nullptr;
         }
         sl.n_iters = iter + 1;
         q_cur = q_next;
@@ -347,6 +405,7 @@ int yk_context_activate(yk_context* c) {
 extern "C" {
 
 int yk_context_create(int device_id, yk_context** out) {
+    return yk_guard("yk_context_create", [&]() -> int {
     if (!out) return yk_set_error(YK_ERR_INVALID, "yk_context_create: null output");
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -368,6 +427,9 @@ int yk_context_create(int device_id, yk_context** out) {
     CUDA_TRY(cudaEventCreate(&c->ev[3]));
     if (const char* np = getenv("YK_PIPES")) c->n_pipes_env = std::max(1, std::min(kMaxPipes, atoi(np)));
     if (const char* st = getenv("YK_STAGE_TIMING")) c->stage_timing = std::max(0, std::min(2, atoi(st)));
+    if (const char* sm = getenv("YK_SHADOW_MODE")) c->shadow_mode = atoi(sm) ? 1 : 0;
+    if (const char* sk = getenv("YK_SORT_KEY")) c->sort_key = std::max(-1, std::min(2, atoi(sk)));
+    if (const char* so = getenv("YK_SORT_ORDER")) c->sort_order = std::max(1, std::min(2, atoi(so)));
     for (int i = 0; i < kMaxPipes; ++i) {
         Pipe& p = c->pipe[i];
         if (i == 0) p.stream = c->stream;
@@ -382,8 +444,10 @@ int yk_context_create(int device_id, yk_context** out) {
     }
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace_closest<false, false>, kTraceThreads, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace_shadow<false>, kTraceThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_rays, k_trace_shadow_rays<false>, kTraceThreads, 0));
     *out = c;
     return YK_OK;
+    });
 }
 
 void yk_context_destroy(yk_context* c) {
@@ -417,25 +481,38 @@ void yk_context_destroy(yk_context* c) {
 
 void* yk_context_stream(yk_context* c) { return c ? (void*)c->stream : nullptr; }
 
-int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
+}  // extern "C"
+
+// What the host-side validation of a flattened scene yields (and what the device repack needs from it). yk_multi_scene_create
+// validates once and uploads to every device with the result (`pre`).
+struct SceneCheck {
+    const char* error = nullptr;
+    uint32_t n_interior = 0, kinds = 0;
+    bool small_leaves = true;
+};
+static int scene_create_impl(yk_context* c, const yk_scene_desc* d, const SceneCheck* pre, SceneCheck* check_out, yk_scene** out) {
     if (!c || !d || !out) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: null argument");
     if (!d->n_nodes || !d->nodes || !d->n_tris || !d->tri_vertices || !d->tri_orig_id || !d->tri_material || !d->tri_area_light ||
         !d->tri_flags)
         return yk_set_error(YK_ERR_INVALID, "yk_scene_create: missing node / triangle arrays");
     if (d->n_lights > (uint32_t)kMaxLights) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 32 lights");
+    if ((d->n_materials && !d->materials) || (d->n_lights && !d->lights) || (d->n_textures && !d->textures) || (d->n_spheres && !d->spheres))
+        return yk_set_error(YK_ERR_INVALID, "yk_scene_create: null material / light / texture / sphere table with a non-zero count");
     if (d->n_materials > 0xffffffu) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: too many materials");
     CUDA_TRY(cudaSetDevice(c->device));
+    const bool timing = getenv("YK_SCENE_TIMING") != nullptr;  // development: phase times to stderr
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (timing) fprintf(stderr, "yk_scene_create: %-28s at %8.2f ms\n", what,
+                            1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    };
     auto sc = std::make_unique<yk_scene>();
     sc->ctx = c;
     sc->device = c->device;
     int rc;
     // The reference-layout arrays go to the device as they are and are repacked there (k_scene_*): no host-side copy of
     // the scene is built. Meanwhile host threads validate the same arrays (indices, ranges, flags).
-    struct Check {
-        const char* error = nullptr;
-        uint32_t n_interior = 0, kinds = 0;
-        bool small_leaves = true;
-    };
+    using Check = SceneCheck;
     const unsigned n_workers = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     auto validate = [d, n_workers](unsigned wi) -> Check {
         Check ck;
@@ -459,7 +536,7 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
             if (m >= d->n_materials) { fail("yk_scene_create: material index out of range"); continue; }
             if (d->materials[m].kind <= YK_MAT_GLOSSY) ck.kinds |= 1u << d->materials[m].kind;
             const int32_t al = d->tri_area_light[i];
-            if (al >= (int32_t)d->n_lights) fail("yk_scene_create: area light out of range");
+            if (al >= (int32_t)d->n_lights || al < -1) fail("yk_scene_create: area light out of range");
             else if (al >= 0 && d->lights[al].kind != YK_LIGHT_RECT) fail("yk_scene_create: area light must be rectangular");
             const uint8_t f = d->tri_flags[i];
             if ((f & YK_TRI_HAS_NORMALS) && !d->tri_normals) fail("yk_scene_create: normals flagged but absent");
@@ -474,8 +551,10 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     for (uint32_t i = 0; i < d->n_lights; ++i)
         if (d->lights[i].kind > YK_LIGHT_DISTANT) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: unknown light kind");
     std::vector<std::future<Check>> checks;
-    for (unsigned wi = 0; wi < n_workers; ++wi) checks.push_back(std::async(std::launch::async, validate, wi));
+    if (!pre)
+        for (unsigned wi = 0; wi < n_workers; ++wi) checks.push_back(std::async(std::launch::async, validate, wi));
     auto join_checks = [&](Check* total) {
+        if (pre) *total = *pre;
         for (auto& f : checks) {
             const Check ck = f.get();
             if (ck.error && !total->error) total->error = ck.error;
@@ -505,7 +584,9 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     const uint8_t *r_flags = nullptr, *r_kinds = nullptr;
     std::vector<uint8_t> kinds(std::max(d->n_materials, 1u), 0);
     for (uint32_t i = 0; i < d->n_materials; ++i) kinds[i] = (uint8_t)d->materials[i].kind;
+    lap("validators started");
     if ((rc = dev_upload(temps, &r_nodes, d->nodes, d->n_nodes)) != YK_OK) return rc;
+    lap("nodes uploaded");
     if ((rc = dev_upload(temps, &r_verts, d->tri_vertices, (size_t)d->n_tris * 9)) != YK_OK) return rc;
     if ((rc = dev_upload(temps, &r_orig, d->tri_orig_id, d->n_tris)) != YK_OK) return rc;
     if ((rc = dev_upload(temps, &r_mat, d->tri_material, d->n_tris)) != YK_OK) return rc;
@@ -515,9 +596,12 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     if ((rc = dev_upload(temps, &r_kinds, kinds.data(), kinds.size())) != YK_OK) return rc;
     if (d->tri_normals && (rc = dev_upload(sc->allocs, &sc->dev.normals, d->tri_normals, (size_t)d->n_tris * 9)) != YK_OK) return rc;
     if (d->tri_uvs && (rc = dev_upload(sc->allocs, &sc->dev.uvs, d->tri_uvs, (size_t)d->n_tris * 6)) != YK_OK) return rc;
+    lap("arrays uploaded");
     Check total;
     join_checks(&total);
+    lap("validation joined");
     if (total.error) return yk_set_error(YK_ERR_INVALID, total.error);
+    if (check_out) *check_out = total;
     if (total.n_interior > kRefIndexMask) return yk_set_error(YK_ERR_INVALID, "yk_scene_create: more than 2^29 interior nodes");
     sc->material_kinds = total.kinds;
     const uint32_t n_interior = total.n_interior, n_leaves = d->n_nodes - n_interior;
@@ -562,7 +646,9 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
         sc->dev.tris = d_tris;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(st));
+        lap("repacked on the device");
         free_bag(temps);
+        lap("temporaries freed");
     }
 
     std::vector<DevTexture> tex(d->n_textures);
@@ -614,8 +700,15 @@ int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
     sc->dev.n_nodes = d->n_nodes;
     std::memcpy(sc->dev.background, d->background, 12);
     cleanup.armed = false;
+    lap("done");
     *out = sc.release();
     return YK_OK;
+}
+
+extern "C" {
+
+int yk_scene_create(yk_context* c, const yk_scene_desc* d, yk_scene** out) {
+    return yk_guard("yk_scene_create", [&]() -> int { return scene_create_impl(c, d, nullptr, nullptr, out); });
 }
 
 void yk_scene_destroy(yk_scene* s) {
@@ -626,6 +719,9 @@ void yk_scene_destroy(yk_scene* s) {
 }
 
 }  // extern "C"
+
+// Internal yk_render_opts.flags bit (yk_multi_render's workers): the caller initialised the hit-id image, do not refill it.
+constexpr uint32_t kRenderAuxInitialised = 0x100u;
 
 // yk_render, and yk_debug_ray's single path (`debug_log` = device ray list, `debug_px` = the film pixel of its camera sample).
 static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_film_settings* fs, const yk_sampler* sm,
@@ -686,6 +782,22 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
     cfg.aux_sample = opts ? opts->aux_sample : 0u;
     cfg.debug_log = debug_log;
     if (debug_log) { cfg.debug_px[0] = debug_px[0]; cfg.debug_px[1] = debug_px[1]; }
+    {   // ray sort between bounces (path tracing only; Whitted's tree walk re-queues rays in DFS order)
+        int key = c->sort_key;
+        cfg.sort_order = (uint32_t)c->sort_order;
+        if (opts && (opts->ray_sort & 0xfu)) key = (int)(opts->ray_sort & 0xfu) - 1;
+        if (opts && (opts->ray_sort & YK_RAY_SORT_TRACE_ONLY)) cfg.sort_order = 1;
+        if (key < 0) key = 0;  // default
+        if (in->kind != YK_INTEGRATOR_PATH || in->max_depth < 2 || debug_log) key = 0;
+        cfg.sort_key_mode = (uint32_t)std::min(key, 2);
+        uint32_t bits = 0;
+        while (bits < 32 && ((uint64_t)1 << bits) < sc->dev.n_tris) ++bits;  // leaf slots fit `bits` bits
+        cfg.sort_slot_shift = bits > kSortKeyBits - 3 ? bits - (kSortKeyBits - 3) : 0u;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = sc->dev.root_max[a] - sc->dev.root_min[a];
+            cfg.sort_cell_scale[a] = ext > 0.0f ? 32.0f / ext : 0.0f;
+        }
+    }
 
     // Device film / accumulators.
     if (c->film_cap < n_pixels) {
@@ -706,7 +818,7 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
     int32_t* d_ids = nullptr;
     if (opts && opts->hit_ids) {
         d_ids = on_device ? opts->hit_ids : c->d_hit_ids;
-        k_fill_i32<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s>>>(d_ids, n_pixels, -1);
+        if (!(flags & kRenderAuxInitialised)) k_fill_i32<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s>>>(d_ids, n_pixels, -1);
     }
     cfg.hit_ids = d_ids;
 
@@ -770,7 +882,7 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
         CUDA_TRY(cudaEventRecord(c->ev[0], s));
         for (int pi = 0; pi < n_pipes; ++pi) {
             Pipe& p = c->pipe[pi];
-            if ((rc = ensure_wave(&p, wave_cap, sc->dev.n_lights, stack_entries)) != YK_OK) return rc;
+            if ((rc = ensure_wave(&p, wave_cap, sc->dev.n_lights, stack_entries, cfg.sort_key_mode != 0)) != YK_OK) return rc;
             if (pi > 0) CUDA_TRY(cudaStreamWaitEvent(p.stream, c->ev[0], 0));
             CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), p.stream));
             p.hash_group = (size_t)-1;
@@ -926,7 +1038,9 @@ extern "C" {
 int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_film_settings* fs, const yk_sampler* sm,
               const yk_integrator* in, const yk_tile* tiles, uint32_t n_tiles, const yk_render_opts* opts, float* film_rgb,
               yk_stats* stats) {
+    return yk_guard("yk_render", [&]() -> int {
     return render_impl(c, sc, cam, fs, sm, in, tiles, n_tiles, opts, film_rgb, stats, nullptr, nullptr);
+    });
 }
 
 // launch_debug_ray (app/window.rs:812-905): one path, its rays collected by k_debug_log between the wavefront stages. The
@@ -935,6 +1049,7 @@ int yk_render(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_
 int yk_debug_ray(yk_context* c, const yk_scene* sc, const yk_camera* cam, const yk_sampler* sm, const yk_integrator* in,
                  uint32_t film_px_x, uint32_t film_px_y, yk_integrator_ray* rays, uint32_t cap, uint32_t* n_rays, float* li_rgb,
                  uint64_t* ray_count) {
+    return yk_guard("yk_debug_ray", [&]() -> int {
     if (!c || !sc || !cam || !sm || !in || !n_rays || (cap && !rays)) return yk_set_error(YK_ERR_INVALID, "yk_debug_ray: null argument");
     if (film_px_x > 0xffffu || film_px_y > 0xffffu) return yk_set_error(YK_ERR_INVALID, "yk_debug_ray: film pixel must fit u16");
     *n_rays = 0;
@@ -987,6 +1102,7 @@ int yk_debug_ray(yk_context* c, const yk_scene* sc, const yk_camera* cam, const 
     if (li_rgb) { li_rgb[0] = li[0]; li_rgb[1] = li[1]; li_rgb[2] = li[2]; }
     if (ray_count) *ray_count = st.ray_count;
     return YK_OK;
+    });
 }
 
 
@@ -1020,6 +1136,7 @@ int query_prepare(yk_context* c, const yk_scene* sc, uint32_t n, const char* who
 // BoundingVolumeHierarchy::intersect (bvh.rs:160-232) for n caller rays.
 int yk_trace(yk_context* c, const yk_scene* sc, const float* o_xyz, const float* d_xyz, const float* t_max, uint32_t n, float* t_out,
              int32_t* orig_id_out, uint32_t* counts_out) {
+    return yk_guard("yk_trace", [&]() -> int {
     if (!c || !sc || (n && (!o_xyz || !d_xyz || !t_out || !orig_id_out))) return yk_set_error(YK_ERR_INVALID, "yk_trace: null argument");
     if (n == 0) return YK_OK;
     for (size_t i = 0; t_max && i < n; ++i)
@@ -1046,8 +1163,8 @@ int yk_trace(yk_context* c, const yk_scene* sc, const float* o_xyz, const float*
         CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), s));
         k_query_pack<<<(m + T - 1) / T, T, 0, s>>>(p.wave, d_o, d_d, t_max ? d_tm : nullptr, m);
         const int blocks = grid_for(m, kTraceThreads, c->sm_count * std::max(1, c->occ_trace_closest));
-        if (generic) k_trace_closest<true, true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 0, &p.d_ctr[0]);
-        else k_trace_closest<true, false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 0, &p.d_ctr[0]);
+        if (generic) k_trace_closest<true, true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 0, &p.d_ctr[0], nullptr);
+        else k_trace_closest<true, false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 0, &p.d_ctr[0], nullptr);
         k_query_unpack<<<(m + T - 1) / T, T, 0, s>>>(sc->dev, p.wave, m, d_t, d_id, counts_out ? d_cnt : nullptr);
         CUDA_TRY(cudaMemcpyAsync(t_out + first, d_t, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(orig_id_out + first, d_id, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -1056,11 +1173,13 @@ int yk_trace(yk_context* c, const yk_scene* sc, const float* o_xyz, const float*
     }
     CUDA_TRY(cudaGetLastError());
     return YK_OK;
+    });
 }
 
 // VisibilityTester::unoccluded's traversal (visibility.rs:6-23 -> any_intersect, bvh.rs:235-302) for n caller segments
 // o -> o + d, cut at t_max = 0.9999 like every shadow ray of the reference (interaction.rs:57-58).
 int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const float* d_xyz, uint32_t n, uint8_t* occluded_out) {
+    return yk_guard("yk_occluded", [&]() -> int {
     if (!c || !sc || (n && (!o_xyz || !d_xyz || !occluded_out))) return yk_set_error(YK_ERR_INVALID, "yk_occluded: null argument");
     if (n == 0) return YK_OK;
     std::lock_guard<std::recursive_mutex> guard(c->mu);
@@ -1084,21 +1203,29 @@ int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const flo
         CUDA_TRY(cudaMemcpyAsync(&p.d_ctr[0], &ctr, sizeof(ctr), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), s));
         k_query_pack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, d_o, d_d, m);
-        const int blocks = grid_for(m, kTraceThreads, c->sm_count * std::max(1, c->occ_trace_any));
-        if (generic) k_trace_shadow<true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
-        else k_trace_shadow<false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
-        k_query_unpack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, m, d_out);
+        if (c->shadow_mode == 1) {
+            const int blocks = grid_for(m, kTraceThreads, c->sm_count * std::max(1, c->occ_trace_rays));
+            if (generic) k_trace_shadow_rays<true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 1u, &p.d_ctr[0]);
+            else k_trace_shadow_rays<false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 1u, &p.d_ctr[0]);
+        } else {
+            const int blocks = grid_for(m, kTraceThreads, c->sm_count * std::max(1, c->occ_trace_any));
+            if (generic) k_trace_shadow<true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
+            else k_trace_shadow<false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
+        }
+        k_query_unpack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, m, c->shadow_mode == 1 ? 1 : 0, d_out);
         CUDA_TRY(cudaMemcpyAsync(occluded_out + first, d_out, m, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
     }
     CUDA_TRY(cudaGetLastError());
     return YK_OK;
+    });
 }
 
 
 // Sampler::{start_pixel_sample, get_1d, get_2d} evaluated on the device for n (pixel x, pixel y, sample index) triples.
 int yk_sampler_draws(yk_context* c, const yk_sampler* sm, const uint32_t* pixel_index_xyi, uint32_t n, const uint8_t* pattern,
                      uint32_t n_pattern, float* out) {
+    return yk_guard("yk_sampler_draws", [&]() -> int {
     if (!c || !sm || (n && (!pixel_index_xyi || !out)) || (n_pattern && !pattern)) return yk_set_error(YK_ERR_INVALID, "yk_sampler_draws: null argument");
     if (sm->kind > YK_SAMPLER_STRATIFIED) return yk_set_error(YK_ERR_INVALID, "yk_sampler_draws: unknown sampler");
     const uint32_t spp = sm->kind == YK_SAMPLER_UNIFORM ? sm->nx : sm->nx * sm->ny;
@@ -1145,6 +1272,9 @@ int yk_sampler_draws(yk_context* c, const yk_sampler* sm, const uint32_t* pixel_
     free_bag(bag);
     if (e != cudaSuccess) return yk_set_error(YK_ERR_CUDA, std::string("yk_sampler_draws: ") + cudaGetErrorString(e));
     return YK_OK;
+    });
 }
 
 }  // extern "C"
+
+#include "multi.inl"

@@ -159,6 +159,7 @@ struct Wave {
     // position* g (position in the concatenation of this bounce's four material queues), not by path: the shading
     // kernels write them fully coalesced and the shadow kernel streams them with no dependent gather.
     uint32_t* sh_path;   // path of shading position g
+    uint32_t* sh_mask;   // bit k: light k's shadow ray of shading position g is to be traced / (after k_trace_shadow_rays) is unoccluded
     float4* pend_beta;   // path: weight to apply to this bounce's radiance; w = clamp flag. whitted: node depth | has-children << 8, sampler dimension, -, -1
     float4* pend_extra;  // emitted term of this bounce; w = bit mask of the lights whose shadow ray must be traced
     float4* lt_o;        // cap * n_lights: shadow ray o.xyz | contribution.r   (contribution = f * li * cos / pdf)
@@ -170,8 +171,16 @@ struct Wave {
     uint32_t* q_mat;     // 4 * cap: paths per material kind
     uint32_t* q_mat_tri; // 4 * cap: the hit shape slot of each entry
     uint32_t* q_mat_slot; // 4 * cap: the entry's slot in this bounce's active queue (index of st[] / hit[])
+    // Ray sort (wf_sort.cuh): the shading kernels leave a coherence key per survivor, a counting sort turns the keys into
+    // `perm` (sorted position -> queue slot), and the next bounce's traversal (and optionally its material sort) walks the
+    // queue through it. Null when the render does not sort.
+    uint32_t* sort_key;  // cap
+    uint32_t* perm;      // cap
+    uint32_t* sort_bins; // kSortBins + 1: histogram, then the bins' write cursors
     Totals* totals;
 };
+constexpr uint32_t kSortKeyBits = 18;  // 15 spatial bits (major) + 3 direction-octant bits
+constexpr uint32_t kSortBins = 1u << kSortKeyBits;
 // beta.w flag word
 constexpr uint32_t kFlagSpecular = 0x100u;   // path: specular_bounce / whitted: is_specular
 constexpr uint32_t kFlagAlive = 0x200u;
@@ -198,6 +207,12 @@ struct RenderCfg {
     int32_t* hit_ids;  // device, or null
     DebugLog* debug_log;  // yk_debug_ray only: the single path's rays; the camera sample lands on film pixel debug_px
     float debug_px[2];
+    // ray sort: 0 = none; 1 = key from the hit shape's leaf slot (BVH order is a spatial order) + direction octant;
+    // 2 = key from the Morton cell of the ray origin inside the scene bounds + direction octant
+    uint32_t sort_key_mode;
+    uint32_t sort_order;          // 1 = the closest-hit kernel walks the sorted order; 2 = the material sort (hence shading, shadow rays) too
+    uint32_t sort_slot_shift;     // mode 1: leaf slot >> shift gives the 15 spatial key bits
+    float sort_cell_scale[3];     // mode 2: (o - root_min) * scale = cell coordinate in [0, 32)
 };
 
 // ---- helpers --------------------------------------------------------------------------------------

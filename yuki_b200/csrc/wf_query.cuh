@@ -34,6 +34,7 @@ __global__ void k_query_pack_segments(Wave w, const float* __restrict__ o, const
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     w.sh_path[i] = i;
+    w.sh_mask[i] = 1u;
     w.pend_extra[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(1u));
     w.pend_beta[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     w.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -41,10 +42,11 @@ __global__ void k_query_pack_segments(Wave w, const float* __restrict__ o, const
     w.lt_d[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], 0.0f);
     w.lt_c[i] = make_float2(0.0f, __int_as_float(-1));
 }
-__global__ void k_query_unpack_segments(Wave w, uint32_t n, uint8_t* __restrict__ out) {
+// per_ray: the segments went through k_trace_shadow_rays (an occluded segment lost its bit); else through k_trace_shadow's fold
+__global__ void k_query_unpack_segments(Wave w, uint32_t n, int per_ray, uint8_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = w.L[i].x == 0.0f ? 1 : 0;
+    out[i] = per_ray ? ((w.sh_mask[i] & 1u) ? 0 : 1) : (w.L[i].x == 0.0f ? 1 : 0);
 }
 
 // Sampler::{start_pixel_sample(p, index, 0), get_1d, get_2d} (sampling/mod.rs:46-57, uniform.rs:72-94, stratified.rs:90-143)

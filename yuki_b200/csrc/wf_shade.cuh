@@ -4,6 +4,7 @@
 #pragma once
 #include "wf_common.cuh"
 #include "wf_trace.cuh"
+#include "wf_sort.cuh"
 
 namespace {
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ void stream_node(const Wave::Stream& st, uint32_t pos
 #endif
 template <int K, bool WHITTED>
 __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, int b, IterCounters* cur,
-                           IterCounters* nxt, int first_iteration, uint32_t* q_next) {
+                           IterCounters* nxt, int first_iteration, uint32_t* q_next, const uint32_t* perm) {
     const uint32_t n = cur->n_active;
     const uint32_t per_round = gridDim.x * blockDim.x * K;
     const uint32_t rounds = (n + per_round - 1) / per_round;
@@ -80,10 +81,12 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
         unsigned long long hh = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const uint32_t i = block_first + k * blockDim.x + threadIdx.x;
-            idx[k] = i;
+            const uint32_t j = block_first + k * blockDim.x + threadIdx.x;
+            idx[k] = j;
             path[k] = 0; hit_slot[k] = kMiss; key[k] = -1;
-            if (i >= n) continue;
+            if (j >= n) continue;
+            const uint32_t i = perm ? __ldg(&perm[j]) : j;  // the ray's queue slot (sorted renders walk the queue through perm)
+            idx[k] = i;
             path[k] = queue ? queue[i] : i;
             const uint2 h = ld_once(&w.hit[i]);
             hit_slot[k] = h.y;
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         // the survivor's state for the next bounce, written after the compaction assigns its position
         float4 nx_o = make_float4(0, 0, 0, 0), nx_d = make_float4(0, 0, 0, 0), nx_beta = make_float4(0, 0, 0, 0);
         unsigned long long nx_rng = 0;
+        uint32_t nx_key = 0;  // ray sort: the survivor's coherence key (wf_sort.cuh)
         if (i < n) {
             path = ld_once(&queue[i]);
             const uint32_t g = g_base + i;
@@ -406,6 +410,8 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                 }
             }
 
+            st_once(&w.sh_mask[g], shadow_mask);
+
             // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
             RGB le = gray(0.0f);
             // The integrators pass -ray.d here and (Path) to sample_f, but si.wo to Bsdf::f; the two differ for spheres, whose
@@ -440,6 +446,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     nx_o = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
                     nx_d = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
                     nx_beta = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
+                    if (cfg.sort_key_mode) nx_key = ray_sort_key(sc, cfg, hit_slot, nr.o.x, nr.o.y, nr.o.z, nr.d.x, nr.d.y, nr.d.z);
                 }
             } else {
                 // whitted.rs:128-170: this node's own terms go to the shadow / fold kernel; k_tree_return then either parks
@@ -497,6 +504,7 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             st_once(&out.ray_d[npos], nx_d);
             st_once(&out.beta[npos], nx_beta);
             st_once(&out.rng[npos], nx_rng);
+            if (PATH && cfg.sort_key_mode) w.sort_key[npos] = nx_key;
         }
     }
 }

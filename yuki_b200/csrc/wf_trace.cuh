@@ -310,7 +310,7 @@ struct TraceLane {
 
 // Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
 template <bool COUNTS, bool SPHERES>
-__global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_closest(DevScene sc, Wave w, int b, IterCounters* cur) {
+__global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_closest(DevScene sc, Wave w, int b, IterCounters* cur, const uint32_t* perm) {
     __shared__ uint2 s_stack[kShortStack][kTraceThreads];
     uint32_t deep_ref[kDeepStack];
     float deep_key[kDeepStack];
@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
             if (!exhausted) {
                 const uint32_t mine = chunk_next + __popc(idle & lt_mask);
                 if (!live && mine < chunk_end) {
-                    path = mine;  // the queue slot: rays, hits and counters of a bounce are all in queue order
+                    // the queue slot: rays, hits and counters of a bounce are all in queue order (sorted renders fetch it through perm)
+                    path = perm ? __ldg(&perm[mine]) : mine;
                     const float4 ro = ld_once(&w.st[b].ray_o[path]);
                     const float4 rd = ld_once(&w.st[b].ray_d[path]);
                     if (COUNTS) tests_before = tl.n_tests;
@@ -365,7 +366,10 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
         // ---- trace until too few lanes are live -----------------------------------------------------------
         for (;;) {
             YK_TRACE_PHASES(tl, live, COUNTS, false, SPHERES, {
-                if (SPHERES && det_ != det_) {  // a sphere slot (NaN vertex lanes): shapes/sphere.rs:36-77
+                // A sphere slot is recognised by its tag (row 0's w = -2 - sphere index; triangles carry an area light >= -1),
+                // not by the NaN determinant its NaN vertex lanes produce: a real triangle gives a NaN determinant too (zero-length
+                // or NaN direction, non-finite vertex) and must stay on the triangle branch, where the reference returns a NaN-t hit.
+                if (SPHERES && al_ <= -2) {  // shapes/sphere.rs:36-77
                     float t_s;
                     /* the direction is not kept in registers: re-read it on this rare path */
                     if (sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.st[b].ray_d[path], tl.t_max, &t_s)) {
@@ -374,6 +378,11 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
                 } else {
                     const float inv_det = 1.0f / det_;  // triangle.rs:133-139
                     hit_tri = tri_; hit_t = ts_ * inv_det; tl.t_max = hit_t;  // later equal-t hit replaces (bvh.rs:204-207)
+                    // A NaN hit distance (NaN determinant: zero-length or NaN direction) makes the reference's later box tests
+                    // `lo <= min(hi, NaN)`: `lo <= hi` for a box with a numeric exit distance — what the stacked keys encode — but
+                    // false for a box whose own exit distance is NaN too, i.e. every box when all three direction components are
+                    // NaN. Those rays drop their stack here (their popped nodes are already counted as tested, none would pass).
+                    if (hit_t != hit_t && tl.ix != tl.ix && tl.iy != tl.iy && tl.iz != tl.iz) tl.sp = sbase + kStackStride;
                 }
             })
             if (live && !tl.wants_box()) {  // retire
@@ -521,7 +530,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             YK_TRACE_PHASES(tl, live, false, true, SPHERES, {
                 (void)tri_; (void)ts_;
                 bool blocks = true;
-                if (SPHERES && det_ != det_) {  // sphere slot: run the real test; spheres carry no area light
+                if (SPHERES && al_ <= -2) {  // sphere slot (tag, see k_trace_closest): run the real test; spheres carry no area light
                     float t_s;
                     blocks = sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.lt_d[(size_t)(__ffs(mask) - 1) * w.cap + pos],
                                               tl.t_max, &t_s);
@@ -549,6 +558,125 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
         atomicAdd(&w.totals->any_nodes, sum_nodes);
         atomicAdd(&w.totals->any_tris, sum_tris);
         atomicAdd(&w.totals->shadow_rays, sum_rays);
+    }
+}
+// ---- shadow rays, one per lane ---------------------------------------------------------------------------------------
+// The alternative to k_trace_shadow's one-path-per-lane walk (a path's lights traced back to back by one lane: with L lights
+// the lane's dependent chain and the warp's refill imbalance grow L-fold). Here the work item is one (shading position g,
+// light k) pair. Items are enumerated light-major in chunks of kChunk consecutive shading positions, so the lanes of a warp
+// trace rays towards the same light from neighbouring hit points — coherent any-hit walks, coalesced hand-over reads. A lane
+// whose item's bit is clear in sh_mask[g] (no shadow ray for that light) takes another item. An occluded ray clears its bit
+// (only the lane that owns (g, k) ever touches bit k, so reading it needs no ordering); k_shadow_fold then adds the
+// contributions of the bits that are left, in light order, exactly like the reference's fold (path.rs:102-119).
+template <bool SPHERES>
+__global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_shadow_rays(DevScene sc, Wave w, uint32_t n_lights, IterCounters* cur) {
+    uint32_t* const cursor = &cur->work_shadow;
+    __shared__ uint2 s_stack[kShortStack][kTraceThreads];
+    uint32_t deep_ref[kDeepStack];
+    float deep_key[kDeepStack];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&s_stack[0][tid]);
+    sts_entry(sbase, kNoNode, 0.0f);
+    const uint32_t n = cur->mat[0] + cur->mat[1] + cur->mat[2] + cur->mat[3];
+    const uint32_t chunks_per_light = (n + kChunk - 1) / kChunk;
+    const uint32_t n_chunks = chunks_per_light * n_lights;
+    uint32_t n_rays = 0;
+    uint32_t chunk_next = 0, chunk_end = 0, chunk_light = 0;  // warp-uniform
+    bool exhausted = false;
+
+    TraceLane tl;
+    tl.idle(sbase);
+    bool live = false, occluded = false;
+    uint32_t my_g = 0, my_k = 0;
+    int target_light = -1;
+
+    for (;;) {
+        for (int round = 0; round < 4; ++round) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !live);
+            if (!idle || exhausted) break;
+            if (chunk_next >= chunk_end) {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(cursor, 1u);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= n_chunks) { exhausted = true; chunk_next = chunk_end = 0; break; }
+                chunk_light = c / chunks_per_light;
+                chunk_next = (c - chunk_light * chunks_per_light) * kChunk;
+                chunk_end = chunk_next + kChunk < n ? chunk_next + kChunk : n;
+            }
+            const uint32_t mine = chunk_next + __popc(idle & lt_mask);
+            if (!live && mine < chunk_end && ((w.sh_mask[mine] >> chunk_light) & 1u)) {
+                my_g = mine; my_k = chunk_light;
+                const size_t ref = (size_t)my_k * w.cap + my_g;
+                const float4 ro = ld_once(&w.lt_o[ref]), rd = ld_once(&w.lt_d[ref]);
+                target_light = __float_as_int(ld_once(&w.lt_c[ref]).y);
+                tl.template start<false, SPHERES>(sc, sbase, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, 0.9999f);  // interaction.rs:57-58
+                occluded = false;
+                live = true;
+                n_rays += 1;
+            }
+            const uint32_t taken = chunk_next + __popc(idle);
+            chunk_next = taken < chunk_end ? taken : chunk_end;
+        }
+        if (__ballot_sync(0xffffffffu, live) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        for (;;) {
+            YK_TRACE_PHASES(tl, live, false, true, SPHERES, {
+                (void)tri_; (void)ts_; (void)det_;
+                bool blocks = true;
+                if (SPHERES && al_ <= -2) {  // sphere slot: run the real test; spheres carry no area light
+                    float t_s;
+                    blocks = sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.lt_d[(size_t)my_k * w.cap + my_g], tl.t_max, &t_s);
+                } else if (target_light >= 0 && al_ >= 0 && al_ == target_light) {
+                    blocks = false;  // bvh.rs:269-280: the target light's own emissive triangles do not occlude
+                }
+                if (blocks) { occluded = true; tl.stop(sbase); }
+            })
+            if (live && !tl.wants_box()) {  // this shadow ray is done
+                if (occluded) atomicAnd(&w.sh_mask[my_g], ~(1u << my_k));
+                live = false;
+            }
+            const int busy = __popc(__ballot_sync(0xffffffffu, live));
+            if (busy == 0 || (!exhausted && busy < kRefillBelow)) break;
+        }
+    }
+    const unsigned long long sum_nodes = warp_sum((unsigned long long)tl.n_tests), sum_tris = warp_sum((unsigned long long)tl.n_tris);
+    const unsigned long long sum_rays = warp_sum((unsigned long long)n_rays);
+    if (lane == 0 && (sum_nodes | sum_tris | sum_rays)) {
+        atomicAdd(&w.totals->any_nodes, sum_nodes);
+        atomicAdd(&w.totals->any_tris, sum_tris);
+        atomicAdd(&w.totals->shadow_rays, sum_rays);
+    }
+}
+
+// The fold after k_trace_shadow_rays: `c + f*li*cos/pdf` over the unoccluded lights in light order, `radiance += beta * Le`,
+// the indirect clamp and `L += beta * radiance` (path.rs:113-129); Whitted leaves the node's radiance for k_tree_return
+// (whitted.rs:120-130). One shading position per thread, streamed.
+__global__ void k_shadow_fold(Wave w, RenderCfg cfg, const IterCounters* cur) {
+    const uint32_t n = cur->mat[0] + cur->mat[1] + cur->mat[2] + cur->mat[3];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        uint32_t mask = ld_once(&w.sh_mask[g]);
+        RGB radiance = gray(0.0f);
+        while (mask) {
+            const size_t ref = (size_t)(__ffs(mask) - 1) * w.cap + g;
+            radiance = radiance + rgb(ld_once(&w.lt_o[ref]).w, ld_once(&w.lt_d[ref]).w, ld_once(&w.lt_c[ref]).x);
+            mask &= mask - 1;
+        }
+        const float4 pe = ld_once(&w.pend_extra[g]), pb = ld_once(&w.pend_beta[g]);
+        RGB r = radiance + rgb(pe.x, pe.y, pe.z);
+        if (pb.w > 0.0f) r = rgb(fminf(r.r, cfg.clamp), fminf(r.g, cfg.clamp), fminf(r.b, cfg.clamp));
+        if (pb.w < 0.0f) {  // whitted.rs:109-130 (w = -1): the node's own radiance, summed up the tree by k_tree_return
+            w.pend_extra[g] = make_float4(r.r, r.g, r.b, pe.w);
+            continue;
+        }
+        const uint32_t path = ld_once(&w.sh_path[g]);
+        float4 L = w.L[path];
+        L.x = L.x + pb.x * r.r;
+        L.y = L.y + pb.y * r.g;
+        L.z = L.z + pb.z * r.b;
+        w.L[path] = L;
     }
 }
 
