@@ -13,6 +13,11 @@ ranks (tile i -> rank i mod N, no data-path collective) and the film is summed t
 `value` is measured with the scene and the film resident in HBM (CUDA events on the renderer's stream, max over
 ranks). `e2e` is the same metric through the C-ABI call with host buffers: scene upload, tile/job upload and the
 film read-back are all inside its timed region.
+
+The line also carries `large_scene`: BASELINE.json configs[4]'s geometry (the 10 M-triangle scene at 3840x2160, Path 8) at
+16 spp, run by ALL ranks (tiles interleaved, film reduced to rank 0) — the workload whose BVH cannot live in the caches,
+with its own clocks, roofline (algorithmic bytes next to the ncu-measured DRAM / L2 bytes per launch) and per-rank busy
+times. Films are checked against stored digests (tests/golden/bench_film_digests.json) outside the timed regions.
 """
 import argparse
 import json
@@ -78,9 +83,23 @@ def workload(xf):
     return scene, cam, film, sampler, integ
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of this command (profiles/<round>/traffic.json, written by scripts/ncu_traffic.py). None when absent."""
+def kernel_source_hash():
+    """sha256 over the CUDA sources the kernels are compiled from: what a committed ncu capture is valid for."""
+    import hashlib
+    h = hashlib.sha256()
+    src = os.path.join(ROOT, "yuki_b200", "csrc")
+    for name in sorted(os.listdir(src)):
+        if name.endswith((".cu", ".cuh", ".h", ".inl")):
+            with open(os.path.join(src, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(workload):
+    """DRAM and L2 bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this command
+    (profiles/<round>/traffic.json, written by scripts/gpu_bench_profile.sh + scripts/ncu_traffic.py). A capture is only
+    reported when it was taken from the kernels that are running now (its kernel_hash equals the hash of today's sources):
+    a stale capture yields None and says so."""
     best = None
     pdir = os.path.join(ROOT, "profiles")
     for rnd in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
@@ -88,7 +107,16 @@ def ncu_traffic():
         if os.path.exists(f):
             with open(f) as fh:
                 best = json.load(fh)
-    return best
+    entry = (best or {}).get(workload) if isinstance((best or {}).get(workload), dict) else None
+    if entry is None:
+        return {"dram_bytes_per_launch": None, "l2_bytes_per_launch": None, "traffic_state": "no capture for this workload"}
+    now = kernel_source_hash()
+    if entry.get("kernel_hash") != now:
+        return {"dram_bytes_per_launch": None, "l2_bytes_per_launch": None,
+                "traffic_state": f"stale: captured at kernel_hash {entry.get('kernel_hash')} (commit {entry.get('commit')}), sources are {now}"}
+    return {"dram_bytes_per_launch": entry.get("dram_bytes_per_launch"), "l2_bytes_per_launch": entry.get("l2_bytes_per_launch"),
+            "traffic_state": "current", "traffic_commit": entry.get("commit"), "traffic_kernel_hash": now, "traffic_source": entry.get("source"),
+            "ncu": entry.get("ncu")}
 
 
 def peaks():
@@ -193,36 +221,140 @@ def run_reference(args):
     emit(line)
 
 
-def large_scene_leg(api, xf, ctx, peak):
-    """Supplementary measurement (N == 1 only, not the contract's `value`): the geometry of BASELINE.json configs[4] — the
-    10 M-triangle terrain at 3840x2160, Path max_depth 8 — at 4 spp on one pipe, so that the line also carries the
-    closest-hit kernel's roofline on a scene whose BVH (554 MB of records + 480 MB of triangles) cannot live in the caches.
-    Same accounting as `roofline`: (32 B x node visits + 36 B x shape tests) / CUDA-event time of the k_trace_closest launches."""
+C5_SPP_SIDE = 4          # the large-scene leg: 4 x 4 = 16 spp of configs[4]'s 4096
+C5_STEPS, C5_WARMUP = 10, 2
+DIGESTS = os.path.join(ROOT, "tests", "golden", "bench_film_digests.json")
+
+
+def film_digest(t):
+    """sha256 of a film tensor's bytes. Renders are bit-reproducible (no result depends on the processing order)
+    and tiles are disjoint, so the digest is the same at every N."""
+    import hashlib
+    return hashlib.sha256(t.detach().cpu().numpy().tobytes()).hexdigest()[:32]
+
+
+def check_digest(key, digest, update):
+    """Compares with the stored digest of this workload (tests/golden/bench_film_digests.json). Returns 'ok' / 'written' /
+    'absent'; raises on a mismatch — a bench that timed the wrong picture must not print a line."""
+    stored = {}
+    if os.path.exists(DIGESTS):
+        with open(DIGESTS) as f:
+            stored = json.load(f)
+    if update:
+        stored[key] = digest
+        with open(DIGESTS, "w") as f:
+            json.dump(stored, f, indent=1, sort_keys=True)
+        return "written"
+    if key not in stored:
+        return "absent"
+    if stored[key] != digest:
+        raise SystemExit(f"bench.py: film digest of '{key}' is {digest}, expected {stored[key]} (tests/golden/bench_film_digests.json)")
+    return "ok"
+
+
+def large_scene_leg(args, api, capi, xf, ctx, stream, rank, world, local, peak):
+    """BASELINE.json configs[4]'s geometry — the 10 M-triangle terrain + material objects at 3840x2160, Path max_depth 8 — at
+    16 spp, on every rank: spiral tiles interleaved over the ranks, the scene built and uploaded once per rank OUTSIDE the
+    timed region, the film summed to rank 0 (NCCL) inside it. Timed like the main leg (barrier + synchronize on both sides,
+    CUDA events, max over ranks, L2 flushed between steps). Then, on one pipe (exclusive kernel times), the closest-hit
+    kernel's roofline on this scene: its BVH (554 MB of records + 480 MB of triangles) cannot live in the 126 MB L2."""
+    import torch
+    import torch.distributed as dist
     from yuki_b200 import scenes
     t0 = time.perf_counter()
     scene, cam = scenes.terrain_room(xf)
-    dev = api.Scene(ctx, scene)
+    host = api.HostScene(scene)
     t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    dev = api.Scene(ctx, scene, host=host)
+    t_upload = time.perf_counter() - t0
     rn = api.Renderer(ctx)
     film = D.FilmSettings((3840, 2160), 16)
-    sampler, integ = D.SamplerType.stratified(2, 2, jitter=True), D.IntegratorType.path(MAX_DEPTH)
-    rn.render(dev, cam, film, sampler, integ, pipes=1)  # warm-up
-    steps, ms, cms, nodes, tris, rays, shadow, samples, launches = 2, 0.0, 0.0, 0, 0, 0, 0, 0, 0
-    for _ in range(steps):
-        st = rn.render(dev, cam, film, sampler, integ, pipes=1).stats
-        ms += st.device_ms; cms += st.trace_closest_ms; nodes += st.closest_nodes; tris += st.closest_tris
-        rays += st.ray_count; shadow += st.shadow_rays; samples += st.samples; launches += st.trace_closest_launches
+    sampler, integ = D.SamplerType.stratified(C5_SPP_SIDE, C5_SPP_SIDE, jitter=True), D.IntegratorType.path(MAX_DEPTH)
+    all_tiles = api.film_tiles(film)
+    my_tiles = np.ascontiguousarray(all_tiles[rank::world])
+    n_pix = film.res[0] * film.res[1]
+    total_samples = n_pix * sampler.samples_per_pixel()
+    with torch.cuda.stream(stream):
+        d_film = torch.zeros(n_pix * 3, dtype=torch.float32, device="cuda")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+        def step(pipes=0):
+            flush.zero_()
+            d_film.zero_()
+            r = rn.render(dev, cam, film, sampler, integ, tiles=my_tiles, device_film_ptr=d_film.data_ptr(), pipes=pipes)
+            if world > 1:
+                dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
+            return r.stats
+
+        for _ in range(C5_WARMUP):
+            step()
+        torch.cuda.synchronize()
+        digest_state = check_digest("c5_16spp", film_digest(d_film), args.write_digests) if rank == 0 else None
+        if world > 1:
+            dist.barrier()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        busy_ms, rays, shadow, launches = 0.0, 0, 0, 0
+        for _ in range(C5_STEPS):
+            st = step()
+            busy_ms += st.device_ms; rays += st.ray_count; shadow += st.shadow_rays; launches += st.kernel_launches
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = clocks.stop() if rank == 0 else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        counts = torch.tensor([rays, shadow, launches], dtype=torch.float64, device="cuda")
+        per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
+        per_rank[rank] = busy_ms / C5_STEPS
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+            dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+        ms_total = float(ms.item())
+        # roofline pass: rank 0, its own tiles, one pipe
+        roof = None
+        if rank == 0:
+            cms, nodes, tris, r_rays, cl = 0.0, 0, 0, 0, 0
+            dms = 0.0
+            for _ in range(3):
+                st = step(pipes=1) if world == 1 else rn.render(dev, cam, film, sampler, integ, tiles=my_tiles, device_film_ptr=d_film.data_ptr(), pipes=1).stats
+                cms += st.trace_closest_ms; nodes += st.closest_nodes; tris += st.closest_tris; r_rays += st.ray_count
+                cl += st.trace_closest_launches; dms += st.device_ms
+            alg = 32 * nodes + 36 * tris
+            achieved = alg / (max(cms, 1e-9) / 1e3) / 1e9
+            tr = ncu_traffic("c5")
+            roof = {"bound": "latency/issue", "roofline_axis": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "algorithmic_bytes_per_launch": alg / max(cl, 1), "avg_launch_ms": cms / max(cl, 1), "launches": cl,
+                    "share_of_step": cms / max(dms, 1e-9), "nodes_per_ray": nodes / max(r_rays, 1), "shape_tests_per_ray": tris / max(r_rays, 1),
+                    "dram_bytes_per_launch": tr["dram_bytes_per_launch"], "l2_bytes_per_launch": tr["l2_bytes_per_launch"],
+                    "traffic": tr["dram_bytes_per_launch"], "traffic_state": tr["traffic_state"], "traffic_commit": tr.get("traffic_commit"),
+                    "ncu": tr.get("ncu"),
+                    "note": "achieved = (32 B x node visits + 36 B x shape tests) / CUDA-event time of the closest-hit launches, one pipe, rank 0's tiles. "
+                            "ncu on this scene: DRAM 4-6 % of peak, L1 hit 43-57 %, L2 hit 62-65 %, 16-17.5 of 32 lanes, issue-active 53-63 %, "
+                            "long-scoreboard 5-6.5 warps per issue (profiles/r02): the walk is bound by dependent-load latency and issue slots, "
+                            "most algorithmic bytes are served by L1/L2, so frac is a throughput in the roofline's unit, not DRAM utilisation"}
+        if world > 1:
+            dist.barrier()
     n_tris, n_nodes = dev.host.n_tris, dev.host.n_nodes
     dev.close()
-    alg = 32 * nodes + 36 * tris
-    achieved = alg / (max(cms, 1e-9) / 1e3) / 1e9
-    return {"workload": "configs[4] geometry: 10M-triangle terrain + material objects 3840x2160, Path max_depth 8, 4 spp stratified 2x2, one pipe",
-            "triangles": n_tris, "bvh_nodes": n_nodes, "host_build_and_upload_s": t_build, "steps": steps,
-            "msamples_per_s": samples / (ms / 1e3) / 1e6, "mrays_per_s": rays / (ms / 1e3) / 1e6,
-            "mrays_per_s_total": (rays + shadow) / (ms / 1e3) / 1e6,
-            "roofline": {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "algorithmic_bytes_per_launch": alg / max(launches, 1), "avg_launch_ms": cms / max(launches, 1), "launches": launches,
-                         "share_of_step": cms / ms, "nodes_per_ray": nodes / max(rays, 1), "shape_tests_per_ray": tris / max(rays, 1)}}
+    host.close()
+    if rank != 0:
+        return None
+    s = ms_total / 1e3
+    return {"workload": f"configs[4] geometry: 10M-triangle terrain + material objects 3840x2160, Path max_depth 8, {C5_SPP_SIDE * C5_SPP_SIDE} spp "
+                        f"stratified {C5_SPP_SIDE}x{C5_SPP_SIDE}, spiral tiles interleaved over {world} rank(s), film summed to rank 0",
+            "triangles": n_tris, "bvh_nodes": n_nodes, "host_build_s": t_build, "upload_s": t_upload, "steps": C5_STEPS, "warmup": C5_WARMUP,
+            "msamples_per_s": total_samples * C5_STEPS / s / 1e6, "c5_msamples_per_s": total_samples * C5_STEPS / s / 1e6,
+            "ms_per_step": ms_total / C5_STEPS, "mrays_per_s": float(counts[0].item()) / s / 1e6,
+            "mrays_per_s_total": float((counts[0] + counts[1]).item()) / s / 1e6, "gpu_launches": int(counts[2].item()),
+            "per_rank_device_ms": [float(v) for v in per_rank.tolist()], "clocks": clk, "film_digest": digest_state,
+            "pipes": "library default (two) for msamples_per_s; one for the roofline pass", "roofline": roof}
 
 
 def run_ours(args):
@@ -266,6 +398,10 @@ def run_ours(args):
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize()
+        # the film the timed steps produce (every step renders the same picture), checked outside the timed region
+        digest_state = None
+        if rank == 0 and args.warmup > 0 and not args.spp_side:
+            digest_state = check_digest("c2_1024spp" if SCENE == "cornell" else "c5_4096spp", film_digest(d_film), args.write_digests)
         if world > 1:
             dist.barrier()
         clocks = ClockSampler(local)
@@ -329,12 +465,12 @@ def run_ours(args):
         e2e_value = total_samples * e2e_steps / float(e2e_s.item()) / 1e6
 
     large = None
-    if rank == 0 and world == 1 and not args.no_large_scene and SCENE == "cornell":
-        large = large_scene_leg(api, xf, ctx, peaks()[0])
+    if not args.no_large_scene and SCENE == "cornell":
+        large = large_scene_leg(args, api, capi, xf, ctx, stream, rank, world, local, peaks()[0])
 
     if rank == 0:
         peak, peak_src = peaks()
-        traffic = ncu_traffic()
+        traffic = ncu_traffic("c2" if SCENE == "cornell" else "c5")
         alg_bytes = 32 * agg["closest_nodes"] + 36 * agg["closest_tris"]
         launches = max(agg["trace_closest_launches"], 1)
         t_closest = max(agg["trace_closest_ms"], 1e-9) / 1e3
@@ -356,12 +492,18 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "includes": "yk_scene_create + yk_render with host film (pinned staging inside the library)" if world == 1 else
                     "per rank yk_scene_create + yk_render of its tiles, NCCL sum-reduce of the film to rank 0, read-back to pinned host memory there"},
-            "roofline": {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+            "film_digest": digest_state,
+            "roofline": {"bound": "issue (cache-resident scene)" if SCENE == "cornell" else "latency/issue", "roofline_axis": "hbm",
+                         "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"], "dram_bytes_per_launch": traffic["dram_bytes_per_launch"],
+                         "l2_bytes_per_launch": traffic["l2_bytes_per_launch"], "traffic_state": traffic["traffic_state"],
+                         "traffic_commit": traffic.get("traffic_commit"), "traffic_source": traffic.get("traffic_source"),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / launches, "avg_launch_ms": 1e3 * t_closest / launches,
                          "launches": launches, "share_of_step": agg["trace_closest_ms"] / ms_total,
-                         "note": "rank 0; 32 B per node visit + 36 B per triangle test (SURVEY.md §8d); the 37-node scene is L1/L2-resident, so achieved can exceed the HBM peak"},
+                         "note": "rank 0; 32 B per node visit + 36 B per triangle test (SURVEY.md §8d). The 37-node scene is L1-resident: no node byte comes from HBM, the kernel is "
+                                 "instruction-issue bound (ncu: issue-active 74-77 %, l1tex hit 85-92 %, DRAM 3-9 %), so achieved is a throughput in the roofline's unit and can "
+                                 "exceed the HBM peak; the bandwidth-relevant roofline is large_scene.roofline"},
             "stage_ms_per_step": {k: v / args.steps for k, v in (("trace_closest", agg["trace_closest_ms"]), ("trace_any", agg["trace_any_ms"]),
                                                                  ("shade", agg["shade_ms"])) if v > 0},  # any / shade only with YK_STAGE_TIMING=2
         }
@@ -387,7 +529,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-large-scene", action="store_true", help="skip the supplementary 10 M-triangle roofline leg (N == 1 only)")
+    ap.add_argument("--no-large-scene", action="store_true", help="skip the 10 M-triangle leg (large_scene)")
+    ap.add_argument("--write-digests", action="store_true", help="store the films' digests in tests/golden/bench_film_digests.json instead of checking them")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = BASELINE.json configs[1] (default, the contract's line); c5 = configs[4]")
     ap.add_argument("--spp-side", type=int, default=0, help="override the stratified grid side (spp = side^2); the line's config says so")
     args = ap.parse_args()

@@ -144,3 +144,6 @@ if which == "room4":  # one batch of the material room for ncu captures
 if which == "whitted1":
     s, c = scenes.cornell(xf, light="point", tall_box="glass")
     probe("cornell 1024^2 whitted4 4spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(2, 2), D.IntegratorType.whitted(4), reps=0)
+if which == "terrain16":  # the render of bench.py's large_scene leg (one pipe), for its ncu capture
+    s, c = scenes.terrain_room(xf)
+    probe("terrain 10M path8 3840x2160 16spp", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=0, pipes=1)

@@ -104,8 +104,11 @@ struct yk_context {
     // Environment: YK_SORT_KEY, YK_SORT_ORDER; yk_render_opts.ray_sort overrides the key per render.
     int sort_key = -1, sort_order = 2;
     // Shadow rays: 1 = one ray per lane (k_trace_shadow_rays + k_shadow_fold), 0 = one path per lane with the fold fused
-    // (k_trace_shadow). Environment: YK_SHADOW_MODE.
-    int shadow_mode = 1;
+    // (k_trace_shadow), -1 = by scene: per ray when several lights meet a BVH too large for the caches. Measured, one pipe
+    // (profiles/r02/ab_shadow_mode.txt): 10 M-triangle terrain with 3 lights 17.2 -> 14.5 ms of shadow time (render +6 %);
+    // material room (6.6 K triangles, 3 lights) 22.7 -> 25.6 ms, Cornell box (1 light) 14.6 -> 18.2 ms: on cache-resident
+    // scenes the serial walk was not the limiter and the separate fold costs more than it saves. Environment: YK_SHADOW_MODE.
+    int shadow_mode = -1;
     int stage_timing = 1;  // CUDA events per bounce: 1 = around the closest-hit kernel (the roofline figure), 2 = every stage
                            // (costs ~1.5 % of a Cornell render), 0 = none; environment variable YK_STAGE_TIMING
 };
@@ -120,10 +123,15 @@ struct yk_scene {
 
 namespace {
 
+// Device buffers come from the device's stream-ordered memory pool, whose release threshold yk_context_create raises to
+// "never": a freed scene / wavefront buffer stays mapped and the next allocation of that size is a pool hit. Measured on the
+// 10 M-triangle scene: cudaFree of the ~1 GB upload temporaries took 3 ms ... 970 ms (unmapping), and the next
+// yk_scene_create paid for mapping them again (profiles/r02: e2e_probe).
 template <class T>
 int dev_alloc(std::vector<void*>& bag, T** out, size_t count) {
     void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    CUDA_TRY(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), cudaStreamPerThread));
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamPerThread));  // usable on every stream from here on
     bag.push_back(p);
     *out = (T*)p;
     return YK_OK;
@@ -138,7 +146,10 @@ int dev_upload(std::vector<void*>& bag, const T** out, const T* src, size_t coun
     return YK_OK;
 }
 void free_bag(std::vector<void*>& bag) {
-    for (void* p : bag) cudaFree(p);
+    if (bag.empty()) return;
+    cudaDeviceSynchronize();  // what cudaFree did implicitly: nothing in flight may still use the buffers
+    for (void* p : bag) cudaFreeAsync(p, cudaStreamPerThread);
+    cudaStreamSynchronize(cudaStreamPerThread);
     bag.clear();
 }
 
@@ -344,7 +355,8 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         }
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
         nvtxRangePushA("yk shadow rays + fold");
-        if (c->shadow_mode == 1 && sc->dev.n_lights > 0) {  // one shadow ray per lane, then the fold (wf_trace.cuh)
+        const bool rays_per_lane = c->shadow_mode == 1 || (c->shadow_mode < 0 && sc->dev.n_lights >= 2 && sc->dev.n_tris >= (1u << 18));
+        if (rays_per_lane && sc->dev.n_lights > 0) {  // one shadow ray per lane, then the fold (wf_trace.cuh)
             if (spheres) k_trace_shadow_rays<true><<<shadow_rays_blocks, kTraceThreads, 0, s>>>(sc->dev, w, sc->dev.n_lights, cur);
             else k_trace_shadow_rays<false><<<shadow_rays_blocks, kTraceThreads, 0, s>>>(sc->dev, w, sc->dev.n_lights, cur);
             k_shadow_fold<<<fold_blocks, 256, 0, s>>>(w, cfg, cur);
@@ -419,6 +431,12 @@ int yk_context_create(int device_id, yk_context** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
     c->sm_count = prop.multiProcessorCount;
+    {   // keep freed device buffers in the pool (dev_alloc)
+        cudaMemPool_t pool = nullptr;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        (void)cudaGetLastError();
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(cudaEventDestroy(c->ev[2]));
@@ -427,7 +445,7 @@ int yk_context_create(int device_id, yk_context** out) {
     CUDA_TRY(cudaEventCreate(&c->ev[3]));
     if (const char* np = getenv("YK_PIPES")) c->n_pipes_env = std::max(1, std::min(kMaxPipes, atoi(np)));
     if (const char* st = getenv("YK_STAGE_TIMING")) c->stage_timing = std::max(0, std::min(2, atoi(st)));
-    if (const char* sm = getenv("YK_SHADOW_MODE")) c->shadow_mode = atoi(sm) ? 1 : 0;
+    if (const char* sm = getenv("YK_SHADOW_MODE")) c->shadow_mode = std::max(-1, std::min(1, atoi(sm)));
     if (const char* sk = getenv("YK_SORT_KEY")) c->sort_key = std::max(-1, std::min(2, atoi(sk)));
     if (const char* so = getenv("YK_SORT_ORDER")) c->sort_order = std::max(1, std::min(2, atoi(so)));
     for (int i = 0; i < kMaxPipes; ++i) {
@@ -1203,7 +1221,8 @@ int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const flo
         CUDA_TRY(cudaMemcpyAsync(&p.d_ctr[0], &ctr, sizeof(ctr), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemsetAsync(p.wave.totals, 0, sizeof(Totals), s));
         k_query_pack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, d_o, d_d, m);
-        if (c->shadow_mode == 1) {
+        const bool per_ray = c->shadow_mode != 0;  // one segment per lane either way; the per-ray kernel needs no fold
+        if (per_ray) {
             const int blocks = grid_for(m, kTraceThreads, c->sm_count * std::max(1, c->occ_trace_rays));
             if (generic) k_trace_shadow_rays<true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 1u, &p.d_ctr[0]);
             else k_trace_shadow_rays<false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, 1u, &p.d_ctr[0]);
@@ -1212,7 +1231,7 @@ int yk_occluded(yk_context* c, const yk_scene* sc, const float* o_xyz, const flo
             if (generic) k_trace_shadow<true><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
             else k_trace_shadow<false><<<blocks, kTraceThreads, 0, s>>>(sc->dev, p.wave, cfg, &p.d_ctr[0]);
         }
-        k_query_unpack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, m, c->shadow_mode == 1 ? 1 : 0, d_out);
+        k_query_unpack_segments<<<(m + T - 1) / T, T, 0, s>>>(p.wave, m, per_ray ? 1 : 0, d_out);
         CUDA_TRY(cudaMemcpyAsync(occluded_out + first, d_out, m, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
     }

@@ -22,7 +22,11 @@ constexpr int kStackDepth = 64;  // bvh.rs:172
 constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 #ifndef YK_SHADE_THREADS
-#define YK_SHADE_THREADS 128
+// 256 threads with the phase barriers of k_shade (YK_SHADE_PHASED): the blocks' warps stay inside the same part of the ~100 KB
+// kernel, whose top stall at 128 unsynchronised threads was `no_instruction` (32 KB instruction cache). Measured (one pipe,
+// profiles/r02/ab_shade_phased.txt): shading time of the material room 29.0 -> 23.9 ms (render +7.5 %), terrain 6.9 -> 6.6 ms,
+// Cornell box unchanged; 512 threads = 256, 1024 threads and barriers without larger blocks are slower.
+#define YK_SHADE_THREADS 256
 #endif
 constexpr int kShadeThreads = YK_SHADE_THREADS;
 #ifndef YK_TRACE_MIN_BLOCKS
@@ -224,13 +228,13 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 // Block-aggregated append to one of NQ queues: one global atomic per queue per block (same-address atomics were the
 // bottleneck of classify / resolve with one atomic per warp, profiles/r01). `key` in [0, NQ) selects the queue, any
-// other value appends nothing. Must be reached by every thread of the block (blockDim.x <= 256).
+// other value appends nothing. Must be reached by every thread of the block (blockDim.x <= 1024).
 // Returns the slot the value was written to (undefined when nothing was appended).
 // `K` items per thread share the block's atomics: K * blockDim.x items per global atomic and queue.
 template <int NQ, int K>
 __device__ __forceinline__ void block_scatter_multi(const int (&key)[K], const uint32_t (&value)[K], uint32_t* const (&queues)[NQ],
                                                     uint32_t* const (&counters)[NQ], uint32_t (&pos)[K]) {
-    __shared__ uint32_t s_cnt[8][NQ];
+    __shared__ uint32_t s_cnt[32][NQ];
     __shared__ uint32_t s_base[NQ];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
     const unsigned lt = (1u << lane) - 1u;

@@ -333,6 +333,14 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 #define YK_SHADE_PREFETCH 1
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef YK_SHADE_PHASED
+#define YK_SHADE_PHASED 1
+#endif
+#if YK_SHADE_PHASED
+#define YK_SHADE_SYNC() __syncthreads()
+#else
+#define YK_SHADE_SYNC() ((void)0)
+#endif
 
 template <uint32_t KIND, bool PATH>
 __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
@@ -361,28 +369,38 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         float4 nx_o = make_float4(0, 0, 0, 0), nx_d = make_float4(0, 0, 0, 0), nx_beta = make_float4(0, 0, 0, 0);
         unsigned long long nx_rng = 0;
         uint32_t nx_key = 0;  // ray sort: the survivor's coherence key (wf_sort.cuh)
-        if (i < n) {
+        // The kernel is ~100 KB of straight-line code against a 32 KB instruction cache: with the block's warps spread all over it
+        // the top stall is `no_instruction` (profiles/r02). YK_SHADE_SYNC() (a block barrier when YK_SHADE_PHASED) keeps the
+        // warps of a block inside the same phase of the code: surface + BSDF set-up | one light | emission + BSDF sampling.
+        const bool active = i < n;
+        uint32_t g = 0, hit_slot = 0, depth = 0, shadow_mask = 0;
+        bool was_specular = false;
+        V3 d = mk(0.0f, 0.0f, 0.0f);
+        Surface si;
+        Bsdf bsdf;
+        RGB beta = gray(0.0f);
+        SamplerState smp;
+        if (active) {
             path = ld_once(&queue[i]);
-            const uint32_t g = g_base + i;
+            g = g_base + i;
             st_once(&w.sh_path[g], path);
-            const uint32_t hit_slot = ld_once(&queue_tri[i]), slot = ld_once(&queue_slot[i]);
+            hit_slot = ld_once(&queue_tri[i]);
+            const uint32_t slot = ld_once(&queue_slot[i]);
             const float4 ro = ld_once(&w.st[b].ray_o[slot]), rd = ld_once(&w.st[b].ray_d[slot]);
-            const V3 o = f4v(ro), d = f4v(rd);
-            Surface si;
+            const V3 o = f4v(ro);
+            d = f4v(rd);
             uint32_t mat_index;
             make_surface(sc, hit_slot, o, d, &si, &mat_index);
-            Bsdf bsdf;
             make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
 
             const float4 beta4 = ld_once(&w.st[b].beta[slot]);
-            RGB beta = rgb(beta4.x, beta4.y, beta4.z);
+            beta = rgb(beta4.x, beta4.y, beta4.z);
             const uint32_t flags = __float_as_uint(beta4.w) & kFlagMask;
-            const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
-            const bool was_specular = (flags & kFlagSpecular) != 0;
+            depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
+            was_specular = (flags & kFlagSpecular) != 0;
 
             const uint32_t sample_i = bt.div_jobs.div(path), job_i = path - sample_i * bt.n_jobs;
             const Job job = bt.jobs[job_i];
-            SamplerState smp;
             smp.rng.state = ld_once(&w.st[b].rng[slot]);
             smp.rng.inc = job.rng_inc;
             smp.dim = __float_as_uint(beta4.w) >> kDimShift;
@@ -390,10 +408,12 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             smp.py = job.y;
             smp.index = job.sample_begin + bt.sample_off + sample_i;
             smp.job = job_i;
+        }
 
-            // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
-            uint32_t shadow_mask = 0;
-            for (uint32_t k = 0; k < sc.n_lights; ++k) {
+        // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
+        for (uint32_t k = 0; k < sc.n_lights; ++k) {
+            YK_SHADE_SYNC();
+            if (active) {
                 const V2 u = smp.get_2d(cfg.sampler);
                 LightSample ls;
                 sample_light(sc.lights[k], (int)k, si, u, &ls);
@@ -409,7 +429,9 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
                     }
                 }
             }
-
+        }
+        YK_SHADE_SYNC();
+        if (active) {
             st_once(&w.sh_mask[g], shadow_mask);
 
             // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
