@@ -54,8 +54,19 @@ def test_resume_equals_uninterrupted_render_with_the_oracle_as_renderer(tmp_path
     # guards
     with pytest.raises(ValueError, match="other settings"):
         rn.render_progressive(None, cam, api.Film.load(ck), D.SamplerType.stratified(3, 3, jitter=False), integ, render_fn=render_fn_for(whole))
+    with pytest.raises(ValueError, match="other settings"):   # another indirect clamp / another camera is another render
+        rn.render_progressive(None, cam, api.Film.load(ck), smp, D.IntegratorType.path(5, indirect_clamp=2.0), render_fn=render_fn_for(whole))
+    other_cam = D.CameraParameters((0.1, 0.2, 0.9), cam.target, fov_axis=cam.fov_axis, fov_deg=cam.fov_deg)
+    with pytest.raises(ValueError, match="other settings"):
+        rn.render_progressive(None, other_cam, api.Film.load(ck), smp, integ, render_fn=render_fn_for(whole))
     with pytest.raises(ValueError, match="another render"):
         api.Film.load(ck, expect_meta={"spp": 16})
+    # per-tile sample counts are u32 like the reference's Vec<u32> (film.rs:74): 65536 passes do not wrap to zero
+    assert whole.samples.dtype == np.uint32
+    big = api.Film(fs)
+    big.samples[...] = 65535
+    big.samples += 1
+    assert int(big.samples.min()) == 65536
     uneven = api.Film.load(ck)
     uneven.samples[0] -= 1
     with pytest.raises(ValueError, match="different sample counts"):

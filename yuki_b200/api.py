@@ -378,7 +378,7 @@ class Film:
         w, h = int(settings.res[0]), int(settings.res[1])
         self.pixels = np.zeros((h, w, 3), np.float32)
         n_tiles = ((w + settings.tile_dim - 1) // settings.tile_dim) * ((h + settings.tile_dim - 1) // settings.tile_dim)
-        self.samples = np.zeros(n_tiles, np.uint16) if settings.accumulate else None
+        self.samples = np.zeros(n_tiles, np.uint32) if settings.accumulate else None   # Vec<u32>, film.rs:74
         self.dirty = False
         self.meta = None   # what was rendered into it (set by render_progressive / Film.load)
 
@@ -423,6 +423,8 @@ class Film:
             if film.samples is not None:
                 if "samples" not in z or z["samples"].shape != film.samples.shape:
                     raise ValueError(f"{path}: per-tile sample counts missing or of the wrong size")
+                if z["samples"].dtype.kind not in "ui":
+                    raise ValueError(f"{path}: per-tile sample counts are not integers")
                 film.samples[...] = z["samples"]
             meta = json.loads(bytes(z["meta"]).decode() or "{}")
         if expect_meta is not None and json.loads(json.dumps(expect_meta, sort_keys=True)) != meta:
@@ -527,10 +529,13 @@ class Renderer:
                     if rid == self._render_id:
                         self.last_result = res
                         self._messages.append(RenderFinished(int(res.stats.ray_count)))
-            except capi.YukiGpuError as e:
+            except Exception as e:  # noqa: BLE001 — whatever went wrong, the task posts its terminal message (the reference always
+                # sends Finished, render_manager.rs:170-190); a poller of check_status must not spin forever
+                cancelled = isinstance(e, capi.YukiGpuError) and e.code == capi.ERR_CANCELLED
                 with self._lock:
-                    if rid == self._render_id and e.code != capi.ERR_CANCELLED:
-                        self.last_error = e
+                    if rid == self._render_id:
+                        if not cancelled:
+                            self.last_error = e
                         self._messages.append(RenderFinished(0))
 
         self._thread = threading.Thread(target=work, daemon=True)
@@ -553,8 +558,18 @@ class Renderer:
             raise ValueError("film tiles hold different sample counts: not a checkpoint of complete passes")
         if done > spp:
             raise ValueError(f"film already holds {done} samples per pixel, the sampler has {spp}")
+        import hashlib
+        clamp = getattr(integrator, "indirect_clamp", None)
+        cam_bytes = np.asarray(list(camera_params.position) + list(camera_params.target) + list(camera_params.up) +
+                               [float(camera_params.fov_axis), float(camera_params.fov_deg)], np.float32).tobytes()
+        scene_id = None
+        if getattr(scene, "host", None) is not None:
+            flat = scene.host.flat
+            scene_id = hashlib.sha256(C.string_at(flat.nodes, min(flat.n_nodes, 4096) * 32) + C.string_at(flat.tri_vertices, min(flat.n_tris, 4096) * 36) +
+                                      np.asarray([flat.n_nodes, flat.n_tris, flat.n_lights, flat.n_materials], np.int64).tobytes()).hexdigest()[:16]
         meta = {"spp": spp, "sampler": [sampler.kind, sampler.nx, sampler.ny, bool(sampler.jitter), int(sampler.seed)],
-                "integrator": [integrator.kind, integrator.max_depth]}
+                "integrator": [integrator.kind, integrator.max_depth, None if clamp is None else float(clamp)],
+                "camera": hashlib.sha256(cam_bytes).hexdigest()[:16], "scene": scene_id}
         if film.meta and film.meta != json_roundtrip(meta):
             raise ValueError(f"film was rendered with other settings: {film.meta}")
         film.meta = json_roundtrip(meta)

@@ -390,7 +390,8 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             CUDA_TRY(cudaMemcpyAsync(p->h_ctr, nxt, sizeof(IterCounters), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
             if (p->h_ctr->n_active == 0) break;
-            if (iter > (1u << 20)) return yk_set_error(YK_ERR_INVALID, "yk_render: bounce loop did not terminate");
+            // one iteration per node of the deepest path's recursion tree: at most 2^max_depth - 1 (whitted.rs:132-170)
+            if ((uint64_t)iter + 1 > ((uint64_t)1 << std::min(cfg.max_depth, 40u))) return yk_set_error(YK_ERR_INVALID, "yk_render: bounce loop did not terminate");
         }
     }
     if (accumulate_film) {
@@ -996,7 +997,12 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
                     // the batch's first sample index: s0, or the sample of the group's tiles (accumulating films: one per group)
                     const uint32_t first_sample = accumulate ? (uint32_t)tiles[groups[group].t_lo].sample : s0;
                     rc = run_batch(c, &p, sc, gcfg, bt, first_sample, accumulate, d_film, &tm, &done);
-                    if (rc != YK_OK) { cudaDeviceSynchronize(); return rc; }
+                    if (rc != YK_OK) {  // nothing may stay in flight or marked busy behind an error return
+                        cudaDeviceSynchronize();
+                        for (Pipe& q : c->pipe)
+                            for (auto& slot : q.slot) slot.busy = false;
+                        return rc;
+                    }
                     if (!accumulate && s0 + m >= samples_per_job) {
                         // the group's last samples are queued: `color /= sample_count` + Film::update_tile for its pixels
                         k_film_store<<<(nj + 255) / 256, 256, 0, p.stream>>>(p.d_jobs, nj, c->d_accum, d_film, fs->res_x, (float)spp);
