@@ -38,6 +38,13 @@ def tonemap_filmic(film, exposure=1.0, tile_samples=None, tile_dim=16):
     return np.clip(out, F(0.0), F(1.0)).astype(np.float32)
 
 
+def linear_to_srgb_shader(c):
+    """The output pass's transfer function when the backbuffer is not sRGB (`gamma_before_output`, scale_output.rs:150-169):
+    `x <= 0.0031308 ? 12.92 x : 1.055 pow(x, 1 / 2.2) - 0.055` — note the 2.2 where sRGB proper has 2.4."""
+    c = np.asarray(c, np.float32)
+    return np.where(c <= F(0.0031308), F(12.92) * c, F(1.055) * np.power(c, F(1.0 / 2.2)) - F(0.055)).astype(np.float32)
+
+
 def _luminance(p):
     return F(0.2126) * p[..., 0] + F(0.7152) * p[..., 1] + F(0.0722) * p[..., 2]
 

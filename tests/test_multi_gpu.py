@@ -89,6 +89,10 @@ def _check_group(xf, oracle, monkeypatch, no_peer):
             a = api.Renderer(single).render(dev, cam, acc, smp, integ, tiles=rep)
             b, _ = api.multi_render(mctx, ms, cam, acc, smp, integ, tiles=rep)
             assert np.array_equal(a.film.view(np.uint32), b.film.view(np.uint32))
+            # ... also onto a film that already holds a sum (a resumed render): (film + s0) + s1 ... on every device
+            a = api.Renderer(single).render(dev, cam, acc, smp, integ, tiles=rep, film_out=base.copy())
+            b, _ = api.multi_render(mctx, ms, cam, acc, smp, integ, tiles=rep, film_out=base.copy())
+            assert np.array_equal(a.film.view(np.uint32), b.film.view(np.uint32))
             o_img, _, _ = oracle.OracleScene(scene).render(cam, film, smp, integ)
             assert np.array_equal(r.film.view(np.uint32), o_img.view(np.uint32))
             ms.close(); dev.close()

@@ -1,0 +1,126 @@
+"""The reference's only published output of the hot path: readme.md:3 embeds screenshot.png, a 1920 x 1080, 1024 spp path-traced
+render of Scene::cornell() with every setting visible in the UI panel (tests/golden/make_screenshot_regions.py lists them and
+measured the picture into tests/golden/reference_screenshot_regions.json). Rendering the same scene with the same settings
+and passing it through the reference's display passes (filmic tone map, tonemap.rs:318-399; output transfer function,
+scale_output.rs:150-169) must reproduce those measurements: where the box opening and the light quad land on the film
+(camera, fov axis, handedness), and the colour of every flat region — directly lit walls and floor (light radiance, the
+rectangular light's pdf, Lambert, cosine terms), the ceiling that only sees bounced light with the red and green colour
+bleeding in the right corners (path integrator, throughput, indirect clamp), the sphere's shadow (visibility) and the two
+floor profiles across the shadows of the sphere and the glass box.
+
+The one thing the checkout cannot supply is the back wall's marble texture (res/tiling_58-1K/tiling_58_basecolor-1K.png,
+.MISSING_LARGE_BLOBS); a constant albedo (0.85, 0.85, 0.80), fitted to the screenshot's own back wall region, stands in for
+it. That region is therefore not evidence; every other comparison has no free parameter. Tolerances are in 8-bit display
+values (the screenshot is an 8-bit PNG of a noisy render): 2.5 for region means on the full-resolution GPU render, 4 on the
+quarter-resolution oracle render.
+
+This pins the ORACLE (and the GPU path, bit-identical to it) against a reference-produced artefact — the only check that can
+catch a misreading shared by both (light scale, Fresnel, handedness)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from yuki_b200 import desc as D, scenes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BACK_WALL = (0.85, 0.85, 0.80)
+FLAT = ["red wall", "green wall", "ceiling left", "ceiling right", "floor front", "floor right", "sphere shadow", "light", "outside the box"]
+
+
+def _fixture():
+    with open(os.path.join(HERE, "golden", "reference_screenshot_regions.json")) as f:
+        return json.load(f)
+
+
+def _setup(xf, fx, scale):
+    st = fx["settings"]
+    scene, _ = scenes.cornell(xf, light="rect", tall_box="glass", sphere=True, split_method=D.SPLIT_SAH, back_wall_albedo=BACK_WALL)
+    cam = D.CameraParameters(tuple(st["camera_position"]), tuple(st["camera_target"]), fov_axis=D.FOV_X, fov_deg=st["fov_x_deg"])
+    film = D.FilmSettings((fx["film"][0] // scale, fx["film"][1] // scale), st["tile_dim"])
+    integ = D.IntegratorType.path(st["max_depth"], indirect_clamp=st["indirect_clamp"])
+    return scene, cam, film, integ
+
+
+def _published_rays_per_sample(fx):
+    """The status line "Render finished in 272.10s / 20.47 Mrays/s" is ray_count / elapsed (app/window.rs:907-916), ray_count
+    being the closest-hit rays of the whole render (path.rs:87): 20.47e6 x 272.10 = 5.570e9 rays over 1920 x 1080 x 1024
+    samples = 2.6231 rays per sample (+-0.03 % from the two roundings). The path-length statistics — Russian roulette on the
+    throughput's green channel from the fifth vertex, termination on black BSDF samples, max_depth — must reproduce it."""
+    p = fx["published"]
+    return p["mrays_per_s"] * 1e6 * p["render_seconds"] / (fx["film"][0] * fx["film"][1] * 1024)
+
+
+def _display(tone_mapped):
+    from oracle import post
+    return np.asarray(post.linear_to_srgb_shader(tone_mapped), np.float64) * 255.0
+
+
+def _compare(fx, disp, scale, tol, profile_tol):
+    worst = {}
+    for name in FLAT + ["back wall"]:
+        x0, y0, x1, y1 = fx["regions"][name]["box"]
+        got = disp[y0 // scale:y1 // scale, x0 // scale:x1 // scale].mean(axis=(0, 1))
+        want = np.array(fx["regions"][name]["mean_rgb8"])
+        worst[name] = float(np.abs(got - want).max())
+    for name in FLAT:
+        assert worst[name] <= tol, (name, worst)
+    assert worst["back wall"] <= 3 * tol, worst   # fitted stand-in for the missing texture: a sanity bound only
+    # colour bleeding: the ceiling's left corner is tinted by the red wall, its right corner by the green wall
+    cl = np.array([disp[y0 // scale:y1 // scale, x0 // scale:x1 // scale].mean(axis=(0, 1)) for x0, y0, x1, y1 in
+                   (fx["regions"]["ceiling left"]["box"], fx["regions"]["ceiling right"]["box"])])
+    assert cl[0][0] > cl[0][1] > cl[0][2] and cl[1][1] > cl[1][0] > cl[1][2]
+    for key in ("floor profile y=1030", "floor profile y=960"):
+        p = fx[key]
+        b = p["block"]
+        got = np.array([disp[p["y"] // scale:(p["y"] + b) // scale, x // scale:(x + b) // scale].mean(axis=(0, 1)) for x in p["x"]])
+        want = np.array(p["mean_rgb8"])
+        # (blocks the glass box covers show the refracted back wall texture: skipped where the screenshot's own profile is
+        # far from smooth is not needed — the rows chosen run in front of the box)
+        assert np.abs(got - want).mean() <= profile_tol, (key, float(np.abs(got - want).mean()), float(np.abs(got - want).max()))
+    return worst
+
+
+def test_oracle_reproduces_the_reference_screenshot(oracle, xf):
+    """Quarter resolution, 36 spp through the CPU oracle and the numpy restatement of the tone map (a few seconds)."""
+    from oracle import post
+    fx = _fixture()
+    scene, cam, film, integ = _setup(oracle.transforms, fx, 4)
+    img, _, st = oracle.OracleScene(scene).render(cam, film, D.SamplerType.stratified(6, 6), integ)
+    disp = _display(post.tonemap_filmic(img, fx["settings"]["exposure"]))
+    _compare(fx, disp, 4, tol=4.0, profile_tol=5.0)
+    assert abs(st.ray_count / st.samples / _published_rays_per_sample(fx) - 1.0) <= 4e-3   # (466 560 samples: sampling noise)
+    # geometry: the box opening's edges on the film, from the same row / column the fixture measured
+    lit = disp.sum(axis=2) > 30
+    cols, rows = np.where(lit[562 // 4])[0], np.where(lit[:, 960 // 4])[0]
+    bo = fx["box_opening"]
+    assert abs(cols[0] * 4 - bo["x_first"]) <= 4 and abs(cols[-1] * 4 + 3 - bo["x_last"]) <= 4
+    assert abs(rows[0] * 4 - bo["y_first"]) <= 4 and abs(rows[-1] * 4 + 3 - bo["y_last"]) <= 4
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_the_reference_screenshot(gpu_ctx, xf):
+    """The screenshot's own resolution and sample count through yk_render and yk_tonemap_filmic."""
+    from yuki_b200 import api
+    fx = _fixture()
+    scene, cam, film, integ = _setup(xf, fx, 1)
+    dev = api.Scene(gpu_ctx, scene)
+    assert dev.host.n_tris == fx["settings"]["shapes"]
+    r = api.Renderer(gpu_ctx).render(dev, cam, film, D.SamplerType.stratified(32, 32), integ)
+    disp = _display(api.tonemap_filmic(gpu_ctx, r.film, exposure=fx["settings"]["exposure"]))
+    worst = _compare(fx, disp, 1, tol=2.5, profile_tol=3.0)
+    print("largest |difference| per region (8-bit display values):", {k: round(v, 2) for k, v in worst.items()})
+    lit = disp.sum(axis=2) > 30
+    cols, rows = np.where(lit[562])[0], np.where(lit[:, 960])[0]
+    bo, lq = fx["box_opening"], fx["light_quad"]
+    assert abs(cols[0] - bo["x_first"]) <= 1 and abs(cols[-1] - bo["x_last"]) <= 1
+    assert abs(rows[0] - bo["y_first"]) <= 1 and abs(rows[-1] - bo["y_last"]) <= 1
+    ys, xs = np.where((disp.min(axis=2) >= 250)[:400])
+    assert abs(xs.min() - lq["x_min"]) <= 2 and abs(xs.max() - lq["x_max"]) <= 2
+    assert abs(ys.min() - lq["y_min"]) <= 2 and abs(ys.max() - lq["y_max"]) <= 2
+    # the render's closest-hit ray count against the reference's published one (2.6231 rays per sample)
+    got = r.stats.ray_count / r.stats.samples
+    print(f"rays per sample: {got:.5f}, the reference's status line gives {_published_rays_per_sample(fx):.5f}")
+    assert abs(got / _published_rays_per_sample(fx) - 1.0) <= 2e-3
+    dev.close()

@@ -9,7 +9,7 @@
 //   * no gather step: the film lives on the first device and every other device's film kernels (k_film_store / k_film_add,
 //     and the primary-hit id image) store their finished pixels straight into it through peer mappings, i.e. as NVLink
 //     writes overlapped with the rendering of the following batches. Without peer access the devices render into local
-//     films that are copied over and summed on the first device at the end (tiles are disjoint: x + 0).
+//     films whose rendered pixels are copied over to the first device at the end.
 // Accumulating films add a pixel once per sample index; to keep the order of those adds fixed (the reference's is
 // whatever its workers' timing makes it) a tile always goes to device `tile.index mod G` there.
 // Part of the translation unit render.cu (uses render_impl / scene_create_impl).
@@ -18,7 +18,7 @@ struct yk_multi {
     std::vector<yk_context*> ctx;     // ctx[0] owns the film
     std::vector<int> peer_ok;         // device i can store into device 0's memory
     std::mutex mu;                    // one render at a time
-    float* merge_stage = nullptr;     // device 0: staging for the fallback gather
+    float* merge_stage = nullptr;     // device 0: staging for the fallback gather (+ the initial film of accumulating renders)
     size_t merge_cap = 0;
 };
 struct yk_multi_scene {
@@ -28,9 +28,21 @@ struct yk_multi_scene {
 
 namespace {
 
-__global__ void k_film_merge(float* film, const float* part, size_t n) {
+// Gather of a device that could not store into the first device's film: the pixels the device wrote replace the film's, every
+// other pixel is left alone (like Film::update_tile touches only its tile, film.rs:260-279). Averaging films: the local film
+// started as kUnrendered (a NaN payload no kernel produces). Accumulating films: the local film started as a copy of the
+// initial film, so that a pixel's adds associate exactly as on one device ((film + s0) + s1 ...); a pixel is the device's own
+// iff it differs from that initial film (an unchanged own pixel needs no copy).
+constexpr uint32_t kUnrendered = 0x7fc0dead;
+__global__ void k_film_merge(float* film, const float* part, const float* initial, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) film[i] = film[i] + part[i];
+    if (i >= n) return;
+    const uint32_t v = __float_as_uint(part[i]);
+    if (v != (initial ? __float_as_uint(initial[i]) : kUnrendered)) film[i] = part[i];
+}
+__global__ void k_fill_u32(uint32_t* p, size_t n, uint32_t v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 __global__ void k_ids_merge(int32_t* ids, const int32_t* part, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,7 +201,19 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
     }
     CUDA_TRY(cudaStreamSynchronize(s0));
 
-    // Devices without a peer mapping render into a local film (zeroed here) that is gathered at the end.
+    bool any_gather = false;
+    for (size_t i = 1; i < G; ++i) any_gather = any_gather || !m->peer_ok[i];
+    if (any_gather) {
+        if (m->merge_cap < 2 * film_bytes) {
+            cudaFree(m->merge_stage);
+            m->merge_stage = nullptr;
+            m->merge_cap = 0;
+            CUDA_TRY(cudaMalloc((void**)&m->merge_stage, 2 * film_bytes));
+            m->merge_cap = 2 * film_bytes;
+        }
+        if (accumulate) CUDA_TRY(cudaMemcpy(m->merge_stage, d_film, film_bytes, cudaMemcpyDeviceToDevice));  // the initial film
+    }
+    // Devices without a peer mapping render into a local film that is gathered at the end.
     std::vector<float*> local_film(G, nullptr);
     std::vector<int32_t*> local_ids(G, nullptr);
     for (size_t i = 1; i < G; ++i) {
@@ -206,7 +230,8 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
             CUDA_TRY(cudaMalloc((void**)&c->d_hit_ids, n_pixels * sizeof(int32_t)));
             c->film_cap = n_pixels;
         }
-        CUDA_TRY(cudaMemsetAsync(c->d_film, 0, film_bytes, c->stream));
+        if (accumulate) CUDA_TRY(cudaMemcpyPeer(c->d_film, c->device, d_film, root->device, film_bytes));
+        else k_fill_u32<<<(unsigned)((n_pixels * 3 + 255) / 256), 256, 0, c->stream>>>((uint32_t*)c->d_film, n_pixels * 3, kUnrendered);
         local_film[i] = c->d_film;
         if (d_ids) {
             k_fill_i32<<<(unsigned)((n_pixels + 255) / 256), 256, 0, c->stream>>>(c->d_hit_ids, n_pixels, -1);
@@ -291,18 +316,12 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
     CUDA_TRY(cudaSetDevice(root->device));
     for (size_t i = 1; i < G; ++i) {
         if (m->peer_ok[i]) continue;
-        if (m->merge_cap < film_bytes) {
-            cudaFree(m->merge_stage);
-            m->merge_stage = nullptr;
-            m->merge_cap = 0;
-            CUDA_TRY(cudaMalloc((void**)&m->merge_stage, film_bytes));
-            m->merge_cap = film_bytes;
-        }
-        CUDA_TRY(cudaMemcpyPeerAsync(m->merge_stage, root->device, local_film[i], m->ctx[i]->device, film_bytes, s0));
-        k_film_merge<<<(unsigned)((n_pixels * 3 + 255) / 256), 256, 0, s0>>>(d_film, m->merge_stage, n_pixels * 3);
+        float* stage = m->merge_stage + n_pixels * 3;
+        CUDA_TRY(cudaMemcpyPeerAsync(stage, root->device, local_film[i], m->ctx[i]->device, film_bytes, s0));
+        k_film_merge<<<(unsigned)((n_pixels * 3 + 255) / 256), 256, 0, s0>>>(d_film, stage, accumulate ? m->merge_stage : nullptr, n_pixels * 3);
         if (d_ids) {
-            CUDA_TRY(cudaMemcpyPeerAsync(m->merge_stage, root->device, local_ids[i], m->ctx[i]->device, n_pixels * sizeof(int32_t), s0));
-            k_ids_merge<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s0>>>(d_ids, (const int32_t*)m->merge_stage, n_pixels);
+            CUDA_TRY(cudaMemcpyPeerAsync(stage, root->device, local_ids[i], m->ctx[i]->device, n_pixels * sizeof(int32_t), s0));
+            k_ids_merge<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s0>>>(d_ids, (const int32_t*)stage, n_pixels);
         }
     }
     if (!on_device) {

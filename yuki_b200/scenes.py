@@ -35,7 +35,7 @@ def checker_texture(size=256, cells=8, a=(0.8, 0.8, 0.8), b=(0.2, 0.3, 0.7)) -> 
 
 
 def cornell(xf, light="rect", tall_box="glass", textured_back_wall=False, split_method=D.SPLIT_SAH, max_shapes_in_node=1,
-            sphere=False):
+            sphere=False, back_wall_albedo=None):
     """Cornell box in metres, camera looking down -z (scene/mod.rs:154-531). `sphere=True` adds the copper sphere of
     scene/mod.rs:497-501 (with `split_method=D.SPLIT_MIDDLE` this is `Scene::cornell()` up to the missing back-wall PNG)."""
     LEFT, RIGHT, BOTTOM, TOP, FRONT, BACK = F(555.0), F(0.0), F(0.0), F(550.0), F(0.0), F(560.0)
@@ -63,6 +63,8 @@ def cornell(xf, light="rect", tall_box="glass", textured_back_wall=False, split_
     back = white
     if textured_back_wall:
         back = s.add_material(D.Material(D.MAT_MATTE, (s.add_texture(D.Texture.from_image(checker_texture())), zero)))
+    elif back_wall_albedo is not None:  # a constant stand-in for the marble PNG missing from the reference checkout (scene/mod.rs:193-200)
+        back = s.add_material(D.Material(D.MAT_MATTE, (s.add_texture(D.Texture.constant(*back_wall_albedo)), zero)))
 
     area_light = -1
     if light == "rect":  # scene/mod.rs:230-240
