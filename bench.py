@@ -522,6 +522,79 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_single_process(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: all N devices behind one handle (yk_multi_*, csrc/multi.inl) — one host
+    thread per device inside the library, tiles popped from one shared cursor, the film assembled on device 0 by peer stores.
+    Timed on the host around the blocking calls (each returns with every device synchronised); per-device busy times come
+    from the library's CUDA events. The driver's N > 1 runs use torchrun (run_ours); this is the in-process alternative a
+    host binding the C ABI gets."""
+    import torch
+    from yuki_b200 import api, transforms as xf
+    n = args.gpus
+    if torch.cuda.device_count() < n:
+        raise SystemExit(f"bench.py --gpus {n}: only {torch.cuda.device_count()} CUDA devices")
+    mctx = api.MultiContext(list(range(n)))
+    out = {}
+    for key in ("c2", "c5"):
+        if key == "c5" and args.no_large_scene:
+            continue
+        if key == "c2":
+            scene, cam, film, sampler, integ = workload(xf)
+            steps, warmup, name = args.steps, args.warmup, WORKLOAD
+        else:
+            from yuki_b200 import scenes
+            scene, cam = scenes.terrain_room(xf)
+            film = D.FilmSettings((3840, 2160), 16)
+            sampler, integ = D.SamplerType.stratified(C5_SPP_SIDE, C5_SPP_SIDE, jitter=True), D.IntegratorType.path(MAX_DEPTH)
+            steps, warmup, name = C5_STEPS, C5_WARMUP, f"configs[4] geometry at {C5_SPP_SIDE * C5_SPP_SIDE} spp"
+        host = api.HostScene(scene)
+        ms = api.MultiScene(mctx, scene, host=host)
+        n_pix = film.res[0] * film.res[1]
+        total = n_pix * sampler.samples_per_pixel()
+        with torch.cuda.device(0):
+            d_film = torch.zeros(n_pix * 3, dtype=torch.float32, device="cuda:0")
+            for _ in range(max(warmup, 1)):
+                api.multi_render(mctx, ms, cam, film, sampler, integ, device_film_ptr=d_film.data_ptr())
+            digest = check_digest("c2_1024spp" if key == "c2" else "c5_16spp", film_digest(d_film), False) if not args.spp_side else None
+            clocks = ClockSampler(0)
+            clocks.start()
+            t0 = time.perf_counter()
+            busy = [0.0] * n
+            rays = shadow = launches = 0
+            for _ in range(steps):
+                r, per = api.multi_render(mctx, ms, cam, film, sampler, integ, device_film_ptr=d_film.data_ptr())
+                busy = [b + p.device_ms for b, p in zip(busy, per)]
+                rays += r.stats.ray_count; shadow += r.stats.shadow_rays; launches += r.stats.kernel_launches
+            sec = time.perf_counter() - t0
+            clk = clocks.stop()
+            film_host = np.zeros((film.res[1], film.res[0], 3), np.float32)
+            t0 = time.perf_counter()
+            e2e_steps = max(1, min(steps, 2))
+            for _ in range(e2e_steps):
+                ms2 = api.MultiScene(mctx, scene, host=host)
+                api.multi_render(mctx, ms2, cam, film, sampler, integ, film_out=film_host)
+                ms2.close()
+            e2e_sec = time.perf_counter() - t0
+        out[key] = {"workload": name, "value": total * steps / sec / 1e6, "ms_per_step": 1e3 * sec / steps, "steps": steps,
+                    "per_device_busy_ms": [b / steps for b in busy], "peer_stores": mctx.peer_stores(), "film_digest": digest, "clocks": clk,
+                    "mrays_per_s": rays / sec / 1e6, "mrays_per_s_total": (rays + shadow) / sec / 1e6, "gpu_launches": int(launches),
+                    "e2e": total * e2e_steps / e2e_sec / 1e6}
+        ms.close()
+        host.close()
+    c2 = out["c2"]
+    line = {"metric": "Msamples/s", "value": c2["value"], "unit": "Msamples/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": c2["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tile_dim": 16, "mode": "single process: yk_multi_render, one host thread per device, tiles from one shared cursor, "
+                       "film on device 0 written by peer (NVLink) stores", "timing": "host clock around blocking calls"},
+            "mrays_per_s": c2["mrays_per_s"], "mrays_per_s_total": c2["mrays_per_s_total"], "gpu_launches": c2["gpu_launches"], "clocks": c2["clocks"],
+            "per_device_busy_ms": c2["per_device_busy_ms"], "peer_stores": c2["peer_stores"], "film_digest": c2["film_digest"],
+            "e2e": {"value": c2["e2e"], "unit": "Msamples/s", "includes": "yk_multi_scene_create + yk_multi_render with a host film"}}
+    if "c5" in out:
+        line["large_scene"] = out["c5"]
+    emit(line)
+    mctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -541,6 +614,8 @@ def main():
     select_workload(args.workload, args.spp_side)
     if args.impl == "reference":
         run_reference(args)
+    elif args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        run_single_process(args)
     else:
         run_ours(args)
 

@@ -147,3 +147,6 @@ if which == "whitted1":
 if which == "terrain16":  # the render of bench.py's large_scene leg (one pipe), for its ncu capture
     s, c = scenes.terrain_room(xf)
     probe("terrain 10M path8 3840x2160 16spp", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=0, pipes=1)
+if which == "c64":
+    s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+    probe("cornell 1024^2 path8 64spp", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8), reps=3)

@@ -11,7 +11,7 @@ floor profiles across the shadows of the sphere and the glass box.
 The one thing the checkout cannot supply is the back wall's marble texture (res/tiling_58-1K/tiling_58_basecolor-1K.png,
 .MISSING_LARGE_BLOBS); a constant albedo (0.85, 0.85, 0.80), fitted to the screenshot's own back wall region, stands in for
 it. That region is therefore not evidence; every other comparison has no free parameter. Tolerances are in 8-bit display
-values (the screenshot is an 8-bit PNG of a noisy render): 2.5 for region means on the full-resolution GPU render, 4 on the
+values (the screenshot is an 8-bit PNG of a noisy render): 1.5 for region means on the full-resolution GPU render (measured: at most 0.9), 4 on the
 quarter-resolution oracle render.
 
 This pins the ORACLE (and the GPU path, bit-identical to it) against a reference-produced artefact — the only check that can
@@ -109,7 +109,7 @@ def test_gpu_reproduces_the_reference_screenshot(gpu_ctx, xf):
     assert dev.host.n_tris == fx["settings"]["shapes"]
     r = api.Renderer(gpu_ctx).render(dev, cam, film, D.SamplerType.stratified(32, 32), integ)
     disp = _display(api.tonemap_filmic(gpu_ctx, r.film, exposure=fx["settings"]["exposure"]))
-    worst = _compare(fx, disp, 1, tol=2.5, profile_tol=3.0)
+    worst = _compare(fx, disp, 1, tol=1.5, profile_tol=2.0)
     print("largest |difference| per region (8-bit display values):", {k: round(v, 2) for k, v in worst.items()})
     lit = disp.sum(axis=2) > 30
     cols, rows = np.where(lit[562])[0], np.where(lit[:, 960])[0]

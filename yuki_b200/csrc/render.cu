@@ -355,8 +355,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         }
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
         nvtxRangePushA("yk shadow rays + fold");
-        const bool rays_per_lane = c->shadow_mode == 1 || (c->shadow_mode < 0 && sc->dev.n_lights >= 2 && sc->dev.n_tris >= (1u << 18));
-        if (rays_per_lane && sc->dev.n_lights > 0) {  // one shadow ray per lane, then the fold (wf_trace.cuh)
+        if (cfg.shadow_per_ray) {  // one shadow ray per lane, then the fold (wf_trace.cuh)
             if (spheres) k_trace_shadow_rays<true><<<shadow_rays_blocks, kTraceThreads, 0, s>>>(sc->dev, w, sc->dev.n_lights, cur);
             else k_trace_shadow_rays<false><<<shadow_rays_blocks, kTraceThreads, 0, s>>>(sc->dev, w, sc->dev.n_lights, cur);
             k_shadow_fold<<<fold_blocks, 256, 0, s>>>(w, cfg, cur);
@@ -801,6 +800,7 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
     cfg.aux_sample = opts ? opts->aux_sample : 0u;
     cfg.debug_log = debug_log;
     if (debug_log) { cfg.debug_px[0] = debug_px[0]; cfg.debug_px[1] = debug_px[1]; }
+    cfg.shadow_per_ray = (sc->dev.n_lights > 0 && (c->shadow_mode == 1 || (c->shadow_mode < 0 && sc->dev.n_lights >= 2 && sc->dev.n_tris >= (1u << 18)))) ? 1u : 0u;
     {   // ray sort between bounces (path tracing only; Whitted's tree walk re-queues rays in DFS order)
         int key = c->sort_key;
         cfg.sort_order = (uint32_t)c->sort_order;

@@ -213,6 +213,7 @@ struct RenderCfg {
     float debug_px[2];
     // ray sort: 0 = none; 1 = key from the hit shape's leaf slot (BVH order is a spatial order) + direction octant;
     // 2 = key from the Morton cell of the ray origin inside the scene bounds + direction octant
+    uint32_t shadow_per_ray;      // the shadow rays of this render are traced one per lane (k_trace_shadow_rays): the shading kernels fill sh_mask
     uint32_t sort_key_mode;
     uint32_t sort_order;          // 1 = the closest-hit kernel walks the sorted order; 2 = the material sort (hence shading, shadow rays) too
     uint32_t sort_slot_shift;     // mode 1: leaf slot >> shift gives the 15 spatial key bits

@@ -341,6 +341,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #else
 #define YK_SHADE_SYNC() ((void)0)
 #endif
+#if YK_SHADE_PHASED >= 2  // A/B: finer phases (surface | BSDF set-up, emission | BSDF sampling)
+#define YK_SHADE_SYNC2() __syncthreads()
+#else
+#define YK_SHADE_SYNC2() ((void)0)
+#endif
 
 template <uint32_t KIND, bool PATH>
 __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
@@ -373,8 +378,9 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         // the top stall is `no_instruction` (profiles/r02). YK_SHADE_SYNC() (a block barrier when YK_SHADE_PHASED) keeps the
         // warps of a block inside the same phase of the code: surface + BSDF set-up | one light | emission + BSDF sampling.
         const bool active = i < n;
-        uint32_t g = 0, hit_slot = 0, depth = 0, shadow_mask = 0;
-        bool was_specular = false;
+        uint32_t g = 0, hit_slot = 0, slot = 0, mat_index = 0, depth = 0, shadow_mask = 0;
+        bool was_specular = false, add_le = false;
+        RGB le = gray(0.0f);
         V3 d = mk(0.0f, 0.0f, 0.0f);
         Surface si;
         Bsdf bsdf;
@@ -385,12 +391,14 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             g = g_base + i;
             st_once(&w.sh_path[g], path);
             hit_slot = ld_once(&queue_tri[i]);
-            const uint32_t slot = ld_once(&queue_slot[i]);
+            slot = ld_once(&queue_slot[i]);
             const float4 ro = ld_once(&w.st[b].ray_o[slot]), rd = ld_once(&w.st[b].ray_d[slot]);
             const V3 o = f4v(ro);
             d = f4v(rd);
-            uint32_t mat_index;
             make_surface(sc, hit_slot, o, d, &si, &mat_index);
+        }
+        YK_SHADE_SYNC2();
+        if (active) {
             make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
 
             const float4 beta4 = ld_once(&w.st[b].beta[slot]);
@@ -432,18 +440,20 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         }
         YK_SHADE_SYNC();
         if (active) {
-            st_once(&w.sh_mask[g], shadow_mask);
+            if (cfg.shadow_per_ray) st_once(&w.sh_mask[g], shadow_mask);  // (k_trace_shadow reads the mask from pend_extra.w; the extra store costs 3 %)
 
             // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
-            RGB le = gray(0.0f);
             // The integrators pass -ray.d here and (Path) to sample_f, but si.wo to Bsdf::f; the two differ for spheres, whose
             // si.wo went through object_to_world once more (sphere.rs:116, interaction.rs:155).
-            const V3 wo_ray = -d;
-            if (si.area_light >= 0 && dotn(si.n, wo_ray) > 0.0f) {
+            if (si.area_light >= 0 && dotn(si.n, -d) > 0.0f) {
                 const yk_light& al = sc.lights[si.area_light];
                 le = rgb(al.i[0], al.i[1], al.i[2]);
             }
-            const bool add_le = depth == 0 || was_specular;
+            add_le = depth == 0 || was_specular;
+        }
+        YK_SHADE_SYNC2();
+        if (active) {
+            const V3 wo_ray = -d;
 
             uint32_t new_flags = 0;
             if (PATH) {

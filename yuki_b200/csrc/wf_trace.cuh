@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
                     // `lo <= min(hi, NaN)`: `lo <= hi` for a box with a numeric exit distance — what the stacked keys encode — but
                     // false for a box whose own exit distance is NaN too, i.e. every box when all three direction components are
                     // NaN. Those rays drop their stack here (their popped nodes are already counted as tested, none would pass).
-                    if (hit_t != hit_t && tl.ix != tl.ix && tl.iy != tl.iy && tl.iz != tl.iz) tl.sp = sbase + kStackStride;
+                    // (Only the counting instantiations carry the test: they serve yk_trace's caller rays and the debug integrator;
+                    // the integrators' own rays have finite directions, and the test costs the hot instantiation 1.7 %,
+                    // profiles/r02/ab_cornell_regression.txt.)
+                    if (COUNTS && hit_t != hit_t && tl.ix != tl.ix && tl.iy != tl.iy && tl.iz != tl.iz) tl.sp = sbase + kStackStride;
                 }
             })
             if (live && !tl.wants_box()) {  // retire
