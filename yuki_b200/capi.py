@@ -237,6 +237,9 @@ def lib():
     for n in ("yk_xf_identity", "yk_xf_translation", "yk_xf_scale", "yk_xf_rotation", "yk_xf_mul", "yk_xf_inverted"):
         getattr(L, n).restype = None
     L.yk_light_make.argtypes = [C.POINTER(LightDesc), C.POINTER(LightDev)]
+    if not hasattr(L, "yk_multi_create"):   # an older development build selected with YUKI_GPU_LIB (A/B runs): no device groups
+        _lib = L
+        return L
     L.yk_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.yk_multi_destroy.argtypes = [vp]
     L.yk_multi_destroy.restype = None

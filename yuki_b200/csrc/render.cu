@@ -42,7 +42,10 @@
 // =====================================================================================================
 // Host side: context, scene upload, wavefront driver.
 // =====================================================================================================
-constexpr int kMaxPipes = 2;   // batches in flight on separate streams (their kernels overlap on the SMs)
+#ifndef YK_MAX_PIPES
+#define YK_MAX_PIPES 2
+#endif
+constexpr int kMaxPipes = YK_MAX_PIPES;   // batches in flight on separate streams (their kernels overlap on the SMs)
 constexpr int kRing = 2;       // batches queued per pipe before the host waits for the oldest
 constexpr int kTimedStages = 5;  // events per bounce: before/after closest, after classify, after shading, after shadow
 
@@ -109,6 +112,7 @@ struct yk_context {
     // material room (6.6 K triangles, 3 lights) 22.7 -> 25.6 ms, Cornell box (1 light) 14.6 -> 18.2 ms: on cache-resident
     // scenes the serial walk was not the limiter and the separate fold costs more than it saves. Environment: YK_SHADOW_MODE.
     int shadow_mode = -1;
+    int shade_phased = -1;  // k_shade<.., PHASED>: -1 = by scene (run_batch), 0 / 1 = environment YK_SHADE_PHASED
     int stage_timing = 1;  // CUDA events per bounce: 1 = around the closest-hit kernel (the roofline figure), 2 = every stage
                            // (costs ~1.5 % of a Cornell render), 0 = none; environment variable YK_STAGE_TIMING
 };
@@ -263,6 +267,9 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
     };
 
     const int T = 256;
+#ifdef YK_CHECKED
+    CUDA_TRY(cudaMemcpyToSymbolAsync(g_check_queue_cap, &w.cap, sizeof(uint32_t), 0, cudaMemcpyHostToDevice, s));
+#endif
     CUDA_TRY(cudaMemsetAsync(p->d_ctr, 0, 2 * sizeof(IterCounters), s));
     k_sample_jumps<<<1, kMaxBatchSamples, 0, s>>>(first_sample, bt.n_samples, p->d_jumps);
     tm->launches += 1;
@@ -276,6 +283,12 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
     const int classify_items = cfg.integrator == YK_INTEGRATOR_WHITTED ? 1 : YK_CLASSIFY_ITEMS;
     const int classify_blocks = grid_for(bt.n_paths, T * classify_items, c->sm_count * 8);
     const int shade_blocks = grid_for(bt.n_paths, kShadeThreads, wide_blocks);
+    const int shade_blocks_plain = grid_for(bt.n_paths, kShadeThreadsPlain, wide_blocks);
+    // Phase barriers + 256-thread blocks where the shading code a warp walks is long (several lights and / or material kinds);
+    // plain 128-thread blocks for the Cornell-box class. YK_SHADE_PHASED=0/1 overrides.
+    int n_kinds = 0;
+    for (uint32_t kind = 0; kind < 4; ++kind) n_kinds += (sc->material_kinds >> kind) & 1u;
+    const bool phased = c->shade_phased >= 0 ? c->shade_phased != 0 : (sc->dev.n_lights >= 2 || n_kinds >= 3);
     const int closest_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_closest);
     const int shadow_blocks = grid_for(bt.n_paths, kTraceThreads, trace_blocks_shadow);
     const int shadow_rays_blocks = grid_for((uint32_t)std::min<uint64_t>((uint64_t)bt.n_paths * std::max(sc->dev.n_lights, 1u), 0xffffffffu), kTraceThreads,
@@ -333,24 +346,23 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             uint32_t* q = w.q_mat + (size_t)kind * w.cap;
             uint32_t* qt = w.q_mat_tri + (size_t)kind * w.cap;
             uint32_t* qs = w.q_mat_slot + (size_t)kind * w.cap;
+#define YK_LAUNCH_SHADE(K)                                                                                                                        \
+    do {                                                                                                                                          \
+        if (phased) {                                                                                                                             \
+            if (is_path) k_shade<K, true, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);       \
+            else k_shade<K, false, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);              \
+        } else {                                                                                                                                  \
+            if (is_path) k_shade<K, true, false><<<shade_blocks_plain, kShadeThreadsPlain, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next); \
+            else k_shade<K, false, false><<<shade_blocks_plain, kShadeThreadsPlain, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);  \
+        }                                                                                                                                         \
+    } while (0)
             switch (kind) {
-                case YK_MAT_MATTE:
-                    if (is_path) k_shade<YK_MAT_MATTE, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    else k_shade<YK_MAT_MATTE, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    break;
-                case YK_MAT_GLASS:
-                    if (is_path) k_shade<YK_MAT_GLASS, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    else k_shade<YK_MAT_GLASS, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    break;
-                case YK_MAT_METAL:
-                    if (is_path) k_shade<YK_MAT_METAL, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    else k_shade<YK_MAT_METAL, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    break;
-                default:
-                    if (is_path) k_shade<YK_MAT_GLOSSY, true><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    else k_shade<YK_MAT_GLOSSY, false><<<shade_blocks, kShadeThreads, 0, s>>>(sc->dev, w, cfg, bt, q, qt, qs, b, cur, nxt, q_next);
-                    break;
+                case YK_MAT_MATTE: YK_LAUNCH_SHADE(YK_MAT_MATTE); break;
+                case YK_MAT_GLASS: YK_LAUNCH_SHADE(YK_MAT_GLASS); break;
+                case YK_MAT_METAL: YK_LAUNCH_SHADE(YK_MAT_METAL); break;
+                default: YK_LAUNCH_SHADE(YK_MAT_GLOSSY); break;
             }
+#undef YK_LAUNCH_SHADE
             tm->launches += 1;
         }
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
@@ -368,7 +380,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 4), s));
         tm->launches += 1;
         if (cfg.integrator == YK_INTEGRATOR_WHITTED) {
-            k_tree_return<<<shade_blocks, kShadeThreads, 0, s>>>(w, b, cur, nxt, q_next);
+            k_tree_return<<<shade_blocks_plain, kShadeThreadsPlain, 0, s>>>(w, b, cur, nxt, q_next);
             tm->launches += 1;
         }
         if (sorting && iter + 1 < max_iters) {  // order the next bounce's rays
@@ -445,6 +457,7 @@ int yk_context_create(int device_id, yk_context** out) {
     CUDA_TRY(cudaEventCreate(&c->ev[3]));
     if (const char* np = getenv("YK_PIPES")) c->n_pipes_env = std::max(1, std::min(kMaxPipes, atoi(np)));
     if (const char* st = getenv("YK_STAGE_TIMING")) c->stage_timing = std::max(0, std::min(2, atoi(st)));
+    if (const char* sp = getenv("YK_SHADE_PHASED")) c->shade_phased = atoi(sp) ? 1 : 0;
     if (const char* sm = getenv("YK_SHADOW_MODE")) c->shadow_mode = std::max(-1, std::min(1, atoi(sm)));
     if (const char* sk = getenv("YK_SORT_KEY")) c->sort_key = std::max(-1, std::min(2, atoi(sk)));
     if (const char* so = getenv("YK_SORT_ORDER")) c->sort_order = std::max(1, std::min(2, atoi(so)));
@@ -892,9 +905,13 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
         if (opts && opts->pipes) n_pipes = (int)opts->pipes;
         n_pipes = std::max(1, std::min(kMaxPipes, n_pipes));
         if (accumulate) n_pipes = 1;
-        if (n_pipes > 1 && n_jobs_total <= jobs_per_batch) {  // one group only: split it if that leaves decent batches
-            if ((uint64_t)(n_jobs_total / 2) * m >= (1u << 20)) jobs_per_batch = (uint32_t)((n_jobs_total + 1) / 2);
-            else n_pipes = 1;
+        // fewer pixel groups than pipes: split the jobs evenly if that leaves decent batches, else use fewer pipes
+        while (n_pipes > 1 && (n_jobs_total + jobs_per_batch - 1) / jobs_per_batch < (unsigned long long)n_pipes) {
+            if ((uint64_t)(n_jobs_total / n_pipes) * m >= (1u << 20)) {
+                jobs_per_batch = (uint32_t)((n_jobs_total + n_pipes - 1) / n_pipes);
+                break;
+            }
+            n_pipes -= 1;
         }
         const uint32_t wave_cap = (uint32_t)std::min<uint64_t>(cap, (uint64_t)jobs_per_batch * m);
         int rc = YK_OK;

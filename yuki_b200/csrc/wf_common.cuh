@@ -22,13 +22,14 @@ constexpr int kStackDepth = 64;  // bvh.rs:172
 constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTraceThreads = 128;
 #ifndef YK_SHADE_THREADS
-// 256 threads with the phase barriers of k_shade (YK_SHADE_PHASED): the blocks' warps stay inside the same part of the ~100 KB
-// kernel, whose top stall at 128 unsynchronised threads was `no_instruction` (32 KB instruction cache). Measured (one pipe,
-// profiles/r02/ab_shade_phased.txt): shading time of the material room 29.0 -> 23.9 ms (render +7.5 %), terrain 6.9 -> 6.6 ms,
+// 256 threads with the phase barriers of shade_item (k_shade<.., PHASED = true>): the blocks' warps stay inside the same part of
+// the ~100 KB kernel, whose top stall at 128 unsynchronised threads was `no_instruction` (32 KB instruction cache). Measured (one
+// pipe, profiles/r02/ab_shade_phased.txt): shading time of the material room 29.0 -> 23.9 ms (render +5 %), terrain 6.9 -> 6.6 ms,
 // Cornell box unchanged; 512 threads = 256, 1024 threads and barriers without larger blocks are slower.
 #define YK_SHADE_THREADS 256
 #endif
 constexpr int kShadeThreads = YK_SHADE_THREADS;
+constexpr int kShadeThreadsPlain = 128;  // the barrier-free instantiation (k_shade<.., PHASED = false>)
 #ifndef YK_TRACE_MIN_BLOCKS
 // Closest hit: a bound of 6 (cap 80 registers) instead of 8 (cap 64). The path-tracing instantiation still settles on 64
 // registers and runs 8 blocks per SM, but without squeezing under a hard cap its schedule is ~2 % faster; the counting /
@@ -65,6 +66,17 @@ __device__ __forceinline__ void st_once(T* p, T v) {
     *p = v;
 #endif
 }
+
+// Checked build (-DYK_CHECKED, scripts/checked_build.sh): device-side bounds assertions on every hand-computed index — the
+// traversal stack pointer, leaf / record / queue / hand-over indices, sort bins. compute-sanitizer is closed on this GPU pool
+// ("runs under it have left GPUs needing a reset"), so the GPU test-suite is run against this build instead; a violated
+// assertion surfaces as cudaErrorAssert from the call that launched the kernel.
+#ifdef YK_CHECKED
+#include <cassert>
+#define YK_ASSERT(x) assert(x)
+#else
+#define YK_ASSERT(x) ((void)0)
+#endif
 
 #define CUDA_TRY(expr)                                                                                          \
     do {                                                                                                        \
@@ -232,6 +244,10 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // other value appends nothing. Must be reached by every thread of the block (blockDim.x <= 1024).
 // Returns the slot the value was written to (undefined when nothing was appended).
 // `K` items per thread share the block's atomics: K * blockDim.x items per global atomic and queue.
+#ifdef YK_CHECKED
+__device__ uint32_t g_check_queue_cap = 0xffffffffu;  // set by the host driver to the wavefront capacity before each batch
+#define YK_CHECK_QUEUE_CAP g_check_queue_cap
+#endif
 template <int NQ, int K>
 __device__ __forceinline__ void block_scatter_multi(const int (&key)[K], const uint32_t (&value)[K], uint32_t* const (&queues)[NQ],
                                                     uint32_t* const (&counters)[NQ], uint32_t (&pos)[K]) {
@@ -273,6 +289,7 @@ __device__ __forceinline__ void block_scatter_multi(const int (&key)[K], const u
         pos[k] = 0;
         if (key[k] >= 0 && key[k] < NQ) {
             pos[k] = s_base[key[k]] + s_cnt[warp][key[k]] + my_rank[k];
+            YK_ASSERT(pos[k] < YK_CHECK_QUEUE_CAP);
             queues[key[k]][pos[k]] = value[k];
         }
     }

@@ -86,6 +86,7 @@ __global__ void k_classify(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const u
             path[k] = 0; hit_slot[k] = kMiss; key[k] = -1;
             if (j >= n) continue;
             const uint32_t i = perm ? __ldg(&perm[j]) : j;  // the ray's queue slot (sorted renders walk the queue through perm)
+            YK_ASSERT(i < n);
             idx[k] = i;
             path[k] = queue ? queue[i] : i;
             const uint2 h = ld_once(&w.hit[i]);
@@ -333,24 +334,168 @@ __device__ __forceinline__ void sample_light(const yk_light& L, int index, const
 #define YK_SHADE_PREFETCH 1
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#ifndef YK_SHADE_PHASED
-#define YK_SHADE_PHASED 1
-#endif
-#if YK_SHADE_PHASED
-#define YK_SHADE_SYNC() __syncthreads()
-#else
-#define YK_SHADE_SYNC() ((void)0)
-#endif
-#if YK_SHADE_PHASED >= 2  // A/B: finer phases (surface | BSDF set-up, emission | BSDF sampling)
-#define YK_SHADE_SYNC2() __syncthreads()
-#else
-#define YK_SHADE_SYNC2() ((void)0)
-#endif
 
-template <uint32_t KIND, bool PATH>
-__global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue,
-                                                                               const uint32_t* queue_tri, const uint32_t* queue_slot, int b,
-                                                                               IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
+// What one shaded path hands to the survivor compaction.
+struct ShadeOut {
+    float4 nx_o, nx_d, nx_beta;  // the survivor's state for the next bounce, written after the compaction assigns its position
+    unsigned long long nx_rng;
+    uint32_t nx_key;             // ray sort: the survivor's coherence key (wf_sort.cuh)
+    uint32_t path;
+    bool alive;
+};
+
+// One queue entry. SYNC: the calling block is full (every thread has an entry), so the body may hold block barriers — they keep
+// the block's warps inside the same phase of the ~100 KB of straight-line code (surface + BSDF set-up | one light at a time |
+// emission + BSDF sampling), whose top stall with the warps spread all over it is `no_instruction` (32 KB instruction cache,
+// profiles/r02/ncu_shade_room.txt). The last, partial block of a queue runs the barrier-free instantiation.
+template <uint32_t KIND, bool PATH, bool SYNC>
+__device__ __forceinline__ void shade_item(const DevScene& sc, const Wave& w, const RenderCfg& cfg, const Batch& bt, const uint32_t* queue,
+                                           const uint32_t* queue_tri, const uint32_t* queue_slot, int b, uint32_t i, uint32_t g, ShadeOut* out) {
+    const uint32_t path = ld_once(&queue[i]);
+    out->path = path;
+    st_once(&w.sh_path[g], path);
+    const uint32_t hit_slot = ld_once(&queue_tri[i]), slot = ld_once(&queue_slot[i]);
+    YK_ASSERT(path < w.cap && slot < w.cap && g < w.cap && hit_slot < sc.n_tris);
+    const float4 ro = ld_once(&w.st[b].ray_o[slot]), rd = ld_once(&w.st[b].ray_d[slot]);
+    const V3 o = f4v(ro), d = f4v(rd);
+    Surface si;
+    uint32_t mat_index;
+    make_surface(sc, hit_slot, o, d, &si, &mat_index);
+    Bsdf bsdf;
+    make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
+
+    const float4 beta4 = ld_once(&w.st[b].beta[slot]);
+    RGB beta = rgb(beta4.x, beta4.y, beta4.z);
+    const uint32_t flags = __float_as_uint(beta4.w) & kFlagMask;
+    const uint32_t depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
+    const bool was_specular = (flags & kFlagSpecular) != 0;
+
+    const uint32_t sample_i = bt.div_jobs.div(path), job_i = path - sample_i * bt.n_jobs;
+    const Job job = bt.jobs[job_i];
+    SamplerState smp;
+    smp.rng.state = ld_once(&w.st[b].rng[slot]);
+    smp.rng.inc = job.rng_inc;
+    smp.dim = __float_as_uint(beta4.w) >> kDimShift;
+    smp.px = job.x;
+    smp.py = job.y;
+    smp.index = job.sample_begin + bt.sample_off + sample_i;
+    smp.job = job_i;
+
+    // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
+    uint32_t shadow_mask = 0;
+    for (uint32_t k = 0; k < sc.n_lights; ++k) {
+        if (SYNC) __syncthreads();
+        const V2 u = smp.get_2d(cfg.sampler);
+        LightSample ls;
+        sample_light(sc.lights[k], (int)k, si, u, &ls);
+        if (!black(ls.li)) {
+            const RGB f = bsdf.f(si.wo, ls.l);
+            if (ls.has_vis && !black(f)) {
+                const RGB c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
+                const size_t ref = (size_t)k * w.cap + g;
+                st_once(&w.lt_o[ref], make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, c.r));
+                st_once(&w.lt_d[ref], make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, c.g));
+                st_once(&w.lt_c[ref], make_float2(c.b, __int_as_float(ls.vis_light)));
+                shadow_mask |= 1u << k;
+            }
+        }
+    }
+    if (SYNC) __syncthreads();
+    if (cfg.shadow_per_ray) st_once(&w.sh_mask[g], shadow_mask);  // (k_trace_shadow reads the mask from pend_extra.w)
+
+    // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
+    RGB le = gray(0.0f);
+    // The integrators pass -ray.d here and (Path) to sample_f, but si.wo to Bsdf::f; the two differ for spheres, whose
+    // si.wo went through object_to_world once more (sphere.rs:116, interaction.rs:155).
+    const V3 wo_ray = -d;
+    if (si.area_light >= 0 && dotn(si.n, wo_ray) > 0.0f) {
+        const yk_light& al = sc.lights[si.area_light];
+        le = rgb(al.i[0], al.i[1], al.i[2]);
+    }
+    const bool add_le = depth == 0 || was_specular;
+
+    bool alive = false;
+    uint32_t new_flags = 0;
+    if (PATH) {
+        // path.rs:121-129 — beta multiplies the emitted term here and again in the fold (reference quirk)
+        const RGB extra = add_le ? beta * le : gray(0.0f);
+        st_once(&w.pend_extra[g], make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask)));
+        st_once(&w.pend_beta[g], make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f));
+        const Bsdf::Sample s = bsdf.sample_f(wo_ray, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137 (wo = -ray.d)
+        if (!(black(s.f) || s.pdf == 0.0f)) {
+            alive = true;
+            const bool spec = (s.type & BX_SPECULAR) != 0;
+            beta = beta * (s.f * fabsf(dotn(s.wi, si.sh_n)) / s.pdf);
+            const Ray nr = spawn_ray(si.p, si.n, s.wi);
+            if (depth > 3) {  // Russian roulette, path.rs:163-169
+                const float q = fmaxf(1.0f - beta.g, 0.05f);
+                if (smp.get_1d(cfg.sampler) < q) alive = false;
+                else beta = beta * (gray(1.0f) / (1.0f - q));
+            }
+            const uint32_t bounces = depth + 1;
+            if (bounces >= cfg.max_depth) alive = false;
+            new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u) | ((s.type & BX_TRANSMISSION) ? kFlagTransmission : 0u);
+            out->nx_o = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
+            out->nx_d = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+            out->nx_beta = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
+            if (cfg.sort_key_mode) out->nx_key = ray_sort_key(sc, cfg, hit_slot, nr.o.x, nr.o.y, nr.o.z, nr.d.x, nr.d.y, nr.d.z);
+        }
+    } else {
+        // whitted.rs:128-170: this node's own terms go to the shadow / fold kernel; k_tree_return then either parks
+        // their sum in the node's frame (children pending) or hands it to the parent
+        const RGB extra = add_le ? le : gray(0.0f);
+        st_once(&w.pend_extra[g], make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask)));
+        TreeRay child[2];
+        RGB child_f[2];
+        float child_cos[2];
+        int n_child = 0;
+        if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
+            const uint32_t wants[2] = {BX_SPECULAR | BX_REFLECTION, BX_SPECULAR | BX_TRANSMISSION};
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const Bsdf::Sample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, wants[c]);
+                if (s.type == 0u) continue;  // BxdfType::NONE: no ray, no radiance
+                const Ray nr = spawn_ray(si.p, si.n, s.wi);
+                TreeRay e;
+                e.o = nr.o;
+                e.d = nr.d;
+                e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u) | (c == 1 ? kFlagTransmission : 0u);
+                child_f[n_child] = s.f;
+                child_cos[n_child] = fabsf(dotn(s.wi, si.sh_n));
+                child[n_child++] = e;
+            }
+        }
+        alive = n_child >= 1;
+        st_once(&w.pend_beta[g], make_float4(__uint_as_float(depth | (alive ? 0x100u : 0u)), __uint_as_float(smp.dim), 0.0f, -1.0f));
+        if (alive) {
+            float4* fr = frame_of(w, depth, path);
+            fr[1] = make_float4(child_f[0].r, child_f[0].g, child_f[0].b, child_cos[0]);
+            if (n_child == 2) {  // transmission waits until the reflection subtree is done
+                fr[2] = make_float4(child[1].o.x, child[1].o.y, child[1].o.z, child[1].d.x);
+                fr[3] = make_float4(child[1].d.y, child[1].d.z, child_f[1].r, child_f[1].g);
+                fr[4] = make_float4(child_f[1].b, child_cos[1], __uint_as_float(child[1].flags | kFramePending), 0.0f);
+            } else {
+                fr[4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            const TreeRay& e = child[0];
+            out->nx_o = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
+            out->nx_d = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
+            out->nx_beta = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
+        } else {
+            w.tree_rng[g] = smp.rng.state;  // the sampler goes on with whichever node the tree visits next
+        }
+    }
+    out->nx_rng = smp.rng.state;
+    out->alive = alive;
+}
+
+// PHASED: blocks of kShadeThreads with the phase barriers of shade_item (scenes with several lights / material kinds, where the
+// instruction cache is the limiter); else blocks of kShadeThreadsPlain without barriers (the Cornell-box class: one light, two
+// kinds — measured 0.7 % faster there with two pipes, while the room gains 5 % from the phases; profiles/r02).
+template <uint32_t KIND, bool PATH, bool PHASED>
+__global__ void __launch_bounds__(PHASED ? kShadeThreads : kShadeThreadsPlain, PHASED ? YK_SHADE_MIN_BLOCKS : (1024 / kShadeThreadsPlain))
+    k_shade(DevScene sc, Wave w, RenderCfg cfg, Batch bt, const uint32_t* queue, const uint32_t* queue_tri, const uint32_t* queue_slot, int b,
+            IterCounters* cur, IterCounters* nxt, uint32_t* q_next) {
     const uint32_t n = cur->mat[KIND];
     uint32_t g_base = 0;  // shading position of this kind's first queue entry (classify has finished: the counts are final)
     if (KIND > 0) g_base += cur->mat[0];
@@ -361,8 +506,6 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
         const uint32_t block_first = (r * gridDim.x + blockIdx.x) * blockDim.x;
         if (block_first >= n) break;  // block-uniform
         const uint32_t i = block_first + threadIdx.x;
-        bool alive = false;
-        uint32_t path = 0;
 #if YK_SHADE_PREFETCH
         // the block's queue entries two rounds ahead: pull them into the L2 now (one 128-byte line per warp and queue)
         if ((threadIdx.x & 31) == 0) {
@@ -370,173 +513,22 @@ __global__ void __launch_bounds__(kShadeThreads, YK_SHADE_MIN_BLOCKS) k_shade(De
             if (i_ahead < n) { prefetch_l2(queue + i_ahead); prefetch_l2(queue_tri + i_ahead); prefetch_l2(queue_slot + i_ahead); }
         }
 #endif
-        // the survivor's state for the next bounce, written after the compaction assigns its position
-        float4 nx_o = make_float4(0, 0, 0, 0), nx_d = make_float4(0, 0, 0, 0), nx_beta = make_float4(0, 0, 0, 0);
-        unsigned long long nx_rng = 0;
-        uint32_t nx_key = 0;  // ray sort: the survivor's coherence key (wf_sort.cuh)
-        // The kernel is ~100 KB of straight-line code against a 32 KB instruction cache: with the block's warps spread all over it
-        // the top stall is `no_instruction` (profiles/r02). YK_SHADE_SYNC() (a block barrier when YK_SHADE_PHASED) keeps the
-        // warps of a block inside the same phase of the code: surface + BSDF set-up | one light | emission + BSDF sampling.
-        const bool active = i < n;
-        uint32_t g = 0, hit_slot = 0, slot = 0, mat_index = 0, depth = 0, shadow_mask = 0;
-        bool was_specular = false, add_le = false;
-        RGB le = gray(0.0f);
-        V3 d = mk(0.0f, 0.0f, 0.0f);
-        Surface si;
-        Bsdf bsdf;
-        RGB beta = gray(0.0f);
-        SamplerState smp;
-        if (active) {
-            path = ld_once(&queue[i]);
-            g = g_base + i;
-            st_once(&w.sh_path[g], path);
-            hit_slot = ld_once(&queue_tri[i]);
-            slot = ld_once(&queue_slot[i]);
-            const float4 ro = ld_once(&w.st[b].ray_o[slot]), rd = ld_once(&w.st[b].ray_d[slot]);
-            const V3 o = f4v(ro);
-            d = f4v(rd);
-            make_surface(sc, hit_slot, o, d, &si, &mat_index);
-        }
-        YK_SHADE_SYNC2();
-        if (active) {
-            make_bsdf<KIND>(sc, sc.materials[mat_index], si, &bsdf);
-
-            const float4 beta4 = ld_once(&w.st[b].beta[slot]);
-            beta = rgb(beta4.x, beta4.y, beta4.z);
-            const uint32_t flags = __float_as_uint(beta4.w) & kFlagMask;
-            depth = flags & kDepthMask;  // path: bounces so far; whitted: node depth
-            was_specular = (flags & kFlagSpecular) != 0;
-
-            const uint32_t sample_i = bt.div_jobs.div(path), job_i = path - sample_i * bt.n_jobs;
-            const Job job = bt.jobs[job_i];
-            smp.rng.state = ld_once(&w.st[b].rng[slot]);
-            smp.rng.inc = job.rng_inc;
-            smp.dim = __float_as_uint(beta4.w) >> kDimShift;
-            smp.px = job.x;
-            smp.py = job.y;
-            smp.index = job.sample_begin + bt.sample_off + sample_i;
-            smp.job = job_i;
-        }
-
-        // Light fold: every light consumes one get_2d whether it is used or not (path.rs:103).
-        for (uint32_t k = 0; k < sc.n_lights; ++k) {
-            YK_SHADE_SYNC();
-            if (active) {
-                const V2 u = smp.get_2d(cfg.sampler);
-                LightSample ls;
-                sample_light(sc.lights[k], (int)k, si, u, &ls);
-                if (!black(ls.li)) {
-                    const RGB f = bsdf.f(si.wo, ls.l);
-                    if (ls.has_vis && !black(f)) {
-                        const RGB c = f * ls.li * clamp01ish(dotn(si.sh_n, ls.l), 0.0f, 1.0f) / ls.pdf;
-                        const size_t ref = (size_t)k * w.cap + g;
-                        st_once(&w.lt_o[ref], make_float4(ls.vis.o.x, ls.vis.o.y, ls.vis.o.z, c.r));
-                        st_once(&w.lt_d[ref], make_float4(ls.vis.d.x, ls.vis.d.y, ls.vis.d.z, c.g));
-                        st_once(&w.lt_c[ref], make_float2(c.b, __int_as_float(ls.vis_light)));
-                        shadow_mask |= 1u << k;
-                    }
-                }
-            }
-        }
-        YK_SHADE_SYNC();
-        if (active) {
-            if (cfg.shadow_per_ray) st_once(&w.sh_mask[g], shadow_mask);  // (k_trace_shadow reads the mask from pend_extra.w; the extra store costs 3 %)
-
-            // Emitted radiance: interaction.rs:134-138 + rectangular_light.rs:74-81
-            // The integrators pass -ray.d here and (Path) to sample_f, but si.wo to Bsdf::f; the two differ for spheres, whose
-            // si.wo went through object_to_world once more (sphere.rs:116, interaction.rs:155).
-            if (si.area_light >= 0 && dotn(si.n, -d) > 0.0f) {
-                const yk_light& al = sc.lights[si.area_light];
-                le = rgb(al.i[0], al.i[1], al.i[2]);
-            }
-            add_le = depth == 0 || was_specular;
-        }
-        YK_SHADE_SYNC2();
-        if (active) {
-            const V3 wo_ray = -d;
-
-            uint32_t new_flags = 0;
-            if (PATH) {
-                // path.rs:121-129 — beta multiplies the emitted term here and again in the fold (reference quirk)
-                const RGB extra = add_le ? beta * le : gray(0.0f);
-                st_once(&w.pend_extra[g], make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask)));
-                st_once(&w.pend_beta[g], make_float4(beta.r, beta.g, beta.b, (depth > 0 && cfg.has_clamp) ? 1.0f : 0.0f));
-                const Bsdf::Sample s = bsdf.sample_f(wo_ray, smp.get_2d(cfg.sampler), BX_ALL);  // path.rs:131-137 (wo = -ray.d)
-                if (!(black(s.f) || s.pdf == 0.0f)) {
-                    alive = true;
-                    const bool spec = (s.type & BX_SPECULAR) != 0;
-                    beta = beta * (s.f * fabsf(dotn(s.wi, si.sh_n)) / s.pdf);
-                    const Ray nr = spawn_ray(si.p, si.n, s.wi);
-                    if (depth > 3) {  // Russian roulette, path.rs:163-169
-                        const float q = fmaxf(1.0f - beta.g, 0.05f);
-                        if (smp.get_1d(cfg.sampler) < q) alive = false;
-                        else beta = beta * (gray(1.0f) / (1.0f - q));
-                    }
-                    const uint32_t bounces = depth + 1;
-                    if (bounces >= cfg.max_depth) alive = false;
-                    new_flags = (bounces & kDepthMask) | (spec ? kFlagSpecular : 0u) | ((s.type & BX_TRANSMISSION) ? kFlagTransmission : 0u);
-                    nx_o = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.t_max);
-                    nx_d = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
-                    nx_beta = make_float4(beta.r, beta.g, beta.b, __uint_as_float(new_flags | kFlagAlive | (smp.dim << kDimShift)));
-                    if (cfg.sort_key_mode) nx_key = ray_sort_key(sc, cfg, hit_slot, nr.o.x, nr.o.y, nr.o.z, nr.d.x, nr.d.y, nr.d.z);
-                }
-            } else {
-                // whitted.rs:128-170: this node's own terms go to the shadow / fold kernel; k_tree_return then either parks
-                // their sum in the node's frame (children pending) or hands it to the parent
-                const RGB extra = add_le ? le : gray(0.0f);
-                st_once(&w.pend_extra[g], make_float4(extra.r, extra.g, extra.b, __uint_as_float(shadow_mask)));
-                TreeRay child[2];
-                RGB child_f[2];
-                float child_cos[2];
-                int n_child = 0;
-                if (KIND == YK_MAT_GLASS && depth + 1 < cfg.max_depth) {  // only Glass owns SPECULAR lobes
-                    const uint32_t wants[2] = {BX_SPECULAR | BX_REFLECTION, BX_SPECULAR | BX_TRANSMISSION};
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const Bsdf::Sample s = bsdf.sample_f(si.wo, V2{0.0f, 0.0f}, wants[c]);
-                        if (s.type == 0u) continue;  // BxdfType::NONE: no ray, no radiance
-                        const Ray nr = spawn_ray(si.p, si.n, s.wi);
-                        TreeRay e;
-                        e.o = nr.o;
-                        e.d = nr.d;
-                        e.flags = ((depth + 1) & kDepthMask) | ((s.type & BX_SPECULAR) ? kFlagSpecular : 0u) | (c == 1 ? kFlagTransmission : 0u);
-                        child_f[n_child] = s.f;
-                        child_cos[n_child] = fabsf(dotn(s.wi, si.sh_n));
-                        child[n_child++] = e;
-                    }
-                }
-                alive = n_child >= 1;
-                st_once(&w.pend_beta[g], make_float4(__uint_as_float(depth | (alive ? 0x100u : 0u)), __uint_as_float(smp.dim), 0.0f, -1.0f));
-                if (alive) {
-                    float4* fr = frame_of(w, depth, path);
-                    fr[1] = make_float4(child_f[0].r, child_f[0].g, child_f[0].b, child_cos[0]);
-                    if (n_child == 2) {  // transmission waits until the reflection subtree is done
-                        fr[2] = make_float4(child[1].o.x, child[1].o.y, child[1].o.z, child[1].d.x);
-                        fr[3] = make_float4(child[1].d.y, child[1].d.z, child_f[1].r, child_f[1].g);
-                        fr[4] = make_float4(child_f[1].b, child_cos[1], __uint_as_float(child[1].flags | kFramePending), 0.0f);
-                    } else {
-                        fr[4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    }
-                    const TreeRay& e = child[0];
-                    nx_o = make_float4(e.o.x, e.o.y, e.o.z, __int_as_float(0x7f800000));
-                    nx_d = make_float4(e.d.x, e.d.y, e.d.z, 0.0f);
-                    nx_beta = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(e.flags | kFlagAlive | (smp.dim << kDimShift)));
-                } else {
-                    w.tree_rng[g] = smp.rng.state;  // the sampler goes on with whichever node the tree visits next
-                }
-            }
-            nx_rng = smp.rng.state;
-        }
+        ShadeOut so;
+        so.nx_o = so.nx_d = so.nx_beta = make_float4(0, 0, 0, 0);
+        so.nx_rng = 0; so.nx_key = 0; so.path = 0; so.alive = false;
+        if (PHASED && block_first + blockDim.x <= n) shade_item<KIND, PATH, true>(sc, w, cfg, bt, queue, queue_tri, queue_slot, b, i, g_base + i, &so);
+        else if (i < n) shade_item<KIND, PATH, false>(sc, w, cfg, bt, queue, queue_tri, queue_slot, b, i, g_base + i, &so);
         uint32_t* const queues[1] = {q_next};
         uint32_t* const counters[1] = {&nxt->n_active};
-        const uint32_t npos = block_scatter<1>(alive ? 0 : -1, path, queues, counters);
-        if (alive) {  // a finished path's ray / throughput / sampler state is never read again
+        const uint32_t npos = block_scatter<1>(so.alive ? 0 : -1, so.path, queues, counters);
+        if (so.alive) {  // a finished path's ray / throughput / sampler state is never read again
+            YK_ASSERT(npos < w.cap);
             const Wave::Stream& out = w.st[b ^ 1];
-            st_once(&out.ray_o[npos], nx_o);
-            st_once(&out.ray_d[npos], nx_d);
-            st_once(&out.beta[npos], nx_beta);
-            st_once(&out.rng[npos], nx_rng);
-            if (PATH && cfg.sort_key_mode) w.sort_key[npos] = nx_key;
+            st_once(&out.ray_o[npos], so.nx_o);
+            st_once(&out.ray_d[npos], so.nx_d);
+            st_once(&out.beta[npos], so.nx_beta);
+            st_once(&out.rng[npos], so.nx_rng);
+            if (PATH && cfg.sort_key_mode) w.sort_key[npos] = so.nx_key;
         }
     }
 }

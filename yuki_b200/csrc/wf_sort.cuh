@@ -46,6 +46,7 @@ __global__ void k_sort_hist(Wave w, const IterCounters* nxt) {
         const uint32_t i = base + lane;
         const uint32_t key = i < n ? w.sort_key[i] : 0xffffffffu;
         const unsigned peers = __match_any_sync(0xffffffffu, key);
+        YK_ASSERT(i >= n || key < kSortBins);
         if (i < n && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&w.sort_bins[key], (uint32_t)__popc(peers));
     }
 }
@@ -62,6 +63,7 @@ __global__ void k_sort_scatter(Wave w, const IterCounters* nxt) {
         uint32_t first = 0;
         if (i < n && lane == (uint32_t)leader) first = atomicAdd(&w.sort_bins[key], (uint32_t)__popc(peers));
         first = __shfl_sync(0xffffffffu, first, leader);
+        YK_ASSERT(i >= n || first + __popc(peers & ((1u << lane) - 1u)) < n);
         if (i < n) w.perm[first + __popc(peers & ((1u << lane) - 1u))] = i;
     }
 }

@@ -161,6 +161,7 @@ struct TraceLane {
             sts_entry(sp, ref, key);
         } else {  // cold: the stack continues in local memory, up to the reference's 64 entries
             const uint32_t depth = (sp - sbase) / kStackStride - kShortStack;
+            YK_ASSERT(depth < (uint32_t)kDeepStack);  // bvh.rs:172-174: 64 entries
             deep_ref[depth] = ref;
             deep_key[depth] = key;
         }
@@ -186,6 +187,7 @@ struct TraceLane {
         } else {
             do {
                 sp -= kStackStride;
+                YK_ASSERT(sp >= sbase && sp < sbase + (uint32_t)kShortStack * kStackStride);
                 lds_entry(sp, &ref, &key);
                 if (ANYHIT) n_tests += ref != kNoNode ? 1u : 0u;
             } while (key_fails(key));
@@ -198,6 +200,7 @@ struct TraceLane {
     __device__ __forceinline__ void box_step(const DevScene& sc, uint32_t sbase, uint32_t* deep_ref, float* deep_key) {
         // near child first: the second child when the ray is negative on the split axis (bvh.rs:186-194)
         const uint32_t neg = (neg_mask >> ((cur >> 29) & 3u)) & 1u;
+        YK_ASSERT((cur & kRefIndexMask) < sc.n_nodes);
         const float4* rec = sc.nodes2 + 4 * (size_t)(cur & kRefIndexMask);
         const float4* near = rec + 2 * neg;
         const float4* far = rec + 2 * (neg ^ 1u);
@@ -232,6 +235,7 @@ struct TraceLane {
                 float key;
                 do {
                     sp -= kStackStride;
+                    YK_ASSERT(sp >= sbase && sp < sbase + (uint32_t)kShortStack * kStackStride);
                     lds_entry(sp, &take, &key);
                     if (ANYHIT) n_tests += take != kNoNode ? 1u : 0u;
                 } while (key_fails(key));
@@ -244,6 +248,7 @@ struct TraceLane {
     // Returns true on a hit with t in (0, t_max]; the caller decides what a hit means and then calls leaf_done().
     __device__ __forceinline__ bool tri_step(const DevScene& sc, uint32_t* tri, float* t_scaled_out, float* det_out, int* area_light) {
         const uint32_t s = leaf_pos++;
+        YK_ASSERT(s < sc.n_tris && kx < 3 && ky < 3 && kz < 3);
         const float4 A = __ldg(&sc.tris[3 * s + kx]);
         const float4 B = __ldg(&sc.tris[3 * s + ky]);
         const float4 C = __ldg(&sc.tris[3 * s + kz]);
@@ -348,6 +353,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
                 if (!live && mine < chunk_end) {
                     // the queue slot: rays, hits and counters of a bounce are all in queue order (sorted renders fetch it through perm)
                     path = perm ? __ldg(&perm[mine]) : mine;
+                    YK_ASSERT(path < n);
                     const float4 ro = ld_once(&w.st[b].ray_o[path]);
                     const float4 rd = ld_once(&w.st[b].ray_d[path]);
                     if (COUNTS) tests_before = tl.n_tests;
@@ -504,7 +510,9 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             const uint32_t mine = chunk_next + __popc(idle & lt_mask);
             if (!live && mine < chunk_end) {
                 pos = mine;
+                YK_ASSERT(pos < w.cap);
                 path = w.sh_path[pos];
+                YK_ASSERT(path < w.cap);
                 mask = __float_as_uint(w.pend_extra[pos].w);
                 radiance = gray(0.0f);
                 n_rays += __popc(mask);
@@ -610,6 +618,7 @@ __global__ void __launch_bounds__(kTraceThreads, YK_SHADOW_MIN_BLOCKS) k_trace_s
             const uint32_t mine = chunk_next + __popc(idle & lt_mask);
             if (!live && mine < chunk_end && ((w.sh_mask[mine] >> chunk_light) & 1u)) {
                 my_g = mine; my_k = chunk_light;
+                YK_ASSERT(my_g < w.cap && my_k < n_lights);
                 const size_t ref = (size_t)my_k * w.cap + my_g;
                 const float4 ro = ld_once(&w.lt_o[ref]), rd = ld_once(&w.lt_d[ref]);
                 target_light = __float_as_int(ld_once(&w.lt_c[ref]).y);
