@@ -167,6 +167,9 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+CPU_TILES = 128        # bounded CPU sample of the headline workload: ~128 tiles spread evenly over the spiral list, all of their samples
+
+
 def cpu_sample_tiles(film, first_sample=0, n=CPU_SAMPLE_SPP):
     """Accumulate-mode tile list covering sample indices [first, first+n) of every pixel (render_manager.rs:135-143)."""
     from oracle import oracle as O
@@ -179,15 +182,37 @@ def cpu_sample_tiles(film, first_sample=0, n=CPU_SAMPLE_SPP):
     return np.concatenate(out)
 
 
-def time_cpu(threads=0, first_sample=0):
-    """Times the CPU restatement of yuki's renderer (oracle) on a bounded sample of the workload."""
+def time_cpu(threads=0, first_sample=0, step=0):
+    """Times the CPU restatement of yuki's renderer (oracle) on a bounded sample of the workload. Headline workload: the way a
+    headless 1024-spp render runs in the reference — non-accumulating, one task = one 16x16 tile with all of its samples
+    (render_manager.rs:135-143 replicates tiles per sample only for accumulating films) — on ~CPU_TILES tiles spread evenly over
+    the spiral list (a whole number per worker thread; ~34 M samples, ~10 s on 15 threads). Measured on this container's 7 worker threads the
+    accumulate-mode micro-tasks round 1 timed are ~10 % slower per sample (0.90 vs 1.00 Msamples/s): queue and film mutex
+    per 256 samples. `--workload c5` keeps one accumulate-mode sample index of every pixel (a 4096-spp tile is 1 M samples)."""
     from oracle import oracle as O
     scene, cam, film, sampler, integ = workload(O.transforms)
     osc = O.OracleScene(scene)
+    if SCENE == "cornell":
+        # a whole number of tiles per worker (the reference runs hardware_concurrency() - 1 of them), so that the sample's tail does not
+        # penalise the CPU arm: a full render has 4096 tiles and no such tail
+        workers = threads or max(1, (os.cpu_count() or 2) - 1)
+        all_tiles = O.film_tiles(film)
+        n = min(len(all_tiles), workers * max(1, round(CPU_TILES / workers)))
+        pick = (np.arange(n) * len(all_tiles) // n + step) % len(all_tiles)
+        tiles = np.ascontiguousarray(all_tiles[pick])
+        _, _, st = osc.render(cam, film, sampler, integ, tiles=tiles, threads=threads)
+        return st
     acc = D.FilmSettings(film.res, film.tile_dim, accumulate=True)
     tiles = cpu_sample_tiles(film, first_sample)
     _, _, st = osc.render(cam, acc, sampler, integ, tiles=tiles, threads=threads)
     return st
+
+
+def cpu_sample_text(samples):
+    if SCENE == "cornell":
+        return (f"{samples // (256 * SPP_NX * SPP_NY)} 16x16 tiles spread evenly over the spiral list with all {SPP_NX * SPP_NY} samples of their pixels, "
+                f"non-accumulating like a headless render of the reference ({samples} samples), same scene/sampler/integrator")
+    return f"{CPU_SAMPLE_SPP} of the {SPP_NX * SPP_NY} samples of every pixel ({samples} samples), same scene/sampler/integrator"
 
 
 def run_reference(args):
@@ -201,14 +226,14 @@ def run_reference(args):
         time_cpu(first_sample=0)  # one untimed pass warms caches/page tables; repeating it W times would only burn minutes
     t_total, samples, rays, shadow, threads = 0.0, 0, 0, 0, 0
     for k in range(args.steps):
-        st = time_cpu(first_sample=(k * CPU_SAMPLE_SPP) % max(1, SPP_NX * SPP_NY - CPU_SAMPLE_SPP))
+        st = time_cpu(first_sample=(k * CPU_SAMPLE_SPP) % max(1, SPP_NX * SPP_NY - CPU_SAMPLE_SPP), step=k)
         t_total += st.seconds
         samples += st.samples
         rays += st.ray_count
         shadow += st.shadow_rays
         threads = st.threads
     v = samples / t_total / 1e6
-    sample = f"{CPU_SAMPLE_SPP} of the {SPP_NX * SPP_NY} samples of every pixel per step ({samples // args.steps} samples/step), same scene/sampler/integrator"
+    sample = cpu_sample_text(samples // max(args.steps, 1)) + " per step"
     line = {
         "impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -261,13 +286,31 @@ def large_scene_leg(args, api, capi, xf, ctx, stream, rank, world, local, peak):
     import torch
     import torch.distributed as dist
     from yuki_b200 import scenes
+    # One host build per node: local rank 0 builds the 10 M-triangle BVH and leaves the flattened arrays under /dev/shm; the other
+    # ranks map them (api.HostScene.save / load) instead of repeating the 6 s build N times on contended cores.
     t0 = time.perf_counter()
     scene, cam = scenes.terrain_room(xf)
-    host = api.HostScene(scene)
+    share_dir = None
+    if world > 1:
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        share_dir = os.path.join(base, f"yuki_b200_c5_{os.environ.get('MASTER_PORT', '0')}_{kernel_source_hash()}")
+    if share_dir is None or local == 0:
+        host = api.HostScene(scene)
+        if share_dir is not None:
+            host.save(share_dir)
+    if world > 1:
+        dist.barrier()
+        if local != 0:
+            host = api.HostScene.load(share_dir)
     t_build = time.perf_counter() - t0
     t0 = time.perf_counter()
     dev = api.Scene(ctx, scene, host=host)
     t_upload = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+        if local == 0:
+            import shutil
+            shutil.rmtree(share_dir, ignore_errors=True)
     rn = api.Renderer(ctx)
     film = D.FilmSettings((3840, 2160), 16)
     sampler, integ = D.SamplerType.stratified(C5_SPP_SIDE, C5_SPP_SIDE, jitter=True), D.IntegratorType.path(MAX_DEPTH)
@@ -510,7 +553,7 @@ def run_ours(args):
         # CPU baseline (rank 0, N == 1 only): bounded sample of the same workload on the host cores.
         if world == 1 and not args.no_cpu_baseline:
             st = time_cpu()
-            sample = f"{CPU_SAMPLE_SPP} of the {spp} samples of every pixel ({st.samples} samples), same scene/sampler/integrator"
+            sample = cpu_sample_text(st.samples)
             line["cpu_baseline"] = {"value": st.samples / st.seconds / 1e6, "unit": "Msamples/s", "cores": st.threads, "kind": "port",
                                     "sample": sample, "seconds": st.seconds}
         if large is not None:

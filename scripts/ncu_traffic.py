@@ -14,7 +14,8 @@ def num(r, name):
     return float(r[idx[name]]) if name in idx and r[idx[name]] not in ("", "n/a") else None
 sel = [r for r in rows[2:] if kernel in r[idx["Kernel Name"]]]
 dram = [to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum") for r in sel]
-l2 = [to_bytes(r, "lts__t_bytes.sum") for r in sel]
+l2 = [float(r[idx["lts__t_sectors.sum"]]) * 32.0 for r in sel]            # 32-byte L2 sectors (all sources)
+l1 = [float(r[idx["l1tex__t_sectors.sum"]]) * 32.0 for r in sel] if "l1tex__t_sectors.sum" in idx else []
 dur = [float(r[idx["gpu__time_duration.sum"]]) for r in sel]
 def mean(name):
     v = [num(r, name) for r in sel]
@@ -26,7 +27,7 @@ except Exception:
     commit = None
 entry = {"kernel": kernel, "kernel_hash": khash, "commit": commit, "launches_profiled": len(sel),
          "dram_bytes_per_launch": sum(dram) / max(len(dram), 1), "l2_bytes_per_launch": sum(l2) / max(len(l2), 1),
-         "dram_bytes": dram, "l2_bytes": l2, "duration_" + units[idx["gpu__time_duration.sum"]]: dur,
+         "l1_bytes_per_launch": (sum(l1) / len(l1)) if l1 else None, "dram_bytes": dram, "l2_bytes": l2, "duration_" + units[idx["gpu__time_duration.sum"]]: dur,
          "ncu": {"dram_throughput_pct": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                  "l1_hit_pct": mean("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": mean("lts__t_sector_hit_rate.pct"),
                  "lanes_per_instruction": mean("smsp__thread_inst_executed_per_inst_executed.ratio"),

@@ -102,3 +102,33 @@ def test_division_by_invariant_matches_integer_division():
         n = np.concatenate([edge, near, rng.integers(0, 2**32, size=20000, dtype=np.uint64)]).astype(np.uint32)
         n = np.ascontiguousarray(n)
         assert capi.lib().yk_selftest_fastdiv(d, n.ctypes.data, len(n)) == 0, d
+
+
+def test_host_scene_save_load_round_trip(tmp_path, xf):
+    """HostScene.save / load: the flattened arrays a rank built are mapped back byte for byte by the other ranks of a node."""
+    import ctypes as C
+    from yuki_b200 import api, scenes
+    for scene in (scenes.material_room(xf)[0], scenes.cornell(xf, light="rect", tall_box="glass", sphere=True, textured_back_wall=True)[0]):
+        a = api.HostScene(scene)
+        a.save(str(tmp_path / "hs"))
+        b = api.HostScene.load(str(tmp_path / "hs"))
+        fa, fb = a.flat, b.flat
+        for k in ("n_nodes", "n_tris", "n_textures", "n_materials", "n_lights", "n_spheres"):
+            assert getattr(fa, k) == getattr(fb, k), k
+        assert list(fa.background) == list(fb.background)
+
+        def raw(ptr, nbytes):
+            return C.string_at(C.cast(ptr, C.c_void_p), nbytes) if ptr and nbytes else b""
+        for name, count, per, dtype in api.HostScene._ARRAYS:
+            n = getattr(fa, count) * per * np.dtype(dtype).itemsize
+            assert bool(getattr(fa, name)) == bool(getattr(fb, name)), name
+            assert raw(getattr(fa, name), n) == raw(getattr(fb, name), n), name
+        assert raw(fa.materials, fa.n_materials * C.sizeof(capi.MaterialDesc)) == raw(fb.materials, fb.n_materials * C.sizeof(capi.MaterialDesc))
+        assert raw(fa.lights, fa.n_lights * C.sizeof(capi.LightDev)) == raw(fb.lights, fb.n_lights * C.sizeof(capi.LightDev))
+        assert raw(fa.spheres, fa.n_spheres * C.sizeof(capi.SphereDev)) == raw(fb.spheres, fb.n_spheres * C.sizeof(capi.SphereDev))
+        for i in range(fa.n_textures):
+            ta, tb = fa.textures[i], fb.textures[i]
+            assert (ta.kind, ta.width, ta.height, list(ta.value)) == (tb.kind, tb.width, tb.height, list(tb.value))
+            if ta.kind == 1:
+                assert raw(ta.texels, ta.width * ta.height * 12) == raw(tb.texels, tb.width * tb.height * 12)
+        a.close(); b.close()

@@ -69,10 +69,96 @@ class HostScene:
     def tri_vertices(self) -> np.ndarray:
         return np.ctypeslib.as_array(self.flat.tri_vertices, shape=(self.flat.n_tris, 3, 3)).copy()
 
+    # ---- one host build shared by the ranks of a node ---------------------------------------------------------------
+    # The BVH build is the slow host step (6 s for 10 M triangles); with one process per GPU every rank would repeat it.
+    # `save` writes the flattened arrays (the exact bytes yk_scene_create takes) as .npy files, e.g. under /dev/shm;
+    # `load` maps them back without copying, so N ranks share one build and one page-cache copy.
+    _ARRAYS = (("nodes", "n_nodes", 32, np.uint8), ("tri_vertices", "n_tris", 9, np.float32), ("tri_normals", "n_tris", 9, np.float32),
+               ("tri_uvs", "n_tris", 6, np.float32), ("tri_orig_id", "n_tris", 1, np.uint32), ("tri_material", "n_tris", 1, np.uint32),
+               ("tri_area_light", "n_tris", 1, np.int32), ("tri_flags", "n_tris", 1, np.uint8), ("tri_sphere", "n_tris", 1, np.int32))
+
+    def save(self, directory: str):
+        import json
+        os.makedirs(directory, exist_ok=True)
+        for stale in os.listdir(directory):   # a directory holds one scene
+            if stale.endswith(".npy") or stale.startswith("tables.json"):
+                os.remove(os.path.join(directory, stale))
+        f = self.flat
+        for name, count, per, dtype in self._ARRAYS:
+            ptr = getattr(f, name)
+            if not ptr:
+                continue
+            n = getattr(f, count) * per
+            arr = np.frombuffer(C.string_at(C.cast(ptr, C.c_void_p), n * np.dtype(dtype).itemsize), dtype=dtype)
+            np.save(os.path.join(directory, name + ".npy"), arr)
+        tables = {"n_nodes": f.n_nodes, "n_tris": f.n_tris, "background": [float(v) for v in f.background],
+                  "materials": C.string_at(C.cast(f.materials, C.c_void_p), f.n_materials * C.sizeof(capi.MaterialDesc)).hex() if f.n_materials else "",
+                  "lights": C.string_at(C.cast(f.lights, C.c_void_p), f.n_lights * C.sizeof(capi.LightDev)).hex() if f.n_lights else "",
+                  "spheres": C.string_at(C.cast(f.spheres, C.c_void_p), f.n_spheres * C.sizeof(capi.SphereDev)).hex() if f.n_spheres else "",
+                  "n_materials": f.n_materials, "n_lights": f.n_lights, "n_spheres": f.n_spheres, "textures": []}
+        for i in range(f.n_textures):
+            t = f.textures[i]
+            tables["textures"].append({"kind": t.kind, "value": [float(v) for v in t.value], "width": t.width, "height": t.height})
+            if t.kind == D.TEX_IMAGE:
+                np.save(os.path.join(directory, f"texture{i}.npy"), np.ctypeslib.as_array(t.texels, shape=(t.height * t.width * 3,)).copy())
+        tmp = os.path.join(directory, "tables.json.tmp")
+        with open(tmp, "w") as fh:
+            json.dump(tables, fh)
+        os.replace(tmp, os.path.join(directory, "tables.json"))   # written last: its presence marks a complete directory
+
+    @classmethod
+    def load(cls, directory: str) -> "HostScene":
+        import json
+        with open(os.path.join(directory, "tables.json")) as fh:
+            tables = json.load(fh)
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        keep = []
+        f = capi.SceneDescFlat()
+        f.n_nodes, f.n_tris = tables["n_nodes"], tables["n_tris"]
+        for name, _count, _per, _dtype in cls._ARRAYS:
+            path = os.path.join(directory, name + ".npy")
+            if os.path.exists(path):
+                arr = np.load(path, mmap_mode="r")
+                keep.append(arr)
+                field_type = dict(capi.SceneDescFlat._fields_)[name]
+                setattr(f, name, C.cast(C.c_void_p(arr.ctypes.data), field_type))
+        def table(key, struct, n):
+            if not n:
+                return None
+            buf = (struct * n).from_buffer_copy(bytes.fromhex(tables[key]))
+            keep.append(buf)
+            return buf
+        f.n_materials, f.n_lights, f.n_spheres = tables["n_materials"], tables["n_lights"], tables["n_spheres"]
+        mats, lights, spheres = table("materials", capi.MaterialDesc, f.n_materials), table("lights", capi.LightDev, f.n_lights), table("spheres", capi.SphereDev, f.n_spheres)
+        if mats is not None:
+            f.materials = C.cast(mats, C.POINTER(capi.MaterialDesc))
+        if lights is not None:
+            f.lights = C.cast(lights, C.POINTER(capi.LightDev))
+        if spheres is not None:
+            f.spheres = C.cast(spheres, C.POINTER(capi.SphereDev))
+        f.n_textures = len(tables["textures"])
+        if f.n_textures:
+            tex = (capi.TextureDesc * f.n_textures)()
+            for i, t in enumerate(tables["textures"]):
+                tex[i].kind, tex[i].width, tex[i].height = t["kind"], t["width"], t["height"]
+                tex[i].value[:] = t["value"]
+                if t["kind"] == D.TEX_IMAGE:
+                    texels = np.load(os.path.join(directory, f"texture{i}.npy"), mmap_mode="r")
+                    keep.append(texels)
+                    tex[i].texels = C.cast(C.c_void_p(texels.ctypes.data), C.POINTER(C.c_float))
+            keep.append(tex)
+            f.textures = C.cast(tex, C.POINTER(capi.TextureDesc))
+        f.background[:] = tables["background"]
+        self.flat = f
+        self._keep = keep
+        return self
+
     def close(self):
         if self._h:
             capi.lib().yk_host_scene_destroy(self._h)
             self._h = C.c_void_p()
+        self._keep = None
 
     def __del__(self):
         try:
