@@ -400,6 +400,37 @@ def large_scene_leg(args, api, capi, xf, ctx, stream, rank, world, local, peak):
             "pipes": "library default (two) for msamples_per_s; one for the roofline pass", "roofline": roof}
 
 
+def published_config_leg(api, xf, ctx):
+    """The one configuration the reference publishes a number for (BASELINE.md §1): its README screenshot — Scene::cornell()
+    (37 shapes), 1920x1080, Path max_depth 10, indirect clamp 2.0, Stratified 32x32, tile 32 — "272.10 s, 20.47 Mrays/s"
+    (closest-hit rays / wall time, app/window.rs:907-916) on the author's CPU. Rendered here end to end (host film out) with the
+    library defaults, after one warm-up; tests/test_screenshot_pin.py checks the same render against the screenshot itself."""
+    from yuki_b200 import scenes
+    fx_path = os.path.join(ROOT, "tests", "golden", "reference_screenshot_regions.json")
+    with open(fx_path) as f:
+        fx = json.load(f)
+    st = fx["settings"]
+    scene, _ = scenes.cornell(xf, light="rect", tall_box="glass", sphere=True, split_method=D.SPLIT_SAH, back_wall_albedo=(0.85, 0.85, 0.80))
+    cam = D.CameraParameters(tuple(st["camera_position"]), tuple(st["camera_target"]), fov_axis=D.FOV_X, fov_deg=st["fov_x_deg"])
+    film = D.FilmSettings(tuple(fx["film"]), st["tile_dim"])
+    sampler, integ = D.SamplerType.stratified(32, 32, jitter=True), D.IntegratorType.path(st["max_depth"], indirect_clamp=st["indirect_clamp"])
+    dev = api.Scene(ctx, scene)
+    rn = api.Renderer(ctx)
+    out = np.zeros((film.res[1], film.res[0], 3), np.float32)
+    rn.render(dev, cam, film, sampler, integ, film_out=out)
+    t0 = time.perf_counter()
+    r = rn.render(dev, cam, film, sampler, integ, film_out=out)
+    sec = time.perf_counter() - t0
+    dev.close()
+    pub = fx["published"]
+    mrays = r.stats.ray_count / sec / 1e6
+    return {"workload": "the reference's README screenshot: Scene::cornell() 1920x1080, Path max_depth 10, indirect clamp 2.0, 1024 spp stratified 32x32",
+            "seconds": sec, "msamples_per_s": r.stats.samples / sec / 1e6, "mrays_per_s": mrays, "rays_per_sample": r.stats.ray_count / r.stats.samples,
+            "published": {"seconds": pub["render_seconds"], "mrays_per_s": pub["mrays_per_s"], "rays_per_sample": pub["mrays_per_s"] * 1e6 * pub["render_seconds"] / r.stats.samples,
+                          "hardware": "the author's CPU (not stated; sampling/mod.rs:92-96 mentions a Ryzen 5900X)", "source": "screenshot.png via readme.md:3"},
+            "vs_published": mrays / pub["mrays_per_s"], "timing": "host clock around the blocking call, host film out, one GPU"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -558,6 +589,8 @@ def run_ours(args):
                                     "sample": sample, "seconds": st.seconds}
         if large is not None:
             line["large_scene"] = large
+        if world == 1 and not args.no_large_scene and SCENE == "cornell":
+            line["published_config"] = published_config_leg(api, xf, ctx)
         emit(line)
     dev.close()
     ctx.close()

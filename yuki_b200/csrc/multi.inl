@@ -3,9 +3,10 @@
 // 197-236; render_worker.rs:172-198 `pop_tile_or_signal_finish`).
 //   * one yk_context + one host worker thread per device, the scene replicated (validated once, uploaded to all devices
 //     in parallel from the caller's one host copy);
-//   * the tile list is consumed through ONE shared cursor: a worker pops the next run of tiles in list order (spiral,
-//     centre-out), renders it with the wavefront pipeline of its device and comes back for more — a device that drew
-//     cheap tiles (sky) simply takes more of them, so no device idles while another still has a backlog;
+//   * the tile list is consumed through ONE shared cursor: a worker pops the next run of tiles (every n_runs-th tile of the
+//     spiral list, so that each run covers the film centre-out and costs about the same), renders it with the wavefront
+//     pipeline of its device and comes back for more — a slower or busier device simply takes fewer runs, so no device idles
+//     while another still has a backlog;
 //   * no gather step: the film lives on the first device and every other device's film kernels (k_film_store / k_film_add,
 //     and the primary-hit id image) store their finished pixels straight into it through peer mappings, i.e. as NVLink
 //     writes overlapped with the rendering of the following batches. Without peer access the devices render into local
@@ -240,17 +241,19 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
 
-    // Work distribution. Non-accumulating: runs of tiles popped from one cursor; a run holds enough paths for a few
-    // wavefront batches yet is a small fraction of a device's share, so the finish times differ by at most one run.
-    // Accumulating: tile.index mod G (fixed add order per pixel).
+    // Work distribution. Non-accumulating: runs of tiles popped from one cursor. A run should hold several wavefront batches
+    // (each yk_render-style call ends with a synchronisation and un-overlapped kernel tails: measured on 2 GPUs, runs of a
+    // quarter batch made the 16-spp large scene 35 % slower than one call per device), yet leave every device at least four
+    // runs so that the finish times differ by a fraction of the render. Accumulating: tile.index mod G (fixed add order per pixel).
     uint32_t run = 1;
     if (!accumulate && n_tiles) {
         const unsigned long long paths_per_tile = std::max<unsigned long long>(1, area / n_tiles) * spp;
-        const unsigned long long want_paths = 32ull << 20;  // ~2 batches of 16 Mi paths
+        const unsigned long long want_paths = 128ull << 20;  // ~8 batches of 16 Mi paths
         run = (uint32_t)std::max<unsigned long long>(1, want_paths / paths_per_tile);
-        run = std::max(1u, std::min(run, (uint32_t)((n_tiles + G * 16 - 1) / (G * 16))));  // at least ~16 runs per device when possible
+        run = std::max(1u, std::min(run, (uint32_t)std::max<size_t>(1, n_tiles / (G * 4))));
         if (const char* e = getenv("YK_MULTI_RUN_TILES")) run = (uint32_t)std::max(1, atoi(e));
     }
+    const uint32_t n_runs = n_tiles ? (n_tiles + run - 1) / run : 0;
     std::vector<std::vector<yk_tile>> fixed(accumulate ? G : 0);
     if (accumulate)
         for (uint32_t t = 0; t < n_tiles; ++t) fixed[tiles[t].index % G].push_back(tiles[t]);
@@ -297,10 +300,16 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
             if (!fixed[i].empty()) render_run(fixed[i].data(), (uint32_t)fixed[i].size());
             return;
         }
+        // Run k = tiles k, k + n_runs, k + 2 n_runs, ... of the list: every run samples the whole spiral (centre-out within the
+        // run), so runs cost about the same and a device's last run ends close to everybody else's, while a slower or busier
+        // device simply pops fewer of them.
+        std::vector<yk_tile> mine;
         while (!stop) {
-            const uint32_t lo = cursor.fetch_add(run);
-            if (lo >= n_tiles) break;
-            render_run(tiles + lo, std::min(run, n_tiles - lo));
+            const uint32_t k = cursor.fetch_add(1);
+            if (k >= n_runs) break;
+            mine.clear();
+            for (uint32_t t = k; t < n_tiles; t += n_runs) mine.push_back(tiles[t]);
+            render_run(mine.data(), (uint32_t)mine.size());
         }
     };
     {
