@@ -3,10 +3,11 @@
 // 197-236; render_worker.rs:172-198 `pop_tile_or_signal_finish`).
 //   * one yk_context + one host worker thread per device, the scene replicated (validated once, uploaded to all devices
 //     in parallel from the caller's one host copy);
-//   * the tile list is consumed through ONE shared cursor: a worker pops the next run of tiles (every n_runs-th tile of the
-//     spiral list, so that each run covers the film centre-out and costs about the same), renders it with the wavefront
-//     pipeline of its device and comes back for more — a slower or busier device simply takes fewer runs, so no device idles
-//     while another still has a backlog;
+//   * the tile list is consumed through ONE shared cursor by guided self-scheduling: a worker pops the next run of tiles (a
+//     range of a strided order of the spiral list, so that each run covers the film centre-out and costs about the same per
+//     tile; remaining / 2G tiles, i.e. large runs first and small ones last), renders it with the wavefront pipeline of its
+//     device and comes back for more — a slower or busier device simply takes fewer tiles, so no device idles while another
+//     still has a backlog;
 //   * no gather step: the film lives on the first device and every other device's film kernels (k_film_store / k_film_add,
 //     and the primary-hit id image) store their finished pixels straight into it through peer mappings, i.e. as NVLink
 //     writes overlapped with the rendering of the following batches. Without peer access the devices render into local
@@ -241,19 +242,25 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
 
-    // Work distribution. Non-accumulating: runs of tiles popped from one cursor. A run should hold several wavefront batches
-    // (each yk_render-style call ends with a synchronisation and un-overlapped kernel tails: measured on 2 GPUs, runs of a
-    // quarter batch made the 16-spp large scene 35 % slower than one call per device), yet leave every device at least four
-    // runs so that the finish times differ by a fraction of the render. Accumulating: tile.index mod G (fixed add order per pixel).
-    uint32_t run = 1;
+    // Work distribution. Non-accumulating: runs of tiles popped from one cursor, *guided self-scheduling*: a pop takes
+    // remaining / 2G tiles, so the first runs are large (half a device's fair share: few synchronisations and un-overlapped
+    // kernel tails — measured on 2 GPUs, runs of a quarter batch made the 16-spp large scene 35 % slower than one call per
+    // device) and the last ones small (the finish times differ by at most one small run, whatever the devices' speeds),
+    // never below ~64 Mi paths (four wavefront batches, two per pipe). A job whose fair share is below two such runs is split
+    // statically, one run per device. The runs are ranges of a *strided* order of the tile list (position j -> tile
+    // j * stride mod n_tiles, stride ~ 0.618 n_tiles and coprime to it), so every run samples the whole spiral and costs
+    // about the same per tile. Accumulating: tile.index mod G (fixed add order per pixel).
+    uint32_t run_floor = 1, run_fixed = 0, stride = 1;
     if (!accumulate && n_tiles) {
         const unsigned long long paths_per_tile = std::max<unsigned long long>(1, area / n_tiles) * spp;
-        const unsigned long long want_paths = 128ull << 20;  // ~8 batches of 16 Mi paths
-        run = (uint32_t)std::max<unsigned long long>(1, want_paths / paths_per_tile);
-        run = std::max(1u, std::min(run, (uint32_t)std::max<size_t>(1, n_tiles / (G * 4))));
-        if (const char* e = getenv("YK_MULTI_RUN_TILES")) run = (uint32_t)std::max(1, atoi(e));
+        run_floor = (uint32_t)std::max<unsigned long long>(1, (64ull << 20) / paths_per_tile);
+        const uint32_t fair = (uint32_t)((n_tiles + G - 1) / G);
+        if (fair < 2 * run_floor) run_fixed = fair;
+        if (const char* e = getenv("YK_MULTI_RUN_TILES")) run_fixed = (uint32_t)std::max(1, atoi(e));
+        auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+        stride = std::max(1u, (uint32_t)(0.6180339887 * n_tiles));
+        while (stride > 1 && gcd(stride, n_tiles) != 1) --stride;
     }
-    const uint32_t n_runs = n_tiles ? (n_tiles + run - 1) / run : 0;
     std::vector<std::vector<yk_tile>> fixed(accumulate ? G : 0);
     if (accumulate)
         for (uint32_t t = 0; t < n_tiles; ++t) fixed[tiles[t].index % G].push_back(tiles[t]);
@@ -300,15 +307,22 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
             if (!fixed[i].empty()) render_run(fixed[i].data(), (uint32_t)fixed[i].size());
             return;
         }
-        // Run k = tiles k, k + n_runs, k + 2 n_runs, ... of the list: every run samples the whole spiral (centre-out within the
-        // run), so runs cost about the same and a device's last run ends close to everybody else's, while a slower or busier
-        // device simply pops fewer of them.
         std::vector<yk_tile> mine;
+        std::vector<uint32_t> idx;
         while (!stop) {
-            const uint32_t k = cursor.fetch_add(1);
-            if (k >= n_runs) break;
+            uint32_t lo = cursor.load(), n_take = 0;
+            do {  // guided pop
+                if (lo >= n_tiles) break;
+                const uint32_t remaining = n_tiles - lo;
+                n_take = run_fixed ? run_fixed : std::max(run_floor, (uint32_t)((remaining + 2 * G - 1) / (2 * G)));
+                n_take = std::min(n_take, remaining);
+            } while (!cursor.compare_exchange_weak(lo, lo + n_take));
+            if (lo >= n_tiles) break;
+            idx.clear();
+            for (uint32_t j = lo; j < lo + n_take; ++j) idx.push_back((uint32_t)(((uint64_t)j * stride) % n_tiles));
+            std::sort(idx.begin(), idx.end());  // list (spiral) order inside the run
             mine.clear();
-            for (uint32_t t = k; t < n_tiles; t += n_runs) mine.push_back(tiles[t]);
+            for (uint32_t t : idx) mine.push_back(tiles[t]);
             render_run(mine.data(), (uint32_t)mine.size());
         }
     };

@@ -211,6 +211,17 @@ int staged_upload(int device, const std::vector<CopyJob>& jobs) {
         for (size_t off = 0; off < j.bytes; off += PinnedPool::kBytes)
             chunks.push_back(Chunk{(char*)j.dst + off, (const char*)j.src + off, std::min(PinnedPool::kBytes, j.bytes - off)});
     if (chunks.empty()) return YK_OK;
+    size_t total_bytes = 0;
+    for (const CopyJob& j : jobs) total_bytes += j.bytes;
+    if (total_bytes <= (4u << 20) && !getenv("YK_UPLOAD_STAGED")) {  // small scenes (the Cornell box is 13 KB): threads, streams and events would cost more than the copy
+        for (const CopyJob& j : jobs)
+            if (cudaMemcpy(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+                return yk_set_error(YK_ERR_CUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+        // (a pageable cudaMemcpy may return once the data is staged: wait for the DMA before kernels on other streams read it)
+        if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess)
+            return yk_set_error(YK_ERR_CUDA, std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+        return YK_OK;
+    }
     const unsigned n_threads = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)6, chunks.size(), (size_t)std::max(1u, std::thread::hardware_concurrency() / 2)}));
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
