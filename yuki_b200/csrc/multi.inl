@@ -246,14 +246,14 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
     // remaining / 2G tiles, so the first runs are large (half a device's fair share: few synchronisations and un-overlapped
     // kernel tails — measured on 2 GPUs, runs of a quarter batch made the 16-spp large scene 35 % slower than one call per
     // device) and the last ones small (the finish times differ by at most one small run, whatever the devices' speeds),
-    // never below ~64 Mi paths (four wavefront batches, two per pipe). A job whose fair share is below two such runs is split
-    // statically, one run per device. The runs are ranges of a *strided* order of the tile list (position j -> tile
+    // never below ~16 Mi paths (two wavefront batches of 8 Mi, one per pipe; with 64 Mi the two devices of a 0.4 s render
+    // finished 39 ms apart). A job whose fair share is below two such runs is split statically, one run per device. The runs are ranges of a *strided* order of the tile list (position j -> tile
     // j * stride mod n_tiles, stride ~ 0.618 n_tiles and coprime to it), so every run samples the whole spiral and costs
     // about the same per tile. Accumulating: tile.index mod G (fixed add order per pixel).
     uint32_t run_floor = 1, run_fixed = 0, stride = 1;
     if (!accumulate && n_tiles) {
         const unsigned long long paths_per_tile = std::max<unsigned long long>(1, area / n_tiles) * spp;
-        run_floor = (uint32_t)std::max<unsigned long long>(1, (64ull << 20) / paths_per_tile);
+        run_floor = (uint32_t)std::max<unsigned long long>(1, (16ull << 20) / paths_per_tile);
         const uint32_t fair = (uint32_t)((n_tiles + G - 1) / G);
         if (fair < 2 * run_floor) run_fixed = fair;
         if (const char* e = getenv("YK_MULTI_RUN_TILES")) run_fixed = (uint32_t)std::max(1, atoi(e));

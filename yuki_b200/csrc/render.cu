@@ -95,6 +95,7 @@ struct yk_context {
     int32_t* d_hit_ids = nullptr;
     size_t film_cap = 0;
     int occ_trace_closest = 0, occ_trace_any = 0, occ_trace_rays = 0;
+    int wide_per_sm = 16;  // grid cap of the grid-stride kernels, blocks per SM (development override: YK_WIDE_PER_SM)
     int n_pipes_env = 0;  // YK_PIPES override (development)
     uint64_t mem_budget = 0;  // bytes of wavefront state per pipe the default batch size may use (set at the first render)
     std::vector<void*> query_allocs;  // yk_trace / yk_occluded staging (rays in, results out), kept between calls
@@ -271,7 +272,8 @@ float host_roughness_to_alpha(float r) {
 }
 
 int ensure_wave(Pipe* p, uint32_t cap, uint32_t n_lights, uint32_t stack_entries, bool sort = false) {
-    if (p->wave_cap == cap && p->wave_lights == n_lights && p->wave_stack == stack_entries && (p->wave_sort || !sort)) return YK_OK;
+    // (a larger allocation serves a smaller batch: Wave::cap is only the stride of the per-light / per-kind arrays)
+    if (p->wave_cap >= cap && p->wave_cap && p->wave_lights == n_lights && p->wave_stack == stack_entries && (p->wave_sort || !sort)) return YK_OK;
     free_bag(p->wave_allocs);
     p->wave_cap = 0;
     p->wave_sort = false;
@@ -378,15 +380,17 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
     CUDA_TRY(cudaMemcpyToSymbolAsync(g_check_queue_cap, &w.cap, sizeof(uint32_t), 0, cudaMemcpyHostToDevice, s));
 #endif
     CUDA_TRY(cudaMemsetAsync(p->d_ctr, 0, 2 * sizeof(IterCounters), s));
+    nvtxRangePushA("yk raygen");
     k_sample_jumps<<<1, kMaxBatchSamples, 0, s>>>(first_sample, bt.n_samples, p->d_jumps);
     tm->launches += 1;
     k_raygen<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, cfg, bt, first_sample, bt.n_samples, p->d_jumps, &p->d_ctr[0]);
+    nvtxRangePop();
     tm->launches += 1;
     const bool debug = cfg.integrator >= YK_INTEGRATOR_BVH_INTERSECTIONS;
     const bool sync_loop = cfg.integrator == YK_INTEGRATOR_WHITTED;
     const int trace_blocks_closest = c->sm_count * std::max(1, c->occ_trace_closest);
     const int trace_blocks_shadow = c->sm_count * std::max(1, c->occ_trace_any);
-    const int wide_blocks = c->sm_count * 16;
+    const int wide_blocks = c->sm_count * c->wide_per_sm;
     const int classify_items = cfg.integrator == YK_INTEGRATOR_WHITTED ? 1 : YK_CLASSIFY_ITEMS;
     const int classify_blocks = grid_for(bt.n_paths, T * classify_items, c->sm_count * 8);
     const int shade_blocks = grid_for(bt.n_paths, kShadeThreads, wide_blocks);
@@ -419,6 +423,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
         if (iter > 0) CUDA_TRY(cudaMemsetAsync(nxt, 0, sizeof(IterCounters), s));
         if (c->stage_timing > 0) CUDA_TRY(cudaEventRecord(stage_event(iter, 0), s));
         const bool spheres = sc->dev.spheres != nullptr || sc->dev.leaf_table != nullptr;  // the generic instantiations: sphere slots, leaf table
+        nvtxRangePushA("yk closest hit");
         if (cfg.integrator == YK_INTEGRATOR_BVH_INTERSECTIONS) {
             if (spheres) k_trace_closest<true, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
             else k_trace_closest<true, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
@@ -426,6 +431,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             if (spheres) k_trace_closest<false, true><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
             else k_trace_closest<false, false><<<closest_blocks, kTraceThreads, 0, s>>>(sc->dev, w, b, cur, perm_trace);
         }
+        nvtxRangePop();
         if (c->stage_timing > 0) CUDA_TRY(cudaEventRecord(stage_event(iter, 1), s));
         tm->launches += 1;
         tm->closest_launches += 1;
@@ -443,10 +449,13 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             sl.n_iters = iter + 1;
             break;
         }
+        nvtxRangePushA("yk classify (misses, material queues)");
         if (cfg.integrator == YK_INTEGRATOR_WHITTED) k_classify<1, true><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next, nullptr);
         else k_classify<YK_CLASSIFY_ITEMS, false><<<classify_blocks, T, 0, s>>>(sc->dev, w, cfg, bt, q_cur, b, cur, nxt, iter == 0 ? 1 : 0, q_next, perm_classify);
+        nvtxRangePop();
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 2), s));
         tm->launches += 1;
+        nvtxRangePushA("yk shade (per material kind)");
         const bool is_path = cfg.integrator == YK_INTEGRATOR_PATH;
         for (uint32_t kind = 0; kind < 4; ++kind) {
             if (!(sc->material_kinds & (1u << kind))) continue;  // no triangle of the scene has this material kind
@@ -472,6 +481,7 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
 #undef YK_LAUNCH_SHADE
             tm->launches += 1;
         }
+        nvtxRangePop();
         if (c->stage_timing > 1) CUDA_TRY(cudaEventRecord(stage_event(iter, 3), s));
         nvtxRangePushA("yk shadow rays + fold");
         if (cfg.shadow_per_ray) {  // one shadow ray per lane, then the fold (wf_trace.cuh)
@@ -512,11 +522,13 @@ int run_batch(yk_context* c, Pipe* p, const yk_scene* sc, const RenderCfg& cfg, 
             if ((uint64_t)iter + 1 > ((uint64_t)1 << std::min(cfg.max_depth, 40u))) return yk_set_error(YK_ERR_INVALID, "yk_render: bounce loop did not terminate");
         }
     }
+    nvtxRangePushA("yk film");
     if (accumulate_film) {
         k_film_add<<<(bt.n_paths + T - 1) / T, T, 0, s>>>(w, bt, d_film, cfg.res_x);
     } else {
         k_film_accumulate<<<(bt.n_jobs + T - 1) / T, T, 0, s>>>(w, bt, c->d_accum, cfg.res_x);
     }
+    nvtxRangePop();
     tm->launches += 1;
     CUDA_TRY(cudaEventRecord(sl.done, s));
     CUDA_TRY(cudaGetLastError());
@@ -583,6 +595,9 @@ int yk_context_create(int device_id, yk_context** out) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_closest, k_trace_closest<false, false>, kTraceThreads, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_any, k_trace_shadow<false>, kTraceThreads, 0));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_trace_rays, k_trace_shadow_rays<false>, kTraceThreads, 0));
+    // development overrides (A/B of co-resident kernels of two pipes): blocks per SM of the persistent / grid-stride kernels
+    if (const char* e = getenv("YK_TRACE_PER_SM")) c->occ_trace_closest = c->occ_trace_any = c->occ_trace_rays = std::max(1, atoi(e));
+    if (const char* e = getenv("YK_WIDE_PER_SM")) c->wide_per_sm = std::max(1, atoi(e));
     *out = c;
     return YK_OK;
     });
@@ -1024,13 +1039,21 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
         if (opts && opts->pipes) n_pipes = (int)opts->pipes;
         n_pipes = std::max(1, std::min(kMaxPipes, n_pipes));
         if (accumulate) n_pipes = 1;
-        // fewer pixel groups than pipes: split the jobs evenly if that leaves decent batches, else use fewer pipes
-        while (n_pipes > 1 && (n_jobs_total + jobs_per_batch - 1) / jobs_per_batch < (unsigned long long)n_pipes) {
-            if ((uint64_t)(n_jobs_total / n_pipes) * m >= (1u << 20)) {
-                jobs_per_batch = (uint32_t)((n_jobs_total + n_pipes - 1) / n_pipes);
-                break;
+        // Pixel groups of equal size, their number a multiple of the pipe count: a ragged tail (a last group of a fraction of a
+        // batch, or an odd group that runs on one pipe with nothing beside it) cost a 2-GPU yk_multi_render whose runs are
+        // not multiples of a group 8 ms per run. Fewer pixel groups than pipes: split the jobs evenly if that leaves decent
+        // batches, else use fewer pipes.
+        if (!accumulate) {
+            for (;;) {
+                unsigned long long n_g = (n_jobs_total + jobs_per_batch - 1) / jobs_per_batch;
+                n_g = (n_g + n_pipes - 1) / n_pipes * n_pipes;
+                const unsigned long long per = (n_jobs_total + n_g - 1) / n_g;
+                if (n_pipes == 1 || per * m >= (1u << 20) || n_g > (unsigned long long)n_pipes) {
+                    jobs_per_batch = (uint32_t)std::max<unsigned long long>(1, per);
+                    break;
+                }
+                n_pipes -= 1;
             }
-            n_pipes -= 1;
         }
         const uint32_t wave_cap = (uint32_t)std::min<uint64_t>(cap, (uint64_t)jobs_per_batch * m);
         int rc = YK_OK;
