@@ -83,9 +83,12 @@ struct TraceLane {
     uint32_t sp;  // shared-memory byte address of the lane's next free stack entry (level 0 holds the sentinel)
     uint32_t n_tests, n_tris;  // running totals of the lane (all of its rays): box tests, shape tests
     uint32_t n_hits;           // passed box tests of the current ray (COUNTS only)
+    uint32_t pend_ref;         // POST only: a second leaf waiting behind the current one (kNoNode = none) and its box key
+    float pend_key;
 
     __device__ __forceinline__ void idle(uint32_t sbase) {
         cur = kNoNode; sp = sbase + kStackStride; leaf_pos = leaf_end = 0; n_tests = n_hits = n_tris = 0;
+        pend_ref = kNoNode; pend_key = 0.0f;
         ox = oy = oz = ix = iy = iz = t_max = okx = oky = okz = sx = sy = sz = 0.0f;
         kx = ky = kz = neg_mask = 0;
     }
@@ -136,6 +139,7 @@ struct TraceLane {
         sp = sbase + kStackStride; n_tests += 1; n_hits = 0;
         leaf_pos = leaf_end = 0;
         cur = kNoNode;
+        pend_ref = kNoNode;
         // the root's own box (bvh.rs:176-179 on node 0)
         float lo, hi;
         slab(sc.root_min[0], sc.root_min[1], sc.root_min[2], sc.root_max[0], sc.root_max[1], sc.root_max[2], &lo, &hi);
@@ -283,6 +287,94 @@ struct TraceLane {
     __device__ __forceinline__ void leaf_done(const DevScene& sc, uint32_t sbase, const uint32_t* deep_ref, const float* deep_key) {
         if (leaf_pos == leaf_end) enter<GENERIC>(sc, pop_passing<COUNTS, ANYHIT>(sbase, deep_ref, deep_key));
     }
+
+    // ---- postponed leaves (YK_POSTPONE, closest hit without per-ray counters) ---------------------------------------
+    // A lane that reaches a leaf during the box phase keeps walking with that leaf pending; a second leaf parks it. Pending
+    // leaves are tested in the order they were found, the second one behind a re-test of its own box key against the t_max
+    // the first one left — a child's slab entry is never below its parent's, so a leaf the reference would have culled
+    // through any ancestor fails its own key — hence exactly the reference's sequence of shape tests and the same hit, ties
+    // included; only the number of *box* tests grows (those taken with the stale t_max). scripts/sim_spec.py is the model.
+    template <bool GENERIC>
+    __device__ __forceinline__ void set_leaf(const DevScene& sc, uint32_t ref) {
+        uint32_t first, count;
+        if (GENERIC && sc.leaf_table) {
+            const uint2 l = __ldg(&sc.leaf_table[ref]);
+            first = l.x; count = l.y;
+        } else {
+            first = ref & ((1u << kLeafFirstBits) - 1u);
+            count = (ref >> kLeafFirstBits) + 1u;
+        }
+        leaf_pos = first; leaf_end = first + count;
+    }
+    // pop_passing that also returns the key and leaves the sentinel in place (it may be popped again after the pending leaves)
+    __device__ __forceinline__ uint32_t pop_keyed(uint32_t sbase, const uint32_t* deep_ref, const float* deep_key, float* key_out) {
+        uint32_t ref;
+        float key;
+        do {
+            sp -= kStackStride;
+            if (sp < sbase + (uint32_t)kShortStack * kStackStride) {
+                lds_entry(sp, &ref, &key);
+            } else {
+                const uint32_t depth = (sp - sbase) / kStackStride - kShortStack;
+                ref = deep_ref[depth];
+                key = deep_key[depth];
+            }
+        } while (key_fails(key));
+        sp += ref == kNoNode ? kStackStride : 0u;
+        *key_out = key;
+        return ref;
+    }
+    template <bool GENERIC>
+    __device__ __forceinline__ void enter_post(const DevScene& sc, uint32_t sbase, const uint32_t* deep_ref, const float* deep_key, uint32_t ref, float key) {
+        if ((int32_t)ref < 0) { cur = ref; return; }  // interior, or the sentinel
+        cur = kNoNode;
+        if (leaf_pos < leaf_end) { pend_ref = ref; pend_key = key; return; }  // a second leaf: parked
+        set_leaf<GENERIC>(sc, ref);
+        float k2;
+        const uint32_t r2 = pop_keyed(sbase, deep_ref, deep_key, &k2);  // walk on (t_max is stale until the leaf is tested)
+        if ((int32_t)r2 < 0) cur = r2;
+        else { pend_ref = r2; pend_key = k2; }
+    }
+    template <bool GENERIC>
+    __device__ __forceinline__ void leaf_done_post(const DevScene& sc, uint32_t sbase, const uint32_t* deep_ref, const float* deep_key) {
+        if (leaf_pos != leaf_end) return;
+        if (pend_ref != kNoNode) {
+            const uint32_t r = pend_ref;
+            const float k = pend_key;
+            pend_ref = kNoNode;
+            if (!key_fails(k)) { set_leaf<GENERIC>(sc, r); return; }  // the pending leaf's deferred box test, with the current t_max
+        }
+        if (cur == kNoNode) {  // parked (or finished): next entry; no speculation inside the shape phase
+            float k2;
+            const uint32_t r2 = pop_keyed(sbase, deep_ref, deep_key, &k2);
+            if ((int32_t)r2 < 0) cur = r2;
+            else set_leaf<GENERIC>(sc, r2);
+        }
+    }
+    template <bool GENERIC>
+    __device__ __forceinline__ void box_step_post(const DevScene& sc, uint32_t sbase, uint32_t* deep_ref, float* deep_key) {
+        const uint32_t neg = (neg_mask >> ((cur >> 29) & 3u)) & 1u;
+        const float4* rec = sc.nodes2 + 4 * (size_t)(cur & kRefIndexMask);
+        const float4* near = rec + 2 * neg;
+        const float4* far = rec + 2 * (neg ^ 1u);
+        float4 n0, n1, f0, f1;
+        ldg256(near, &n0, &n1);
+        ldg256(far, &f0, &f1);
+        float lo_n, hi_n, lo_f, hi_f;
+        slab(n0.x, n0.y, n0.z, n1.x, n1.y, n1.z, &lo_n, &hi_n);
+        slab(f0.x, f0.y, f0.z, f1.x, f1.y, f1.z, &lo_f, &hi_f);
+        const uint32_t ref_n = __float_as_uint(n0.w), ref_f = __float_as_uint(f0.w);
+        const bool hit_n = lo_n <= fminf(hi_n, t_max);
+        const bool ok_f = !(lo_f > hi_f);
+        const float key_f = ok_f ? lo_f : __uint_as_float(kKeyNever);
+        const bool hit_f = !hit_n && !key_fails(key_f);
+        n_tests += 2u;
+        if (hit_n && ok_f) push(sbase, deep_ref, deep_key, ref_f, key_f);
+        uint32_t take = hit_n ? ref_n : ref_f;
+        float take_key = hit_n ? lo_n : key_f;
+        if (!(hit_n || hit_f)) take = pop_keyed(sbase, deep_ref, deep_key, &take_key);
+        enter_post<GENERIC>(sc, sbase, deep_ref, deep_key, take, take_key);
+    }
     // ends the ray: the next pop (leaf_done) takes the sentinel
     __device__ __forceinline__ void stop(uint32_t sbase) { cur = kNoNode; leaf_pos = leaf_end = 0; sp = sbase + kStackStride; }
 };
@@ -312,6 +404,29 @@ struct TraceLane {
             (LANE).template leaf_done<COUNTS, ANYHIT, GENERIC>(sc, sbase, deep_ref, deep_key);                    \
         }                                                                                                         \
     }
+
+
+// The same two phases with postponed leaves (closest hit, no per-ray counters): see TraceLane::enter_post.
+#define YK_TRACE_PHASES_POST(LANE, LIVE, GENERIC, ON_HIT)                                                         \
+    for (;;) {                                                                                                    \
+        const bool want_n = (LANE).wants_box();                                                                   \
+        const int n_n = __popc(__ballot_sync(0xffffffffu, want_n));                                               \
+        if (n_n == 0) break;                                                                                      \
+        if (n_n < kNodePhaseMin && __ballot_sync(0xffffffffu, (LIVE) && !want_n)) break;                          \
+        if (want_n) (LANE).template box_step_post<GENERIC>(sc, sbase, deep_ref, deep_key);                        \
+        if (YK_BOX_STEPS_PER_VOTE > 1 && (LANE).wants_box()) (LANE).template box_step_post<GENERIC>(sc, sbase, deep_ref, deep_key); \
+        if (YK_BOX_STEPS_PER_VOTE > 2 && (LANE).wants_box()) (LANE).template box_step_post<GENERIC>(sc, sbase, deep_ref, deep_key); \
+    }                                                                                                             \
+    while (__ballot_sync(0xffffffffu, (LANE).wants_tri())) {                                                      \
+        if ((LANE).wants_tri()) {                                                                                 \
+            uint32_t tri_; float ts_, det_; int al_;                                                              \
+            if ((LANE).tri_step(sc, &tri_, &ts_, &det_, &al_)) { ON_HIT }                                         \
+            (LANE).template leaf_done_post<GENERIC>(sc, sbase, deep_ref, deep_key);                               \
+        }                                                                                                         \
+    }
+#ifndef YK_POSTPONE
+#define YK_POSTPONE 0
+#endif
 
 // Closest hit: BoundingVolumeHierarchy::intersect (bvh.rs:160-232). One ray per queue entry.
 template <bool COUNTS, bool SPHERES>
@@ -371,29 +486,36 @@ __global__ void __launch_bounds__(kTraceThreads, YK_TRACE_MIN_BLOCKS) k_trace_cl
         }
         // ---- trace until too few lanes are live -----------------------------------------------------------
         for (;;) {
-            YK_TRACE_PHASES(tl, live, COUNTS, false, SPHERES, {
-                // A sphere slot is recognised by its tag (row 0's w = -2 - sphere index; triangles carry an area light >= -1),
-                // not by the NaN determinant its NaN vertex lanes produce: a real triangle gives a NaN determinant too (zero-length
-                // or NaN direction, non-finite vertex) and must stay on the triangle branch, where the reference returns a NaN-t hit.
-                if (SPHERES && al_ <= -2) {  // shapes/sphere.rs:36-77
-                    float t_s;
-                    /* the direction is not kept in registers: re-read it on this rare path */
-                    if (sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.st[b].ray_d[path], tl.t_max, &t_s)) {
-                        hit_tri = tri_; hit_t = t_s; tl.t_max = t_s;
-                    }
-                } else {
-                    const float inv_det = 1.0f / det_;  // triangle.rs:133-139
-                    hit_tri = tri_; hit_t = ts_ * inv_det; tl.t_max = hit_t;  // later equal-t hit replaces (bvh.rs:204-207)
-                    // A NaN hit distance (NaN determinant: zero-length or NaN direction) makes the reference's later box tests
-                    // `lo <= min(hi, NaN)`: `lo <= hi` for a box with a numeric exit distance — what the stacked keys encode — but
-                    // false for a box whose own exit distance is NaN too, i.e. every box when all three direction components are
-                    // NaN. Those rays drop their stack here (their popped nodes are already counted as tested, none would pass).
-                    // (Only the counting instantiations carry the test: they serve yk_trace's caller rays and the debug integrator;
-                    // the integrators' own rays have finite directions, and the test costs the hot instantiation 1.7 %,
-                    // profiles/r02/ab_cornell_regression.txt.)
-                    if (COUNTS && hit_t != hit_t && tl.ix != tl.ix && tl.iy != tl.iy && tl.iz != tl.iz) tl.sp = sbase + kStackStride;
-                }
-            })
+            // What a closest-hit walk does with an accepted shape test.
+            //  * A sphere slot is recognised by its tag (row 0's w = -2 - sphere index; triangles carry an area light >= -1), not
+            //    by the NaN determinant its NaN vertex lanes produce: a real triangle gives a NaN determinant too (zero-length or
+            //    NaN direction, non-finite vertex) and must stay on the triangle branch, where the reference returns a NaN-t hit.
+            //    The sphere test (shapes/sphere.rs:36-77) re-reads the direction, which is not kept in registers, on this rare path.
+            //  * Triangle (triangle.rs:133-139): a later equal-t hit replaces the earlier one (bvh.rs:204-207).
+            //  * A NaN hit distance (NaN determinant: zero-length or NaN direction) makes the reference's later box tests
+            //    `lo <= min(hi, NaN)`: `lo <= hi` for a box with a numeric exit distance — what the stacked keys encode — but false
+            //    for a box whose own exit distance is NaN too, i.e. every box when all three direction components are NaN. Those
+            //    rays drop their stack here (their popped nodes are already counted as tested, none would pass). Only the counting
+            //    instantiations carry the test: they serve yk_trace's caller rays and the debug integrator; the integrators' own
+            //    rays have finite directions, and the test costs the hot instantiation 1.7 % (profiles/r02/ab_cornell_regression.txt).
+#define YK_CLOSEST_ON_HIT {                                                                                                     \
+                if (SPHERES && al_ <= -2) {                                                                                      \
+                    float t_s;                                                                                                   \
+                    if (sphere_slot_test(sc.spheres, al_, tl.ox, tl.oy, tl.oz, w.st[b].ray_d[path], tl.t_max, &t_s)) {           \
+                        hit_tri = tri_; hit_t = t_s; tl.t_max = t_s;                                                            \
+                    }                                                                                                            \
+                } else {                                                                                                         \
+                    const float inv_det = 1.0f / det_;                                                                           \
+                    hit_tri = tri_; hit_t = ts_ * inv_det; tl.t_max = hit_t;                                                     \
+                    if (COUNTS && hit_t != hit_t && tl.ix != tl.ix && tl.iy != tl.iy && tl.iz != tl.iz) tl.sp = sbase + kStackStride; \
+                }                                                                                                                \
+            }
+            if constexpr (YK_POSTPONE != 0 && !COUNTS) {
+                YK_TRACE_PHASES_POST(tl, live, SPHERES, YK_CLOSEST_ON_HIT)
+            } else {
+                YK_TRACE_PHASES(tl, live, COUNTS, false, SPHERES, YK_CLOSEST_ON_HIT)
+            }
+#undef YK_CLOSEST_ON_HIT
             if (live && !tl.wants_box()) {  // retire
                 st_once(&w.hit[path], make_uint2(__float_as_uint(hit_t), hit_tri));
                 if (COUNTS) w.bvh_counts[path] = make_uint2(tl.n_tests - tests_before, tl.n_hits);
