@@ -279,6 +279,31 @@ def check_digest(key, digest, update):
     return "ok"
 
 
+def shared_host_scene(api, scene, world, local, tag, big):
+    """One host BVH build per node: local rank 0 builds and (for the 10 M-triangle scene, `big`) leaves the flattened arrays under
+    /dev/shm; the other ranks map them (api.HostScene.save / load) instead of repeating the 6 s build N times on contended cores.
+    Returns (host scene, clean-up function to call once every rank holds its device copy)."""
+    import torch.distributed as dist
+    if world == 1 or not big:
+        return api.HostScene(scene), (lambda: None)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    share_dir = os.path.join(base, f"yuki_b200_{tag}_{os.environ.get('MASTER_PORT', '0')}_{kernel_source_hash()}")
+    host = None
+    if local == 0:
+        host = api.HostScene(scene)
+        host.save(share_dir)
+    dist.barrier()
+    if local != 0:
+        host = api.HostScene.load(share_dir)
+
+    def done():
+        dist.barrier()
+        if local == 0:
+            import shutil
+            shutil.rmtree(share_dir, ignore_errors=True)
+    return host, done
+
+
 def large_scene_leg(args, api, capi, xf, ctx, stream, rank, world, local, peak):
     """BASELINE.json configs[4]'s geometry — the 10 M-triangle terrain + material objects at 3840x2160, Path max_depth 8 — at
     64 spp, on every rank: spiral tiles interleaved over the ranks, the scene built and uploaded once per rank OUTSIDE the
@@ -288,31 +313,14 @@ def large_scene_leg(args, api, capi, xf, ctx, stream, rank, world, local, peak):
     import torch
     import torch.distributed as dist
     from yuki_b200 import scenes
-    # One host build per node: local rank 0 builds the 10 M-triangle BVH and leaves the flattened arrays under /dev/shm; the other
-    # ranks map them (api.HostScene.save / load) instead of repeating the 6 s build N times on contended cores.
     t0 = time.perf_counter()
     scene, cam = scenes.terrain_room(xf)
-    share_dir = None
-    if world > 1:
-        base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        share_dir = os.path.join(base, f"yuki_b200_c5_{os.environ.get('MASTER_PORT', '0')}_{kernel_source_hash()}")
-    if share_dir is None or local == 0:
-        host = api.HostScene(scene)
-        if share_dir is not None:
-            host.save(share_dir)
-    if world > 1:
-        dist.barrier()
-        if local != 0:
-            host = api.HostScene.load(share_dir)
+    host, shared_done = shared_host_scene(api, scene, world, local, "c5leg", True)
     t_build = time.perf_counter() - t0
     t0 = time.perf_counter()
     dev = api.Scene(ctx, scene, host=host)
     t_upload = time.perf_counter() - t0
-    if world > 1:
-        dist.barrier()
-        if local == 0:
-            import shutil
-            shutil.rmtree(share_dir, ignore_errors=True)
+    shared_done()
     rn = api.Renderer(ctx)
     film = D.FilmSettings((3840, 2160), 16)
     sampler, integ = D.SamplerType.stratified(C5_SPP_SIDE, C5_SPP_SIDE, jitter=True), D.IntegratorType.path(MAX_DEPTH)
@@ -450,8 +458,9 @@ def run_ours(args):
     scene, cam, film, sampler, integ = workload(xf)
     ctx = api.Context(local)
     stream = torch.cuda.ExternalStream(capi.lib().yk_context_stream(ctx._h), device=torch.device("cuda", local))
-    host_scene = api.HostScene(scene)
+    host_scene, shared_done = shared_host_scene(api, scene, world, local, "main", SCENE != "cornell")
     dev = api.Scene(ctx, scene, host=host_scene)
+    shared_done()
     rn = api.Renderer(ctx)
     all_tiles = api.film_tiles(film)
     my_tiles = np.ascontiguousarray(all_tiles[rank::world])  # spiral order interleaved over ranks (render_manager.rs:206-210 TODO)

@@ -50,6 +50,34 @@ def test_group_of_one_device_equals_yk_render(gpu_ctx, xf):
     ms.close(); mctx.close(); dev.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("run_tiles", [None, "5"])
+def test_tile_cursor_runs_on_one_device_give_the_single_call_film(gpu_ctx, xf, monkeypatch, run_tiles):
+    """The shared tile cursor on a one-GPU box: a render large enough for guided self-scheduling (remaining / 2G tiles per pop,
+    never below ~16 Mi paths: 1024 tiles of 64 Ki paths -> runs of 512, 256, 256 tiles), and fixed runs of five tiles of the strided
+    order, against one yk_render call: the same film, ids and counters whatever the partition into runs."""
+    monkeypatch.setenv("YK_MULTI_FORCE_CURSOR", "1")   # a group of one device normally forwards to yk_render
+    if run_tiles:
+        monkeypatch.setenv("YK_MULTI_RUN_TILES", run_tiles)
+    else:
+        monkeypatch.delenv("YK_MULTI_RUN_TILES", raising=False)
+        monkeypatch.setenv("YK_MULTI_STATIC_BELOW", "0")   # (jobs this short are split statically by default)
+    scene, cam = scenes.cornell(xf, light="rect", tall_box="glass", sphere=True)
+    film = D.FilmSettings((512, 512), 16) if run_tiles is None else D.FilmSettings((150, 100), 16)
+    smp = D.SamplerType.stratified(16, 16) if run_tiles is None else D.SamplerType.stratified(2, 2)
+    integ = D.IntegratorType.path(4)
+    dev = api.Scene(gpu_ctx, scene)
+    ref = api.Renderer(gpu_ctx).render(dev, cam, film, smp, integ, want_hit_ids=True)
+    mctx = api.MultiContext([0])
+    ms = api.MultiScene(mctx, scene)
+    r, per = api.multi_render(mctx, ms, cam, film, smp, integ, want_hit_ids=True)
+    assert np.array_equal(r.film.view(np.uint32), ref.film.view(np.uint32)) and np.array_equal(r.hit_ids, ref.hit_ids)
+    for k in ("ray_count", "shadow_rays", "samples", "closest_nodes", "closest_tris", "any_nodes", "any_tris", "primary_hit_hash"):
+        assert getattr(r.stats, k) == getattr(ref.stats, k) == getattr(per[0], k), k
+    assert r.stats.kernel_launches > ref.stats.kernel_launches   # several runs: more launches than the single call
+    ms.close(); mctx.close(); dev.close()
+
+
 def _check_group(xf, oracle, monkeypatch, no_peer):
     if no_peer:
         monkeypatch.setenv("YK_MULTI_NO_PEER", "1")

@@ -158,7 +158,7 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
     if (!fs->res_x || !fs->res_y || fs->res_x > 0xffffu || fs->res_y > 0xffffu)
         return yk_set_error(YK_ERR_INVALID, "yk_multi_render: film resolution must fit u16 (integrators/mod.rs:140-141)");
     const size_t G = m->ctx.size();
-    if (G == 1) {  // nothing to share
+    if (G == 1 && !getenv("YK_MULTI_FORCE_CURSOR")) {  // nothing to share (tests force the cursor path on one-GPU boxes)
         const int rc = render_impl(m->ctx[0], ms->scene[0], cam, fs, sm, in, tiles, n_tiles, opts, film_rgb, stats, nullptr, nullptr);
         if (rc == YK_OK && stats && per_device) per_device[0] = *stats;
         return rc;
@@ -247,7 +247,7 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
     // kernel tails — measured on 2 GPUs, runs of a quarter batch made the 16-spp large scene 35 % slower than one call per
     // device) and the last ones small (the finish times differ by at most one small run, whatever the devices' speeds),
     // never below ~16 Mi paths (two wavefront batches of 8 Mi, one per pipe; with 64 Mi the two devices of a 0.4 s render
-    // finished 39 ms apart). A job whose fair share is below two such runs is split statically, one run per device. The runs are ranges of a *strided* order of the tile list (position j -> tile
+    // finished 39 ms apart). A job whose fair share is below 256 Mi paths is split statically, one run per device. The runs are ranges of a *strided* order of the tile list (position j -> tile
     // j * stride mod n_tiles, stride ~ 0.618 n_tiles and coprime to it), so every run samples the whole spiral and costs
     // about the same per tile. Accumulating: tile.index mod G (fixed add order per pixel).
     uint32_t run_floor = 1, run_fixed = 0, stride = 1;
@@ -255,7 +255,11 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
         const unsigned long long paths_per_tile = std::max<unsigned long long>(1, area / n_tiles) * spp;
         run_floor = (uint32_t)std::max<unsigned long long>(1, (16ull << 20) / paths_per_tile);
         const uint32_t fair = (uint32_t)((n_tiles + G - 1) / G);
-        if (fair < 2 * run_floor) run_fixed = fair;
+        // Short jobs are split statically: the devices of a box are alike, and the last guided runs (one floor = ~13 ms of a
+        // B200) would leave them up to that far apart — 12 % of an 8-GPU render of 0.1 s, 0.3 % of the 4.6 s of the 4K config.
+        unsigned long long static_below = 256ull << 20;  // paths per device
+        if (const char* e = getenv("YK_MULTI_STATIC_BELOW")) static_below = strtoull(e, nullptr, 10);
+        if (fair < 2 * run_floor || (unsigned long long)fair * paths_per_tile < static_below) run_fixed = fair;
         if (const char* e = getenv("YK_MULTI_RUN_TILES")) run_fixed = (uint32_t)std::max(1, atoi(e));
         auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
         stride = std::max(1u, (uint32_t)(0.6180339887 * n_tiles));
