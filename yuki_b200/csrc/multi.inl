@@ -122,12 +122,18 @@ int yk_multi_scene_create(yk_multi* m, const yk_scene_desc* d, yk_multi_scene** 
     SceneCheck check;
     int rc = scene_create_impl(m->ctx[0], d, nullptr, &check, &ms->scene[0]);
     if (rc != YK_OK) return rc;
+    const bool no_clone = getenv("YK_MULTI_NO_CLONE") != nullptr;  // development / tests: every device uploads for itself
     std::vector<int> rcs(m->ctx.size(), YK_OK);
     std::vector<std::string> errs(m->ctx.size());
     std::vector<std::thread> th;
     for (size_t i = 1; i < m->ctx.size(); ++i)
         th.emplace_back([&, i] {
-            rcs[i] = yk_guard("yk_multi_scene_create", [&]() -> int { return scene_create_impl(m->ctx[i], d, &check, nullptr, &ms->scene[i]); });
+            rcs[i] = yk_guard("yk_multi_scene_create", [&]() -> int {
+                // a device with a peer mapping of device 0 pulls the repacked scene from there (NVLink) instead of uploading and
+                // repacking the host arrays again
+                if (m->peer_ok[i] && !no_clone) return scene_clone_impl(m->ctx[i], ms->scene[0], &ms->scene[i]);
+                return scene_create_impl(m->ctx[i], d, &check, nullptr, &ms->scene[i]);
+            });
             if (rcs[i] != YK_OK) errs[i] = yk_last_error();  // (the message is thread-local)
         });
     for (auto& t : th) t.join();
