@@ -89,7 +89,9 @@ def kernel_source_hash():
     h = hashlib.sha256()
     src = os.path.join(ROOT, "yuki_b200", "csrc")
     for name in sorted(os.listdir(src)):
-        if name.endswith((".cu", ".cuh", ".h", ".inl")):
+        # the wavefront kernels, their device headers and the driver that sizes their grids (not the loaders, the display passes
+        # or the device-group layer, none of which can change what the profiled kernel does)
+        if name.endswith(".cuh") or name in ("render.cu", "yk_libm.h", "yk_fastdiv.h"):
             with open(os.path.join(src, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]

@@ -278,12 +278,13 @@ void yk_multi_destroy(yk_multi*);
 int yk_multi_device_count(const yk_multi*);
 yk_context* yk_multi_context(yk_multi*, int i);      /* the i-th device's context (owned by the group) */
 int yk_multi_peer_stores(const yk_multi*, int i);    /* 1: device i stores into the first device's film directly */
-/* yk_scene_create on every device: validated once, uploaded in parallel from the caller's host arrays. */
+/* yk_scene_create on every device: the first device validates, uploads and repacks the caller's host arrays; devices with a
+ * peer mapping of it copy the repacked scene over NVLink, the others upload for themselves. */
 int yk_multi_scene_create(yk_multi*, const yk_scene_desc*, yk_multi_scene** out);
 void yk_multi_scene_destroy(yk_multi_scene*);
 /* yk_render over all devices of the group. Same arguments and film semantics; `film_rgb` / opts->hit_ids are host
  * buffers, or (YK_RENDER_FILM_ON_DEVICE) buffers on the FIRST device. Non-accumulating renders hand out runs of tiles
- * dynamically; accumulating renders send a tile to device `tile.index mod G`, so that a pixel's per-sample adds keep the
+ * dynamically (guided self-scheduling: remaining / 2G tiles per pop; jobs below ~256 Mi paths per device are split evenly); accumulating renders send a tile to device `tile.index mod G`, so that a pixel's per-sample adds keep the
  * tile-list order (film.rs:260-272) and the film equals the single-device one bit for bit. `stats` = sums over the
  * devices with device_ms = the busiest device's; `per_device` (NULL or G entries) = each device's own sums, device_ms
  * being its busy time. */
