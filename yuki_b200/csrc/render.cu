@@ -176,6 +176,7 @@ struct CopyJob {
 class PinnedPool {
 public:
     static constexpr size_t kBytes = 16u << 20;
+    static constexpr size_t kKeep = 12;  // six upload threads x two buffers
     static PinnedPool& get() {
         static PinnedPool p;
         return p;
@@ -197,8 +198,14 @@ public:
         return p;
     }
     void give(void* p) {
-        std::lock_guard<std::mutex> g(mu_);
-        free_.push_back(p);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (free_.size() < kKeep) {
+                free_.push_back(p);
+                return;
+            }
+        }
+        cudaFreeHost(p);  // beyond what one upload's threads use: do not keep page-locked memory for ever
     }
 
 private:
@@ -230,8 +237,16 @@ int staged_upload(int device, const std::vector<CopyJob>& jobs) {
     const unsigned n_threads = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)6, chunks.size(), (size_t)std::max(1u, std::thread::hardware_concurrency() / 2)}));
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
+    std::mutex err_mu;
+    std::string err_text;
+    auto note_error = [&](const char* what) {  // (cudaGetLastError is per thread: read it where the call failed)
+        const cudaError_t e = cudaGetLastError();
+        std::lock_guard<std::mutex> g(err_mu);
+        if (err_text.empty()) err_text = std::string(what) + ": " + cudaGetErrorString(e);
+        failed = 1;
+    };
     auto worker = [&]() {
-        if (cudaSetDevice(device) != cudaSuccess) { failed = 1; return; }
+        if (cudaSetDevice(device) != cudaSuccess) { note_error("cudaSetDevice"); return; }
         cudaStream_t st = nullptr;
         cudaEvent_t ev[2] = {nullptr, nullptr};
         void* buf[2] = {PinnedPool::get().take(), PinnedPool::get().take()};
@@ -251,7 +266,7 @@ int staged_upload(int device, const std::vector<CopyJob>& jobs) {
             k ^= 1;
         }
         if (st && cudaStreamSynchronize(st) != cudaSuccess) ok = false;
-        if (!ok) failed = 1;
+        if (!ok) note_error(buf[0] && buf[1] ? "pinned staging copy" : "cudaMallocHost");
         for (int i = 0; i < 2; ++i) {
             if (ev[i]) cudaEventDestroy(ev[i]);
             if (buf[i]) PinnedPool::get().give(buf[i]);
@@ -262,10 +277,7 @@ int staged_upload(int device, const std::vector<CopyJob>& jobs) {
     for (unsigned i = 1; i < n_threads; ++i) th.emplace_back(worker);
     worker();
     for (auto& t : th) t.join();
-    if (failed) {
-        const cudaError_t e = cudaGetLastError();
-        return yk_set_error(YK_ERR_CUDA, std::string("staged upload failed: ") + cudaGetErrorString(e));
-    }
+    if (failed) return yk_set_error(YK_ERR_CUDA, "staged upload failed: " + err_text);
     return YK_OK;
 }
 
