@@ -36,6 +36,14 @@ if which == "capsweep":
     s, c = scenes.cornell(xf, light="rect", tall_box="glass")
     for cap in (1 << 25, 1 << 24, 1 << 23, 1 << 22, 1 << 21):
         probe(f"cornell 1024^2 path8 64spp cap {cap}", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(8, 8), D.IntegratorType.path(8), reps=2, wavefront_paths=cap)
+if which == "capsweep2":  # larger batches than the default 16 Mi paths (HBM is 180 GB): Cornell at 256 spp and the 10 M-triangle scene at 16 spp
+    s, c = scenes.cornell(xf, light="rect", tall_box="glass")
+    for pipes in (2, 1):
+        for cap in (1 << 24, 1 << 25, 1 << 26):
+            probe(f"cornell 1024^2 path8 256spp pipes {pipes} cap {cap >> 20} Mi", s, c, D.FilmSettings((1024, 1024), 16), D.SamplerType.stratified(16, 16), D.IntegratorType.path(8), reps=1, wavefront_paths=cap, pipes=pipes)
+    s, c = scenes.terrain_room(xf)
+    for cap in (1 << 24, 1 << 25, 1 << 26):
+        probe(f"terrain 10M path8 4K 16spp pipes 2 cap {cap >> 20} Mi", s, c, D.FilmSettings((3840, 2160), 16), D.SamplerType.stratified(4, 4), D.IntegratorType.path(8), reps=1, wavefront_paths=cap, pipes=2)
 if which == "terrain":
     import time as _t
     t0 = _t.time(); s, c = scenes.terrain_room(xf); print(f"terrain scene desc {_t.time()-t0:.1f}s", flush=True)

@@ -89,6 +89,25 @@ int yk_multi_create(const int* device_ids, int n_devices, yk_multi** out) {
             const cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[0], 0);
             if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) m->peer_ok[(size_t)i] = 1;
             (void)cudaGetLastError();
+            // ... and the other way round, so that the scene clone's peer copies (device 0 -> i) run device to device on every
+            // driver instead of being staged through the host
+            int back = 0;
+            if (cudaDeviceCanAccessPeer(&back, device_ids[0], device_ids[i]) == cudaSuccess && back && cudaSetDevice(device_ids[0]) == cudaSuccess)
+                (void)cudaDeviceEnablePeerAccess(device_ids[i], 0);
+            (void)cudaGetLastError();
+            // Scenes live in device 0's stream-ordered memory pool (dev_alloc), whose memory cudaDeviceEnablePeerAccess does not
+            // map: without this grant the clone's 1 GB of peer copies were staged through the host at 23 GB/s.
+            if (m->peer_ok[(size_t)i]) {
+                cudaMemPool_t pool = nullptr;
+                if (cudaDeviceGetDefaultMemPool(&pool, device_ids[0]) == cudaSuccess) {
+                    cudaMemAccessDesc desc{};
+                    desc.location.type = cudaMemLocationTypeDevice;
+                    desc.location.id = device_ids[i];
+                    desc.flags = cudaMemAccessFlagsProtReadWrite;
+                    (void)cudaMemPoolSetAccess(pool, &desc, 1);
+                }
+                (void)cudaGetLastError();
+            }
         }
     }
     if (getenv("YK_MULTI_NO_PEER"))  // development / tests: force the gather fallback

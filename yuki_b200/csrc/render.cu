@@ -897,6 +897,7 @@ static int scene_create_impl(yk_context* c, const yk_scene_desc* d, const SceneC
 // and 8 PCIe links -> one upload + 7 NVLink copies).
 static int scene_clone_impl(yk_context* c, const yk_scene* src, yk_scene** out) {
     if (!c || !src || !out) return yk_set_error(YK_ERR_INVALID, "scene clone: null argument");
+    const auto t_start = std::chrono::steady_clock::now();
     CUDA_TRY(cudaSetDevice(c->device));
     auto sc = std::make_unique<yk_scene>();
     sc->ctx = c;
@@ -937,6 +938,9 @@ static int scene_clone_impl(yk_context* c, const yk_scene* src, yk_scene** out) 
     sc->dev.textures = nullptr;
     if ((rc = dev_upload(sc->allocs, &sc->dev.textures, tex.data(), tex.size())) != YK_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (getenv("YK_SCENE_TIMING"))
+        fprintf(stderr, "scene clone to device %d: %.2f ms\n", c->device,
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
     cleanup.armed = false;
     *out = sc.release();
     return YK_OK;
