@@ -1081,20 +1081,21 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
         }
         CUDA_TRY(cudaMemcpyAsync(c->d_tiles, tiles, (size_t)n_tiles * sizeof(yk_tile), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->d_tile_off, tile_off.data(), tile_off.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
-        // Wavefront capacity: paths in flight per batch.
-        // Default: as many as ~6 GB of wavefront state per pipe hold, at most 16 Mi (measured on the Cornell bench: 4 Mi -> 8 Mi ->
-        // 16 Mi -> 32 Mi paths = +8 %, +12 %, +14 %: fewer, longer launches amortise the kernels' tails and the launch gaps),
-        // and never more than a quarter of the free device memory.
+        // Wavefront capacity: paths in flight per batch. Fewer, longer launches amortise the persistent kernels' tails and the
+        // launch gaps, and HBM is 180 GB: measured 4 Mi -> 8 Mi -> 16 Mi paths = +8 %, +12 % on the Cornell bench (round 1), and
+        // 16 Mi -> 32 Mi -> 64 Mi = +0.7 %, +0.8 % there with two pipes (+2.5 %, +3.9 % with one) and +4.1 %, +6.4 % on the
+        // 10 M-triangle scene (profiles/r02/capsweep_large_batches.txt). Default: as many as ~24 GB of wavefront state per pipe
+        // hold (~360 B per path with one light), at most 64 Mi, and never more than a sixth of the free device memory per pipe.
         const uint32_t stack_entries = in->kind == YK_INTEGRATOR_WHITTED ? std::max(in->max_depth, 1u) : 0u;
         uint32_t cap = opts ? opts->wavefront_paths : 0u;
         if (!cap) {
             const uint64_t bytes_per_path = 320ull + 40ull * std::max(sc->dev.n_lights, 1u) + (80ull * stack_entries + (stack_entries ? 8ull : 0ull));
             if (!c->mem_budget) {  // asked once per context: cudaMemGetInfo can take milliseconds
                 size_t free_b = 0, total_b = 0;
-                c->mem_budget = 6ull << 30;
-                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->mem_budget = std::min<uint64_t>(c->mem_budget, (uint64_t)free_b / 8);
+                c->mem_budget = 24ull << 30;
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->mem_budget = std::min<uint64_t>(c->mem_budget, (uint64_t)free_b / 6);
             }
-            cap = (uint32_t)std::min<uint64_t>(1u << 24, std::max<uint64_t>(1u << 20, c->mem_budget / bytes_per_path));
+            cap = (uint32_t)std::min<uint64_t>(1u << 26, std::max<uint64_t>(1u << 20, c->mem_budget / bytes_per_path));
         }
         const uint64_t total_paths = (uint64_t)n_jobs_total * samples_per_job;
         if (cap > total_paths) cap = (uint32_t)total_paths;
@@ -1102,6 +1103,7 @@ static int render_impl(yk_context* c, const yk_scene* sc, const yk_camera* cam, 
         // Samples of one pixel per batch: enough to amortise per-batch fixed costs, few enough that many pixels
         // (>= 64 Ki when available) share a batch.
         uint32_t m = std::min(samples_per_job, kMaxBatchSamples);
+        if (const char* e = getenv("YK_MAX_BATCH_SAMPLES")) m = std::min<uint32_t>(m, (uint32_t)std::max(1, atoi(e)));  // development: A/B of the batch shape
         while (m > 1 && (uint64_t)m * std::min<uint64_t>(n_jobs_total, 65536) > cap) m >>= 1;
         uint32_t jobs_per_batch = std::max(1u, cap / m);
         // Pipes: pixel groups alternate between the streams, so one group's latency-bound shading overlaps the other's

@@ -50,7 +50,7 @@ __global__ void k_dim_hashes(const Job* jobs, uint32_t n_jobs, uint32_t n_dims, 
 // with M, P functions of the distance only (the jump's additive term is linear in the stream increment). A tiny kernel
 // (k_sample_jumps) tabulates (M, P) for the batch's consecutive sample indices, so seeking costs two multiplies instead of the
 // O(log n) loop — which was most of this kernel's instructions.
-constexpr uint32_t kMaxBatchSamples = 256;  // consecutive sample indices of a pixel per batch (size of the jump table)
+constexpr uint32_t kMaxBatchSamples = 1024;  // consecutive sample indices of a pixel per batch (size of the jump table)
 struct SampleJump {
     unsigned long long mult, plus;
 };
