@@ -140,7 +140,20 @@ namespace {
 template <class T>
 int dev_alloc(std::vector<void*>& bag, T** out, size_t count) {
     void* p = nullptr;
-    CUDA_TRY(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), cudaStreamPerThread));
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMallocAsync(&p, bytes, cudaStreamPerThread);
+    if (e == cudaErrorMemoryAllocation) {
+        // The pool keeps every freed block (release threshold "never"): blocks of other sizes, left by earlier scenes / batch
+        // shapes / contexts of this device, can crowd out a large request. Hand the unused ones back and try once more.
+        (void)cudaGetLastError();
+        int dev = 0;
+        cudaMemPool_t pool = nullptr;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            (void)cudaMemPoolTrimTo(pool, 0);
+        if (getenv("YK_SCENE_TIMING")) fprintf(stderr, "dev_alloc: %zu bytes did not fit, memory pool trimmed, retrying\n", bytes);
+        e = cudaMallocAsync(&p, bytes, cudaStreamPerThread);
+    }
+    CUDA_TRY(e);
     CUDA_TRY(cudaStreamSynchronize(cudaStreamPerThread));  // usable on every stream from here on
     bag.push_back(p);
     *out = (T*)p;
