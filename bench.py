@@ -567,8 +567,8 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "tile_dim": 16, "partition": f"spiral tiles interleaved over {world} rank(s)",
-                       "l2": "256 MB L2 flush between steps; wavefront state (several GB per batch) exceeds the 126 MB L2" + ("; the 37-node scene is cache-resident by nature" if SCENE == "cornell" else ""),
-                       "wavefront": "up to 16 Mi paths per batch, queue lengths on the device (no host sync per bounce)",
+                       "l2": "256 MB L2 flush between steps; wavefront state (tens of GB per batch) exceeds the 126 MB L2" + ("; the 37-node scene is cache-resident by nature" if SCENE == "cornell" else ""),
+                       "wavefront": "up to 64 Mi paths per batch (~24 GB of wavefront state per pipe), queue lengths on the device (no host sync per bounce)",
                        "pipes": ("value / roofline: one pipe, so that a kernel's event-bracketed time is its own; e2e: the library default, "
                                  "two pipes overlapping one batch's shading with the other's traversal") if VALUE_PIPES == 1
                        else "library default (two pipes) on every leg"},
