@@ -1,8 +1,8 @@
 // Several GPUs behind one handle (SURVEY.md §8b "one context per process owning G devices"; §8e): the counterpart of the
 // reference's RenderManager driving all of its workers from one shared tile queue (renderer/render_manager.rs:78-97,
 // 197-236; render_worker.rs:172-198 `pop_tile_or_signal_finish`).
-//   * one yk_context + one host worker thread per device, the scene replicated (validated once, uploaded to all devices
-//     in parallel from the caller's one host copy);
+//   * one yk_context + one host worker thread per device, the scene replicated: the first device validates, uploads and
+//     repacks the caller's one host copy, the others pull the repacked scene from it over NVLink (scene_clone_impl);
 //   * the tile list is consumed through ONE shared cursor by guided self-scheduling: a worker pops the next run of tiles (a
 //     range of a strided order of the spiral list, so that each run covers the film centre-out and costs about the same per
 //     tile; remaining / 2G tiles, i.e. large runs first and small ones last), renders it with the wavefront pipeline of its
@@ -272,9 +272,10 @@ int yk_multi_render(yk_multi* m, const yk_multi_scene* ms, const yk_camera* cam,
     // kernel tails — measured on 2 GPUs, runs of a quarter batch made the 16-spp large scene 35 % slower than one call per
     // device) and the last ones small (the finish times differ by at most one small run, whatever the devices' speeds),
     // never below ~16 Mi paths (two wavefront batches of 8 Mi, one per pipe; with 64 Mi the two devices of a 0.4 s render
-    // finished 39 ms apart). A job whose fair share is below 256 Mi paths is split statically, one run per device. The runs are ranges of a *strided* order of the tile list (position j -> tile
-    // j * stride mod n_tiles, stride ~ 0.618 n_tiles and coprime to it), so every run samples the whole spiral and costs
-    // about the same per tile. Accumulating: tile.index mod G (fixed add order per pixel).
+    // finished 39 ms apart). A job whose fair share is below 256 Mi paths is split statically, one run per device. The runs
+    // are ranges of a *strided* order of the tile list (position j -> tile j * stride mod n_tiles, stride ~ 0.618 n_tiles and
+    // coprime to it), so every run samples the whole spiral and costs about the same per tile. Accumulating: tile.index mod G
+    // (fixed add order per pixel).
     uint32_t run_floor = 1, run_fixed = 0, stride = 1;
     if (!accumulate && n_tiles) {
         const unsigned long long paths_per_tile = std::max<unsigned long long>(1, area / n_tiles) * spp;
