@@ -191,7 +191,8 @@ typedef int (*yk_progress_fn)(void* user, uint64_t samples_done, uint64_t sample
 
 typedef struct {
     uint32_t flags;
-    uint32_t wavefront_paths;   /* paths in flight per batch; 0 = default */
+    uint32_t wavefront_paths;   /* paths in flight per batch; 0 = default: what ~24 GB of device memory per pipe hold (~360 B per
+                                 * path with one light), at most 64 Mi, never more than a sixth of the free memory */
     int32_t* hit_ids;           /* optional res_x*res_y out: original triangle id of the primary hit of sample `aux_sample` (-1 miss) */
     uint32_t aux_sample;
     uint32_t pipes;             /* wavefront batches in flight on separate CUDA streams: 1 or 2; 0 = default (2; 1 for Whitted) */
