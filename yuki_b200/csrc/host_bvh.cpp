@@ -159,9 +159,16 @@ struct Builder {
         return mid;
     }
 
+    // What a SAH split already knows about its two sides: the unions of the bucket boxes on either side of the chosen plane are
+    // the children's shape bounds and "centroid" bounds (min / max unions are exact and association-free), so the children
+    // need not scan their primitives again for them — two of the four passes a node makes over its primitives.
+    struct ChildBounds {
+        bool valid = false;
+        box3 box[2], kb[2];
+    };
     // Returns the split position, `lo` when the method declines (caller falls back to the median), or
     // SIZE_MAX when SAH prefers a leaf (bvh.rs:510-521).
-    size_t choose_split(const box3& box, const box3& kb, size_t lo, size_t hi, int axis) {
+    size_t choose_split(const box3& box, const box3& kb, size_t lo, size_t hi, int axis, ChildBounds* cb) {
         const size_t n = hi - lo;
         if (method == YK_SPLIT_EQUAL_COUNTS) return median_split(lo, hi, axis);
         if (method == YK_SPLIT_MIDDLE) {  // split_middle, bvh.rs:438-450
@@ -170,28 +177,35 @@ struct Builder {
         }
         if (n <= 2) return lo;  // bvh.rs:461-462
         size_t count[kBuckets] = {};
-        box3 bbox[kBuckets];
+        box3 bbox[kBuckets], kbox[kBuckets];
         for (auto& b : bbox) b = empty_box();
+        for (auto& b : kbox) b = empty_box();
         if (workers > 1 && n >= kWideNode) {
-            struct Part { size_t count[kBuckets]; box3 bbox[kBuckets]; };
+            struct Part { size_t count[kBuckets]; box3 bbox[kBuckets], kbox[kBuckets]; };
             std::vector<Part> part(workers);
             for (Part& p : part)
-                for (int b = 0; b < kBuckets; ++b) { p.count[b] = 0; p.bbox[b] = empty_box(); }
+                for (int b = 0; b < kBuckets; ++b) { p.count[b] = 0; p.bbox[b] = empty_box(); p.kbox[b] = empty_box(); }
             for_chunks(n, [&](unsigned c, size_t b0, size_t e0) {
                 Part& p = part[c];
                 for (size_t i = lo + b0; i < lo + e0; ++i) {
                     const int b = bucket_index(kb, prims[i], axis);
                     p.count[b] += 1;
                     p.bbox[b] = merge(p.bbox[b], prims[i].box);
+                    p.kbox[b] = grow(p.kbox[b], prims[i].key);
                 }
             });
             for (const Part& p : part)
-                for (int b = 0; b < kBuckets; ++b) { count[b] += p.count[b]; bbox[b] = merge(bbox[b], p.bbox[b]); }
+                for (int b = 0; b < kBuckets; ++b) {
+                    count[b] += p.count[b];
+                    bbox[b] = merge(bbox[b], p.bbox[b]);
+                    kbox[b] = merge(kbox[b], p.kbox[b]);
+                }
         } else {
             for (size_t i = lo; i < hi; ++i) {
                 const int b = bucket_index(kb, prims[i], axis);
                 count[b] += 1;
                 bbox[b] = merge(bbox[b], prims[i].box);
+                kbox[b] = grow(kbox[b], prims[i].key);
             }
         }
         // Suffix boxes/counts once instead of the reference's O(buckets^2) folds; min/max unions are exact
@@ -222,6 +236,16 @@ struct Builder {
             }
         }
         if (!(best_cost < (float)n)) return SIZE_MAX;
+        if (cb) {
+            for (int side = 0; side < 2; ++side) { cb->box[side] = empty_box(); cb->kb[side] = empty_box(); }
+            for (int b = 0; b < kBuckets; ++b) {
+                if (!count[b]) continue;
+                const int side = b <= best ? 0 : 1;
+                cb->box[side] = merge(cb->box[side], bbox[b]);
+                cb->kb[side] = merge(cb->kb[side], kbox[b]);
+            }
+            cb->valid = true;
+        }
         return lo + front_partition(prims + lo, n, [&](const Prim& p) { return bucket_index(kb, p, axis) <= best; });
     }
 
@@ -237,21 +261,26 @@ struct Builder {
 
     // Appends the subtree over prims[lo, hi) to `out` in pre-order; returns its bounds. Node indices
     // written into `offset` are relative to out[0]; `depth` bounds how far down subtrees run as tasks.
-    box3 emit(std::vector<yk_bvh_node>& out, size_t lo, size_t hi, int task_depth) {
-        const box3 box = prim_bounds(lo, hi);
+    // (`known_box` / `known_kb`: the node's bounds when its parent's SAH split already produced them, else null.)
+    box3 emit(std::vector<yk_bvh_node>& out, size_t lo, size_t hi, int task_depth, const box3* known_box = nullptr, const box3* known_kb = nullptr) {
+        const box3 box = known_box ? *known_box : prim_bounds(lo, hi);
         const size_t n = hi - lo;
         if (n <= leaf_max) {
             emit_leaf(out, box, lo, hi);
             return box;
         }
-        const box3 kb = key_bounds(lo, hi);
+        const box3 kb = known_kb ? *known_kb : key_bounds(lo, hi);
         const int axis = widest_axis(kb);
         if (kb.hi.get(axis) == kb.lo.get(axis)) {  // bvh.rs:343
             emit_leaf(out, box, lo, hi);
             return box;
         }
-        size_t mid = choose_split(box, kb, lo, hi, axis);
-        if (method != YK_SPLIT_EQUAL_COUNTS && (mid == lo || mid == hi)) mid = median_split(lo, hi, axis);
+        ChildBounds cb;
+        size_t mid = choose_split(box, kb, lo, hi, axis, &cb);
+        if (method != YK_SPLIT_EQUAL_COUNTS && (mid == lo || mid == hi)) {
+            mid = median_split(lo, hi, axis);
+            cb.valid = false;  // another partition than the one the bucket unions describe
+        }
         if (mid == lo) {  // assert_ne!(mid, start, "BVH: Split failed") — bvh.rs:368
             failed = true;
             emit_leaf(out, box, lo, hi);
@@ -267,8 +296,10 @@ struct Builder {
         uint32_t second;
         if (task_depth > 0 && n >= kParallelCutoff) {
             std::vector<yk_bvh_node> lsub, rsub;
-            auto fut = std::async(std::launch::async, [&] { return emit(rsub, mid, hi, task_depth - 1); });
-            lbox = emit(lsub, lo, mid, task_depth - 1);
+            const box3 *lb = cb.valid ? &cb.box[0] : nullptr, *lk = cb.valid ? &cb.kb[0] : nullptr;
+            const box3 *rb = cb.valid ? &cb.box[1] : nullptr, *rk = cb.valid ? &cb.kb[1] : nullptr;
+            auto fut = std::async(std::launch::async, [&] { return emit(rsub, mid, hi, task_depth - 1, rb, rk); });
+            lbox = emit(lsub, lo, mid, task_depth - 1, lb, lk);
             rbox = fut.get();
             const uint32_t lbase = (uint32_t)out.size();
             for (auto nd : lsub) {
@@ -281,9 +312,9 @@ struct Builder {
                 out.push_back(nd);
             }
         } else {
-            lbox = emit(out, lo, mid, 0);
+            lbox = emit(out, lo, mid, 0, cb.valid ? &cb.box[0] : nullptr, cb.valid ? &cb.kb[0] : nullptr);
             second = (uint32_t)out.size();
-            rbox = emit(out, mid, hi, 0);
+            rbox = emit(out, mid, hi, 0, cb.valid ? &cb.box[1] : nullptr, cb.valid ? &cb.kb[1] : nullptr);
         }
         const box3 both = merge(lbox, rbox);  // BVHBuildNode::interior, bvh.rs:605-614
         yk_bvh_node& nd = out[self];
