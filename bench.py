@@ -392,7 +392,7 @@ def large_scene_leg(args, api, capi, xf, ctx, stream, rank, world, local, peak):
                     "ncu": tr.get("ncu"),
                     "note": "achieved = (32 B x node visits + 36 B x shape tests) / CUDA-event time of the closest-hit launches, one pipe, rank 0's tiles. "
                             "ncu on this scene: DRAM 4-6 % of peak, L1 hit 43-57 %, L2 hit 62-65 %, 16-17.5 of 32 lanes, issue-active 53-63 %, "
-                            "long-scoreboard 5-6.5 warps per issue (profiles/r02): the walk is bound by dependent-load latency and issue slots, "
+                            "long-scoreboard 3-6.5 warps per issue, L1TEX pipe 68-80 % (profiles/r02): the walk is bound by the load pipe, dependent-load latency and issue slots, "
                             "most algorithmic bytes are served by L1/L2, so frac is a throughput in the roofline's unit, not DRAM utilisation"}
         if world > 1:
             dist.barrier()
