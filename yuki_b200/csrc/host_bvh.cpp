@@ -27,6 +27,7 @@ struct Prim {
 struct Builder {
     Prim* prims;
     uint32_t leaf_max;
+    uint32_t n_total = 0;
     uint32_t method;
     std::atomic<bool> failed{false};
 
@@ -180,6 +181,9 @@ struct Builder {
         box3 bbox[kBuckets], kbox[kBuckets];
         for (auto& b : bbox) b = empty_box();
         for (auto& b : kbox) b = empty_box();
+        // The partition below asks for every primitive's bucket again: keep it, in the top four bits of the primitive's index
+        // (scenes below 2^28 shapes; the bits are masked off when the leaf order is read out), instead of dividing twice.
+        const bool tag = n_total < (1u << 28);
         if (workers > 1 && n >= kWideNode) {
             struct Part { size_t count[kBuckets]; box3 bbox[kBuckets], kbox[kBuckets]; };
             std::vector<Part> part(workers);
@@ -189,6 +193,7 @@ struct Builder {
                 Part& p = part[c];
                 for (size_t i = lo + b0; i < lo + e0; ++i) {
                     const int b = bucket_index(kb, prims[i], axis);
+                    if (tag) prims[i].index = (prims[i].index & 0x0fffffffu) | ((uint32_t)b << 28);
                     p.count[b] += 1;
                     p.bbox[b] = merge(p.bbox[b], prims[i].box);
                     p.kbox[b] = grow(p.kbox[b], prims[i].key);
@@ -203,6 +208,7 @@ struct Builder {
         } else {
             for (size_t i = lo; i < hi; ++i) {
                 const int b = bucket_index(kb, prims[i], axis);
+                if (tag) prims[i].index = (prims[i].index & 0x0fffffffu) | ((uint32_t)b << 28);
                 count[b] += 1;
                 bbox[b] = merge(bbox[b], prims[i].box);
                 kbox[b] = grow(kbox[b], prims[i].key);
@@ -246,6 +252,7 @@ struct Builder {
             }
             cb->valid = true;
         }
+        if (tag) return lo + front_partition(prims + lo, n, [best](const Prim& p) { return (int)(p.index >> 28) <= best; });
         return lo + front_partition(prims + lo, n, [&](const Prim& p) { return bucket_index(kb, p, axis) <= best; });
     }
 
@@ -385,6 +392,7 @@ int bvh_build_boxes(const float* boxes6, uint32_t n_tris, uint32_t max_shapes_in
     Builder bld;
     bld.prims = prims.data();
     bld.leaf_max = max_shapes_in_node;
+    bld.n_total = n_tris;
     bld.method = split_method;
     nodes->clear();
     nodes->reserve((size_t)2 * n_tris);
@@ -402,7 +410,7 @@ int bvh_build_boxes(const float* boxes6, uint32_t n_tris, uint32_t max_shapes_in
         return YK_ERR_BVH;
     }
     order->resize(n_tris);
-    for (uint32_t i = 0; i < n_tris; ++i) (*order)[i] = prims[i].index;
+    for (uint32_t i = 0; i < n_tris; ++i) (*order)[i] = n_tris < (1u << 28) ? (prims[i].index & 0x0fffffffu) : prims[i].index;
     return YK_OK;
 }
 
